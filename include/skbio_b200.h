@@ -1,0 +1,170 @@
+/*
+ * skbio_b200.h - C ABI of the B200-native all-pairs beta-diversity engine (libskbb200.so).
+ *
+ * This is the drop-in boundary for ONE path of scikit-bio:
+ *
+ *     skbio.diversity.beta_diversity(metric, counts, ids, tree=..., taxa=...)
+ *         /root/reference/skbio/diversity/_driver.py:231-355
+ *
+ * for metric in {unweighted_unifrac, weighted_unifrac (normalized or not), braycurtis,
+ * jaccard}.  The Python host (scikit-bio_b200/_driver.py) keeps the reference's signature,
+ * validation and error behaviour, flattens the TreeNode into parent/length arrays, turns the
+ * counts table into CSR and calls the functions below through ctypes - the same plugin
+ * convention the reference already uses for its optional accelerator library
+ * (ctypes.CDLL("libskbb.so"), /root/reference/skbio/binaries/_util.py:28-67; entry points
+ * taking raw caller-owned buffers, /root/reference/skbio/binaries/_distance.py:161-193).
+ * Unlike libskbb, every call returns an int status and b2d_last_error() explains a failure.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; all pointers are HOST pointers to
+ *     caller-owned, C-contiguous buffers; the library never frees caller memory;
+ *   - nodes are numbered as TreeNode.assign_ids numbers them
+ *     (/root/reference/skbio/tree/_tree.py:5337-5359): parent[k] > k for every non-root
+ *     node, exactly one node has parent[k] == -1 (the last one);
+ *   - results are SciPy "condensed" order: row-major upper triangle, element (i<j) at
+ *     i*n + j - (i+2)(i+1)/2  (/root/reference/skbio/stats/distance/_base.py:2453), fp64;
+ *   - one b2d_problem lives on one GPU and may own only a SHARD of the triangle: the
+ *     128-sample row stripes are dealt to n_shards in snake order; a shard writes only its
+ *     own stripes of the condensed vector (disjoint contiguous slices), so N processes or
+ *     N threads - one per GPU - fill one result with no inter-GPU exchange;
+ *   - thread-compatible: one call at a time per b2d_problem; different problems may be
+ *     driven from different host threads.
+ */
+#ifndef SKBIO_B200_H
+#define SKBIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_API_VERSION 1
+
+/* status codes */
+#define B2D_OK 0
+#define B2D_ERR_INVALID_ARGUMENT 1
+#define B2D_ERR_CUDA 2
+#define B2D_ERR_OUT_OF_MEMORY 3
+#define B2D_ERR_NO_DEVICE 4
+#define B2D_ERR_STATE 5
+
+/* metrics */
+#define B2D_UNWEIGHTED_UNIFRAC 0          /* replaces _unweighted_unifrac, beta/_unifrac.py:340-371 */
+#define B2D_WEIGHTED_UNIFRAC 1            /* replaces _weighted_unifrac, beta/_unifrac.py:374-418 */
+#define B2D_WEIGHTED_UNIFRAC_NORMALIZED 2 /* replaces _weighted_unifrac_normalized, :421-471 */
+#define B2D_BRAYCURTIS 3                  /* replaces scipy pdist 'braycurtis' called at _driver.py:349-354 */
+#define B2D_JACCARD 4                     /* replaces scipy pdist 'jaccard'    called at _driver.py:349-354 */
+
+/* Mirrors skbb_get_api_version (/root/reference/skbio/binaries/_util.py:92-110). */
+int b2d_api_version(void);
+/* Number of CUDA devices visible; 0 when there is none (then every compute call fails). */
+int b2d_device_count(void);
+/* Message of the last failure on the calling thread ("" if none). */
+const char* b2d_last_error(void);
+
+/* Page-locked host memory for result vectors (so device->host copies are true DMA). */
+void* b2d_host_alloc(size_t bytes);
+void b2d_host_free(void* ptr);
+
+typedef struct b2d_problem b2d_problem;
+
+/*
+ * Tree-based problem (UniFrac).  Replaces, on the device,
+ *   vectorize_counts_and_tree  /root/reference/skbio/diversity/_util.py:123-170
+ *   _nodes_by_counts           /root/reference/skbio/diversity/_phylogenetic.pyx:148-222
+ *   _traverse_reduce           /root/reference/skbio/diversity/_phylogenetic.pyx:73-143
+ *   _tip_distances             /root/reference/skbio/diversity/_phylogenetic.pyx:24-68
+ *
+ *   parent[n_nodes], length[n_nodes]  flat tree (length: NaN/None already replaced by 0.0)
+ *   indptr[n_samples+1], node_ids[nnz], values[nnz]
+ *       CSR sample x node table: the non-zero counts of each sample with the NODE id each
+ *       observed taxon maps to (the host applies the reference's name lookup).  values are
+ *       int64 (the reference truncates to int64, _phylogenetic.pyx:186); values may be NULL
+ *       for presence/absence input (unweighted UniFrac only).  A node id may appear at most
+ *       once per sample.
+ *   shard, n_shards   this problem owns row stripes {b : snake(b, n_shards) == shard}.
+ */
+int b2d_problem_create_tree(b2d_problem** out, int device,
+                            int64_t n_samples, int64_t n_nodes,
+                            const int32_t* parent, const double* length,
+                            const int64_t* indptr, const int32_t* node_ids,
+                            const int64_t* values,
+                            int shard, int n_shards);
+
+/*
+ * Feature-table problem (Bray-Curtis, Jaccard): CSR sample x feature, values fp64 (SciPy
+ * promotes the table to double, scipy/spatial/distance.py pdist); values may be NULL for
+ * presence/absence input (Jaccard only).
+ */
+int b2d_problem_create_features(b2d_problem** out, int device,
+                                int64_t n_samples, int64_t n_features,
+                                const int64_t* indptr, const int32_t* feature_ids,
+                                const double* values,
+                                int shard, int n_shards);
+
+/* Build the per-node sample embedding and run the pair kernels for `metric` on the
+ * problem's device.  Blocks until the shard's distances are complete in device memory. */
+int b2d_problem_compute(b2d_problem* p, int metric);
+
+/* Number of condensed elements this shard owns. */
+int64_t b2d_problem_result_len(const b2d_problem* p);
+
+/* Copy the shard's slices into the FULL condensed vector out[n(n-1)/2] (device->host). Only
+ * the owned slices are written.  `out` may be pageable or page-locked memory. */
+int b2d_problem_fetch(b2d_problem* p, double* out_condensed);
+
+/* Copy the shard's result COMPACTLY (owned stripes back to back, ascending stripe order)
+ * into out[b2d_problem_result_len]; stripe_offsets (may be NULL) receives, for every owned
+ * stripe, {first condensed index, count} pairs - at most 2*ceil(n/128) int64. */
+int b2d_problem_fetch_compact(b2d_problem* p, double* out, int64_t* stripe_offsets,
+                              int64_t* n_stripes_out);
+
+/* Per-sample vector computed on the way (length n_samples): Faith's PD for a tree problem
+ * after an unweighted compute (sum of branch lengths of observed nodes; replaces
+ * _faith_pd, /root/reference/skbio/diversity/alpha/_pd.py:19-51). */
+int b2d_problem_sample_vector(b2d_problem* p, double* out_n);
+
+/* Device-side phase timings of the last compute, milliseconds (CUDA events on the
+ * problem's stream): [0] embedding build, [1] pair kernels, [2] total compute,
+ * [3] last fetch (D2H), [4] upload at create (H2D), [5] last pair-kernel launch count,
+ * [6] nodes resident per pass, [7] number of passes. */
+int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
+
+int b2d_problem_destroy(b2d_problem* p);
+
+/* One-shot convenience: create + compute + fetch + destroy (host buffers in, host buffer
+ * out; this is the end-to-end call the Python host makes for a single GPU). */
+int b2d_beta_diversity_tree(int metric, int device,
+                            int64_t n_samples, int64_t n_nodes,
+                            const int32_t* parent, const double* length,
+                            const int64_t* indptr, const int32_t* node_ids,
+                            const int64_t* values,
+                            int shard, int n_shards, double* out_condensed);
+int b2d_beta_diversity_features(int metric, int device,
+                                int64_t n_samples, int64_t n_features,
+                                const int64_t* indptr, const int32_t* feature_ids,
+                                const double* values,
+                                int shard, int n_shards, double* out_condensed);
+
+/* Tuning knobs (0 keeps the default): nodes per pair-kernel launch (two-level fp64
+ * summation granularity) and a cap on the embedding bytes resident per pass. */
+int b2d_set_option(const char* name, int64_t value);
+
+/* On-device micro-benchmarks used by bench.py for the roofline denominators:
+ * kind 0: FP64 pipe, returns DFMA instructions/s;  kind 1: HBM copy, returns bytes/s. */
+int b2d_microbench(int device, int kind, double* result);
+
+/* Test hook (host only, no GPU needed): the engine's node order for a flat tree.  Arrays
+ * sized n_nodes (q_of_id) or n_nodes rounded up to a multiple of 128 (the others); any may
+ * be NULL.  flags: bit0 = node has children, bit1 = fold into the sibling accumulator,
+ * bit2 = padding. */
+int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* length,
+                         int32_t* q_of_id, uint8_t* flags_mpad, double* len_q_mpad,
+                         double* tipdist_q_mpad, int32_t* max_depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKBIO_B200_H */

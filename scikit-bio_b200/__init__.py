@@ -2,7 +2,10 @@
 
 Import as ``skbio_b200`` (see ``skbio_b200/__init__.py``).
 """
-from ._tree import (SimpleTreeNode, read_newick, flatten_tree,  # noqa: F401
+from ._tree import (SimpleTreeNode, read_newick, flatten_tree, validate_taxa_and_tree,  # noqa: F401
                     DuplicateNodeError, MissingNodeError)
+from ._dm import DistanceMatrix, SimpleDistanceMatrix  # noqa: F401
+from ._capi import EngineError, available  # noqa: F401
+from ._driver import beta_diversity, install  # noqa: F401
 
 __version__ = "0.1.0"

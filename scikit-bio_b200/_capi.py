@@ -1,0 +1,289 @@
+"""ctypes binding of libskbb200.so (declared in include/skbio_b200.h).
+
+Mirrors how the reference loads its optional accelerator:
+``ctypes.CDLL("libskbb.so")`` cached on first use, a version probe, raw caller-owned NumPy
+buffers passed as pointers (/root/reference/skbio/binaries/_util.py:28-110,
+/root/reference/skbio/binaries/_distance.py:161-193).  There is NO CPU fallback here: when
+the library or a GPU is missing, every compute entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_LIB = None
+_LIB_LOCK = threading.Lock()
+
+METRIC_IDS = {
+    "unweighted_unifrac": 0,
+    "weighted_unifrac": 1,
+    "weighted_unifrac_normalized": 2,
+    "braycurtis": 3,
+    "jaccard": 4,
+}
+
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class EngineError(RuntimeError):
+    """Raised when the native engine reports a failure (status code != 0)."""
+
+
+def library_path():
+    env = os.environ.get("SKBIO_B200_LIB")
+    if env:
+        return env
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libskbb200.so")
+
+
+def _declare(lib):
+    lib.b2d_api_version.restype = ctypes.c_int
+    lib.b2d_device_count.restype = ctypes.c_int
+    lib.b2d_last_error.restype = ctypes.c_char_p
+    lib.b2d_host_alloc.restype = ctypes.c_void_p
+    lib.b2d_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.b2d_host_free.restype = None
+    lib.b2d_host_free.argtypes = [ctypes.c_void_p]
+    lib.b2d_problem_create_tree.restype = ctypes.c_int
+    lib.b2d_problem_create_tree.argtypes = [
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+        _i32p, _f64p, _i64p, _i32p, _i64p, ctypes.c_int, ctypes.c_int]
+    lib.b2d_problem_create_features.restype = ctypes.c_int
+    lib.b2d_problem_create_features.argtypes = [
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+        _i64p, _i32p, _f64p, ctypes.c_int, ctypes.c_int]
+    lib.b2d_problem_compute.restype = ctypes.c_int
+    lib.b2d_problem_compute.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.b2d_problem_result_len.restype = ctypes.c_int64
+    lib.b2d_problem_result_len.argtypes = [ctypes.c_void_p]
+    lib.b2d_problem_fetch.restype = ctypes.c_int
+    lib.b2d_problem_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.b2d_problem_fetch_compact.restype = ctypes.c_int
+    lib.b2d_problem_fetch_compact.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _i64p, _i64p]
+    lib.b2d_problem_sample_vector.restype = ctypes.c_int
+    lib.b2d_problem_sample_vector.argtypes = [ctypes.c_void_p, _f64p]
+    lib.b2d_problem_timings.restype = ctypes.c_int
+    lib.b2d_problem_timings.argtypes = [ctypes.c_void_p, _f64p, ctypes.c_int]
+    lib.b2d_problem_destroy.restype = ctypes.c_int
+    lib.b2d_problem_destroy.argtypes = [ctypes.c_void_p]
+    lib.b2d_beta_diversity_tree.restype = ctypes.c_int
+    lib.b2d_beta_diversity_tree.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _i32p, _f64p, _i64p, _i32p,
+        _i64p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.b2d_beta_diversity_features.restype = ctypes.c_int
+    lib.b2d_beta_diversity_features.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _i64p, _i32p, _f64p,
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.b2d_set_option.restype = ctypes.c_int
+    lib.b2d_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    lib.b2d_microbench.restype = ctypes.c_int
+    lib.b2d_microbench.argtypes = [ctypes.c_int, ctypes.c_int, _f64p]
+    lib.b2d_debug_tree_order.restype = ctypes.c_int
+    lib.b2d_debug_tree_order.argtypes = [
+        ctypes.c_int64, _i32p, _f64p, _i32p, ctypes.POINTER(ctypes.c_uint8), _f64p, _f64p,
+        ctypes.POINTER(ctypes.c_int32)]
+
+
+EXPORTED_SYMBOLS = [
+    "b2d_api_version", "b2d_device_count", "b2d_last_error", "b2d_host_alloc", "b2d_host_free",
+    "b2d_problem_create_tree", "b2d_problem_create_features", "b2d_problem_compute",
+    "b2d_problem_result_len", "b2d_problem_fetch", "b2d_problem_fetch_compact",
+    "b2d_problem_sample_vector", "b2d_problem_timings", "b2d_problem_destroy",
+    "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
+    "b2d_microbench", "b2d_debug_tree_order",
+]
+
+
+def load():
+    """Load (once) and return the native library; raises EngineError if it is missing."""
+    global _LIB
+    with _LIB_LOCK:
+        if _LIB is None:
+            path = library_path()
+            if not os.path.exists(path):
+                raise EngineError(
+                    f"native engine not built: {path} is missing. Run "
+                    "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                    "`make -C scikit-bio_b200/csrc`. There is no CPU fallback.")
+            lib = ctypes.CDLL(path)
+            _declare(lib)
+            _LIB = lib
+    return _LIB
+
+
+def available():
+    """True when the library loads and at least one CUDA device is visible (mirrors
+    skbio.binaries.available)."""
+    try:
+        return load().b2d_device_count() > 0
+    except Exception:
+        return False
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load().b2d_last_error().decode("utf-8", "replace")
+        raise EngineError(f"libskbb200 error {rc}: {msg}")
+
+
+def _ptr(arr, typ):
+    if arr is None:
+        return None
+    return arr.ctypes.data_as(typ)
+
+
+def set_option(name, value):
+    _check(load().b2d_set_option(name.encode(), int(value)))
+
+
+def microbench(kind, device=0):
+    out = ctypes.c_double(0.0)
+    _check(load().b2d_microbench(int(device), int(kind), ctypes.byref(out)))
+    return out.value
+
+
+def debug_tree_order(parent, length):
+    """Engine node order of a flat tree (host-only test hook)."""
+    lib = load()
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    length = np.ascontiguousarray(length, dtype=np.float64)
+    m = len(parent)
+    mpad = (m + 127) // 128 * 128
+    q = np.empty(m, dtype=np.int32)
+    flags = np.empty(mpad, dtype=np.uint8)
+    lq = np.empty(mpad, dtype=np.float64)
+    td = np.empty(mpad, dtype=np.float64)
+    depth = ctypes.c_int32(0)
+    _check(lib.b2d_debug_tree_order(m, _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(q, _i32p),
+                                    flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                    _ptr(lq, _f64p), _ptr(td, _f64p), ctypes.byref(depth)))
+    return {"q_of_id": q, "flags": flags, "len_q": lq, "tipdist_q": td, "max_depth": depth.value}
+
+
+class PinnedBuffer:
+    """fp64 vector in page-locked host memory owned by the native library."""
+
+    def __init__(self, n):
+        self._lib = load()
+        self.n = int(n)
+        self.ptr = self._lib.b2d_host_alloc(max(self.n, 1) * 8)
+        if not self.ptr:
+            raise MemoryError("b2d_host_alloc failed")
+        buf = (ctypes.c_double * max(self.n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=self.n)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.b2d_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Problem:
+    """Inputs of one beta-diversity call resident on one GPU (one shard of the triangle)."""
+
+    def __init__(self, handle, n):
+        self._h = handle
+        self.n = n
+        self._keep = None
+
+    @classmethod
+    def tree(cls, parent, length, indptr, node_ids, values, n_samples, device=0, shard=0,
+             n_shards=1):
+        lib = load()
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        length = np.ascontiguousarray(length, dtype=np.float64)
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        node_ids = np.ascontiguousarray(node_ids, dtype=np.int32)
+        if values is not None:
+            values = np.ascontiguousarray(values, dtype=np.int64)
+        h = ctypes.c_void_p()
+        _check(lib.b2d_problem_create_tree(
+            ctypes.byref(h), int(device), int(n_samples), int(len(parent)),
+            _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(indptr, _i64p),
+            _ptr(node_ids, _i32p), _ptr(values, _i64p), int(shard), int(n_shards)))
+        return cls(h, int(n_samples))
+
+    @classmethod
+    def features(cls, indptr, feature_ids, values, n_samples, n_features, device=0, shard=0,
+                 n_shards=1):
+        lib = load()
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        feature_ids = np.ascontiguousarray(feature_ids, dtype=np.int32)
+        if values is not None:
+            values = np.ascontiguousarray(values, dtype=np.float64)
+        h = ctypes.c_void_p()
+        _check(lib.b2d_problem_create_features(
+            ctypes.byref(h), int(device), int(n_samples), int(n_features),
+            _ptr(indptr, _i64p), _ptr(feature_ids, _i32p), _ptr(values, _f64p),
+            int(shard), int(n_shards)))
+        return cls(h, int(n_samples))
+
+    def compute(self, metric):
+        mid = METRIC_IDS[metric] if isinstance(metric, str) else int(metric)
+        _check(load().b2d_problem_compute(self._h, mid))
+
+    def result_len(self):
+        return int(load().b2d_problem_result_len(self._h))
+
+    def fetch(self, out):
+        """Write the owned slices into the full condensed vector ``out`` (float64)."""
+        assert out.dtype == np.float64 and out.flags.c_contiguous
+        assert out.size == self.n * (self.n - 1) // 2
+        if out.size:
+            _check(load().b2d_problem_fetch(self._h, out.ctypes.data))
+        return out
+
+    def fetch_compact(self, out=None):
+        lib = load()
+        m = self.result_len()
+        if out is None:
+            out = np.empty(m, dtype=np.float64)
+        nb = (self.n + 127) // 128
+        offs = np.zeros(2 * max(nb, 1), dtype=np.int64)
+        cnt = ctypes.c_int64(0)
+        _check(lib.b2d_problem_fetch_compact(self._h, out.ctypes.data, _ptr(offs, _i64p),
+                                             ctypes.byref(cnt)))
+        return out, offs[: 2 * cnt.value].reshape(-1, 2)
+
+    def sample_vector(self):
+        out = np.empty(self.n, dtype=np.float64)
+        if self.n:
+            _check(load().b2d_problem_sample_vector(self._h, _ptr(out, _f64p)))
+        return out
+
+    def timings(self):
+        t = np.zeros(8, dtype=np.float64)
+        _check(load().b2d_problem_timings(self._h, _ptr(t, _f64p), 8))
+        return {"embed_ms": t[0], "pair_ms": t[1], "compute_ms": t[2], "fetch_ms": t[3],
+                "upload_ms": t[4], "pair_launches": int(t[5]), "nodes_resident": int(t[6]),
+                "passes": int(t[7])}
+
+    def destroy(self):
+        if self._h is not None:
+            load().b2d_problem_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.destroy()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.destroy()
+        except Exception:
+            pass

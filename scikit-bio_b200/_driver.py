@@ -1,0 +1,266 @@
+"""``beta_diversity`` - drop-in for ``skbio.diversity.beta_diversity`` on the B200 engine.
+
+Same signature, validation order, exception types/messages and return type as
+/root/reference/skbio/diversity/_driver.py:231-355 for
+
+    unweighted_unifrac, weighted_unifrac (normalized=False|True), braycurtis, jaccard
+
+which run on the GPU through libskbb200.so (no CPU path: a missing library or GPU raises
+``EngineError``).  Every other metric / a user ``pairwise_func`` / a callable metric is not on
+this engine's path and is handed to the reference's own route (scikit-bio if importable,
+else the same ``scipy.spatial.distance.pdist`` call the reference makes).
+
+Engine-only keyword arguments (not forwarded to any metric):
+    devices   : int or list of int, GPUs to shard the pair triangle over (default [0])
+    condensed : keep the result in condensed form (skbio >= 0.7 ``DistanceMatrix(...,
+                condensed=True)``); default False like the reference
+"""
+
+from __future__ import annotations
+
+import threading
+import warnings
+from functools import partial
+from inspect import signature
+
+import numpy as np
+
+from . import _capi
+from ._dm import make_distance_matrix
+from ._table import ingest_table, to_csr, validate_counts_matrix, _is_sparse
+from ._tree import flatten_tree, map_taxa_to_nodes, validate_taxa_and_tree
+
+# /root/reference/skbio/diversity/_driver.py:43-52
+_qualitative_metrics = {
+    "dice", "jaccard", "matching", "rogerstanimoto", "russellrao", "sokalsneath", "yule",
+    "unweighted_unifrac",
+}
+_slow_beta_callables = {"unweighted_unifrac", "weighted_unifrac"}
+# /root/reference/skbio/diversity/_driver.py:58-84
+_pdist_metrics = {
+    "euclidean", "cityblock", "braycurtis", "canberra", "chebyshev", "correlation", "cosine",
+    "dice", "hamming", "jaccard", "jensenshannon", "mahalanobis", "manhattan", "matching",
+    "minkowski", "rogerstanimoto", "russellrao", "seuclidean", "sokalsneath", "sqeuclidean",
+    "yule",
+}
+_engine_metrics = {"unweighted_unifrac", "weighted_unifrac", "braycurtis", "jaccard"}
+_normalize_weighted_unifrac_by_default = False  # beta/_unifrac.py:26
+
+
+def _get_phylogenetic_kwargs(kwargs, taxa):
+    # /root/reference/skbio/diversity/_util.py:173-181
+    if taxa is None:
+        raise ValueError("`taxa` is required for phylogenetic diversity metrics.")
+    try:
+        tree = kwargs.pop("tree")
+    except KeyError:
+        raise ValueError("`tree` is required for phylogenetic diversity metrics.")
+    return taxa, tree, kwargs
+
+
+def _devices_arg(devices):
+    if devices is None:
+        return [0]
+    if isinstance(devices, (int, np.integer)):
+        return [int(devices)]
+    devs = [int(d) for d in devices]
+    if not devs:
+        raise ValueError("`devices` must name at least one GPU.")
+    return devs
+
+
+def _run_sharded(make_problem, metric_key, n, devices):
+    """One problem (shard) per device, each driven by its own host thread; every shard
+    writes its own disjoint slices of one page-locked condensed vector."""
+    if _capi.load().b2d_device_count() <= 0:
+        raise _capi.EngineError(
+            "no CUDA device visible: the B200 engine has no CPU fallback for "
+            f"'{metric_key}'.")
+    total = n * (n - 1) // 2
+    buf = _capi.PinnedBuffer(total)
+    out = buf.array
+    errors = []
+
+    def work(shard, dev):
+        try:
+            with make_problem(dev, shard, len(devices)) as prob:
+                prob.compute(metric_key)
+                prob.fetch(out)
+        except BaseException as e:  # propagate to the caller thread
+            errors.append(e)
+
+    if len(devices) == 1:
+        work(0, devices[0])
+    else:
+        threads = [threading.Thread(target=work, args=(s, d)) for s, d in enumerate(devices)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        buf.free()
+        raise errors[0]
+    result = np.array(out, copy=True)  # detach from pinned memory owned by the library
+    buf.free()
+    return result
+
+
+def _unifrac_engine(metric_key, counts, taxa, tree, validate, devices):
+    """Replaces _setup_multiple_{un,}weighted_unifrac + pdist
+    (/root/reference/skbio/diversity/beta/_unifrac.py:474-584, _driver.py:349-354)."""
+    if validate:
+        validate_taxa_and_tree(taxa, tree)
+    parent, length, names = flatten_tree(tree)
+    mode = "presence" if metric_key == "unweighted_unifrac" else "int64"
+    indptr, cols, vals = to_csr(counts, mode)
+    n = counts.shape[0]
+    observed_cols = np.unique(cols)
+    node_of_col = map_taxa_to_nodes(taxa, observed_cols, names)
+    node_ids = node_of_col[cols]
+    if len(np.unique(node_of_col[observed_cols])) != len(observed_cols):
+        # several observed taxa map to one node (only reachable with validate=False):
+        # the reference assigns, so the last column wins (_phylogenetic.pyx:208-218)
+        indptr, node_ids, vals = _dedupe_last_wins(indptr, node_ids, vals)
+
+    def make(dev, shard, nshards):
+        return _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, device=dev,
+                                  shard=shard, n_shards=nshards)
+
+    return _run_sharded(make, metric_key, n, devices)
+
+
+def _dedupe_last_wins(indptr, node_ids, vals):
+    n = len(indptr) - 1
+    new_ptr = np.zeros(n + 1, dtype=np.int64)
+    ids_out, vals_out = [], []
+    for s in range(n):
+        a, b = indptr[s], indptr[s + 1]
+        seen = {}
+        for e in range(a, b):
+            seen[int(node_ids[e])] = e
+        es = sorted(seen.values())
+        ids_out.append(node_ids[es])
+        if vals is not None:
+            vals_out.append(vals[es])
+        new_ptr[s + 1] = new_ptr[s] + len(es)
+    ids = np.concatenate(ids_out) if ids_out else node_ids[:0]
+    v = None if vals is None else (np.concatenate(vals_out) if vals_out else vals[:0])
+    return new_ptr, ids.astype(np.int32), v
+
+
+def _features_engine(metric_key, counts, devices):
+    mode = "presence" if metric_key == "jaccard" else "float64"
+    indptr, cols, vals = to_csr(counts, mode)
+    n, f = counts.shape
+
+    def make(dev, shard, nshards):
+        return _capi.Problem.features(indptr, cols, vals, n, f, device=dev, shard=shard,
+                                      n_shards=nshards)
+
+    return _run_sharded(make, metric_key, n, devices)
+
+
+def beta_diversity(metric, counts, ids=None, validate=True, pairwise_func=None, **kwargs):
+    r"""Compute distances between all pairs of samples (see the module docstring).
+
+    Parameters and behaviour follow ``skbio.diversity.beta_diversity``
+    (/root/reference/skbio/diversity/_driver.py:231-355).
+    """
+    devices = _devices_arg(kwargs.pop("devices", None))
+    condensed = bool(kwargs.pop("condensed", False))
+    taxa = kwargs.pop("taxa", None)
+    counts, ids, taxa = ingest_table(counts, ids, taxa)
+    if 0 in counts.shape:
+        # _driver.py:295-300
+        return make_distance_matrix(np.zeros((len(ids), len(ids))), ids)
+    if validate:
+        counts = validate_counts_matrix(counts)
+
+    on_engine = isinstance(metric, str) and metric in _engine_metrics and pairwise_func is None
+    if not on_engine:
+        return _reference_route(metric, counts, ids, validate, pairwise_func, taxa, kwargs)
+
+    if ids is not None:
+        ids = tuple(ids)
+    n = counts.shape[0]
+    if metric in ("unweighted_unifrac", "weighted_unifrac"):
+        taxa, tree, kwargs = _get_phylogenetic_kwargs(kwargs, taxa)
+        key = metric
+        if metric == "weighted_unifrac":
+            normalized = kwargs.pop("normalized", _normalize_weighted_unifrac_by_default)
+            if normalized:
+                key = "weighted_unifrac_normalized"
+        if kwargs:
+            # the reference forwards leftovers to the pair function, which rejects them
+            # (test_driver.py:412-428)
+            raise TypeError(
+                f"{metric}() got an unexpected keyword argument '{next(iter(kwargs))}'")
+        vec = _unifrac_engine(key, counts, taxa, tree, validate, devices)
+    else:
+        if kwargs:
+            raise TypeError(
+                f"pdist metric '{metric}' got an unexpected keyword argument "
+                f"'{next(iter(kwargs))}'")
+        vec = _features_engine(metric, counts, devices)
+    return make_distance_matrix(vec, ids, condensed=condensed, n=n)
+
+
+def _reference_route(metric, counts, ids, validate, pairwise_func, taxa, kwargs):
+    """Metrics that are not on the engine's path: run exactly what the reference runs."""
+    if _is_sparse(counts):
+        counts = counts.toarray()
+    try:  # pragma: no cover - depends on the environment
+        from skbio.diversity import beta_diversity as _skbio_beta_diversity  # type: ignore
+    except Exception:
+        _skbio_beta_diversity = None
+    if _skbio_beta_diversity is not None:  # pragma: no cover
+        kw = dict(kwargs)
+        if taxa is not None:
+            kw["taxa"] = taxa
+        return _skbio_beta_diversity(metric, counts, ids, validate=validate,
+                                     pairwise_func=pairwise_func, **kw)
+    # scikit-bio absent: restate _driver.py:303-355 for SciPy / callable metrics
+    if isinstance(metric, str) and metric in _qualitative_metrics:
+        counts = counts > 0.0
+    if metric in ("unweighted_unifrac", "weighted_unifrac"):
+        raise _capi.EngineError(
+            "a custom pairwise_func with a UniFrac metric needs scikit-bio's CPU "
+            "implementation, which is not installed here.")
+    if metric == "manhattan":
+        metric = "cityblock"
+    elif metric == "mahalanobis":
+        nrow, ncol = counts.shape
+        if nrow < ncol:
+            raise ValueError(
+                "Metric 'mahalanobis' requires more samples than features. "
+                f"The input has {nrow} samples and {ncol} features.")
+    elif callable(metric):
+        if getattr(metric, "__name__", None) in _slow_beta_callables:
+            warnings.warn(
+                f"Passing `{metric.__name__}` as a callable invokes a much slower "
+                "implementation. Pass the metric name as a string "
+                f"(e.g., metric='{metric.__name__}') to use the optimized version.",
+                stacklevel=3)
+        if taxa is not None and "taxa" in signature(metric).parameters:
+            kwargs["taxa"] = taxa
+        metric = partial(metric, **kwargs)
+        kwargs = {}
+    elif metric not in _pdist_metrics:
+        raise ValueError(
+            f'"{metric}" is not an available beta diversity metric name. '
+            "Refer to `get_beta_diversity_metrics` for a list of available metrics.")
+    if pairwise_func is None:
+        from scipy.spatial.distance import pdist
+
+        pairwise_func = pdist
+    distances = pairwise_func(counts, metric=metric, **kwargs)
+    return make_distance_matrix(np.asarray(distances, dtype=np.float64), ids)
+
+
+def install():
+    """Rebind ``skbio.diversity.beta_diversity`` to this engine (optional monkey-patch)."""
+    import skbio.diversity as _d  # type: ignore
+    import skbio.diversity._driver as _drv  # type: ignore
+
+    _d.beta_diversity = beta_diversity
+    _drv.beta_diversity = beta_diversity

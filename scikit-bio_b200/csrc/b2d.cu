@@ -1,0 +1,738 @@
+// libskbb200.so - C ABI implementation (see include/skbio_b200.h).
+//
+// One b2d_problem = the inputs of one beta_diversity call resident on one GPU plus the
+// shard of the pair triangle that GPU owns.  compute() = embedding build (scatter +
+// propagation) followed by pair-tile kernel launches over node ranges; fetch() = D2H of the
+// owned condensed slices.
+#include "../../include/skbio_b200.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "b2d_common.cuh"
+#include "b2d_embed.cuh"
+#include "b2d_pair.cuh"
+#include "b2d_tree.h"
+
+namespace b2d {
+thread_local std::string g_last_error;
+
+static int64_t g_chunk_nodes = 8192;           // nodes per pair-kernel launch
+static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
+static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
+
+static bool plain_kernels() {
+    if (g_plain_kernels < 0) {
+        const char* e = getenv("B2D_PLAIN_KERNELS");
+        g_plain_kernels = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_plain_kernels == 1;
+}
+
+__global__ void k_map_ids(const int32_t* ids, const int32_t* __restrict__ q_of_id,
+                          int32_t* qidx, int64_t nnz, int64_t m, int* err) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int32_t id = ids[e];
+    if (id < 0 || id >= m) {
+        *err = 1;
+        qidx[e] = 0;
+        return;
+    }
+    qidx[e] = q_of_id ? q_of_id[id] : id;
+}
+
+__global__ void k_fill_double(double* p, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- micro-benchmarks (roofline denominators measured on the box) -----------------------
+__global__ void k_bench_dfma(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4,
+           a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double x = 1.0000001, y = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+        a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = src[i];
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+struct b2d_problem {
+    int device = 0;
+    int kind = 0;  // 0 tree, 1 features
+    int64_t n = 0, nb = 0, npad = 0;
+    int64_t m = 0, mpad = 0, NS = 0;
+    int64_t nnz = 0;
+    int shard = 0, n_shards = 1;
+    bool has_values = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    TreeOrder order;
+    // device inputs
+    int64_t* d_indptr = nullptr;
+    int32_t* d_qidx = nullptr;
+    void* d_values = nullptr;  // int64 (tree) or double (features)
+    uint8_t* d_flags = nullptr;
+    uint32_t* d_hc = nullptr;
+    uint32_t* d_fold = nullptr;
+    double* d_len = nullptr;
+    double* d_tipdist = nullptr;
+    // shard geometry
+    std::vector<int64_t> owned;      // owned row stripes
+    std::vector<int64_t> row_base;   // [nb] offset in d_out or -1
+    int32_t* d_tiles = nullptr;
+    int64_t ntiles = 0;
+    int64_t* d_row_base = nullptr;
+    double* d_out = nullptr;
+    int64_t out_len = 0;
+    // per sample
+    long long* d_total = nullptr;
+    double* d_svec = nullptr;
+    // embedding
+    void* d_emb = nullptr;
+    size_t emb_bytes = 0;
+    long long* d_state = nullptr;
+    bool computed = false;
+    int last_metric = -1;
+    double t_embed = 0, t_pair = 0, t_total = 0, t_fetch = 0, t_upload = 0;
+    double n_launch = 0, nodes_resident = 0, n_pass = 0;
+};
+
+static void free_problem(b2d_problem* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_indptr); cudaFree(p->d_qidx); cudaFree(p->d_values); cudaFree(p->d_flags);
+    cudaFree(p->d_hc); cudaFree(p->d_fold); cudaFree(p->d_len); cudaFree(p->d_tipdist);
+    cudaFree(p->d_tiles); cudaFree(p->d_row_base); cudaFree(p->d_out); cudaFree(p->d_total);
+    cudaFree(p->d_svec); cudaFree(p->d_emb); cudaFree(p->d_state);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+template <typename T>
+static int upload(T** dst, const T* src, size_t count, cudaStream_t s) {
+    B2D_CUDA(cudaMalloc((void**)dst, std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) B2D_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return B2D_OK;
+}
+
+static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* ids,
+                        const void* values, size_t value_size) {
+    cudaEvent_t e0, e1;
+    B2D_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto& e : p->ev) B2D_CUDA(cudaEventCreate(&e));
+    B2D_CUDA(cudaEventCreate(&e0));
+    B2D_CUDA(cudaEventCreate(&e1));
+    B2D_CUDA(cudaEventRecord(e0, p->stream));
+    const TreeOrder& o = p->order;
+    int rc;
+    if ((rc = upload(&p->d_indptr, indptr, (size_t)p->n + 1, p->stream))) return rc;
+    if ((rc = upload(&p->d_qidx, ids, (size_t)p->nnz, p->stream))) return rc;
+    if (values) {
+        B2D_CUDA(cudaMalloc(&p->d_values, std::max<size_t>(p->nnz, 1) * value_size));
+        if (p->nnz)
+            B2D_CUDA(cudaMemcpyAsync(p->d_values, values, p->nnz * value_size,
+                                     cudaMemcpyHostToDevice, p->stream));
+    }
+    if ((rc = upload(&p->d_flags, o.flags.data(), o.flags.size(), p->stream))) return rc;
+    if ((rc = upload(&p->d_hc, o.hc_mask.data(), o.hc_mask.size(), p->stream))) return rc;
+    if ((rc = upload(&p->d_fold, o.fold_mask.data(), o.fold_mask.size(), p->stream))) return rc;
+    if ((rc = upload(&p->d_len, o.len_q.data(), o.len_q.size(), p->stream))) return rc;
+    if ((rc = upload(&p->d_tipdist, o.tipdist_q.data(), o.tipdist_q.size(), p->stream))) return rc;
+    // node id -> engine position, on the device
+    {
+        int32_t* d_qof = nullptr;
+        int* d_err = nullptr;
+        if (p->kind == 0) {
+            if ((rc = upload(&d_qof, o.q_of_id.data(), o.q_of_id.size(), p->stream))) return rc;
+        }
+        B2D_CUDA(cudaMalloc(&d_err, sizeof(int)));
+        B2D_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), p->stream));
+        if (p->nnz) {
+            int64_t blocks = (p->nnz + 255) / 256;
+            k_map_ids<<<(unsigned)blocks, 256, 0, p->stream>>>(p->d_qidx, d_qof, p->d_qidx, p->nnz,
+                                                               p->m, d_err);
+        }
+        int herr = 0;
+        B2D_CUDA(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        cudaFree(d_qof);
+        cudaFree(d_err);
+        if (herr) return fail(B2D_ERR_INVALID_ARGUMENT, "node/feature id out of range in CSR indices");
+    }
+    // shard geometry: owned row stripes, tiles, compact output offsets
+    p->row_base.assign(p->nb, -1);
+    std::vector<int32_t> tiles;
+    int64_t off = 0;
+    for (int64_t b = 0; b < p->nb; ++b) {
+        if (stripe_owner(b, p->n_shards) != p->shard) continue;
+        int64_t i0 = b * TILE, i1 = std::min<int64_t>(p->n, i0 + TILE);
+        int64_t cnt = 0;
+        for (int64_t i = i0; i < i1; ++i) cnt += p->n - 1 - i;
+        if (cnt == 0) continue;
+        p->owned.push_back(b);
+        p->row_base[b] = off;
+        off += cnt;
+        for (int64_t c = b; c < p->nb; ++c) {
+            tiles.push_back((int32_t)b);
+            tiles.push_back((int32_t)c);
+        }
+    }
+    p->out_len = off;
+    p->ntiles = (int64_t)tiles.size() / 2;
+    if ((rc = upload(&p->d_tiles, tiles.data(), tiles.size(), p->stream))) return rc;
+    if ((rc = upload(&p->d_row_base, p->row_base.data(), p->row_base.size(), p->stream))) return rc;
+    B2D_CUDA(cudaMalloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+    B2D_CUDA(cudaMalloc(&p->d_total, p->npad * sizeof(long long)));
+    B2D_CUDA(cudaMalloc(&p->d_svec, p->npad * sizeof(double)));
+    B2D_CUDA(cudaMemsetAsync(p->d_total, 0, p->npad * sizeof(long long), p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_svec, 0, p->npad * sizeof(double), p->stream));
+    B2D_CUDA(cudaEventRecord(e1, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    p->t_upload = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return B2D_OK;
+}
+
+static int check_common(b2d_problem** out, int device, int64_t n, int64_t m,
+                        const int64_t* indptr, const int32_t* ids, int shard, int n_shards) {
+    if (!out) return fail(B2D_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (n < 0 || m <= 0) return fail(B2D_ERR_INVALID_ARGUMENT, "n_samples must be >= 0 and n_nodes/n_features > 0");
+    if (m > (int64_t)1 << 30) return fail(B2D_ERR_INVALID_ARGUMENT, "too many nodes/features (limit 2^30)");
+    if (!indptr) return fail(B2D_ERR_INVALID_ARGUMENT, "indptr is NULL");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "need 0 <= shard < n_shards");
+    if (indptr[0] != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "indptr[0] must be 0");
+    for (int64_t s = 0; s < n; ++s)
+        if (indptr[s + 1] < indptr[s]) return fail(B2D_ERR_INVALID_ARGUMENT, "indptr must be non-decreasing");
+    if (indptr[n] > 0 && !ids) return fail(B2D_ERR_INVALID_ARGUMENT, "indices is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2D_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(B2D_ERR_INVALID_ARGUMENT, "device index out of range");
+    B2D_CUDA(cudaSetDevice(device));
+    return B2D_OK;
+}
+
+extern "C" {
+
+int b2d_api_version(void) { return B2D_API_VERSION; }
+
+int b2d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* b2d_last_error(void) { return g_last_error.c_str(); }
+
+void* b2d_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        g_last_error = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+
+void b2d_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+int b2d_set_option(const char* name, int64_t value) {
+    if (!name) return fail(B2D_ERR_INVALID_ARGUMENT, "name is NULL");
+    std::string s(name);
+    if (s == "chunk_nodes") {
+        g_chunk_nodes = value <= 0 ? 8192 : (value + 127) / 128 * 128;
+    } else if (s == "emb_budget_bytes") {
+        g_emb_budget_bytes = value < 0 ? 0 : value;
+    } else if (s == "plain_kernels") {
+        g_plain_kernels = value ? 1 : 0;
+    } else {
+        return fail(B2D_ERR_INVALID_ARGUMENT, "unknown option " + s);
+    }
+    return B2D_OK;
+}
+
+int b2d_problem_create_tree(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes,
+                            const int32_t* parent, const double* length, const int64_t* indptr,
+                            const int32_t* node_ids, const int64_t* values, int shard,
+                            int n_shards) {
+    int rc = check_common(out, device, n_samples, n_nodes, indptr, node_ids, shard, n_shards);
+    if (rc) return rc;
+    if (!parent || !length) return fail(B2D_ERR_INVALID_ARGUMENT, "parent/length is NULL");
+    b2d_problem* p = new b2d_problem();
+    p->device = device;
+    p->kind = 0;
+    p->n = n_samples;
+    p->nb = (n_samples + TILE - 1) / TILE;
+    p->npad = std::max<int64_t>(p->nb, 1) * TILE;
+    p->m = n_nodes;
+    p->shard = shard;
+    p->n_shards = n_shards;
+    p->nnz = indptr[n_samples];
+    p->has_values = values != nullptr;
+    std::string err = build_tree_order(n_nodes, parent, length, p->order);
+    if (!err.empty()) {
+        free_problem(p);
+        return fail(B2D_ERR_INVALID_ARGUMENT, err);
+    }
+    p->mpad = p->order.mpad;
+    p->NS = p->mpad / NODE_STRIPE;
+    rc = setup_common(p, indptr, node_ids, values, sizeof(int64_t));
+    if (rc) {
+        free_problem(p);
+        return rc;
+    }
+    *out = p;
+    return B2D_OK;
+}
+
+int b2d_problem_create_features(b2d_problem** out, int device, int64_t n_samples,
+                                int64_t n_features, const int64_t* indptr,
+                                const int32_t* feature_ids, const double* values, int shard,
+                                int n_shards) {
+    int rc = check_common(out, device, n_samples, n_features, indptr, feature_ids, shard, n_shards);
+    if (rc) return rc;
+    b2d_problem* p = new b2d_problem();
+    p->device = device;
+    p->kind = 1;
+    p->n = n_samples;
+    p->nb = (n_samples + TILE - 1) / TILE;
+    p->npad = std::max<int64_t>(p->nb, 1) * TILE;
+    p->m = n_features;
+    p->shard = shard;
+    p->n_shards = n_shards;
+    p->nnz = indptr[n_samples];
+    p->has_values = values != nullptr;
+    TreeOrder& o = p->order;
+    o.m = n_features;
+    o.mpad = (n_features + 127) / 128 * 128;
+    o.flags.assign(o.mpad, NF_PAD);
+    for (int64_t k = 0; k < n_features; ++k) o.flags[k] = NF_FOLD;
+    o.hc_mask.assign(o.mpad / 32, 0u);
+    o.fold_mask.assign(o.mpad / 32, 0xffffffffu);
+    o.len_q.assign(o.mpad, 0.0);
+    for (int64_t k = 0; k < n_features; ++k) o.len_q[k] = 1.0;
+    o.tipdist_q.assign(1, 0.0);
+    o.depth_at.assign(o.mpad / 128 + 1, 0);
+    p->mpad = o.mpad;
+    p->NS = p->mpad / NODE_STRIPE;
+    rc = setup_common(p, indptr, feature_ids, values, sizeof(double));
+    if (rc) {
+        free_problem(p);
+        return rc;
+    }
+    *out = p;
+    return B2D_OK;
+}
+
+static int ensure_emb(b2d_problem* p, size_t bytes) {
+    if (p->emb_bytes >= bytes) return B2D_OK;
+    if (p->d_emb) {
+        cudaFree(p->d_emb);
+        p->d_emb = nullptr;
+        p->emb_bytes = 0;
+    }
+    B2D_CUDA(cudaMalloc(&p->d_emb, bytes));
+    p->emb_bytes = bytes;
+    return B2D_OK;
+}
+
+static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* len_rel,
+                              int64_t q0, int64_t q1, int64_t QR, int epilogue) {
+    // node chunks [qa, qb) relative to the resident range; two-level fp64 summation:
+    // registers within a chunk, `out` across chunks.
+    B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)WK_SMEM));
+    for (int64_t qa = 0; qa < q1 - q0; qa += g_chunk_nodes) {
+        int64_t qb = std::min<int64_t>(q1 - q0, qa + g_chunk_nodes);
+        PairArgs a;
+        a.tiles = p->d_tiles;
+        a.row_base = p->d_row_base;
+        a.out = p->d_out;
+        a.svec = p->d_svec;
+        a.total = p->d_total;
+        a.n = p->n;
+        a.qa = qa;
+        a.qb = qb;
+        a.QR = QR;
+        a.NS = p->NS;
+        a.first = (q0 + qa == 0);
+        a.last = (q0 + qb == p->mpad);
+        a.epilogue = epilogue;
+        if (plain_kernels())
+            k_pair_weighted_plain<<<(unsigned)p->ntiles, 256, 0, p->stream>>>(emb, len_rel, a);
+        else
+            k_pair_weighted<<<(unsigned)p->ntiles, WK_THREADS, WK_SMEM, p->stream>>>(emb, len_rel, a);
+        p->n_launch += 1;
+    }
+    B2D_CUDA(cudaGetLastError());
+    return B2D_OK;
+}
+
+static int compute_dense(b2d_problem* p, int metric) {
+    // fp64 embedding path: weighted UniFrac (tree) and Bray-Curtis (features)
+    const bool tree = p->kind == 0;
+    const unsigned wpb = 8;  // warps per block for the per-sample kernels
+    const unsigned sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    float ms;
+    B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
+    if (tree) {
+        k_sample_totals_tree<<<sblocks, wpb * 32, 0, p->stream>>>(
+            p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->d_flags,
+            metric == B2D_WEIGHTED_UNIFRAC_NORMALIZED ? p->d_tipdist : nullptr, p->n, p->d_total,
+            p->d_svec);
+    } else {
+        k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(
+            p->d_indptr, (const double*)p->d_values, p->n, p->d_svec);
+    }
+    // resident node range
+    size_t free_b = 0, total_b = 0;
+    B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t row_bytes = (size_t)p->nb * TILE * sizeof(double);
+    size_t budget = g_emb_budget_bytes ? (size_t)g_emb_budget_bytes
+                                       : (size_t)((double)(free_b + p->emb_bytes) * 0.85);
+    int64_t QR = (int64_t)(budget / std::max<size_t>(row_bytes, 1));
+    QR = QR / NODE_STRIPE * NODE_STRIPE;
+    if (QR < NODE_STRIPE) return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for one node stripe");
+    QR = std::min<int64_t>(QR, p->mpad);
+    int rc = ensure_emb(p, (size_t)QR * row_bytes);
+    if (rc) return rc;
+    if (tree && !p->d_state)
+        B2D_CUDA(cudaMalloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
+    int epilogue = metric == B2D_WEIGHTED_UNIFRAC_NORMALIZED ? EPI_WEIGHTED_NORM
+                   : metric == B2D_BRAYCURTIS               ? EPI_BRAYCURTIS
+                                                             : EPI_RAW;
+    p->n_launch = 0;
+    p->n_pass = 0;
+    p->nodes_resident = (double)QR;
+    double t_embed = 0, t_pair = 0;
+    cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
+    for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
+        int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
+        B2D_CUDA(cudaEventRecord(ea, p->stream));
+        B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, (size_t)QR * row_bytes, p->stream));
+        if (p->n) {
+            if (tree) {
+                k_scatter_dense<int64_t><<<sblocks, wpb * 32, 0, p->stream>>>(
+                    p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->n, q0, q1, QR,
+                    (unsigned long long*)p->d_emb, 0);
+                k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
+                    (unsigned long long*)p->d_emb, p->d_flags, p->d_total, p->npad, q0, q1, QR,
+                    p->d_state, p->order.depth_at[q0 / NODE_STRIPE]);
+            } else {
+                k_scatter_dense<double><<<sblocks, wpb * 32, 0, p->stream>>>(
+                    p->d_indptr, p->d_qidx, (const double*)p->d_values, p->n, q0, q1, QR,
+                    (unsigned long long*)p->d_emb, 1);
+            }
+        }
+        B2D_CUDA(cudaEventRecord(eb, p->stream));
+        if (p->ntiles) {
+            rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue);
+            if (rc) return rc;
+        }
+        B2D_CUDA(cudaEventRecord(ec, p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        cudaEventElapsedTime(&ms, ea, eb);
+        t_embed += ms;
+        cudaEventElapsedTime(&ms, eb, ec);
+        t_pair += ms;
+        p->n_pass += 1;
+    }
+    B2D_CUDA(cudaGetLastError());
+    p->t_embed = t_embed;
+    p->t_pair = t_pair;
+    return B2D_OK;
+}
+
+static int compute_bits(b2d_problem* p, int metric) {
+    const unsigned wpb = 8;
+    const unsigned sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    float ms;
+    size_t bytes = (size_t)p->nb * p->NS * TILE * sizeof(uint4);
+    int rc = ensure_emb(p, std::max<size_t>(bytes, 16));
+    if (rc) return rc;
+    cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
+    B2D_CUDA(cudaEventRecord(ea, p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, bytes, p->stream));
+    if (p->n) {
+        k_scatter_bits<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->n, p->NS,
+                                                           (uint32_t*)p->d_emb);
+        k_propagate_bits<<<(unsigned)p->nb, TILE, 0, p->stream>>>(
+            (uint4*)p->d_emb, p->d_hc, p->d_fold, p->d_len, p->NS, p->d_svec);
+    }
+    B2D_CUDA(cudaEventRecord(eb, p->stream));
+    p->n_launch = 0;
+    if (p->ntiles) {
+        for (int64_t qa = 0; qa < p->mpad; qa += g_chunk_nodes) {
+            int64_t qb = std::min<int64_t>(p->mpad, qa + g_chunk_nodes);
+            PairArgs a;
+            a.tiles = p->d_tiles;
+            a.row_base = p->d_row_base;
+            a.out = p->d_out;
+            a.svec = p->d_svec;
+            a.total = p->d_total;
+            a.n = p->n;
+            a.qa = qa;
+            a.qb = qb;
+            a.QR = 0;
+            a.NS = p->NS;
+            a.first = (qa == 0);
+            a.last = (qb == p->mpad);
+            a.epilogue = metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED;
+            if (metric == B2D_JACCARD)
+                k_pair_popcount<<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const uint4*)p->d_emb, a);
+            else
+                k_pair_unweighted<<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const uint4*)p->d_emb,
+                                                                             p->d_len, a);
+            p->n_launch += 1;
+        }
+    }
+    B2D_CUDA(cudaEventRecord(ec, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    B2D_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&ms, ea, eb);
+    p->t_embed = ms;
+    cudaEventElapsedTime(&ms, eb, ec);
+    p->t_pair = ms;
+    p->n_pass = 1;
+    p->nodes_resident = (double)p->mpad;
+    return B2D_OK;
+}
+
+int b2d_problem_compute(b2d_problem* p, int metric) {
+    if (!p) return fail(B2D_ERR_INVALID_ARGUMENT, "problem is NULL");
+    B2D_CUDA(cudaSetDevice(p->device));
+    int rc;
+    switch (metric) {
+        case B2D_UNWEIGHTED_UNIFRAC:
+            if (p->kind != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "unweighted_unifrac needs a tree problem");
+            rc = compute_bits(p, metric);
+            break;
+        case B2D_WEIGHTED_UNIFRAC:
+        case B2D_WEIGHTED_UNIFRAC_NORMALIZED:
+            if (p->kind != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "weighted_unifrac needs a tree problem");
+            if (!p->has_values) return fail(B2D_ERR_INVALID_ARGUMENT, "weighted_unifrac needs count values");
+            rc = compute_dense(p, metric);
+            break;
+        case B2D_BRAYCURTIS:
+            if (p->kind != 1) return fail(B2D_ERR_INVALID_ARGUMENT, "braycurtis needs a feature problem");
+            if (!p->has_values) return fail(B2D_ERR_INVALID_ARGUMENT, "braycurtis needs count values");
+            rc = compute_dense(p, metric);
+            break;
+        case B2D_JACCARD:
+            if (p->kind != 1) return fail(B2D_ERR_INVALID_ARGUMENT, "jaccard needs a feature problem");
+            rc = compute_bits(p, metric);
+            break;
+        default:
+            return fail(B2D_ERR_INVALID_ARGUMENT, "unknown metric id");
+    }
+    if (rc) return rc;
+    p->t_total = p->t_embed + p->t_pair;
+    p->computed = true;
+    p->last_metric = metric;
+    return B2D_OK;
+}
+
+int64_t b2d_problem_result_len(const b2d_problem* p) { return p ? p->out_len : 0; }
+
+static void stripe_range(const b2d_problem* p, int64_t b, int64_t* first, int64_t* count) {
+    int64_t i0 = b * TILE, i1 = std::min<int64_t>(p->n, i0 + TILE);
+    int64_t cnt = 0;
+    for (int64_t i = i0; i < i1; ++i) cnt += p->n - 1 - i;
+    *first = cond_row_start(i0, p->n);
+    *count = cnt;
+}
+
+int b2d_problem_fetch(b2d_problem* p, double* out) {
+    if (!p || !out) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!p->computed) return fail(B2D_ERR_STATE, "fetch before compute");
+    B2D_CUDA(cudaSetDevice(p->device));
+    B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
+    for (int64_t b : p->owned) {
+        int64_t first, cnt;
+        stripe_range(p, b, &first, &cnt);
+        B2D_CUDA(cudaMemcpyAsync(out + first, p->d_out + p->row_base[b], cnt * sizeof(double),
+                                 cudaMemcpyDeviceToHost, p->stream));
+    }
+    B2D_CUDA(cudaEventRecord(p->ev[1], p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+    p->t_fetch = ms;
+    return B2D_OK;
+}
+
+int b2d_problem_fetch_compact(b2d_problem* p, double* out, int64_t* stripe_offsets,
+                              int64_t* n_stripes_out) {
+    if (!p || (!out && p->out_len)) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!p->computed) return fail(B2D_ERR_STATE, "fetch before compute");
+    B2D_CUDA(cudaSetDevice(p->device));
+    B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
+    if (p->out_len)
+        B2D_CUDA(cudaMemcpyAsync(out, p->d_out, p->out_len * sizeof(double), cudaMemcpyDeviceToHost,
+                                 p->stream));
+    B2D_CUDA(cudaEventRecord(p->ev[1], p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+    p->t_fetch = ms;
+    if (stripe_offsets) {
+        int64_t k = 0;
+        for (int64_t b : p->owned) {
+            stripe_range(p, b, &stripe_offsets[2 * k], &stripe_offsets[2 * k + 1]);
+            ++k;
+        }
+    }
+    if (n_stripes_out) *n_stripes_out = (int64_t)p->owned.size();
+    return B2D_OK;
+}
+
+int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
+    if (!p || !out_n) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!p->computed) return fail(B2D_ERR_STATE, "sample_vector before compute");
+    B2D_CUDA(cudaSetDevice(p->device));
+    B2D_CUDA(cudaMemcpyAsync(out_n, p->d_svec, p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    return B2D_OK;
+}
+
+int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
+    if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    double v[8] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+                   p->n_launch, p->nodes_resident, p->n_pass};
+    for (int i = 0; i < n && i < 8; ++i) ms[i] = v[i];
+    return B2D_OK;
+}
+
+int b2d_problem_destroy(b2d_problem* p) {
+    free_problem(p);
+    return B2D_OK;
+}
+
+int b2d_beta_diversity_tree(int metric, int device, int64_t n_samples, int64_t n_nodes,
+                            const int32_t* parent, const double* length, const int64_t* indptr,
+                            const int32_t* node_ids, const int64_t* values, int shard,
+                            int n_shards, double* out_condensed) {
+    b2d_problem* p = nullptr;
+    int rc = b2d_problem_create_tree(&p, device, n_samples, n_nodes, parent, length, indptr,
+                                     node_ids, values, shard, n_shards);
+    if (rc) return rc;
+    rc = b2d_problem_compute(p, metric);
+    if (!rc && p->out_len) rc = b2d_problem_fetch(p, out_condensed);
+    free_problem(p);
+    return rc;
+}
+
+int b2d_beta_diversity_features(int metric, int device, int64_t n_samples, int64_t n_features,
+                                const int64_t* indptr, const int32_t* feature_ids,
+                                const double* values, int shard, int n_shards,
+                                double* out_condensed) {
+    b2d_problem* p = nullptr;
+    int rc = b2d_problem_create_features(&p, device, n_samples, n_features, indptr, feature_ids,
+                                         values, shard, n_shards);
+    if (rc) return rc;
+    rc = b2d_problem_compute(p, metric);
+    if (!rc && p->out_len) rc = b2d_problem_fetch(p, out_condensed);
+    free_problem(p);
+    return rc;
+}
+
+int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* length,
+                         int32_t* q_of_id, uint8_t* flags_mpad, double* len_q_mpad,
+                         double* tipdist_q_mpad, int32_t* max_depth) {
+    if (!parent || !length) return fail(B2D_ERR_INVALID_ARGUMENT, "parent/length is NULL");
+    TreeOrder o;
+    std::string err = build_tree_order(n_nodes, parent, length, o);
+    if (!err.empty()) return fail(B2D_ERR_INVALID_ARGUMENT, err);
+    if (q_of_id) memcpy(q_of_id, o.q_of_id.data(), o.q_of_id.size() * sizeof(int32_t));
+    if (flags_mpad) memcpy(flags_mpad, o.flags.data(), o.flags.size());
+    if (len_q_mpad) memcpy(len_q_mpad, o.len_q.data(), o.len_q.size() * sizeof(double));
+    if (tipdist_q_mpad) memcpy(tipdist_q_mpad, o.tipdist_q.data(), o.tipdist_q.size() * sizeof(double));
+    if (max_depth) *max_depth = o.max_depth;
+    return B2D_OK;
+}
+
+int b2d_microbench(int device, int kind, double* result) {
+    if (!result) return fail(B2D_ERR_INVALID_ARGUMENT, "result is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2D_ERR_NO_DEVICE, "no CUDA device");
+    }
+    B2D_CUDA(cudaSetDevice(device));
+    cudaEvent_t e0, e1;
+    B2D_CUDA(cudaEventCreate(&e0));
+    B2D_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    if (kind == 0) {
+        cudaDeviceProp prop;
+        B2D_CUDA(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 14;
+        double* d = nullptr;
+        B2D_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+        for (int rep = 0; rep < 6; ++rep) {
+            B2D_CUDA(cudaEventRecord(e0));
+            k_bench_dfma<<<blocks, threads>>>(d, iters);
+            B2D_CUDA(cudaEventRecord(e1));
+            B2D_CUDA(cudaEventSynchronize(e1));
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaFree(d);
+        *result = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
+    } else if (kind == 1) {
+        const int64_t bytes = (int64_t)2 << 30;
+        uint4 *a = nullptr, *b = nullptr;
+        B2D_CUDA(cudaMalloc(&a, bytes));
+        B2D_CUDA(cudaMalloc(&b, bytes));
+        B2D_CUDA(cudaMemset(a, 1, bytes));
+        for (int rep = 0; rep < 6; ++rep) {
+            B2D_CUDA(cudaEventRecord(e0));
+            k_bench_copy<<<148 * 16, 512>>>(a, b, bytes / 16);
+            B2D_CUDA(cudaEventRecord(e1));
+            B2D_CUDA(cudaEventSynchronize(e1));
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaFree(a);
+        cudaFree(b);
+        *result = 2.0 * (double)bytes / (best * 1e-3);
+    } else {
+        return fail(B2D_ERR_INVALID_ARGUMENT, "unknown microbench kind");
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return B2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// Embedding kernels: CSR scatter + bottom-up tree propagation.
+//
+// Replaces _nodes_by_counts / _traverse_reduce
+// (/root/reference/skbio/diversity/_phylogenetic.pyx:73-222): instead of a dense
+// (n_nodes x n_samples) int64 matrix swept parent-by-parent, every sample (one lane) walks
+// the tree once in the engine's heavy-child-first postorder with a tiny private stack
+// (depth <= log2(n_nodes)+1, see b2d_tree.h), so the sweep is parallel over samples,
+// sequential over nodes and independent of tree shape (a caterpillar costs the same as a
+// balanced tree).  All integer sums are exact and order-independent -> bit-identical node
+// counts.
+#pragma once
+
+#include "b2d_common.cuh"
+
+namespace b2d {
+
+constexpr int MAX_STACK = 64;
+
+// Node flags (one byte per node position q)
+constexpr uint8_t NF_HAS_CHILDREN = 1;  // value = own + pop()
+constexpr uint8_t NF_FOLD = 2;          // fold value into the sibling accumulator (top += v)
+constexpr uint8_t NF_PAD = 4;           // padding position, nothing to do
+
+// ---------------------------------------------------------------------------------------
+// Per-sample totals and normalisers from the CSR table (one warp per sample).
+//   total[s]  = sum of counts placed on TIP nodes      (_unifrac.py:559-560: np.take(u, tip_indices).sum())
+//   norm[s]   = sum_tips d_tip * (count/total)         (branch correction term of one sample,
+//               _unifrac.py:594-619 splits as C_u + C_v because d is zero off the tips)
+// ---------------------------------------------------------------------------------------
+__global__ void k_sample_totals_tree(const int64_t* __restrict__ indptr,
+                                     const int32_t* __restrict__ qidx,
+                                     const int64_t* __restrict__ values,
+                                     const uint8_t* __restrict__ flags,
+                                     const double* __restrict__ tipdist_q,
+                                     int64_t n, long long* __restrict__ total,
+                                     double* __restrict__ norm) {
+    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (s >= n) return;
+    int64_t e0 = indptr[s], e1 = indptr[s + 1];
+    long long t = 0;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        int32_t q = qidx[e];
+        if (!(flags[q] & NF_HAS_CHILDREN)) t += values ? values[e] : 1;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    double c = 0.0;
+    if (tipdist_q != nullptr) {
+        double td = (double)t;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            int32_t q = qidx[e];
+            if (!(flags[q] & NF_HAS_CHILDREN)) {
+                double v = (double)(values ? values[e] : 1);
+                double pr = (t > 0) ? v / td : v;
+                c += tipdist_q[q] * pr;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+        total[s] = t;
+        if (norm) norm[s] = c;
+    }
+}
+
+// Feature tables: per-sample sum of values (Bray-Curtis denominator pieces), fp64.
+__global__ void k_sample_sums_features(const int64_t* __restrict__ indptr,
+                                       const double* __restrict__ values, int64_t n,
+                                       double* __restrict__ sums) {
+    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (s >= n) return;
+    int64_t e0 = indptr[s], e1 = indptr[s + 1];
+    double c = 0.0;
+    for (int64_t e = e0 + lane; e < e1; e += 32) c += values ? values[e] : 1.0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) sums[s] = c;
+}
+
+// ---------------------------------------------------------------------------------------
+// Scatter CSR entries into the (zeroed) embedding buffers.  One warp per sample.
+// ---------------------------------------------------------------------------------------
+// fp64/int64 layout, node range [q0, q1): slot = ((blk*QR + (q-q0))*TILE + sl)
+template <typename V>
+__global__ void k_scatter_dense(const int64_t* __restrict__ indptr,
+                                const int32_t* __restrict__ qidx, const V* __restrict__ values,
+                                int64_t n, int64_t q0, int64_t q1, int64_t QR,
+                                unsigned long long* __restrict__ emb, int as_double) {
+    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (s >= n) return;
+    int64_t blk = s / TILE, sl = s % TILE;
+    int64_t e0 = indptr[s], e1 = indptr[s + 1];
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        int64_t q = qidx[e];
+        if (q < q0 || q >= q1) continue;
+        unsigned long long* slot = emb + ((blk * QR + (q - q0)) * TILE + sl);
+        if (as_double) {
+            double v = values ? (double)values[e] : 1.0;
+            *reinterpret_cast<double*>(slot) = v;  // node ids are unique per sample
+        } else {
+            long long v = values ? (long long)values[e] : 1;
+            *slot = (unsigned long long)v;
+        }
+    }
+}
+
+// bits layout: word = ((blk*NS + q/128)*TILE + sl)*4 + (q%128)/32, bit q%32
+__global__ void k_scatter_bits(const int64_t* __restrict__ indptr,
+                               const int32_t* __restrict__ qidx, int64_t n, int64_t NS,
+                               uint32_t* __restrict__ bits) {
+    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (s >= n) return;
+    int64_t blk = s / TILE, sl = s % TILE;
+    int64_t e0 = indptr[s], e1 = indptr[s + 1];
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        int64_t q = qidx[e];
+        int64_t w = ((blk * NS + (q >> 7)) * TILE + sl) * 4 + ((q & 127) >> 5);
+        atomicOr(bits + w, 1u << (q & 31));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Weighted propagation: lane = sample, walks node positions [q0, q1) of the resident range.
+// In : emb slots hold the int64 counts placed directly on each node (0 elsewhere).
+// Out: emb slots hold fp64 proportions count_subtree / total (count itself if total == 0,
+//      as _weighted_unifrac does, beta/_unifrac.py:399-410).
+// The per-lane stack is carried across calls in `state` ([MAX_STACK][npad] + depth known to
+// the host because it depends on the tree only).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_propagate_weighted(unsigned long long* __restrict__ emb, const uint8_t* __restrict__ flags,
+                     const long long* __restrict__ total, int64_t npad, int64_t q0, int64_t q1,
+                     int64_t QR, long long* __restrict__ state, int depth0) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad) return;
+    int64_t blk = s / TILE, sl = s % TILE;
+    unsigned long long* p = emb + (blk * QR) * TILE + sl;
+    long long S[MAX_STACK];
+    int d = depth0;
+    for (int i = 0; i < d; ++i) S[i] = state[(int64_t)i * npad + s];
+    long long T = d > 0 ? S[d - 1] : 0;
+    long long tot = total[s];
+    double totd = (double)tot;
+    for (int64_t q = q0; q < q1; q += 8) {
+        long long own[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) own[u] = (long long)p[(q - q0 + u) * TILE];
+        unsigned long long f8 = *reinterpret_cast<const unsigned long long*>(flags + q);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            unsigned f = (unsigned)(f8 >> (8 * u)) & 0xffu;
+            if (f & NF_PAD) continue;
+            long long v = own[u];
+            if (f & NF_HAS_CHILDREN) {  // pop the children accumulator
+                v += T;
+                d -= 1;
+                if (d > 0) T = S[d - 1];
+            }
+            double pr = (tot > 0) ? (double)v / totd : (double)v;
+            *reinterpret_cast<double*>(p + (q - q0 + u) * TILE) = pr;
+            if (f & NF_FOLD) {
+                T += v;
+            } else {
+                if (d > 0) S[d - 1] = T;
+                T = v;
+                d += 1;
+            }
+        }
+    }
+    if (d > 0) S[d - 1] = T;
+    for (int i = 0; i < d; ++i) state[(int64_t)i * npad + s] = S[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Presence propagation on node-packed bits: lane = sample, 128 nodes (one uint4) per step.
+// The private stack is a 64-bit shift register (1 bit per level).  Also accumulates
+// Lsum[s] = sum_q len[q] * present(q, s) with two-level fp64 summation (per stripe, then
+// across stripes) - this is Faith's PD of the sample and the per-sample part of the
+// unweighted UniFrac denominator:  [u|v] = ([u] + [v] + [u^v]) / 2.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE)
+k_propagate_bits(uint4* __restrict__ bits, const uint32_t* __restrict__ hc_mask,
+                 const uint32_t* __restrict__ fold_mask, const double* __restrict__ len_q,
+                 int64_t NS, double* __restrict__ Lsum) {
+    __shared__ double s_len[NODE_STRIPE];
+    __shared__ uint32_t s_hc[4], s_fo[4];
+    int64_t blk = blockIdx.x;
+    int sl = threadIdx.x;
+    uint4* p = bits + (blk * NS) * TILE + sl;
+    unsigned long long S = 0;
+    double Ltot = 0.0;
+    for (int64_t st = 0; st < NS; ++st) {
+        __syncthreads();
+        s_len[sl] = len_q[st * NODE_STRIPE + sl];
+        if (sl < 4) {
+            s_hc[sl] = hc_mask[st * 4 + sl];
+            s_fo[sl] = fold_mask[st * 4 + sl];
+        }
+        __syncthreads();
+        uint4 own = p[st * TILE];
+        uint32_t w[4] = {own.x, own.y, own.z, own.w};
+        double Lacc = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            uint32_t word = w[wi], res = 0;
+            uint32_t hc = s_hc[wi], fo = s_fo[wi];
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                uint32_t o = (word >> b) & 1u;
+                if ((hc >> b) & 1u) {
+                    o |= (uint32_t)(S & 1ull);
+                    S >>= 1;
+                }
+                if ((fo >> b) & 1u)
+                    S |= (unsigned long long)o;
+                else
+                    S = (S << 1) | (unsigned long long)o;
+                res |= o << b;
+                if (o) Lacc += s_len[wi * 32 + b];
+            }
+            w[wi] = res;
+        }
+        p[st * TILE] = make_uint4(w[0], w[1], w[2], w[3]);
+        Ltot += Lacc;
+    }
+    Lsum[blk * TILE + sl] = Ltot;
+}
+
+}  // namespace b2d

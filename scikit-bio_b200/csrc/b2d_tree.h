@@ -1,0 +1,137 @@
+// Host-side tree preparation (plain C++, no CUDA): from the reference's flat tree
+// (parent[k] > k, /root/reference/skbio/tree/_tree.py:5337-5359) to the engine's own node
+// order and the per-node step descriptors the propagation kernels execute.
+//
+// Engine order "q": postorder in which the child with the LARGEST subtree is visited first.
+// While a lane sweeps nodes in that order it keeps one accumulator per ancestor that already
+// has a finished child; every later child is at most half its parent's subtree, so at most
+// floor(log2(m)) + 1 accumulators are live - a 64-entry stack is enough for any tree, deep
+// caterpillars included.
+#pragma once
+
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace b2d {
+
+struct TreeOrder {
+    int64_t m = 0, mpad = 0;
+    std::vector<int32_t> q_of_id;   // node id -> position q
+    std::vector<uint8_t> flags;     // [mpad] NF_* per position
+    std::vector<uint32_t> hc_mask;  // [mpad/32] bit = has children
+    std::vector<uint32_t> fold_mask;// [mpad/32] bit = fold into sibling accumulator
+    std::vector<double> len_q;      // [mpad] branch length per position (0 in the padding)
+    std::vector<double> tipdist_q;  // [mpad] tip-to-root distance on tips, 0 elsewhere
+    std::vector<int32_t> depth_at;  // [mpad/128 + 1] stack depth before each 128-node stripe
+    int max_depth = 0;
+};
+
+// Returns "" on success, else an error message.
+inline std::string build_tree_order(int64_t m, const int32_t* parent, const double* length,
+                                    TreeOrder& out) {
+    if (m <= 0) return "tree has no nodes";
+    int64_t root = -1;
+    for (int64_t k = 0; k < m; ++k) {
+        int32_t p = parent[k];
+        if (p < 0) {
+            if (root >= 0) return "tree has more than one root (parent == -1)";
+            root = k;
+        } else if (p <= k || p >= m) {
+            return "parent[k] must satisfy k < parent[k] < n_nodes (reference id order)";
+        }
+    }
+    if (root != m - 1) return "the root must be the last node";
+    // children lists (CSR), siblings in ascending id order
+    std::vector<int64_t> coff(m + 1, 0);
+    for (int64_t k = 0; k < m; ++k)
+        if (parent[k] >= 0) coff[parent[k] + 1]++;
+    for (int64_t k = 0; k < m; ++k) coff[k + 1] += coff[k];
+    std::vector<int32_t> child(m > 1 ? m - 1 : 0);
+    {
+        std::vector<int64_t> fill(coff.begin(), coff.end() - 1);
+        for (int64_t k = 0; k < m; ++k)
+            if (parent[k] >= 0) child[fill[parent[k]]++] = (int32_t)k;
+    }
+    // subtree sizes: children precede parents in id order
+    std::vector<int64_t> size(m, 1);
+    for (int64_t k = 0; k < m; ++k)
+        if (parent[k] >= 0) size[parent[k]] += size[k];
+    // heavy child first (stable for ties)
+    for (int64_t k = 0; k < m; ++k) {
+        int64_t b = coff[k], e = coff[k + 1];
+        if (e - b > 1)
+            std::stable_sort(child.begin() + b, child.begin() + e,
+                             [&](int32_t x, int32_t y) { return size[x] > size[y]; });
+    }
+    out.m = m;
+    out.mpad = (m + 127) / 128 * 128;
+    out.q_of_id.assign(m, -1);
+    out.flags.assign(out.mpad, 4 /*NF_PAD*/);
+    out.len_q.assign(out.mpad, 0.0);
+    out.tipdist_q.assign(out.mpad, 0.0);
+    out.hc_mask.assign(out.mpad / 32, 0u);
+    out.fold_mask.assign(out.mpad / 32, 0xffffffffu);
+    out.depth_at.assign(out.mpad / 128 + 1, 0);
+    // tip-to-root distances exactly as _tip_distances accumulates them
+    // (/root/reference/skbio/diversity/_phylogenetic.pyx:52-56): d[i] = len[i] + d[parent]
+    std::vector<double> d(length, length + m);
+    for (int64_t k = m - 1; k >= 0; --k)
+        if (parent[k] >= 0) d[k] += d[parent[k]];
+    // iterative postorder, heavy child first
+    std::vector<int64_t> st_node, st_next;
+    st_node.push_back(root);
+    st_next.push_back(0);
+    int64_t q = 0;
+    int depth = 0, max_depth = 0;
+    while (!st_node.empty()) {
+        int64_t v = st_node.back();
+        int64_t i = st_next.back();
+        int64_t b = coff[v], e = coff[v + 1];
+        if (b + i < e) {
+            st_next.back() = i + 1;
+            st_node.push_back(child[b + i]);
+            st_next.push_back(0);
+            continue;
+        }
+        st_node.pop_back();
+        st_next.pop_back();
+        if (q % 128 == 0) out.depth_at[q / 128] = depth;
+        out.q_of_id[v] = (int32_t)q;
+        uint8_t f = 0;
+        bool has_children = e > b;
+        bool fold = false;
+        if (parent[v] >= 0) fold = child[coff[parent[v]]] != (int32_t)v;  // not the first visited
+        if (has_children) {
+            f |= 1;
+            depth -= 1;
+            out.hc_mask[q >> 5] |= 1u << (q & 31);
+        }
+        if (fold) {
+            f |= 2;
+        } else {
+            depth += 1;
+            out.fold_mask[q >> 5] &= ~(1u << (q & 31));
+        }
+        if (depth > max_depth) max_depth = depth;
+        out.flags[q] = f;
+        out.len_q[q] = length[v];
+        out.tipdist_q[q] = has_children ? 0.0 : d[v];
+        ++q;
+    }
+    for (int64_t s = (m + 127) / 128; s <= out.mpad / 128; ++s) out.depth_at[s] = depth;
+    if (m % 128 == 0) out.depth_at[m / 128] = depth;
+    out.max_depth = max_depth;
+    if (max_depth > 60) return "internal error: propagation stack deeper than 60";
+    return "";
+}
+
+// snake (boustrophedon) dealing of row stripes to shards: balanced triangle work
+inline int stripe_owner(int64_t b, int n_shards) {
+    int64_t r = b % (2 * (int64_t)n_shards);
+    return (int)(r < n_shards ? r : 2 * n_shards - 1 - r);
+}
+
+}  // namespace b2d

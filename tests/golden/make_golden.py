@@ -89,9 +89,10 @@ def random_case(name, n_samples, n_tips, lam, seed, n_taxa=None, floats=False,
     rng = np.random.default_rng(seed)
     gen = synthetic.caterpillar_tree if caterpillar else synthetic.random_join_tree
     parent, length, names, tip_node = gen(n_tips, seed=seed + 1)
-    newick = synthetic.to_newick(parent, length, names, root_length_none=root_length is None)
     if root_length is not None:
-        newick = newick[:-1] + ":" + repr(float(root_length)) + ";"
+        length = length.copy()
+        length[-1] = root_length
+    newick = synthetic.to_newick(parent, length, names, root_length_none=root_length is None)
     n_taxa = n_tips if n_taxa is None else n_taxa
     tips = rng.permutation(n_tips)[:n_taxa]
     taxa = [f"T{i}" for i in tips]

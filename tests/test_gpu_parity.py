@@ -1,0 +1,216 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI and the
+Python host, against (a) the committed outputs of the reference itself and (b) the oracle on
+seeded random inputs.
+
+Tolerances (BASELINE.json north_star): integer/bit work is bit-exact (Jaccard, integer-count
+Bray-Curtis, presence logic); UniFrac distances within 1e-12 relative in fp64.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_close_rel, case_arrays, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+UNIFRAC_RTOL = 1e-12
+
+
+def _skbio_b200():
+    import skbio_b200
+
+    if not skbio_b200.available():
+        pytest.fail("libskbb200.so missing or no CUDA device: GPU tests need the native engine")
+    return skbio_b200
+
+
+KEYS = [
+    ("unweighted_unifrac", "unweighted_unifrac", {}),
+    ("weighted_unifrac", "weighted_unifrac", {}),
+    ("weighted_unifrac_normalized", "weighted_unifrac", {"normalized": True}),
+    ("braycurtis", "braycurtis", {}),
+    ("jaccard", "jaccard", {}),
+]
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_golden_full_api(case):
+    """Newick text -> tree object -> beta_diversity (engine) == reference output."""
+    sb = _skbio_b200()
+    counts, parent, length, names = case_arrays(case)
+    tree = sb.read_newick(case["newick"])
+    for key, metric, kw in KEYS:
+        exp = np.array(case["results"][key], dtype=np.float64)
+        kwargs = dict(kw)
+        if "unifrac" in metric:
+            kwargs.update(tree=tree, taxa=case["taxa"])
+        dm = sb.beta_diversity(metric, counts, case["ids"], **kwargs)
+        got = dm.condensed_form()
+        assert list(dm.ids) == case["result_ids"]
+        if key == "jaccard":
+            assert np.array_equal(got, exp), f"{case['name']} jaccard not bit-exact"
+        elif key == "braycurtis" and counts.dtype.kind in "iub":
+            assert np.array_equal(got, exp, equal_nan=True), f"{case['name']} braycurtis not bit-exact"
+        else:
+            assert_close_rel(got, exp, UNIFRAC_RTOL, f"{case['name']} {key}")
+
+
+def test_qiime_tiny_test(qiime_tt):
+    sb = _skbio_b200()
+    counts = np.array(qiime_tt["counts"])
+    tree = sb.read_newick(qiime_tt["newick"])
+    n = counts.shape[0]
+    iu = np.triu_indices(n, k=1)
+    for key, metric, kw in KEYS[:3]:
+        dm = sb.beta_diversity(metric, counts, qiime_tt["ids"], tree=tree, taxa=qiime_tt["taxa"], **kw)
+        got = dm.condensed_form()
+        assert_close_rel(got, qiime_tt["reference_run"][key], UNIFRAC_RTOL, key)
+        # QIIME 1.9.1 files carry 12 significant digits
+        exp_q = np.array(qiime_tt["expected"][key])[iu]
+        assert np.allclose(got, exp_q, rtol=0, atol=5e-12)
+
+
+def _random_problem(n, tips, lam, seed, caterpillar=False):
+    from skbio_b200 import synthetic
+
+    gen = synthetic.caterpillar_tree if caterpillar else synthetic.random_join_tree
+    parent, length, names, tip_node = gen(tips, seed=seed + 1)
+    indptr, cols, vals = synthetic.poisson_csr(n, tips, lam, seed=seed)
+    return parent, length, names, tip_node, indptr, cols, vals
+
+
+@pytest.mark.parametrize("n,tips,lam,cat", [(300, 700, 0.05, False), (129, 1500, 0.01, True),
+                                            (257, 64, 0.8, False)])
+def test_random_vs_oracle_c_abi(n, tips, lam, cat):
+    """Flat arrays straight into the C ABI vs the NumPy oracle (dense restatement)."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, lam, 3, cat)
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    node_ids = tip_node[cols]
+    exp = oracle_fast.unifrac_all(dense, tip_node, parent, length)
+    with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+        for key in ("unweighted_unifrac", "weighted_unifrac", "weighted_unifrac_normalized"):
+            prob.compute(key)
+            got = prob.fetch(np.empty(n * (n - 1) // 2))
+            assert_close_rel(got, exp[key], UNIFRAC_RTOL, key)
+            if key == "unweighted_unifrac":
+                assert_close_rel(prob.sample_vector(), exp["faith_pd"], UNIFRAC_RTOL, "faith_pd")
+    with _capi.Problem.features(indptr, cols, vals.astype(np.float64), n, tips) as prob:
+        prob.compute("braycurtis")
+        got = prob.fetch(np.empty(n * (n - 1) // 2))
+        assert np.array_equal(got, exp["braycurtis"], equal_nan=True)
+        prob.compute("jaccard")
+        got = prob.fetch(np.empty(n * (n - 1) // 2))
+        assert np.array_equal(got, exp["jaccard"])
+
+
+def test_plain_and_bulk_copy_kernels_agree_bitwise():
+    _skbio_b200()
+    from skbio_b200 import _capi
+
+    n, tips = 200, 900
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.05, 9)
+    node_ids = tip_node[cols]
+    res = {}
+    for plain in (0, 1):
+        _capi.set_option("plain_kernels", plain)
+        with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+            prob.compute("weighted_unifrac_normalized")
+            res[plain] = prob.fetch(np.empty(n * (n - 1) // 2))
+    _capi.set_option("plain_kernels", 0)
+    assert np.array_equal(res[0], res[1])
+
+
+def test_shards_and_passes_reassemble_the_same_vector():
+    """Row-stripe shards (snake dealing) fill disjoint slices; several node passes (small
+    embedding budget) and small launch chunks give the same distances."""
+    _skbio_b200()
+    from skbio_b200 import _capi
+
+    n, tips = 700, 500
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.1, 5)
+    node_ids = tip_node[cols]
+    total = n * (n - 1) // 2
+    for key in ("weighted_unifrac", "unweighted_unifrac"):
+        with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+            prob.compute(key)
+            full = prob.fetch(np.empty(total))
+        out = np.full(total, -1.0)
+        covered = 0
+        for shard in range(3):
+            with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, shard=shard,
+                                    n_shards=3) as prob:
+                prob.compute(key)
+                covered += prob.result_len()
+                prob.fetch(out)
+        assert covered == total
+        assert np.array_equal(out, full)
+    # multi-pass + small chunks: summation order changes, values agree to 1e-13
+    _capi.set_option("chunk_nodes", 256)
+    _capi.set_option("emb_budget_bytes", 6 * 128 * 8 * 384)  # 384 node rows resident
+    try:
+        with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+            prob.compute("weighted_unifrac")
+            t = prob.timings()
+            multi = prob.fetch(np.empty(total))
+        assert t["passes"] > 1
+    finally:
+        _capi.set_option("chunk_nodes", 0)
+        _capi.set_option("emb_budget_bytes", 0)
+    with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+        prob.compute("weighted_unifrac")
+        single = prob.fetch(np.empty(total))
+    assert_close_rel(multi, single, 1e-13, "multi-pass")
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a larger case: identical samples are at distance 0,
+    unweighted/normalized values lie in [0, 1], symmetric under sample permutation."""
+    _skbio_b200()
+    from skbio_b200 import _capi
+
+    n, tips = 1500, 4000
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.02, 21)
+    # make sample 7 a copy of sample 3
+    rows = [(cols[indptr[s]:indptr[s + 1]], vals[indptr[s]:indptr[s + 1]]) for s in range(n)]
+    rows[7] = rows[3]
+    perm = np.random.default_rng(0).permutation(n)
+
+    def build(order):
+        ip = np.zeros(n + 1, dtype=np.int64)
+        cs, vs = [], []
+        for k, s in enumerate(order):
+            cs.append(rows[s][0]); vs.append(rows[s][1])
+            ip[k + 1] = ip[k] + len(rows[s][0])
+        return ip, np.concatenate(cs), np.concatenate(vs)
+
+    def run(order, key):
+        ip, cs, vs = build(order)
+        with _capi.Problem.tree(parent, length, ip, tip_node[cs], vs, n) as prob:
+            prob.compute(key)
+            return prob.fetch(np.empty(n * (n - 1) // 2))
+
+    from scipy.spatial.distance import squareform
+    for key in ("unweighted_unifrac", "weighted_unifrac_normalized"):
+        a = squareform(run(np.arange(n), key))
+        b = squareform(run(perm, key))
+        assert a[3, 7] == 0.0
+        assert a.min() >= 0.0 and a.max() <= 1.0 + 1e-12
+        inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
+        assert np.array_equal(a, b[np.ix_(inv, inv)])
+
+
+def test_engine_errors_are_loud():
+    sb = _skbio_b200()
+    from skbio_b200 import _capi
+
+    with pytest.raises(_capi.EngineError):
+        _capi.Problem.tree(np.array([0, -1], dtype=np.int32), np.zeros(2), np.array([0, 0]),
+                           np.zeros(0, dtype=np.int32), None, 1)  # parent[0] == 0 is invalid
+    with pytest.raises(_capi.EngineError):
+        _capi.Problem.tree(np.array([1, -1], dtype=np.int32), np.zeros(2), np.array([0, 1]),
+                           np.array([5], dtype=np.int32), None, 1)  # node id out of range

@@ -1,0 +1,35 @@
+"""Quick on-GPU timing probe (development aid, not the benchmark)."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from skbio_b200 import _capi, synthetic
+
+def run(n, tips, lam, keys, feat_keys=()):
+    t0 = time.time()
+    parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=1)
+    indptr, cols, vals = synthetic.poisson_csr(n, tips, lam, seed=0)
+    print(f"gen n={n} tips={tips} nnz={len(cols)} in {time.time()-t0:.1f}s", flush=True)
+    P = n * (n - 1) // 2
+    m = len(parent)
+    with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+        for key in keys:
+            for rep in range(2):
+                t0 = time.time(); prob.compute(key); wall = time.time() - t0
+            t = prob.timings()
+            np_per_s = P * m / (t["pair_ms"] * 1e-3)
+            print(f"{key}: wall {wall*1e3:.1f} ms embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms "
+                  f"launches {t['pair_launches']} passes {t['passes']} -> {P/(t['compute_ms']*1e-3):.3e} pairs/s, "
+                  f"{np_per_s:.3e} node-pairs/s = {np_per_s/148/1.9e9:.1f} np/clk/SM@1.9GHz", flush=True)
+    if feat_keys:
+        with _capi.Problem.features(indptr, cols, vals.astype(np.float64), n, tips) as prob:
+            for key in feat_keys:
+                for rep in range(2):
+                    prob.compute(key)
+                t = prob.timings()
+                print(f"{key}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
+
+if __name__ == "__main__":
+    print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), flush=True)
+    run(4096, 20000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"], ["braycurtis", "jaccard"])
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        run(10000, 100000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"])
