@@ -153,7 +153,8 @@ int b2d_beta_diversity_features(int metric, int device,
 int b2d_set_option(const char* name, int64_t value);
 
 /* On-device micro-benchmarks used by bench.py for the roofline denominators:
- * kind 0: FP64 pipe, returns DFMA instructions/s;  kind 1: HBM copy, returns bytes/s. */
+ * kind 0: FP64 pipe, returns DFMA instructions/s;  kind 1: HBM copy, returns bytes/s;
+ * kind 2: conflict-free 64-bit shared-memory gathers/s (the unweighted kernel's bound). */
 int b2d_microbench(int device, int kind, double* result);
 
 /* Test hook (host only, no GPU needed): the engine's node order for a flat tree.  Arrays

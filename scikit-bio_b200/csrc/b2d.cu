@@ -62,6 +62,24 @@ __global__ void k_bench_dfma(double* out, int iters) {
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+// 64-bit shared-memory gathers, 16 interleaved tables per half-warp (the access pattern of
+// k_pair_unweighted_lut): every lane reads table (lane & 15) at a data-dependent row.
+__global__ void k_bench_lds64(double* out, int iters) {
+    extern __shared__ double s_tab[];  // 256 rows x 32 doubles
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_tab[i] = (double)(i & 7);
+    __syncthreads();
+    const int g = threadIdx.x & 15;
+    unsigned x = threadIdx.x * 2654435761u;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int i = 0; i < iters; ++i) {
+        a0 += s_tab[((x >> 0) & 255) * 32 + g];
+        a1 += s_tab[((x >> 8) & 255) * 32 + g];
+        a2 += s_tab[((x >> 16) & 255) * 32 + g];
+        a3 += s_tab[((x >> 24) & 255) * 32 + g];
+        x = x * 1664525u + 1013904223u;
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
+}
 __global__ void k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -445,8 +463,15 @@ static int compute_dense(b2d_problem* p, int metric) {
                     p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->n, q0, q1, QR,
                     (unsigned long long*)p->d_emb, 0);
                 k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
-                    (unsigned long long*)p->d_emb, p->d_flags, p->d_total, p->npad, q0, q1, QR,
+                    (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR,
                     p->d_state, p->order.depth_at[q0 / NODE_STRIPE]);
+                {
+                    const int64_t threads = p->nb * (TILE / 2);
+                    dim3 grid((unsigned)((threads + 255) / 256),
+                              (unsigned)std::min<int64_t>(q1 - q0, 2048));
+                    k_counts_to_proportions<<<grid, 256, 0, p->stream>>>(
+                        (unsigned long long*)p->d_emb, p->d_total, p->nb, q1 - q0, QR);
+                }
             } else {
                 k_scatter_dense<double><<<sblocks, wpb * 32, 0, p->stream>>>(
                     p->d_indptr, p->d_qidx, (const double*)p->d_values, p->n, q0, q1, QR,
@@ -490,9 +515,13 @@ static int compute_bits(b2d_problem* p, int metric) {
     }
     B2D_CUDA(cudaEventRecord(eb, p->stream));
     p->n_launch = 0;
+    B2D_CUDA(cudaFuncSetAttribute(k_pair_unweighted_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)UL_SMEM));
     if (p->ntiles) {
-        for (int64_t qa = 0; qa < p->mpad; qa += g_chunk_nodes) {
-            int64_t qb = std::min<int64_t>(p->mpad, qa + g_chunk_nodes);
+        // bits kernels touch 8..32 nodes per instruction: use 4x longer node chunks per launch
+        const int64_t chunk = 4 * g_chunk_nodes;
+        for (int64_t qa = 0; qa < p->mpad; qa += chunk) {
+            int64_t qb = std::min<int64_t>(p->mpad, qa + chunk);
             PairArgs a;
             a.tiles = p->d_tiles;
             a.row_base = p->d_row_base;
@@ -509,9 +538,12 @@ static int compute_bits(b2d_problem* p, int metric) {
             a.epilogue = metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED;
             if (metric == B2D_JACCARD)
                 k_pair_popcount<<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const uint4*)p->d_emb, a);
-            else
+            else if (plain_kernels())
                 k_pair_unweighted<<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const uint4*)p->d_emb,
                                                                              p->d_len, a);
+            else
+                k_pair_unweighted_lut<<<(unsigned)p->ntiles, 256, UL_SMEM, p->stream>>>(
+                    (const uint4*)p->d_emb, p->d_len, a);
             p->n_launch += 1;
         }
     }
@@ -727,6 +759,25 @@ int b2d_microbench(int device, int kind, double* result) {
         cudaFree(a);
         cudaFree(b);
         *result = 2.0 * (double)bytes / (best * 1e-3);
+    } else if (kind == 2) {
+        cudaDeviceProp prop;
+        B2D_CUDA(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount * 2, threads = 512, iters = 1 << 13;
+        const int smem = 256 * 32 * sizeof(double);
+        B2D_CUDA(cudaFuncSetAttribute(k_bench_lds64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        double* d = nullptr;
+        B2D_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+        for (int rep = 0; rep < 6; ++rep) {
+            B2D_CUDA(cudaEventRecord(e0));
+            k_bench_lds64<<<blocks, threads, smem>>>(d, iters);
+            B2D_CUDA(cudaEventRecord(e1));
+            B2D_CUDA(cudaEventSynchronize(e1));
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaFree(d);
+        *result = (double)blocks * threads * 4.0 * iters / (best * 1e-3);
     } else {
         return fail(B2D_ERR_INVALID_ARGUMENT, "unknown microbench kind");
     }

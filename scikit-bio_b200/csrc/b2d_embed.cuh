@@ -127,15 +127,18 @@ __global__ void k_scatter_bits(const int64_t* __restrict__ indptr,
 // ---------------------------------------------------------------------------------------
 // Weighted propagation: lane = sample, walks node positions [q0, q1) of the resident range.
 // In : emb slots hold the int64 counts placed directly on each node (0 elsewhere).
-// Out: emb slots hold fp64 proportions count_subtree / total (count itself if total == 0,
-//      as _weighted_unifrac does, beta/_unifrac.py:399-410).
-// The per-lane stack is carried across calls in `state` ([MAX_STACK][npad] + depth known to
-// the host because it depends on the tree only).
+// Out: emb slots hold the int64 count of the node's whole subtree (exact integer sums, so
+//      bit-identical to _traverse_reduce whatever the order).
+// The per-lane stack is carried across calls in `state` ([MAX_STACK][npad]); its depth is
+// known to the host because it depends on the tree only.  The walk is a chain of dependent
+// integer operations per lane, so everything that is not on that chain (the int64 -> fp64
+// proportion conversion, one correctly rounded division per element) lives in the separate,
+// bandwidth-bound kernel k_counts_to_proportions.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_propagate_weighted(unsigned long long* __restrict__ emb, const uint8_t* __restrict__ flags,
-                     const long long* __restrict__ total, int64_t npad, int64_t q0, int64_t q1,
-                     int64_t QR, long long* __restrict__ state, int depth0) {
+                     int64_t npad, int64_t q0, int64_t q1, int64_t QR,
+                     long long* __restrict__ state, int depth0) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= npad) return;
     int64_t blk = s / TILE, sl = s % TILE;
@@ -144,36 +147,75 @@ k_propagate_weighted(unsigned long long* __restrict__ emb, const uint8_t* __rest
     int d = depth0;
     for (int i = 0; i < d; ++i) S[i] = state[(int64_t)i * npad + s];
     long long T = d > 0 ? S[d - 1] : 0;
-    long long tot = total[s];
-    double totd = (double)tot;
-    for (int64_t q = q0; q < q1; q += 8) {
-        long long own[8];
+    // Software pipeline: the counts of group g+PF are requested before group g is processed
+    // (the buffer is updated in place, so the compiler cannot hoist these loads itself).
+    constexpr int G = 8, PF = 3;
+    long long own[PF + 1][G];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) own[u] = (long long)p[(q - q0 + u) * TILE];
-        unsigned long long f8 = *reinterpret_cast<const unsigned long long*>(flags + q);
+    for (int g = 0; g < PF; ++g)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            unsigned f = (unsigned)(f8 >> (8 * u)) & 0xffu;
-            if (f & NF_PAD) continue;
-            long long v = own[u];
-            if (f & NF_HAS_CHILDREN) {  // pop the children accumulator
-                v += T;
-                d -= 1;
-                if (d > 0) T = S[d - 1];
+        for (int u = 0; u < G; ++u)
+            own[g][u] = (q0 + (int64_t)g * G < q1) ? (long long)p[((int64_t)g * G + u) * TILE] : 0;
+    for (int64_t qg = q0; qg < q1; qg += (PF + 1) * G) {
+#pragma unroll
+        for (int ph = 0; ph <= PF; ++ph) {
+            const int64_t q = qg + (int64_t)ph * G;
+            if (q >= q1) break;
+            {   // prefetch group ph+PF (slot (ph+PF) % (PF+1))
+                const int64_t qn = q + (int64_t)PF * G;
+                if (qn < q1) {
+#pragma unroll
+                    for (int u = 0; u < G; ++u)
+                        own[(ph + PF) % (PF + 1)][u] = (long long)p[(qn - q0 + u) * TILE];
+                }
             }
-            double pr = (tot > 0) ? (double)v / totd : (double)v;
-            *reinterpret_cast<double*>(p + (q - q0 + u) * TILE) = pr;
-            if (f & NF_FOLD) {
-                T += v;
-            } else {
-                if (d > 0) S[d - 1] = T;
-                T = v;
-                d += 1;
+            const unsigned long long f8 = *reinterpret_cast<const unsigned long long*>(flags + q);
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const unsigned f = (unsigned)(f8 >> (8 * u)) & 0xffu;
+                long long v = own[ph][u];
+                if (f & NF_PAD) continue;
+                if (f & NF_HAS_CHILDREN) {  // pop the children accumulator
+                    v += T;
+                    d -= 1;
+                    if (d > 0) T = S[d - 1];
+                    p[(q - q0 + u) * TILE] = (unsigned long long)v;  // tips keep their own count
+                }
+                if (f & NF_FOLD) {
+                    T += v;
+                } else {
+                    if (d > 0) S[d - 1] = T;
+                    T = v;
+                    d += 1;
+                }
             }
         }
     }
     if (d > 0) S[d - 1] = T;
     for (int i = 0; i < d; ++i) state[(int64_t)i * npad + s] = S[i];
+}
+
+// int64 subtree counts -> fp64 proportions count/total (the count itself when total == 0,
+// as _weighted_unifrac does, beta/_unifrac.py:399-410).  Elementwise, in place, two samples
+// (16 bytes) per thread; HBM-bound.
+__global__ void __launch_bounds__(256)
+k_counts_to_proportions(unsigned long long* __restrict__ emb, const long long* __restrict__ total,
+                        int64_t nb, int64_t rows, int64_t QR) {
+    // grid.x covers (block, sample pair): nb * 64 threads ; grid.y strides over node rows
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * (TILE / 2)) return;
+    int64_t blk = t / (TILE / 2), sp = t % (TILE / 2);
+    const long long t0 = total[blk * TILE + 2 * sp], t1 = total[blk * TILE + 2 * sp + 1];
+    const double d0 = (double)t0, d1 = (double)t1;
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(emb + (blk * QR) * TILE) + sp;
+    for (int64_t q = blockIdx.y; q < rows; q += gridDim.y) {
+        ulonglong2 v = p[q * (TILE / 2)];
+        double a = (double)(long long)v.x, b = (double)(long long)v.y;
+        if (t0 > 0) a = a / d0;
+        if (t1 > 0) b = b / d1;
+        double2 o = make_double2(a, b);
+        *reinterpret_cast<double2*>(p + q * (TILE / 2)) = o;
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -69,13 +69,17 @@ __device__ __forceinline__ void emit(const PairArgs& a, int64_t base, int64_t i0
 
 // =========================================================================================
 // Weighted kernel: acc[i][j] += len_q * |p_q,i - p_q,j|   (also Bray-Curtis with len == 1)
-// 256 compute threads (16x16, each an 8x8 register tile of fp64 accumulators) + one
-// producer warp that feeds a 4-stage ring of {A rows, B rows, lengths} with bulk copies.
-// FP64-pipe bound: 2 FP64 instructions (DADD + DFMA) per node-pair term.
+// 512 compute threads (16 row groups x 32 column groups, each thread an 8x4 register tile of
+// fp64 accumulators) + one producer warp that feeds a 4-stage ring of {A rows, B rows,
+// lengths} with bulk copies.  FP64-pipe bound: 2 FP64 instructions (DADD + DFMA) per
+// node-pair term.  Four compute warps per SM sub-partition hide the DADD->DFMA latency that
+// ptxas' schedule exposes (ncu round 1: 2 warps/SMSP gave 67 % FP64 pipe utilisation with
+// "wait" as the top stall).
 // =========================================================================================
 constexpr int WK_KS = 16;      // nodes per stage
 constexpr int WK_STAGES = 4;
-constexpr int WK_THREADS = 256 + 32;
+constexpr int WK_CWARPS = 16;  // compute warps
+constexpr int WK_THREADS = WK_CWARPS * 32 + 32;
 constexpr int WK_STAGE_DOUBLES = 2 * WK_KS * TILE + WK_KS;  // A + B + len
 constexpr size_t WK_SMEM = (size_t)WK_STAGES * WK_STAGE_DOUBLES * sizeof(double) + 2 * WK_STAGES * sizeof(uint64_t);
 
@@ -93,15 +97,15 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
     if (tid == 0) {
         for (int s = 0; s < WK_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 8);  // one arrive per compute warp
+            mbar_init(&empty[s], WK_CWARPS);  // one arrive per compute warp
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (tid >= 256) {
+    if (tid >= WK_CWARPS * 32) {
         // ---------------- producer warp ----------------
-        if (tid == 256) {
+        if (tid == WK_CWARPS * 32) {
             const double* Ag = emb + ((int64_t)bi * a.QR + a.qa) * TILE;
             const double* Bg = emb + ((int64_t)bj * a.QR + a.qa) * TILE;
             const double* Lg = len_q + a.qa;
@@ -122,12 +126,13 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
     }
 
     // ---------------- compute warps ----------------
-    const int tx = tid & 15, ty = tid >> 4;
-    double acc[8][8];
+    // thread (ty, tx): rows ty*8 .. ty*8+7 ; columns {tx*2, tx*2+1, 64+tx*2, 64+tx*2+1}
+    const int tx = tid & 31, ty = tid >> 5;
+    double acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
 
     for (int64_t it = 0; it < niter; ++it) {
         int s = (int)(it % WK_STAGES);
@@ -136,15 +141,18 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
         const double* A = stage_base + (size_t)s * WK_STAGE_DOUBLES;
         const double* B = A + WK_KS * TILE;
         const double* L = B + WK_KS * TILE;
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < WK_KS; ++k) {
-            double av[8], bv[8];
+            double av[8], bv[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                double2 t = *reinterpret_cast<const double2*>(A + k * TILE + h * 32 + ty * 2);
+                double2 t = *reinterpret_cast<const double2*>(A + k * TILE + ty * 8 + h * 2);
                 av[2 * h] = t.x;
                 av[2 * h + 1] = t.y;
-                double2 u = *reinterpret_cast<const double2*>(B + k * TILE + h * 32 + tx * 2);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double2 u = *reinterpret_cast<const double2*>(B + k * TILE + h * 64 + tx * 2);
                 bv[2 * h] = u.x;
                 bv[2 * h + 1] = u.y;
             }
@@ -152,7 +160,7 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[r][c] = fma(fabs(av[r] - bv[c]), l, acc[r][c]);
+                for (int c = 0; c < 4; ++c) acc[r][c] = fma(fabs(av[r] - bv[c]), l, acc[r][c]);
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty[s]);
@@ -163,11 +171,11 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
     const int64_t i0 = (int64_t)bi * TILE;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        int64_t i = i0 + (r >> 1) * 32 + ty * 2 + (r & 1);
+        int64_t i = i0 + ty * 8 + r;
         if (i >= a.n) continue;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            int64_t j = (int64_t)bj * TILE + (c >> 1) * 32 + tx * 2 + (c & 1);
+        for (int c = 0; c < 4; ++c) {
+            int64_t j = (int64_t)bj * TILE + (c >> 1) * 64 + tx * 2 + (c & 1);
             emit(a, base, i0, i, j, acc[r][c]);
         }
     }
@@ -313,9 +321,158 @@ k_pair_unweighted(const uint4* __restrict__ bits, const double* __restrict__ len
 }
 
 // =========================================================================================
+// Unweighted kernel, formulation P (node-packed bits + byte look-up tables):
+//   acc[i][j] += LUT_g[ byte_g(u ^ v) ]   for the 16 byte groups g of a 128-node stripe,
+// where LUT_g[x] = sum of the branch lengths of the nodes whose bit is set in x (256 entries
+// per group, rebuilt per stripe by the CTA itself from the 128 staged lengths).  One 8-byte
+// shared-memory gather + one DADD per EIGHT node-pair terms instead of one predicated DADD
+// per term.  The 16 tables are interleaved at 8-byte granularity (entry x of table g at
+// x*256 + g*8, the other half of each 256-byte row holds the second LUT buffer), and at
+// every step the 16 lanes of a half-warp use 16 different tables (lane h takes byte group
+// 4*((h/4 + w) & 3) + ((h%4 + b) & 3) at word step w, byte step b), so every 64-bit gather
+// is bank-conflict free.  Bound by shared-memory bandwidth: 16 gathers/clk/SM = 128 terms.
+// Row/column bits and lengths arrive through a 4-slot ring of bulk copies.
+// =========================================================================================
+constexpr int UL_STAGES = 4;
+constexpr int UL_LUT_BYTES = 256 * 256;  // 256 entries x (2 buffers x 16 tables x 8 B)
+constexpr size_t UL_SMEM = UL_LUT_BYTES + UL_STAGES * sizeof(UStage) + UL_STAGES * sizeof(uint64_t);
+
+__device__ __forceinline__ void ul_build_lut(double* lut, int buf, const double* len, int tid) {
+    const int g = tid & 15, xh = tid >> 4;
+    const double* ln = len + g * 8;
+    const double2 p0 = *reinterpret_cast<const double2*>(ln);
+    const double2 p1 = *reinterpret_cast<const double2*>(ln + 2);
+    const double2 p2 = *reinterpret_cast<const double2*>(ln + 4);
+    const double2 p3 = *reinterpret_cast<const double2*>(ln + 6);
+    const double l[4] = {p0.x, p0.y, p1.x, p1.y};
+    double hs = (xh & 1) ? p2.x : 0.0;
+    hs += (xh & 2) ? p2.y : 0.0;
+    hs += (xh & 4) ? p3.x : 0.0;
+    hs += (xh & 8) ? p3.y : 0.0;
+    double lo[16];
+    lo[0] = 0.0;
+#pragma unroll
+    for (int x = 1; x < 16; ++x) {
+        const int low = x & (x - 1);          // x without its lowest set bit
+        const int bit = (x & 1) ? 0 : (x & 2) ? 1 : (x & 4) ? 2 : 3;
+        lo[x] = lo[low] + l[bit];
+    }
+    double* dst = lut + (size_t)(xh * 16) * 32 + buf * 16 + g;
+#pragma unroll
+    for (int xl = 0; xl < 16; ++xl) dst[xl * 32] = hs + lo[xl];
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_pair_unweighted_lut(const uint4* __restrict__ bits, const double* __restrict__ len_q, PairArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* lut = reinterpret_cast<double*>(smem_raw);
+    UStage* st = reinterpret_cast<UStage*>(smem_raw + UL_LUT_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + UL_LUT_BYTES + UL_STAGES * sizeof(UStage));
+
+    const int tid = threadIdx.x;
+    const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t s0 = a.qa / NODE_STRIPE;
+    const int nst = (int)(a.qb / NODE_STRIPE - s0);
+    const uint4* Rg = bits + ((int64_t)bi * a.NS + s0) * TILE;
+    const uint4* Cg = bits + ((int64_t)bj * a.NS + s0) * TILE;
+    const double* Lg = len_q + s0 * NODE_STRIPE;
+
+    auto issue = [&](int i) {  // stripe i of this launch -> ring slot i % UL_STAGES
+        UStage* d = st + (i % UL_STAGES);
+        uint64_t* bar = full + (i % UL_STAGES);
+        mbar_arrive_expect_tx(bar, (uint32_t)sizeof(UStage));
+        bulk_g2s(d->rows, Rg + (int64_t)i * TILE, TILE * sizeof(uint4), bar);
+        bulk_g2s(d->cols, Cg + (int64_t)i * TILE, TILE * sizeof(uint4), bar);
+        bulk_g2s(d->len, Lg + (int64_t)i * NODE_STRIPE, NODE_STRIPE * sizeof(double), bar);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < UL_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < nst && i < UL_STAGES - 1; ++i) issue(i);
+
+    double acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+
+    if (nst > 0) {
+        mbar_wait(&full[0], 0);
+        ul_build_lut(lut, 0, st[0].len, tid);
+    }
+    const int hq = tx >> 2, hr = tx & 3;
+    const char* lut_bytes = reinterpret_cast<const char*>(lut);
+
+    for (int i = 0; i < nst; ++i) {
+        __syncthreads();  // LUT[i&1] complete; LUT[(i+1)&1] and ring slot (i+3)%4 are free
+        if (tid == 0 && i + UL_STAGES - 1 < nst) issue(i + UL_STAGES - 1);
+        if (i + 1 < nst) {
+            mbar_wait(&full[(i + 1) % UL_STAGES], (uint32_t)(((i + 1) / UL_STAGES) & 1));
+            ul_build_lut(lut, (i + 1) & 1, st[(i + 1) % UL_STAGES].len, tid);
+        }
+        mbar_wait(&full[i % UL_STAGES], (uint32_t)((i / UL_STAGES) & 1));
+        const uint32_t* R = reinterpret_cast<const uint32_t*>(st[i % UL_STAGES].rows);
+        const uint32_t* C = reinterpret_cast<const uint32_t*>(st[i % UL_STAGES].cols);
+        const uint32_t bufoff = (uint32_t)(i & 1) * 128u;
+#pragma unroll 1
+        for (int wt = 0; wt < 4; ++wt) {
+            const int wsel = (hq + wt) & 3;
+            const uint32_t rot = (uint32_t)hr * 8u;
+            uint32_t rw[8], cw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                uint32_t x = R[(ty * 8 + e) * 4 + wsel];
+                uint32_t y = C[(e * 16 + tx) * 4 + wsel];
+                rw[e] = __funnelshift_r(x, x, rot);
+                cw[e] = __funnelshift_r(y, y, rot);
+            }
+            // table offsets (bytes within a 256-byte LUT row) for byte steps 0..3
+            uint32_t o[4];
+#pragma unroll
+            for (int bt = 0; bt < 4; ++bt) o[bt] = 8u * (4u * wsel + ((hr + bt) & 3)) + bufoff;
+            const uint32_t offA = o[0] | (o[1] << 8), offB = o[2] | (o[3] << 8);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t X = rw[r] ^ cw[c];
+                    const uint32_t a0 = __byte_perm(X, offA, 0x7604);
+                    const uint32_t a1 = __byte_perm(X, offA, 0x7615);
+                    const uint32_t a2 = __byte_perm(X, offB, 0x7624);
+                    const uint32_t a3 = __byte_perm(X, offB, 0x7635);
+                    double v = acc[r][c];
+                    v += *reinterpret_cast<const double*>(lut_bytes + a0);
+                    v += *reinterpret_cast<const double*>(lut_bytes + a1);
+                    v += *reinterpret_cast<const double*>(lut_bytes + a2);
+                    v += *reinterpret_cast<const double*>(lut_bytes + a3);
+                    acc[r][c] = v;
+                }
+        }
+    }
+
+    const int64_t base = a.row_base[bi];
+    const int64_t i0 = (int64_t)bi * TILE;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int64_t i = i0 + ty * 8 + r;
+        if (i >= a.n) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            int64_t j = (int64_t)bj * TILE + c * 16 + tx;
+            emit(a, base, i0, i, j, acc[r][c]);
+        }
+    }
+}
+
+// =========================================================================================
 // Jaccard kernel: acc[i][j] += popcount(u ^ v) over feature stripes (exact integers).
 // =========================================================================================
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 1)
 k_pair_popcount(const uint4* __restrict__ bits, PairArgs a) {
     __shared__ uint4 rows[2][TILE];
     __shared__ uint4 cols[2][TILE];

@@ -201,7 +201,10 @@ def test_properties_at_scale():
         assert a[3, 7] == 0.0
         assert a.min() >= 0.0 and a.max() <= 1.0 + 1e-12
         inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
-        assert np.array_equal(a, b[np.ix_(inv, inv)])
+        # the fp64 summation order depends on where a pair sits in its tile, so a permuted
+        # run agrees to rounding, not bitwise
+        assert_close_rel(a, b[np.ix_(inv, inv)], 1e-13, key + " permutation")
+        assert np.array_equal(a, a.T)
 
 
 def test_engine_errors_are_loud():

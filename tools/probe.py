@@ -29,7 +29,7 @@ def run(n, tips, lam, keys, feat_keys=()):
                 print(f"{key}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
 
 if __name__ == "__main__":
-    print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), flush=True)
+    print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), "lds64 gathers/s", _capi.microbench(2), flush=True)
     run(4096, 20000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"], ["braycurtis", "jaccard"])
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         run(10000, 100000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"])
