@@ -381,34 +381,46 @@ def run_ours(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         avg_launch_ms = float(np.mean(pair_ms)) / max(pair_launches_per_step, 1)
         nodes_per_launch = m / max(pair_launches_per_step, 1)
+        sm_count = 148
         if workload in ("weighted", "braycurtis"):
             kernel = "k_pair_weighted"
-            instr_per_term = 2.0   # DADD (pu - pv) + DFMA (|.| * len + acc)
-            bound = "fp64"
+            units_per_term = 2.0   # DADD (pu - pv) + DFMA (|.| * len + acc)
+            bound, unit = "fp64", "Tinst/s (FP64 pipe instructions)"
+            peak = fp64_peak
+            peak_source = ("b2d_microbench(0): dependent DFMA chains on all SMs, measured in this "
+                           "run; nominal 148 SM x 64 lanes x 1.965 GHz = 18.6")
         elif workload == "unweighted":
-            kernel = "k_pair_unweighted"
-            instr_per_term = 1.0   # one predicated DADD per node-pair term (formulation S)
-            bound = "fp64"
+            kernel = "k_pair_unweighted_lut"
+            units_per_term = 1.0 / 8.0   # one 64-bit LUT gather (+ one DADD) per 8 node-pair terms
+            bound, unit = "smem", "Tgather/s (64-bit shared-memory gathers)"
+            peak = _capi.microbench(2, device)
+            peak_source = ("b2d_microbench(2): bank-conflict-free 64-bit shared-memory gathers on "
+                           "all SMs, measured in this run; nominal 148 SM x 16/clk x 1.965 GHz = 4.65")
         else:
             kernel = "k_pair_popcount"
-            instr_per_term = 1.0 / 32.0
-            bound = "alu"
-        alg_instr = P_shard * nodes_per_launch * instr_per_term
-        achieved = alg_instr / (avg_launch_ms * 1e-3) / 1e12
+            units_per_term = 1.0 / 32.0  # one POPC per 32 feature-pair terms
+            bound, unit = "alu", "Tinst/s (POPC)"
+            peak = sm_count * 16 * 1.965e9
+            peak_source = "nominal 148 SM x 16 POPC/clk x 1.965 GHz (not measured)"
+        alg_units = P_shard * nodes_per_launch * units_per_term
+        achieved = alg_units / (avg_launch_ms * 1e-3) / 1e12
         elem_bytes = 8.0 if workload in ("weighted", "braycurtis") else 1.0 / 8.0
-        # unique embedding bytes a launch must read at least once + shard output once
+        # unique embedding bytes a launch must read at least once
         alg_bytes = n * nodes_per_launch * elem_bytes
         roofline = {
             "kernel": kernel, "bound": bound, "achieved": achieved,
-            "peak": fp64_peak / 1e12, "unit": "Tinst/s (FP64 pipe)",
-            "frac": achieved / (fp64_peak / 1e12),
-            "peak_source": "b2d_microbench DFMA chain measured in this run; nominal 18.6",
+            "peak": peak / 1e12, "unit": unit,
+            "frac": achieved / (peak / 1e12),
+            "peak_source": peak_source,
             "traffic": None,
             "avg_launch_ms": avg_launch_ms, "launches_per_step": pair_launches_per_step,
             "algorithmic_terms_per_launch": P_shard * nodes_per_launch,
+            "units_per_term": units_per_term,
             "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                     "achieved_gbs": alg_bytes / (avg_launch_ms * 1e-3) / 1e9,
-                    "peak_gbs": hbm_peak, "peak_source": peak_src},
+                    "peak_gbs": hbm_peak, "peak_source": peak_src,
+                    "note": "not the binding resource: a 128x128 pair tile does 16384 terms per "
+                            "256 embedding elements read"},
         }
         cpu = None
         if not args.no_cpu:

@@ -157,6 +157,13 @@ int b2d_set_option(const char* name, int64_t value);
  * kind 2: conflict-free 64-bit shared-memory gathers/s (the unweighted kernel's bound). */
 int b2d_microbench(int device, int kind, double* result);
 
+/* Host only (no GPU needed): which slices of the condensed vector shard `shard` of
+ * `n_shards` owns: {first condensed index, count} per owned row stripe, ascending (at most
+ * 2*ceil(n/128) int64), the number of stripes and the total element count.  This is the
+ * layout b2d_problem_fetch_compact returns. */
+int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe_offsets,
+                     int64_t* n_stripes_out, int64_t* total_out);
+
 /* Test hook (host only, no GPU needed): the engine's node order for a flat tree.  Arrays
  * sized n_nodes (q_of_id) or n_nodes rounded up to a multiple of 128 (the others); any may
  * be NULL.  flags: bit0 = node has children, bit1 = fold into the sibling accumulator,

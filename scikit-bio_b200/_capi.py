@@ -84,6 +84,8 @@ def _declare(lib):
     lib.b2d_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.b2d_microbench.restype = ctypes.c_int
     lib.b2d_microbench.argtypes = [ctypes.c_int, ctypes.c_int, _f64p]
+    lib.b2d_shard_layout.restype = ctypes.c_int
+    lib.b2d_shard_layout.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _i64p, _i64p, _i64p]
     lib.b2d_debug_tree_order.restype = ctypes.c_int
     lib.b2d_debug_tree_order.argtypes = [
         ctypes.c_int64, _i32p, _f64p, _i32p, ctypes.POINTER(ctypes.c_uint8), _f64p, _f64p,
@@ -96,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "b2d_problem_result_len", "b2d_problem_fetch", "b2d_problem_fetch_compact",
     "b2d_problem_sample_vector", "b2d_problem_timings", "b2d_problem_destroy",
     "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
-    "b2d_microbench", "b2d_debug_tree_order",
+    "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout",
 ]
 
 
@@ -146,6 +148,17 @@ def microbench(kind, device=0):
     out = ctypes.c_double(0.0)
     _check(load().b2d_microbench(int(device), int(kind), ctypes.byref(out)))
     return out.value
+
+
+def shard_layout(n_samples, shard, n_shards):
+    """(offsets[k, 2] = {first condensed index, count} per owned row stripe, total) - host only."""
+    lib = load()
+    nb = (int(n_samples) + 127) // 128
+    offs = np.zeros(2 * max(nb, 1), dtype=np.int64)
+    cnt, tot = ctypes.c_int64(0), ctypes.c_int64(0)
+    _check(lib.b2d_shard_layout(int(n_samples), int(shard), int(n_shards), _ptr(offs, _i64p),
+                                ctypes.byref(cnt), ctypes.byref(tot)))
+    return offs[: 2 * cnt.value].reshape(-1, 2).copy(), int(tot.value)
 
 
 def debug_tree_order(parent, length):

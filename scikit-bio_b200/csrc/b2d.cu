@@ -24,6 +24,7 @@ thread_local std::string g_last_error;
 static int64_t g_chunk_nodes = 8192;           // nodes per pair-kernel launch
 static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
+static int g_weighted_variant = 3;             // 2 = 128x128 tiles / 8x4 threads, 3 = ILP variant
 
 static bool plain_kernels() {
     if (g_plain_kernels < 0) {
@@ -56,6 +57,7 @@ __global__ void k_bench_dfma(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4,
            a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double x = 1.0000001, y = 1e-7;
+#pragma unroll 16
     for (int i = 0; i < iters; ++i) {
         a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
         a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
@@ -290,6 +292,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_chunk_nodes = value <= 0 ? 8192 : (value + 127) / 128 * 128;
     } else if (s == "emb_budget_bytes") {
         g_emb_budget_bytes = value < 0 ? 0 : value;
+    } else if (s == "weighted_variant") {
+        g_weighted_variant = value == 2 ? 2 : 3;
     } else if (s == "plain_kernels") {
         g_plain_kernels = value ? 1 : 0;
     } else {
@@ -389,6 +393,8 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
     // registers within a chunk, `out` across chunks.
     B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)WK_SMEM));
+    B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)W3_SMEM));
     for (int64_t qa = 0; qa < q1 - q0; qa += g_chunk_nodes) {
         int64_t qb = std::min<int64_t>(q1 - q0, qa + g_chunk_nodes);
         PairArgs a;
@@ -407,8 +413,10 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
         a.epilogue = epilogue;
         if (plain_kernels())
             k_pair_weighted_plain<<<(unsigned)p->ntiles, 256, 0, p->stream>>>(emb, len_rel, a);
-        else
+        else if (g_weighted_variant == 2)
             k_pair_weighted<<<(unsigned)p->ntiles, WK_THREADS, WK_SMEM, p->stream>>>(emb, len_rel, a);
+        else
+            k_pair_weighted_v3<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, p->stream>>>(emb, len_rel, a);
         p->n_launch += 1;
     }
     B2D_CUDA(cudaGetLastError());
@@ -695,6 +703,30 @@ int b2d_beta_diversity_features(int metric, int device, int64_t n_samples, int64
     if (!rc && p->out_len) rc = b2d_problem_fetch(p, out_condensed);
     free_problem(p);
     return rc;
+}
+
+int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe_offsets,
+                     int64_t* n_stripes_out, int64_t* total_out) {
+    if (n_samples < 0 || n_shards < 1 || shard < 0 || shard >= n_shards)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "need n_samples >= 0 and 0 <= shard < n_shards");
+    const int64_t nb = (n_samples + TILE - 1) / TILE;
+    int64_t k = 0, total = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+        if (stripe_owner(b, n_shards) != shard) continue;
+        const int64_t i0 = b * TILE, i1 = std::min<int64_t>(n_samples, i0 + TILE);
+        int64_t cnt = 0;
+        for (int64_t i = i0; i < i1; ++i) cnt += n_samples - 1 - i;
+        if (cnt == 0) continue;
+        if (stripe_offsets) {
+            stripe_offsets[2 * k] = cond_row_start(i0, n_samples);
+            stripe_offsets[2 * k + 1] = cnt;
+        }
+        total += cnt;
+        ++k;
+    }
+    if (n_stripes_out) *n_stripes_out = k;
+    if (total_out) *total_out = total;
+    return B2D_OK;
 }
 
 int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* length,

@@ -76,6 +76,12 @@ __device__ __forceinline__ void emit(const PairArgs& a, int64_t base, int64_t i0
 // ptxas' schedule exposes (ncu round 1: 2 warps/SMSP gave 67 % FP64 pipe utilisation with
 // "wait" as the top stall).
 // =========================================================================================
+#define WK_DSUB(d, x, y) asm volatile("sub.f64 %0, %1, %2;" : "=d"(d) : "d"(x), "d"(y))
+#define WK_DFMA_ABS(acc, d, l)                                                       \
+    asm volatile("{\n\t.reg .f64 t;\n\tabs.f64 t, %1;\n\tfma.rn.f64 %0, t, %2, %0;\n\t}" \
+                 : "+d"(acc)                                                         \
+                 : "d"(d), "d"(l))
+
 constexpr int WK_KS = 16;      // nodes per stage
 constexpr int WK_STAGES = 4;
 constexpr int WK_CWARPS = 16;  // compute warps
@@ -157,10 +163,26 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
                 bv[2 * h + 1] = u.y;
             }
             const double l = L[k];
+            // Software-pipelined in batches of 8 terms (2 rows x 4 columns): the DADDs of
+            // batch b+1 are interleaved with the DFMAs of batch b, so a DFMA never issues
+            // right behind the DADD it depends on.  The volatile asm pins this order in the
+            // PTX (nvcc otherwise emits sub/fma back to back and ptxas keeps them so).
+            double d0[8], d1[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int j = 0; j < 8; ++j) WK_DSUB(d0[j], av[j >> 2], bv[j & 3]);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fma(fabs(av[r] - bv[c]), l, acc[r][c]);
+            for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (b & 1) {
+                        WK_DFMA_ABS(acc[2 * b + (j >> 2)][j & 3], d1[j], l);
+                        if (b < 3) WK_DSUB(d0[j], av[2 * (b + 1) + (j >> 2)], bv[j & 3]);
+                    } else {
+                        WK_DFMA_ABS(acc[2 * b + (j >> 2)][j & 3], d0[j], l);
+                        if (b < 3) WK_DSUB(d1[j], av[2 * (b + 1) + (j >> 2)], bv[j & 3]);
+                    }
+                }
+            }
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty[s]);
@@ -176,6 +198,159 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             int64_t j = (int64_t)bj * TILE + (c >> 1) * 64 + tx * 2 + (c & 1);
+            emit(a, base, i0, i, j, acc[r][c]);
+        }
+    }
+}
+
+// =========================================================================================
+// Weighted kernel, variant 3 (default): same arithmetic, scheduled for instruction-level
+// parallelism instead of relying on many warps.
+//   * one CTA owns a 64x128 half tile (grid = 2 x tiles); 8 compute warps, each a 32x32
+//     patch of pairs, each thread an 8x4 register tile; thread patches are 2-D inside the warp
+//     (4 row groups x 8 column groups) so one node costs 6 shared-memory wavefronts per warp;
+//   * the node loop is NOT unrolled and carries the 32 differences d = p_i - p_j of the
+//     current node in registers while the DFMAs consume the differences computed one
+//     iteration earlier: a DFMA is never issued behind the DADD it depends on (ptxas pairs
+//     them back to back whenever both sit in one basic block - ncu round 1: FP64 pipe
+//     67-78 % busy, "wait" stalls on the straggling warps);
+//   * an FP64 warp instruction holds the sub-partition's dispatch port for 2 cycles, so every
+//     other instruction costs FP64 time: the loop body is 64 FP64 + 7 LDS + 7 integer/branch
+//     instructions per node and thread (A and B rows share one shared-memory pitch so one
+//     pointer addresses both).
+// 6-stage ring of {16 x 64 A values (pitch 128), 16 x 128 B values, 16 lengths}, bulk copies.
+// =========================================================================================
+constexpr int W3_KS = 16;
+constexpr int W3_STAGES = 6;
+constexpr int W3_ROWS = 64;
+constexpr int W3_CWARPS = 8;
+constexpr int W3_THREADS = W3_CWARPS * 32 + 32;
+constexpr int W3_STAGE_DOUBLES = 2 * W3_KS * TILE + W3_KS;  // A (pitch 128) + B + len
+constexpr size_t W3_SMEM = (size_t)W3_STAGES * W3_STAGE_DOUBLES * sizeof(double) + 2 * W3_STAGES * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(W3_THREADS, 1)
+k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ len_q, PairArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_base = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)W3_STAGES * W3_STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + W3_STAGES;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int bi = a.tiles[2 * tile], bj = a.tiles[2 * tile + 1];
+    const int64_t nstage = (a.qb - a.qa) / W3_KS;
+
+    if (tid == 0) {
+        for (int s = 0; s < W3_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], W3_CWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid >= W3_CWARPS * 32) {
+        // ---------------- producer warp ----------------
+        if (tid == W3_CWARPS * 32) {
+            const double* Ag = emb + ((int64_t)bi * a.QR + a.qa) * TILE + half * W3_ROWS;
+            const double* Bg = emb + ((int64_t)bj * a.QR + a.qa) * TILE;
+            const double* Lg = len_q + a.qa;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t it = 0; it < nstage; ++it) {
+                if (it >= W3_STAGES) mbar_wait(&empty[s], ph ^ 1u);
+                double* A = stage_base + (size_t)s * W3_STAGE_DOUBLES;
+                double* B = A + W3_KS * TILE;
+                double* L = B + W3_KS * TILE;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)((W3_KS * W3_ROWS + W3_KS * TILE + W3_KS) * sizeof(double)));
+#pragma unroll
+                for (int k = 0; k < W3_KS; ++k)
+                    bulk_g2s(A + k * TILE, Ag + (it * W3_KS + k) * TILE, W3_ROWS * sizeof(double), &full[s]);
+                bulk_g2s(B, Bg + it * W3_KS * TILE, W3_KS * TILE * sizeof(double), &full[s]);
+                bulk_g2s(L, Lg + it * W3_KS, W3_KS * sizeof(double), &full[s]);
+                if (++s == W3_STAGES) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    const int warp = tid >> 5, lane = tid & 31;
+    const int pr = warp >> 2, pc = warp & 3;   // 32x32 patch of the 64x128 half tile
+    const int ty = lane >> 3, tx = lane & 7;   // 8x4 pairs per thread
+    // rows   pr*32 + h*8 + ty*2 + e   (h = 0..3, e = 0..1)  -> acc row index 2h+e
+    // cols   pc*32 + g*16 + tx*2 + e  (g = 0..1, e = 0..1)  -> acc col index 2g+e
+    const int aoff = pr * 32 + ty * 2;
+    const int boff = pc * 32 + tx * 2;
+
+    double acc[8][4], d[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            acc[r][c] = 0.0;
+            d[r][c] = 0.0;
+        }
+    double lc = 0.0;  // length of the node whose differences are held in d
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t it = 0; it < nstage; ++it) {
+        mbar_wait(&full[s], ph);
+        const double* P = stage_base + (size_t)s * W3_STAGE_DOUBLES;  // A row; B row at +16*TILE
+        const double* Lp = P + 2 * W3_KS * TILE;
+        const double* Pend = P + W3_KS * TILE;
+#pragma unroll 1
+        for (; P != Pend; P += TILE, ++Lp) {
+            // operands of this node; the DFMAs below still work on the previous node
+            double av[8], bv[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const double2 t = *reinterpret_cast<const double2*>(P + aoff + h * 8);
+                av[2 * h] = t.x;
+                av[2 * h + 1] = t.y;
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const double2 t = *reinterpret_cast<const double2*>(P + W3_KS * TILE + boff + g * 16);
+                bv[2 * g] = t.x;
+                bv[2 * g + 1] = t.y;
+            }
+            const double ln = *Lp;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc[r][c] = fma(fabs(d[r][c]), lc, acc[r][c]);
+                    d[r][c] = av[r] - bv[c];
+                }
+            lc = ln;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == W3_STAGES) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(fabs(d[r][c]), lc, acc[r][c]);
+
+    // ---------------- epilogue ----------------
+    const int64_t base = a.row_base[bi];
+    const int64_t i0 = (int64_t)bi * TILE;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int64_t i = i0 + half * W3_ROWS + aoff + (r >> 1) * 8 + (r & 1);
+        if (i >= a.n) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int64_t j = (int64_t)bj * TILE + boff + (c >> 1) * 16 + (c & 1);
             emit(a, base, i0, i, j, acc[r][c]);
         }
     }

@@ -131,44 +131,52 @@ def caterpillar_tree(n_tips, seed=1):
     return _finish(spine, left, right, n_tips, rng)
 
 
-def poisson_csr(n_samples, n_cols, lam, seed=0, chunk=256):
+def _zero_truncated_poisson(rng, lam, size):
+    """Poisson(lam) conditioned on being >= 1, by inversion of the CDF."""
+    kmax = int(lam + 12.0 * np.sqrt(lam + 1.0) + 40)
+    k = np.arange(kmax + 1)
+    logpmf = -lam + k * np.log(lam) - np.cumsum(np.log(np.maximum(k, 1)))
+    cdf = np.cumsum(np.exp(logpmf))
+    u = cdf[0] + (1.0 - cdf[0]) * rng.random(size)
+    return np.minimum(np.searchsorted(cdf, u, side="right"), kmax).astype(np.int64)
+
+
+def poisson_csr(n_samples, n_cols, lam, seed=0, chunk_cells=1 << 27):
     """iid Poisson(lam) counts as CSR ``(indptr int64, indices int32, values int64)``.
 
-    Column indices within a row are ascending.  Non-zero positions are Bernoulli
-    (1 - exp(-lam)); values are zero-truncated Poisson(lam) by rejection.
+    Column indices within a row are ascending.  The non-zero cells are iid Bernoulli
+    (1 - exp(-lam)): their positions in the flattened table are generated as cumulative sums
+    of Geometric(p) gaps (fully vectorised, no dense table); values are zero-truncated
+    Poisson(lam) by rejection.
     """
     rng = np.random.default_rng(seed)
     p = 1.0 - np.exp(-lam)
-    indptr = np.zeros(n_samples + 1, dtype=np.int64)
+    rows_per_chunk = max(1, int(chunk_cells // max(n_cols, 1)))
+    counts = np.zeros(n_samples, dtype=np.int64)
     idx_parts, val_parts = [], []
-    for s0 in range(0, n_samples, chunk):
-        s1 = min(n_samples, s0 + chunk)
-        rows = s1 - s0
-        if p > 0.05:
-            mask = rng.random((rows, n_cols)) < p
-            r, c = np.nonzero(mask)
-            cnt = np.bincount(r, minlength=rows)
-        else:
-            cnt = rng.binomial(n_cols, p, size=rows)
-            c_list = []
-            for k in cnt:
-                # distinct columns, ascending
-                cols = np.unique(rng.integers(0, n_cols, size=int(k * 1.05) + 8))
-                while len(cols) < k:
-                    cols = np.unique(np.concatenate([cols, rng.integers(0, n_cols, size=int(k) + 8)]))
-                if len(cols) > k:
-                    cols = np.sort(rng.choice(cols, size=int(k), replace=False))
-                c_list.append(cols)
-            c = np.concatenate(c_list) if c_list else np.zeros(0, dtype=np.int64)
-        nnz = int(cnt.sum())
-        vals = rng.poisson(lam, size=nnz)
-        bad = vals == 0
-        while bad.any():
-            vals[bad] = rng.poisson(lam, size=int(bad.sum()))
-            bad = vals == 0
-        indptr[s0 + 1 : s1 + 1] = indptr[s0] + np.cumsum(cnt)
+    for s0 in range(0, n_samples, rows_per_chunk):
+        s1 = min(n_samples, s0 + rows_per_chunk)
+        cells = (s1 - s0) * n_cols
+        pos_parts, last = [], -1
+        while last < cells - 1:
+            remaining = cells - 1 - last
+            k = int(remaining * p + 6.0 * np.sqrt(remaining * p + 1.0) + 16)
+            gaps = rng.geometric(p, size=k)
+            pos = last + np.cumsum(gaps)
+            pos = pos[pos < cells]
+            pos_parts.append(pos)
+            if len(pos) < k:
+                break
+            last = int(pos[-1])
+        pos = np.concatenate(pos_parts) if pos_parts else np.zeros(0, dtype=np.int64)
+        r = pos // n_cols
+        c = pos - r * n_cols
+        counts[s0:s1] = np.bincount(r, minlength=s1 - s0)
+        vals = _zero_truncated_poisson(rng, lam, len(pos))
         idx_parts.append(c.astype(np.int32))
         val_parts.append(vals.astype(np.int64))
+    indptr = np.zeros(n_samples + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
     indices = np.concatenate(idx_parts) if idx_parts else np.zeros(0, dtype=np.int32)
     values = np.concatenate(val_parts) if val_parts else np.zeros(0, dtype=np.int64)
     return indptr, indices, values
