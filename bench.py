@@ -47,18 +47,21 @@ WORKLOADS = {
                  "weighted normalized UniFrac, 10,000 samples x 100,000 tips (BASELINE configs[1])"),
     "unweighted": ("unweighted_unifrac", 10000, 100000, 0.02,
                    "unweighted UniFrac, random-join tree"),
+    "weighted_unnorm": ("weighted_unifrac", 10000, 100000, 0.02,
+                        "weighted (unnormalized) UniFrac"),
     "braycurtis": ("braycurtis", 10000, 50000, 0.01, "Bray-Curtis, sparse Poisson counts"),
     "jaccard": ("jaccard", 10000, 50000, 0.01, "Jaccard, sparse Poisson counts"),
 }
 
 
-def make_inputs(workload, n, tips):
+def make_inputs(workload, n, tips, tree="random"):
     from skbio_b200 import synthetic
 
     key, _, _, lam, _ = WORKLOADS[workload]
     indptr, cols, vals = synthetic.poisson_csr(n, tips, lam, seed=0)
-    if workload in ("weighted", "unweighted"):
-        parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=1)
+    if workload in ("weighted", "unweighted", "weighted_unnorm"):
+        gen = synthetic.caterpillar_tree if tree == "caterpillar" else synthetic.random_join_tree
+        parent, length, names, tip_node = gen(tips, seed=1)
         return dict(kind="tree", key=key, n=n, parent=parent, length=length, indptr=indptr,
                     ids=tip_node[cols].astype(np.int32), cols=cols, vals=vals, tip_node=tip_node,
                     m=len(parent))
@@ -133,13 +136,17 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------
 # CPU side (oracle port of the reference path) - bounded samples
 # ----------------------------------------------------------------------------------------
-def _np_port_rows(args):
+_JOB = None  # (X, bl, tips, d, normalized, unweighted): inherited by forked workers, not pickled
+
+
+def _np_port_rows(rows):
     """Rows [r0, r1) of the pair triangle with the NumPy port (one process)."""
     from functools import partial
 
     from oracle import oracle_np
 
-    X, bl, tips, d, normalized, unweighted, r0, r1 = args
+    X, bl, tips, d, normalized, unweighted = _JOB
+    r0, r1 = rows
     n = X.shape[0]
     out = []
     if unweighted:
@@ -184,9 +191,10 @@ def cpu_reference_pairs_per_s(inp, workload, n_sub, procs):
         bl = np.ascontiguousarray(inp["length"], dtype=np.float64)
         tipidx = oracle_np.tip_indices_from_parent(inp["parent"])
         d = oracle_np.tip_distances(bl, inp["parent"], tipidx)
-        normalized = workload == "weighted"
-        bounds = _balanced_rows(n_sub, procs)
-        jobs = [(X, bl, tipidx, d, normalized, unweighted, a, b) for a, b in bounds]
+        normalized = workload == "weighted"  # "weighted_unnorm" -> unnormalized
+        global _JOB
+        _JOB = (X, bl, tipidx, d, normalized, unweighted)
+        jobs = _balanced_rows(n_sub, procs)
         if procs > 1:
             import multiprocessing as mp
 
@@ -256,9 +264,10 @@ def run_reference(args):
     n = args.samples or int(round(n_def * np.sqrt(args.gpus)))
     tips = args.tips or tips_def
     procs = min(os.cpu_count() or 1, 32)
-    n_sub = args.cpu_samples or (96 if workload in ("weighted", "unweighted") else 1500)
+    n_sub = args.cpu_samples or (12 * procs if workload in ("weighted", "unweighted", "weighted_unnorm")
+                                 else 1500)
     # only the first n_sub samples are ever touched: generate just those
-    inp = make_inputs(workload, n_sub, tips)
+    inp = make_inputs(workload, n_sub, tips, args.tree)
     vals = []
     for step in range(args.warmup + args.steps):
         v, dt, _, used = cpu_reference_pairs_per_s(inp, workload, n_sub, procs)
@@ -292,6 +301,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    emulate = max(int(args.emulate_shards), 1)  # one process computing shard 0 of `emulate`
     if not _capi.available():
         raise RuntimeError("libskbb200.so missing or no CUDA device: nothing to benchmark "
                            "(the engine has no CPU path)")
@@ -306,9 +316,13 @@ def run_ours(args):
     key, n_def, tips_def, lam, desc = WORKLOADS[workload]
     n = args.samples or int(round(n_def * np.sqrt(world)))
     tips = args.tips or tips_def
-    inp = make_inputs(workload, n, tips)
+    if args.lam:
+        WORKLOADS[workload] = (key, n_def, tips_def, args.lam, desc)
+        lam = args.lam
+    inp = make_inputs(workload, n, tips, args.tree)
     m = inp["m"]
     P_total = n * (n - 1) // 2
+    shard_rank, shard_world = (rank, world) if emulate == 1 else (0, emulate)
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -319,9 +333,10 @@ def run_ours(args):
     def make_problem():
         if inp["kind"] == "tree":
             return _capi.Problem.tree(inp["parent"], inp["length"], inp["indptr"], inp["ids"],
-                                      inp["vals"], n, device=device, shard=rank, n_shards=world)
+                                      inp["vals"], n, device=device, shard=shard_rank,
+                                      n_shards=shard_world)
         return _capi.Problem.features(inp["indptr"], inp["ids"], inp["vals"], n, m, device=device,
-                                      shard=rank, n_shards=world)
+                                      shard=shard_rank, n_shards=shard_world)
 
     # ---------------- device-resident steps ----------------
     prob = make_problem()
@@ -349,29 +364,36 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     step_ms_max, wall_step_ms_max = float(tt[0]), float(tt[1])
-    value = P_total / (step_ms_max * 1e-3)
+    P_done = P_total if emulate == 1 else P_shard   # pairs actually computed by this job
+    value = P_done / (step_ms_max * 1e-3)
 
     # ---------------- end to end through the one-shot C-ABI call, host buffers ----------------
     prob.destroy()
     h2d = (inp["indptr"].nbytes + inp["ids"].nbytes + (inp["vals"].nbytes if inp["vals"] is not None else 0)
            + (inp["parent"].nbytes + inp["length"].nbytes if inp["kind"] == "tree" else 0))
     d2h = P_shard * 8
-    out = _capi.PinnedBuffer(P_total)
+    # one rank: the full condensed vector; several ranks: each rank's own slices, compact
+    # (rank r's page-locked buffer holds only what rank r computed)
+    compact = world > 1 or emulate > 1
+    out = _capi.PinnedBuffer(P_shard if compact else P_total)
     e2e_times = []
     for it in range(2):
         barrier()
         t0 = time.perf_counter()
         with make_problem() as p2:
             p2.compute(key)
-            p2.fetch(out.array)
+            if compact:
+                p2.fetch_compact(out.array)
+            else:
+                p2.fetch(out.array)
         torch.cuda.synchronize(device)
         e2e_times.append(time.perf_counter() - t0)
     e2e_s = min(e2e_times)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{device}")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = P_total / float(te[0])
-    checksum = float(np.nansum(out.array[: min(P_total, 1 << 20)])) if rank == 0 else 0.0
+    e2e_value = P_done / float(te[0])
+    checksum = float(np.nansum(out.array[: min(len(out.array), 1 << 20)])) if rank == 0 else 0.0
 
     line = None
     if rank == 0:
@@ -382,8 +404,8 @@ def run_ours(args):
         avg_launch_ms = float(np.mean(pair_ms)) / max(pair_launches_per_step, 1)
         nodes_per_launch = m / max(pair_launches_per_step, 1)
         sm_count = 148
-        if workload in ("weighted", "braycurtis"):
-            kernel = "k_pair_weighted"
+        if workload in ("weighted", "weighted_unnorm", "braycurtis"):
+            kernel = "k_pair_weighted_v3"
             units_per_term = 2.0   # DADD (pu - pv) + DFMA (|.| * len + acc)
             bound, unit = "fp64", "Tinst/s (FP64 pipe instructions)"
             peak = fp64_peak
@@ -404,7 +426,7 @@ def run_ours(args):
             peak_source = "nominal 148 SM x 16 POPC/clk x 1.965 GHz (not measured)"
         alg_units = P_shard * nodes_per_launch * units_per_term
         achieved = alg_units / (avg_launch_ms * 1e-3) / 1e12
-        elem_bytes = 8.0 if workload in ("weighted", "braycurtis") else 1.0 / 8.0
+        elem_bytes = 8.0 if workload in ("weighted", "weighted_unnorm", "braycurtis") else 1.0 / 8.0
         # unique embedding bytes a launch must read at least once
         alg_bytes = n * nodes_per_launch * elem_bytes
         roofline = {
@@ -423,7 +445,7 @@ def run_ours(args):
                             "256 embedding elements read"},
         }
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1 and emulate == 1:
             n_sub = args.cpu_samples or (64 if inp["kind"] == "tree" else 1000)
             v, dt, vec, used = cpu_reference_pairs_per_s(inp, workload, n_sub, 1)
             # parity spot check of the bench output against the CPU port on the same inputs
@@ -450,7 +472,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": desc if not (args.samples or args.tips) else f"{key} custom size",
                        "metric_key": key, "samples": n, "tips_or_features": tips, "nodes": m,
-                       "lambda": lam, "pairs": P_total, "sharding": f"row-stripe snake x{world}",
+                       "lambda": lam, "pairs": P_total, "pairs_computed": P_done,
+                       "sharding": f"row-stripe snake x{world}" if emulate == 1 else
+                                   f"shard 0 of {emulate} emulated on one GPU",
                        "l2_policy": "inputs larger than L2 (embedding %.1f GB per pass)"
                                     % (n * m * elem_bytes / 1e9)},
             "wall_ms_per_step": wall_step_ms_max,
@@ -483,6 +507,10 @@ def main():
     ap.add_argument("--tips", type=int, default=0)
     ap.add_argument("--cpu-samples", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lam", type=float, default=0.0)
+    ap.add_argument("--tree", default="random", choices=["random", "caterpillar"])
+    ap.add_argument("--emulate-shards", type=int, default=1,
+                    help="compute only shard 0 of N on this GPU (sizing runs for multi-GPU configs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -56,6 +56,8 @@ extern "C" {
 #define B2D_WEIGHTED_UNIFRAC_NORMALIZED 2 /* replaces _weighted_unifrac_normalized, :421-471 */
 #define B2D_BRAYCURTIS 3                  /* replaces scipy pdist 'braycurtis' called at _driver.py:349-354 */
 #define B2D_JACCARD 4                     /* replaces scipy pdist 'jaccard'    called at _driver.py:349-354 */
+#define B2D_FAITH_PD 5                    /* per-sample vector only (no pair kernels): _faith_pd, alpha/_pd.py:34-51;
+                                             read it with b2d_problem_sample_vector */
 
 /* Mirrors skbb_get_api_version (/root/reference/skbio/binaries/_util.py:92-110). */
 int b2d_api_version(void);

@@ -6,6 +6,6 @@ from ._tree import (SimpleTreeNode, read_newick, flatten_tree, validate_taxa_and
                     DuplicateNodeError, MissingNodeError)
 from ._dm import DistanceMatrix, SimpleDistanceMatrix  # noqa: F401
 from ._capi import EngineError, available  # noqa: F401
-from ._driver import beta_diversity, install  # noqa: F401
+from ._driver import alpha_diversity, beta_diversity, install  # noqa: F401
 
 __version__ = "0.1.0"

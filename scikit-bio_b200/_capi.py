@@ -24,6 +24,7 @@ METRIC_IDS = {
     "weighted_unifrac_normalized": 2,
     "braycurtis": 3,
     "jaccard": 4,
+    "faith_pd": 5,
 }
 
 _i64p = ctypes.POINTER(ctypes.c_int64)

@@ -205,6 +205,48 @@ def beta_diversity(metric, counts, ids=None, validate=True, pairwise_func=None, 
     return make_distance_matrix(vec, ids, condensed=condensed, n=n)
 
 
+def alpha_diversity(metric, counts, ids=None, validate=True, **kwargs):
+    """``skbio.diversity.alpha_diversity`` for ``metric='faith_pd'`` on the engine
+    (/root/reference/skbio/diversity/_driver.py:134-228, alpha/_pd.py:19-51): Faith's PD is the
+    per-sample sum of branch lengths of observed nodes, a by-product of the presence
+    propagation.  Other alpha metrics are not on this engine's path and go to scikit-bio."""
+    import pandas as pd
+
+    device = _devices_arg(kwargs.pop("devices", None))[0]
+    if metric != "faith_pd":
+        from skbio.diversity import alpha_diversity as _skbio_alpha  # type: ignore
+
+        return _skbio_alpha(metric, counts, ids, validate=validate, **kwargs)
+    taxa = kwargs.pop("taxa", None)
+    counts, ids, taxa = ingest_table(counts, ids, taxa)
+    if 0 in counts.shape:
+        return pd.Series(np.zeros(len(ids)), index=ids)
+    if validate:
+        counts = validate_counts_matrix(counts)
+    taxa, tree, kwargs = _get_phylogenetic_kwargs(kwargs, taxa)
+    if kwargs:
+        raise TypeError(f"faith_pd() got an unexpected keyword argument '{next(iter(kwargs))}'")
+    if validate:
+        validate_taxa_and_tree(taxa, tree)
+    if _capi.load().b2d_device_count() <= 0:
+        raise _capi.EngineError("no CUDA device visible: the B200 engine has no CPU fallback.")
+    parent, length, names = flatten_tree(tree)
+    # _nodes_by_counts truncates to int64 first (_phylogenetic.pyx:186); presence = count > 0
+    indptr, cols, vals = to_csr(counts, "int64")
+    keep = vals > 0
+    if not keep.all():
+        rows = np.repeat(np.arange(counts.shape[0]), np.diff(indptr))[keep]
+        cols = cols[keep]
+        indptr = np.zeros(counts.shape[0] + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=counts.shape[0]), out=indptr[1:])
+    node_of_col = map_taxa_to_nodes(taxa, np.unique(cols), names)
+    with _capi.Problem.tree(parent, length, indptr, node_of_col[cols], None, counts.shape[0],
+                            device=device) as prob:
+        prob.compute("faith_pd")
+        vec = prob.sample_vector()
+    return pd.Series(vec, index=ids)
+
+
 def _reference_route(metric, counts, ids, validate, pairwise_func, taxa, kwargs):
     """Metrics that are not on the engine's path: run exactly what the reference runs."""
     if _is_sparse(counts):

@@ -525,7 +525,7 @@ static int compute_bits(b2d_problem* p, int metric) {
     p->n_launch = 0;
     B2D_CUDA(cudaFuncSetAttribute(k_pair_unweighted_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)UL_SMEM));
-    if (p->ntiles) {
+    if (p->ntiles && metric != B2D_FAITH_PD) {
         // bits kernels touch 8..32 nodes per instruction: use 4x longer node chunks per launch
         const int64_t chunk = 4 * g_chunk_nodes;
         for (int64_t qa = 0; qa < p->mpad; qa += chunk) {
@@ -573,7 +573,8 @@ int b2d_problem_compute(b2d_problem* p, int metric) {
     int rc;
     switch (metric) {
         case B2D_UNWEIGHTED_UNIFRAC:
-            if (p->kind != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "unweighted_unifrac needs a tree problem");
+        case B2D_FAITH_PD:
+            if (p->kind != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "unweighted_unifrac / faith_pd need a tree problem");
             rc = compute_bits(p, metric);
             break;
         case B2D_WEIGHTED_UNIFRAC:

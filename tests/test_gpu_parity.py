@@ -56,6 +56,16 @@ def test_golden_full_api(case):
             assert_close_rel(got, exp, UNIFRAC_RTOL, f"{case['name']} {key}")
 
 
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_faith_pd_matches_reference(case):
+    sb = _skbio_b200()
+    counts, parent, length, names = case_arrays(case)
+    tree = sb.read_newick(case["newick"])
+    got = sb.alpha_diversity("faith_pd", counts.astype(int) if counts.dtype != bool else counts,
+                             case["ids"], tree=tree, taxa=case["taxa"])
+    assert_close_rel(got.values, case["results"]["faith_pd"], UNIFRAC_RTOL, case["name"] + " faith_pd")
+
+
 def test_qiime_tiny_test(qiime_tt):
     sb = _skbio_b200()
     counts = np.array(qiime_tt["counts"])

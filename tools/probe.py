@@ -28,8 +28,34 @@ def run(n, tips, lam, keys, feat_keys=()):
                 t = prob.timings()
                 print(f"{key}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "e2e"):
     print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), "lds64 gathers/s", _capi.microbench(2), flush=True)
     run(4096, 20000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"], ["braycurtis", "jaccard"])
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         run(10000, 100000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"])
+
+
+def e2e_breakdown(n=10000, tips=100000, lam=0.02, key="weighted_unifrac_normalized"):
+    parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=1)
+    indptr, cols, vals = synthetic.poisson_csr(n, tips, lam, seed=0)
+    ids = tip_node[cols].astype(np.int32)
+    P = n * (n - 1) // 2
+    out = _capi.PinnedBuffer(P)
+    for rep in range(2):
+        t0 = time.perf_counter()
+        prob = _capi.Problem.tree(parent, length, indptr, ids, vals, n)
+        t1 = time.perf_counter()
+        prob.compute(key)
+        t2 = time.perf_counter()
+        prob.fetch(out.array)
+        t3 = time.perf_counter()
+        tm = prob.timings()
+        prob.destroy()
+        t4 = time.perf_counter()
+        print(f"e2e rep{rep}: create {1e3*(t1-t0):.1f} ms (upload {tm['upload_ms']:.1f}) compute {1e3*(t2-t1):.1f} ms "
+              f"(dev {tm['compute_ms']:.1f}) fetch {1e3*(t3-t2):.1f} ms (dev {tm['fetch_ms']:.1f}) destroy {1e3*(t4-t3):.1f} ms "
+              f"total {1e3*(t4-t0):.1f} ms", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "e2e":
+    e2e_breakdown()
