@@ -106,6 +106,13 @@ int b2d_problem_create_features(b2d_problem** out, int device,
                                 const double* values,
                                 int shard, int n_shards);
 
+/* Restrict the problem to an explicit list of 128x128 pair tiles, tiles[2*t] = row stripe,
+ * tiles[2*t+1] = column stripe (row <= column).  The problem then owns exactly the row
+ * stripes named; entries of those stripes outside the selected tiles read 0 after compute.
+ * This is the engine's form of partial_beta_diversity / block_beta_diversity
+ * (/root/reference/skbio/diversity/_driver.py:364-460, _block.py:263-356). */
+int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_tiles);
+
 /* Build the per-node sample embedding and run the pair kernels for `metric` on the
  * problem's device.  Blocks until the shard's distances are complete in device memory. */
 int b2d_problem_compute(b2d_problem* p, int metric);

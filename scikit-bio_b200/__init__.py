@@ -6,6 +6,7 @@ from ._tree import (SimpleTreeNode, read_newick, flatten_tree, validate_taxa_and
                     DuplicateNodeError, MissingNodeError)
 from ._dm import DistanceMatrix, SimpleDistanceMatrix  # noqa: F401
 from ._capi import EngineError, available  # noqa: F401
-from ._driver import alpha_diversity, beta_diversity, install  # noqa: F401
+from ._driver import (alpha_diversity, beta_diversity, block_beta_diversity,  # noqa: F401
+                      partial_beta_diversity, install)
 
 __version__ = "0.1.0"

@@ -59,6 +59,8 @@ def _declare(lib):
     lib.b2d_problem_create_features.argtypes = [
         ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
         _i64p, _i32p, _f64p, ctypes.c_int, ctypes.c_int]
+    lib.b2d_problem_select_tiles.restype = ctypes.c_int
+    lib.b2d_problem_select_tiles.argtypes = [ctypes.c_void_p, _i32p, ctypes.c_int64]
     lib.b2d_problem_compute.restype = ctypes.c_int
     lib.b2d_problem_compute.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.b2d_problem_result_len.restype = ctypes.c_int64
@@ -99,7 +101,7 @@ EXPORTED_SYMBOLS = [
     "b2d_problem_result_len", "b2d_problem_fetch", "b2d_problem_fetch_compact",
     "b2d_problem_sample_vector", "b2d_problem_timings", "b2d_problem_destroy",
     "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
-    "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout",
+    "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout", "b2d_problem_select_tiles",
 ]
 
 
@@ -244,6 +246,11 @@ class Problem:
             _ptr(indptr, _i64p), _ptr(feature_ids, _i32p), _ptr(values, _f64p),
             int(shard), int(n_shards)))
         return cls(h, int(n_samples))
+
+    def select_tiles(self, tiles):
+        """Restrict to 128x128 tiles given as an (k, 2) array of (row stripe, column stripe)."""
+        tiles = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 2)
+        _check(load().b2d_problem_select_tiles(self._h, _ptr(tiles, _i32p), len(tiles)))
 
     def compute(self, metric):
         mid = METRIC_IDS[metric] if isinstance(metric, str) else int(metric)

@@ -107,26 +107,11 @@ def _run_sharded(make_problem, metric_key, n, devices):
 
 def _unifrac_engine(metric_key, counts, taxa, tree, validate, devices):
     """Replaces _setup_multiple_{un,}weighted_unifrac + pdist
-    (/root/reference/skbio/diversity/beta/_unifrac.py:474-584, _driver.py:349-354)."""
-    if validate:
-        validate_taxa_and_tree(taxa, tree)
-    parent, length, names = flatten_tree(tree)
-    mode = "presence" if metric_key == "unweighted_unifrac" else "int64"
-    indptr, cols, vals = to_csr(counts, mode)
-    n = counts.shape[0]
-    observed_cols = np.unique(cols)
-    node_of_col = map_taxa_to_nodes(taxa, observed_cols, names)
-    node_ids = node_of_col[cols]
-    if len(np.unique(node_of_col[observed_cols])) != len(observed_cols):
-        # several observed taxa map to one node (only reachable with validate=False):
-        # the reference assigns, so the last column wins (_phylogenetic.pyx:208-218)
-        indptr, node_ids, vals = _dedupe_last_wins(indptr, node_ids, vals)
-
-    def make(dev, shard, nshards):
-        return _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, device=dev,
-                                  shard=shard, n_shards=nshards)
-
-    return _run_sharded(make, metric_key, n, devices)
+    (/root/reference/skbio/diversity/beta/_unifrac.py:474-584, _driver.py:349-354).  Several
+    observed taxa mapping to one node (only reachable with validate=False) follow the
+    reference's assignment semantics: the last column wins (_phylogenetic.pyx:208-218)."""
+    make = _prepare_unifrac_problem(metric_key, counts, taxa, tree, validate)
+    return _run_sharded(make, metric_key, counts.shape[0], devices)
 
 
 def _dedupe_last_wins(indptr, node_ids, vals):
@@ -203,6 +188,157 @@ def beta_diversity(metric, counts, ids=None, validate=True, pairwise_func=None, 
                 f"'{next(iter(kwargs))}'")
         vec = _features_engine(metric, counts, devices)
     return make_distance_matrix(vec, ids, condensed=condensed, n=n)
+
+
+def _prepare_unifrac_problem(key, counts, taxa, tree, validate):
+    """Host half of the UniFrac path: validate, flatten, CSR, name lookup -> factory of shards."""
+    if validate:
+        validate_taxa_and_tree(taxa, tree)
+    parent, length, names = flatten_tree(tree)
+    mode = "presence" if key == "unweighted_unifrac" else "int64"
+    indptr, cols, vals = to_csr(counts, mode)
+    n = counts.shape[0]
+    observed_cols = np.unique(cols)
+    node_of_col = map_taxa_to_nodes(taxa, observed_cols, names)
+    node_ids = node_of_col[cols]
+    if len(np.unique(node_of_col[observed_cols])) != len(observed_cols):
+        indptr, node_ids, vals = _dedupe_last_wins(indptr, node_ids, vals)
+
+    def make(dev, shard=0, nshards=1):
+        return _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, device=dev,
+                                  shard=shard, n_shards=nshards)
+
+    return make
+
+
+def partial_beta_diversity(metric, counts, ids, id_pairs, validate=True, **kwargs):
+    """Distances only between the given ID pairs; every other entry of the matrix is 0.
+
+    Same contract as the reference (/root/reference/skbio/diversity/_driver.py:364-460): only
+    the optimized UniFrac metric names and callables are accepted, ``id_pairs`` must be a
+    subset of ``ids`` without duplicates or self pairs, the result is ``DistanceMatrix(dm +
+    dm.T, ids)``.  On the engine only the 128x128 tiles that contain a requested pair run.
+    """
+    from itertools import chain
+
+    device = _devices_arg(kwargs.pop("devices", None))[0]
+    taxa = kwargs.pop("taxa", None)
+    counts, ids, taxa = ingest_table(counts, ids, taxa)
+    if validate:
+        counts = validate_counts_matrix(counts)
+    id_pairs = list(id_pairs)
+    all_ids_in_pairs = set(chain.from_iterable(id_pairs))
+    if not all_ids_in_pairs.issubset(ids):
+        raise ValueError("`id_pairs` are not a subset of `ids`")
+    hashes = {i for i in id_pairs}.union({i[::-1] for i in id_pairs})
+    if len(hashes) != len(id_pairs) * 2:
+        raise ValueError("A duplicate or a self-self pair was observed.")
+    n = len(ids)
+    id_index = {id_: idx for idx, id_ in enumerate(ids)}
+    pairs = np.array([(id_index[u], id_index[v]) for u, v in id_pairs], dtype=np.int64).reshape(-1, 2)
+    dm = np.zeros((n, n))
+    if metric in ("unweighted_unifrac", "weighted_unifrac"):
+        key = metric
+        if metric == "weighted_unifrac":
+            normalized = kwargs.pop("normalized", _normalize_weighted_unifrac_by_default)
+            if normalized:
+                key = "weighted_unifrac_normalized"
+        taxa, tree, kwargs = _get_phylogenetic_kwargs(kwargs, taxa)
+        if kwargs:
+            raise TypeError(
+                f"{metric}() got an unexpected keyword argument '{next(iter(kwargs))}'")
+        if _capi.load().b2d_device_count() <= 0:
+            raise _capi.EngineError("no CUDA device visible: the B200 engine has no CPU fallback.")
+        make = _prepare_unifrac_problem(key, counts, taxa, tree, validate)
+        if len(pairs):
+            lo = pairs.min(axis=1)
+            hi = pairs.max(axis=1)
+            tiles = np.unique(np.stack([lo // 128, hi // 128], axis=1), axis=0)
+            with make(device) as prob:
+                prob.select_tiles(tiles)
+                prob.compute(key)
+                compact, layout = prob.fetch_compact()
+            # position of pair (i<j) inside the compact stripes
+            stripe_first = {}
+            pos = 0
+            for first, cnt in layout:
+                stripe_first[int(first)] = pos
+                pos += int(cnt)
+            b = lo // 128
+            first_of_b = (b * 128) * n - ((b * 128) * (b * 128 + 1)) // 2
+            cidx = lo * n - ((lo + 2) * (lo + 1)) // 2 + hi
+            base = np.array([stripe_first[int(f)] for f in first_of_b], dtype=np.int64)
+            vals = compact[base + (cidx - first_of_b)]
+            dm[pairs[:, 0], pairs[:, 1]] = vals
+    elif callable(metric):
+        func = partial(metric, **kwargs)
+        dense = counts.toarray() if _is_sparse(counts) else counts
+        for u, v in pairs:
+            dm[u, v] = func(dense[u], dense[v])
+    else:
+        raise ValueError(
+            "partial_beta_diversity is only compatible with "
+            "optimized unifrac methods and callable functions.")
+    return make_distance_matrix(dm + dm.T, ids)
+
+
+def block_beta_diversity(metric, counts, ids=None, validate=True, k=64, reduce_f=None,
+                         map_f=None, **kwargs):
+    """Block-decomposition beta diversity (/root/reference/skbio/diversity/_block.py:263-356).
+
+    The reference cuts the triangle into k x k blocks so that a user-supplied ``map_f`` can
+    farm them out; the result equals ``beta_diversity`` (its own test_block.py asserts that).
+    The engine already computes in 128 x 128 tiles sharded over GPUs, so without a custom
+    ``map_f``/``reduce_f`` this is the tiled engine call itself.  With one, the reference's
+    structure is kept: blocks of ``k`` ids are mapped through ``partial_beta_diversity``.
+    """
+    if map_f is None and reduce_f is None:
+        return beta_diversity(metric, counts, ids, validate=validate, **kwargs)
+    taxa = kwargs.get("taxa")
+    counts, ids, taxa = ingest_table(counts, ids, taxa)
+    if taxa is not None:
+        kwargs["taxa"] = taxa
+    if validate:
+        counts = validate_counts_matrix(counts)
+    n = counts.shape[0]
+    num_ids = np.arange(n)
+
+    def block_jobs():
+        for r0 in range(0, n, k):
+            for c0 in range(r0, n, k):
+                rids = num_ids[r0:r0 + k]
+                cids = num_ids[c0:c0 + k]
+                keep = np.unique(np.hstack([rids, cids]))
+                if r0 == c0:
+                    pairs = [(int(a), int(b)) for x, a in enumerate(rids) for b in rids[x + 1:]]
+                else:
+                    pairs = [(int(a), int(b)) for a in rids for b in cids]
+                kw = dict(kwargs)
+                kw.update(metric=metric, counts=counts[keep], ids=list(keep), id_pairs=pairs,
+                          validate=False)
+                yield kw
+
+    def compute(**kw):
+        return partial_beta_diversity(**kw)
+
+    if map_f is None:
+        def map_f(func, gen):
+            for kw in gen:
+                yield func(**kw)
+    blocks = list(map_f(compute, block_jobs()))
+    if reduce_f is not None:
+        dm = reduce_f(blocks)
+        try:
+            dm.ids = ids
+        except Exception:
+            pass
+        return dm
+    mat = np.zeros((n, n))
+    for blk in blocks:
+        bid = np.asarray(blk.ids, dtype=np.int64)
+        data = np.asarray(blk.data)
+        mat[np.ix_(bid, bid)] += np.triu(data, k=1)
+    return make_distance_matrix(mat + mat.T, ids)
 
 
 def alpha_diversity(metric, counts, ids=None, validate=True, **kwargs):

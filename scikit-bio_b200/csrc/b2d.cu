@@ -128,6 +128,7 @@ struct b2d_problem {
     size_t emb_bytes = 0;
     long long* d_state = nullptr;
     bool computed = false;
+    bool custom_tiles = false;  // b2d_problem_select_tiles: untouched entries of owned stripes stay 0
     int last_metric = -1;
     double t_embed = 0, t_pair = 0, t_total = 0, t_fetch = 0, t_upload = 0;
     double n_launch = 0, nodes_resident = 0, n_pass = 0;
@@ -570,6 +571,8 @@ static int compute_bits(b2d_problem* p, int metric) {
 int b2d_problem_compute(b2d_problem* p, int metric) {
     if (!p) return fail(B2D_ERR_INVALID_ARGUMENT, "problem is NULL");
     B2D_CUDA(cudaSetDevice(p->device));
+    if (p->custom_tiles && p->out_len)
+        B2D_CUDA(cudaMemsetAsync(p->d_out, 0, p->out_len * sizeof(double), p->stream));
     int rc;
     switch (metric) {
         case B2D_UNWEIGHTED_UNIFRAC:
@@ -599,6 +602,52 @@ int b2d_problem_compute(b2d_problem* p, int metric) {
     p->t_total = p->t_embed + p->t_pair;
     p->computed = true;
     p->last_metric = metric;
+    return B2D_OK;
+}
+
+int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_tiles) {
+    if (!p || (!tiles && n_tiles)) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    B2D_CUDA(cudaSetDevice(p->device));
+    std::vector<uint8_t> want(p->nb, 0);
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        int32_t bi = tiles[2 * t], bj = tiles[2 * t + 1];
+        if (bi < 0 || bj < bi || bj >= p->nb)
+            return fail(B2D_ERR_INVALID_ARGUMENT, "tile (bi, bj) needs 0 <= bi <= bj < ceil(n/128)");
+        want[bi] = 1;
+    }
+    p->owned.clear();
+    p->row_base.assign(p->nb, -1);
+    int64_t off = 0;
+    for (int64_t b = 0; b < p->nb; ++b) {
+        if (!want[b]) continue;
+        int64_t i0 = b * TILE, i1 = std::min<int64_t>(p->n, i0 + TILE);
+        int64_t cnt = 0;
+        for (int64_t i = i0; i < i1; ++i) cnt += p->n - 1 - i;
+        if (cnt == 0) continue;
+        p->owned.push_back(b);
+        p->row_base[b] = off;
+        off += cnt;
+    }
+    std::vector<int32_t> keep;
+    for (int64_t t = 0; t < n_tiles; ++t)
+        if (p->row_base[tiles[2 * t]] >= 0) {
+            keep.push_back(tiles[2 * t]);
+            keep.push_back(tiles[2 * t + 1]);
+        }
+    cudaFree(p->d_tiles);
+    cudaFree(p->d_out);
+    p->d_tiles = nullptr;
+    p->d_out = nullptr;
+    p->out_len = off;
+    p->ntiles = (int64_t)keep.size() / 2;
+    int rc;
+    if ((rc = upload(&p->d_tiles, keep.data(), keep.size(), p->stream))) return rc;
+    B2D_CUDA(cudaMemcpyAsync(p->d_row_base, p->row_base.data(), p->nb * sizeof(int64_t),
+                             cudaMemcpyHostToDevice, p->stream));
+    B2D_CUDA(cudaMalloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    p->custom_tiles = true;
+    p->computed = false;
     return B2D_OK;
 }
 

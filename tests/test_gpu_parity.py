@@ -227,3 +227,43 @@ def test_engine_errors_are_loud():
     with pytest.raises(_capi.EngineError):
         _capi.Problem.tree(np.array([1, -1], dtype=np.int32), np.zeros(2), np.array([0, 1]),
                            np.array([5], dtype=np.int32), None, 1)  # node id out of range
+
+
+def test_partial_and_block_beta_diversity():
+    """partial_beta_diversity computes exactly the requested pairs (others 0) and
+    block_beta_diversity equals the full matrix (reference: test_block.py:31-39,
+    test_driver.py:814-951)."""
+    sb = _skbio_b200()
+    from skbio_b200 import synthetic
+
+    n, tips = 300, 400
+    parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=8)
+    indptr, cols, vals = synthetic.poisson_csr(n, tips, 0.05, seed=9)
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    tree = synthetic.to_nodes(parent, length, names)
+    taxa = [f"T{i}" for i in range(tips)]
+    ids = [f"S{i}" for i in range(n)]
+    for metric, kw in (("unweighted_unifrac", {}), ("weighted_unifrac", {"normalized": True})):
+        full = sb.beta_diversity(metric, dense, ids, tree=tree, taxa=taxa, **kw)
+        fdata = np.asarray(full.data)
+        rng = np.random.default_rng(1)
+        pairs = set()
+        while len(pairs) < 200:
+            i, j = rng.integers(0, n, size=2)
+            if i != j and (j, i) not in pairs:
+                pairs.add((int(i), int(j)))
+        pairs = sorted(pairs)
+        part = sb.partial_beta_diversity(metric, dense, ids, [(ids[i], ids[j]) for i, j in pairs],
+                                         tree=tree, taxa=taxa, **kw)
+        pdata = np.asarray(part.data)
+        mask = np.zeros((n, n), dtype=bool)
+        for i, j in pairs:
+            mask[i, j] = mask[j, i] = True
+        assert_close_rel(pdata[mask], fdata[mask], 1e-13, metric + " partial")
+        assert not pdata[~mask].any()
+        blk = sb.block_beta_diversity(metric, dense, ids, tree=tree, taxa=taxa, k=64, **kw)
+        assert np.array_equal(np.asarray(blk.data), fdata)
+        # the reference's map/reduce structure over k x k blocks of ids
+        blk2 = sb.block_beta_diversity(metric, dense, ids, tree=tree, taxa=taxa, k=100,
+                                       map_f=lambda f, gen: [f(**kwargs) for kwargs in gen], **kw)
+        assert_close_rel(np.asarray(blk2.data), fdata, 1e-13, metric + " block")

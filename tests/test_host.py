@@ -227,3 +227,22 @@ def test_synthetic_generators():
     for k in range(len(p2) - 2, -1, -1):
         depth[k] = depth[p2[k]] + 1
     assert depth.max() > 60
+
+
+def test_partial_beta_diversity_host_contract():
+    """Errors and the callable route of partial_beta_diversity
+    (/root/reference/skbio/diversity/tests/test_driver.py:814-951)."""
+    from skbio_b200 import partial_beta_diversity
+
+    t = skbio_b200.read_newick(T1)
+    ids = ["A", "B"]
+    with pytest.raises(ValueError, match="`id_pairs` are not a subset of `ids`"):
+        partial_beta_diversity("unweighted_unifrac", B1, ids, [("A", "Z")], tree=t, taxa=OIDS)
+    with pytest.raises(ValueError, match="A duplicate or a self-self pair was observed"):
+        partial_beta_diversity("unweighted_unifrac", B1, ids, [("A", "B"), ("B", "A")], tree=t, taxa=OIDS)
+    with pytest.raises(ValueError, match="A duplicate or a self-self pair was observed"):
+        partial_beta_diversity("unweighted_unifrac", B1, ids, [("A", "A")], tree=t, taxa=OIDS)
+    with pytest.raises(ValueError, match="only compatible with optimized unifrac methods"):
+        partial_beta_diversity("braycurtis", B1, ids, [("A", "B")])
+    dm = partial_beta_diversity(lambda u, v: float(np.abs(u - v).sum()), np.asarray(B1), ids, [("B", "A")])
+    assert dm["A", "B"] == 9.0 and dm["B", "A"] == 9.0
