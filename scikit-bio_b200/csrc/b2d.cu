@@ -101,7 +101,9 @@ struct b2d_problem {
     int shard = 0, n_shards = 1;
     bool has_values = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // odd node chunks run here, into d_out2 (tails overlap)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_sync[2] = {nullptr, nullptr};
     TreeOrder order;
     // device inputs
     int64_t* d_indptr = nullptr;
@@ -119,7 +121,10 @@ struct b2d_problem {
     int64_t ntiles = 0;
     int64_t* d_row_base = nullptr;
     double* d_out = nullptr;
+    double* d_out2 = nullptr;
+    int64_t* d_owned = nullptr;
     int64_t out_len = 0;
+    int64_t chunk_counter = 0;        // node chunks launched in the current compute
     // per sample
     long long* d_total = nullptr;
     double* d_svec = nullptr;
@@ -141,8 +146,11 @@ static void free_problem(b2d_problem* p) {
     cudaFree(p->d_hc); cudaFree(p->d_fold); cudaFree(p->d_len); cudaFree(p->d_tipdist);
     cudaFree(p->d_tiles); cudaFree(p->d_row_base); cudaFree(p->d_out); cudaFree(p->d_total);
     cudaFree(p->d_svec); cudaFree(p->d_emb); cudaFree(p->d_state);
+    cudaFree(p->d_out2); cudaFree(p->d_owned);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
     delete p;
 }
 
@@ -157,7 +165,9 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
                         const void* values, size_t value_size) {
     cudaEvent_t e0, e1;
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    B2D_CUDA(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
     for (auto& e : p->ev) B2D_CUDA(cudaEventCreate(&e));
+    for (auto& e : p->ev_sync) B2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     B2D_CUDA(cudaEventCreate(&e0));
     B2D_CUDA(cudaEventCreate(&e1));
     B2D_CUDA(cudaEventRecord(e0, p->stream));
@@ -220,6 +230,7 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     if ((rc = upload(&p->d_tiles, tiles.data(), tiles.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_row_base, p->row_base.data(), p->row_base.size(), p->stream))) return rc;
     B2D_CUDA(cudaMalloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+    if ((rc = upload(&p->d_owned, p->owned.data(), p->owned.size(), p->stream))) return rc;
     B2D_CUDA(cudaMalloc(&p->d_total, p->npad * sizeof(long long)));
     B2D_CUDA(cudaMalloc(&p->d_svec, p->npad * sizeof(double)));
     B2D_CUDA(cudaMemsetAsync(p->d_total, 0, p->npad * sizeof(long long), p->stream));
@@ -388,6 +399,44 @@ static int ensure_emb(b2d_problem* p, size_t bytes) {
     return B2D_OK;
 }
 
+// Node chunk `ci` of a compute runs on stream (ci & 1) into raw-sum buffer (ci & 1): a launch
+// only depends on the launch two chunks earlier, so the partially filled last wave of one
+// launch overlaps the first waves of the next.
+static int chunk_target(b2d_problem* p, cudaStream_t* st, double** out, int* first) {
+    const int64_t ci = p->chunk_counter++;
+    const int side = (int)(ci & 1);
+    if (side == 1 && !p->d_out2)
+        B2D_CUDA(cudaMalloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+    if (side == 1 && ci == 1 && p->custom_tiles && p->out_len)
+        B2D_CUDA(cudaMemsetAsync(p->d_out2, 0, p->out_len * sizeof(double), p->stream2));
+    *st = side ? p->stream2 : p->stream;
+    *out = side ? p->d_out2 : p->d_out;
+    *first = p->custom_tiles ? 0 : (ci < 2);
+    return B2D_OK;
+}
+
+// stream2 may start once everything queued on the main stream so far (embedding) is done
+static int fork_streams(b2d_problem* p) {
+    B2D_CUDA(cudaEventRecord(p->ev_sync[0], p->stream));
+    B2D_CUDA(cudaStreamWaitEvent(p->stream2, p->ev_sync[0], 0));
+    return B2D_OK;
+}
+// the main stream continues once stream2 has drained
+static int join_streams(b2d_problem* p) {
+    B2D_CUDA(cudaEventRecord(p->ev_sync[1], p->stream2));
+    B2D_CUDA(cudaStreamWaitEvent(p->stream, p->ev_sync[1], 0));
+    return B2D_OK;
+}
+
+static int finalize(b2d_problem* p, int epilogue) {
+    if (!p->out_len || p->owned.empty()) return B2D_OK;
+    const double* out2 = p->chunk_counter >= 2 ? p->d_out2 : nullptr;
+    k_finalize<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
+        p->d_out, out2, p->d_owned, p->d_row_base, p->n, epilogue, p->d_svec, p->d_total);
+    B2D_CUDA(cudaGetLastError());
+    return B2D_OK;
+}
+
 static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* len_rel,
                               int64_t q0, int64_t q1, int64_t QR, int epilogue) {
     // node chunks [qa, qb) relative to the resident range; two-level fp64 summation:
@@ -409,15 +458,17 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
         a.qb = qb;
         a.QR = QR;
         a.NS = p->NS;
-        a.first = (q0 + qa == 0);
-        a.last = (q0 + qb == p->mpad);
+        a.last = 0;
         a.epilogue = epilogue;
+        cudaStream_t st;
+        int rc = chunk_target(p, &st, &a.out, &a.first);
+        if (rc) return rc;
         if (plain_kernels())
-            k_pair_weighted_plain<<<(unsigned)p->ntiles, 256, 0, p->stream>>>(emb, len_rel, a);
+            k_pair_weighted_plain<<<(unsigned)p->ntiles, 256, 0, st>>>(emb, len_rel, a);
         else if (g_weighted_variant == 2)
-            k_pair_weighted<<<(unsigned)p->ntiles, WK_THREADS, WK_SMEM, p->stream>>>(emb, len_rel, a);
+            k_pair_weighted<<<(unsigned)p->ntiles, WK_THREADS, WK_SMEM, st>>>(emb, len_rel, a);
         else
-            k_pair_weighted_v3<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, p->stream>>>(emb, len_rel, a);
+            k_pair_weighted_v3<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, st>>>(emb, len_rel, a);
         p->n_launch += 1;
     }
     B2D_CUDA(cudaGetLastError());
@@ -459,6 +510,7 @@ static int compute_dense(b2d_problem* p, int metric) {
                                                              : EPI_RAW;
     p->n_launch = 0;
     p->n_pass = 0;
+    p->chunk_counter = 0;
     p->nodes_resident = (double)QR;
     double t_embed = 0, t_pair = 0;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
@@ -489,8 +541,11 @@ static int compute_dense(b2d_problem* p, int metric) {
         }
         B2D_CUDA(cudaEventRecord(eb, p->stream));
         if (p->ntiles) {
+            if ((rc = fork_streams(p))) return rc;
             rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue);
             if (rc) return rc;
+            if ((rc = join_streams(p))) return rc;
+            if (q1 == p->mpad && (rc = finalize(p, epilogue))) return rc;
         }
         B2D_CUDA(cudaEventRecord(ec, p->stream));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
@@ -526,7 +581,9 @@ static int compute_bits(b2d_problem* p, int metric) {
     p->n_launch = 0;
     B2D_CUDA(cudaFuncSetAttribute(k_pair_unweighted_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)UL_SMEM));
+    p->chunk_counter = 0;
     if (p->ntiles && metric != B2D_FAITH_PD) {
+        if ((rc = fork_streams(p))) return rc;
         // bits kernels touch 8..32 nodes per instruction: use 4x longer node chunks per launch
         const int64_t chunk = 4 * g_chunk_nodes;
         for (int64_t qa = 0; qa < p->mpad; qa += chunk) {
@@ -542,19 +599,22 @@ static int compute_bits(b2d_problem* p, int metric) {
             a.qb = qb;
             a.QR = 0;
             a.NS = p->NS;
-            a.first = (qa == 0);
-            a.last = (qb == p->mpad);
+            a.last = 0;
             a.epilogue = metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED;
+            cudaStream_t st;
+            if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
             if (metric == B2D_JACCARD)
-                k_pair_popcount<<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const uint4*)p->d_emb, a);
+                k_pair_popcount<<<(unsigned)p->ntiles, 256, 0, st>>>((const uint4*)p->d_emb, a);
             else if (plain_kernels())
-                k_pair_unweighted<<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const uint4*)p->d_emb,
-                                                                             p->d_len, a);
+                k_pair_unweighted<<<(unsigned)p->ntiles, 256, 0, st>>>((const uint4*)p->d_emb,
+                                                                       p->d_len, a);
             else
-                k_pair_unweighted_lut<<<(unsigned)p->ntiles, 256, UL_SMEM, p->stream>>>(
+                k_pair_unweighted_lut<<<(unsigned)p->ntiles, 256, UL_SMEM, st>>>(
                     (const uint4*)p->d_emb, p->d_len, a);
             p->n_launch += 1;
         }
+        if ((rc = join_streams(p))) return rc;
+        if ((rc = finalize(p, metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED))) return rc;
     }
     B2D_CUDA(cudaEventRecord(ec, p->stream));
     B2D_CUDA(cudaStreamSynchronize(p->stream));
@@ -636,12 +696,17 @@ int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_til
         }
     cudaFree(p->d_tiles);
     cudaFree(p->d_out);
+    cudaFree(p->d_out2);
+    cudaFree(p->d_owned);
     p->d_tiles = nullptr;
     p->d_out = nullptr;
+    p->d_out2 = nullptr;
+    p->d_owned = nullptr;
     p->out_len = off;
     p->ntiles = (int64_t)keep.size() / 2;
     int rc;
     if ((rc = upload(&p->d_tiles, keep.data(), keep.size(), p->stream))) return rc;
+    if ((rc = upload(&p->d_owned, p->owned.data(), p->owned.size(), p->stream))) return rc;
     B2D_CUDA(cudaMemcpyAsync(p->d_row_base, p->row_base.data(), p->nb * sizeof(int64_t),
                              cudaMemcpyHostToDevice, p->stream));
     B2D_CUDA(cudaMalloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));

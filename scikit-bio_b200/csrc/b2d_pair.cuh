@@ -57,14 +57,32 @@ __device__ __forceinline__ double apply_epilogue(double x, int mode, const doubl
     }
 }
 
-// Write one accumulated value of pair (i, j) (global sample indices).
+// Add one accumulated value of pair (i, j) (global sample indices) into the raw-sum buffer of
+// this launch (store on the buffer's first launch).  The metric's epilogue is applied once at
+// the end by k_finalize.
 __device__ __forceinline__ void emit(const PairArgs& a, int64_t base, int64_t i0, int64_t i,
                                      int64_t j, double v) {
     if (i >= j || j >= a.n) return;
     int64_t off = base + (cond_index(i, j, a.n) - cond_row_start(i0, a.n));
-    double x = a.first ? v : a.out[off] + v;
-    if (a.last) x = apply_epilogue(x, a.epilogue, a.svec, a.total, i, j);
-    a.out[off] = x;
+    a.out[off] = a.first ? v : a.out[off] + v;
+}
+
+// out = epilogue(out + out2): one CTA per owned sample row, its condensed entries are
+// contiguous.  out2 may be NULL (single launch).
+__global__ void __launch_bounds__(256)
+k_finalize(double* __restrict__ out, const double* __restrict__ out2,
+           const int64_t* __restrict__ owned, const int64_t* __restrict__ row_base, int64_t n,
+           int epilogue, const double* __restrict__ svec, const long long* __restrict__ total) {
+    const int64_t b = owned[blockIdx.x / TILE];
+    const int64_t i0 = b * TILE, i = i0 + (blockIdx.x % TILE);
+    if (i >= n - 1) return;
+    const int64_t off = row_base[b] + (cond_row_start(i, n) - cond_row_start(i0, n));
+    const int64_t cnt = n - 1 - i;
+    for (int64_t t = threadIdx.x; t < cnt; t += blockDim.x) {
+        double x = out[off + t];
+        if (out2) x += out2[off + t];
+        out[off + t] = apply_epilogue(x, epilogue, svec, total, i, i + 1 + t);
+    }
 }
 
 // =========================================================================================
