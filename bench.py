@@ -425,6 +425,19 @@ def run_ours(args):
             peak = sm_count * 16 * 1.965e9
             peak_source = "nominal 148 SM x 16 POPC/clk x 1.965 GHz (not measured)"
         alg_units = P_shard * nodes_per_launch * units_per_term
+        sparse_path = inp["kind"] == "features" and t["nodes_resident"] == 0
+        if sparse_path:
+            # integer feature table below 2.5 % density: intersection kernel.  Algorithmic unit =
+            # one accumulator update per (sample pair, shared feature) = sum_f C(n_f, 2).
+            nf = np.bincount(inp["cols"], minlength=m).astype(np.float64)
+            matches = float((nf * (nf - 1.0) / 2.0).sum()) * (P_shard / max(P_total, 1))
+            kernel = "k_pair_sparse"
+            bound, unit = "smem-atomic", "Tatom/s (shared-memory int32 atomic adds)"
+            peak = _capi.microbench(3, device)
+            peak_source = ("b2d_microbench(3): shared-memory atomicAdd on random cells of a 128x128 "
+                           "int32 tile, all SMs, measured in this run")
+            alg_units = matches
+            units_per_term = matches / max(P_shard * nodes_per_launch, 1)
         achieved = alg_units / (avg_launch_ms * 1e-3) / 1e12
         elem_bytes = 8.0 if workload in ("weighted", "weighted_unnorm", "braycurtis") else 1.0 / 8.0
         # unique embedding bytes a launch must read at least once

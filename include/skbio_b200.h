@@ -163,7 +163,8 @@ int b2d_set_option(const char* name, int64_t value);
 
 /* On-device micro-benchmarks used by bench.py for the roofline denominators:
  * kind 0: FP64 pipe, returns DFMA instructions/s;  kind 1: HBM copy, returns bytes/s;
- * kind 2: conflict-free 64-bit shared-memory gathers/s (the unweighted kernel's bound). */
+ * kind 2: conflict-free 64-bit shared-memory gathers/s (the unweighted kernel's bound);
+ * kind 3: shared-memory int32 atomicAdd/s on random cells (the sparse feature kernel's bound). */
 int b2d_microbench(int device, int kind, double* result);
 
 /* Host only (no GPU needed): which slices of the condensed vector shard `shard` of

@@ -16,6 +16,7 @@
 #include "b2d_common.cuh"
 #include "b2d_embed.cuh"
 #include "b2d_pair.cuh"
+#include "b2d_sparse.cuh"
 #include "b2d_tree.h"
 
 namespace b2d {
@@ -25,6 +26,7 @@ static int64_t g_chunk_nodes = 8192;           // nodes per pair-kernel launch
 static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
 static int g_weighted_variant = 3;             // 2 = 128x128 tiles / 8x4 threads, 3 = ILP variant
+static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 
 static bool plain_kernels() {
     if (g_plain_kernels < 0) {
@@ -82,6 +84,19 @@ __global__ void k_bench_lds64(double* out, int iters) {
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
 }
+// shared-memory atomicAdd on pseudo-random cells of a 128x128 int tile (k_pair_sparse's bound)
+__global__ void k_bench_atoms(int* out, int iters) {
+    extern __shared__ int s_acc[];
+    for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) s_acc[i] = 0;
+    __syncthreads();
+    unsigned x = (threadIdx.x + 1) * 2654435761u;
+    for (int i = 0; i < iters; ++i) {
+        atomicAdd(&s_acc[x >> 18], 1);
+        x = x * 1664525u + 1013904223u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = s_acc[0];
+}
 __global__ void k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -132,6 +147,13 @@ struct b2d_problem {
     void* d_emb = nullptr;
     size_t emb_bytes = 0;
     long long* d_state = nullptr;
+    // sparse feature-table path
+    SpEntry* d_sp_entries = nullptr;
+    int64_t* d_sp_ptr = nullptr;
+    int64_t* d_sp_rowchunk = nullptr;
+    int64_t sp_nch = 0;
+    int sp_ready = 0;           // 0 not built, 1 built, -1 not eligible
+    int used_sparse = 0;
     bool computed = false;
     bool custom_tiles = false;  // b2d_problem_select_tiles: untouched entries of owned stripes stay 0
     int last_metric = -1;
@@ -147,6 +169,7 @@ static void free_problem(b2d_problem* p) {
     cudaFree(p->d_tiles); cudaFree(p->d_row_base); cudaFree(p->d_out); cudaFree(p->d_total);
     cudaFree(p->d_svec); cudaFree(p->d_emb); cudaFree(p->d_state);
     cudaFree(p->d_out2); cudaFree(p->d_owned);
+    cudaFree(p->d_sp_entries); cudaFree(p->d_sp_ptr); cudaFree(p->d_sp_rowchunk);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -304,6 +327,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_chunk_nodes = value <= 0 ? 8192 : (value + 127) / 128 * 128;
     } else if (s == "emb_budget_bytes") {
         g_emb_budget_bytes = value < 0 ? 0 : value;
+    } else if (s == "sparse_features") {
+        g_sparse_features = value < 0 ? -1 : (value ? 1 : 0);
     } else if (s == "weighted_variant") {
         g_weighted_variant = value == 2 ? 2 : 3;
     } else if (s == "plain_kernels") {
@@ -628,6 +653,121 @@ static int compute_bits(b2d_problem* p, int metric) {
     return B2D_OK;
 }
 
+// Build the (block, chunk) buckets once per problem; returns eligibility in p->sp_ready.
+static int build_sparse(b2d_problem* p) {
+    if (p->sp_ready) return B2D_OK;
+    p->sp_ready = -1;
+    if (p->kind != 1 || p->nnz == 0 || p->n == 0) return B2D_OK;
+    const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    if (p->has_values) {  // integer counts with row sums below 2^31 only
+        int* d_bad = nullptr;
+        int bad = 0;
+        B2D_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+        B2D_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
+        k_sp_check<<<(unsigned)((p->nnz + 255) / 256), 256, 0, p->stream>>>((const double*)p->d_values,
+                                                                             p->nnz, d_bad);
+        k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, (const double*)p->d_values,
+                                                                    p->n, p->d_svec);
+        std::vector<double> sums(p->n);
+        B2D_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaMemcpyAsync(sums.data(), p->d_svec, p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        cudaFree(d_bad);
+        if (bad) return B2D_OK;
+        for (double v : sums)
+            if (v >= 2147483648.0) return B2D_OK;
+    }
+    const int64_t nch = (p->m + SP_CHUNK - 1) / SP_CHUNK;
+    const int64_t nbuckets = p->nb * nch;
+    unsigned* d_counts = nullptr;
+    B2D_CUDA(cudaMalloc(&d_counts, (nbuckets + 1) * sizeof(unsigned)));
+    B2D_CUDA(cudaMemsetAsync(d_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+    k_sp_count<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->n, nch, d_counts);
+    std::vector<unsigned> counts(nbuckets);
+    B2D_CUDA(cudaMemcpyAsync(counts.data(), d_counts, nbuckets * sizeof(unsigned), cudaMemcpyDeviceToHost, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    std::vector<int64_t> ptr(nbuckets + 1, 0);
+    for (int64_t b = 0; b < nbuckets; ++b) {
+        if (counts[b] > (unsigned)SP_SORT_MAX) {  // too dense for the shared-memory sort
+            cudaFree(d_counts);
+            return B2D_OK;
+        }
+        ptr[b + 1] = ptr[b] + counts[b];
+    }
+    B2D_CUDA(cudaMalloc(&p->d_sp_ptr, (nbuckets + 1) * sizeof(int64_t)));
+    B2D_CUDA(cudaMemcpyAsync(p->d_sp_ptr, ptr.data(), (nbuckets + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+    B2D_CUDA(cudaMalloc(&p->d_sp_entries, std::max<int64_t>(p->nnz, 1) * sizeof(SpEntry)));
+    B2D_CUDA(cudaMemsetAsync(d_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+    if (p->has_values)
+        k_sp_scatter<double><<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, (const double*)p->d_values,
+                                                                  p->n, nch, p->d_sp_ptr, d_counts, p->d_sp_entries);
+    else
+        k_sp_scatter<double><<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, (const double*)nullptr,
+                                                                  p->n, nch, p->d_sp_ptr, d_counts, p->d_sp_entries);
+    B2D_CUDA(cudaFuncSetAttribute(k_sp_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SORT_SMEM));
+    k_sp_sort<<<(unsigned)nbuckets, 256, SP_SORT_SMEM, p->stream>>>(p->d_sp_entries, p->d_sp_ptr);
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    B2D_CUDA(cudaGetLastError());
+    cudaFree(d_counts);
+    p->sp_nch = nch;
+    p->sp_ready = 1;
+    return B2D_OK;
+}
+
+// Sparse intersection path for Bray-Curtis / Jaccard on integer feature tables.
+static int compute_sparse(b2d_problem* p, int metric) {
+    const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    float ms;
+    cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
+    B2D_CUDA(cudaEventRecord(ea, p->stream));
+    // per-sample sums (Bray-Curtis) or feature counts (Jaccard: values ignored)
+    k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(
+        p->d_indptr, metric == B2D_BRAYCURTIS ? (const double*)p->d_values : (const double*)nullptr, p->n,
+        p->d_svec);
+    B2D_CUDA(cudaEventRecord(eb, p->stream));
+    p->n_launch = 0;
+    p->chunk_counter = 0;
+    if (p->ntiles) {
+        B2D_CUDA(cudaFuncSetAttribute(k_pair_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM2));
+        PairArgs a;
+        a.tiles = p->d_tiles;
+        a.row_base = p->d_row_base;
+        a.svec = p->d_svec;
+        a.total = p->d_total;
+        a.n = p->n;
+        a.qa = 0;
+        a.qb = p->mpad;
+        a.QR = 0;
+        a.NS = p->NS;
+        a.last = 0;
+        a.epilogue = 0;
+        cudaStream_t st;
+        int rc = chunk_target(p, &st, &a.out, &a.first);
+        if (rc) return rc;
+        k_pair_sparse<<<(unsigned)p->ntiles, SP_THREADS, SP_SMEM2, st>>>(
+            p->d_sp_entries, p->d_sp_ptr, p->sp_nch, metric == B2D_JACCARD ? 1 : 0, a);
+        p->n_launch = 1;
+        if ((rc = finalize(p, metric == B2D_JACCARD ? EPI_JACCARD_INTERSECT : EPI_BRAYCURTIS_INTERSECT))) return rc;
+    }
+    B2D_CUDA(cudaEventRecord(ec, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    B2D_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&ms, ea, eb);
+    p->t_embed = ms;
+    cudaEventElapsedTime(&ms, eb, ec);
+    p->t_pair = ms;
+    p->n_pass = 1;
+    p->nodes_resident = 0;
+    return B2D_OK;
+}
+
+static bool want_sparse(b2d_problem* p) {
+    if (g_sparse_features == 0 || p->kind != 1 || plain_kernels()) return false;
+    const double density = (double)p->nnz / ((double)std::max<int64_t>(p->n, 1) * (double)p->m);
+    if (g_sparse_features < 0 && density >= 0.025) return false;
+    return true;
+}
+
 int b2d_problem_compute(b2d_problem* p, int metric) {
     if (!p) return fail(B2D_ERR_INVALID_ARGUMENT, "problem is NULL");
     B2D_CUDA(cudaSetDevice(p->device));
@@ -649,10 +789,28 @@ int b2d_problem_compute(b2d_problem* p, int metric) {
         case B2D_BRAYCURTIS:
             if (p->kind != 1) return fail(B2D_ERR_INVALID_ARGUMENT, "braycurtis needs a feature problem");
             if (!p->has_values) return fail(B2D_ERR_INVALID_ARGUMENT, "braycurtis needs count values");
+            p->used_sparse = 0;
+            if (want_sparse(p)) {
+                if ((rc = build_sparse(p))) return rc;
+                if (p->sp_ready == 1) {
+                    p->used_sparse = 1;
+                    rc = compute_sparse(p, metric);
+                    break;
+                }
+            }
             rc = compute_dense(p, metric);
             break;
         case B2D_JACCARD:
             if (p->kind != 1) return fail(B2D_ERR_INVALID_ARGUMENT, "jaccard needs a feature problem");
+            p->used_sparse = 0;
+            if (want_sparse(p)) {
+                if ((rc = build_sparse(p))) return rc;
+                if (p->sp_ready == 1) {
+                    p->used_sparse = 1;
+                    rc = compute_sparse(p, metric);
+                    break;
+                }
+            }
             rc = compute_bits(p, metric);
             break;
         default:
@@ -925,6 +1083,25 @@ int b2d_microbench(int device, int kind, double* result) {
         }
         cudaFree(d);
         *result = (double)blocks * threads * 4.0 * iters / (best * 1e-3);
+    } else if (kind == 3) {
+        cudaDeviceProp prop;
+        B2D_CUDA(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount, threads = 512, iters = 1 << 13;
+        const int smem = 128 * 128 * sizeof(int);
+        B2D_CUDA(cudaFuncSetAttribute(k_bench_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int* d = nullptr;
+        B2D_CUDA(cudaMalloc(&d, (size_t)blocks * sizeof(int)));
+        for (int rep = 0; rep < 6; ++rep) {
+            B2D_CUDA(cudaEventRecord(e0));
+            k_bench_atoms<<<blocks, threads, smem>>>(d, iters);
+            B2D_CUDA(cudaEventRecord(e1));
+            B2D_CUDA(cudaEventSynchronize(e1));
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaFree(d);
+        *result = (double)blocks * threads * (double)iters / (best * 1e-3);
     } else {
         return fail(B2D_ERR_INVALID_ARGUMENT, "unknown microbench kind");
     }

@@ -18,7 +18,9 @@ enum Epilogue : int {
     EPI_WEIGHTED_NORM = 1,  // / (C_i + C_j); both totals zero -> 0   (_unifrac.py:461-471)
     EPI_UNWEIGHTED = 2,     // x / ((L_i + L_j + x)/2); denominator 0 -> 0 (_unifrac.py:366-371)
     EPI_BRAYCURTIS = 3,     // x / (S_i + S_j); 0/0 -> NaN like scipy
-    EPI_JACCARD = 4         // x / ((c_i + c_j + x)/2); denominator 0 -> 0 like scipy
+    EPI_JACCARD = 4,        // x / ((c_i + c_j + x)/2); denominator 0 -> 0 like scipy
+    EPI_BRAYCURTIS_INTERSECT = 5,  // x = sum of minima: (S_i + S_j - 2x) / (S_i + S_j)
+    EPI_JACCARD_INTERSECT = 6      // x = |u and v|: (c_i + c_j - 2x) / (c_i + c_j - x); 0/0 -> 0
 };
 
 struct PairArgs {
@@ -51,6 +53,15 @@ __device__ __forceinline__ double apply_epilogue(double x, int mode, const doubl
         case EPI_JACCARD: {
             double den = 0.5 * (svec[i] + svec[j] + x);
             return den == 0.0 ? 0.0 : x / den;
+        }
+        case EPI_BRAYCURTIS_INTERSECT: {
+            const double t = svec[i] + svec[j];
+            return (t - 2.0 * x) / t;
+        }
+        case EPI_JACCARD_INTERSECT: {
+            const double t = svec[i] + svec[j];
+            const double den = t - x;
+            return den == 0.0 ? 0.0 : (t - 2.0 * x) / den;
         }
         default:
             return x;

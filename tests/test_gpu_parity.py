@@ -267,3 +267,53 @@ def test_partial_and_block_beta_diversity():
         blk2 = sb.block_beta_diversity(metric, dense, ids, tree=tree, taxa=taxa, k=100,
                                        map_f=lambda f, gen: [f(**kwargs) for kwargs in gen], **kw)
         assert_close_rel(np.asarray(blk2.data), fdata, 1e-13, metric + " block")
+
+
+@pytest.mark.parametrize("n,f,lam", [(700, 9000, 0.01), (257, 5000, 0.02), (130, 300, 1.5)])
+def test_sparse_and_dense_feature_paths_are_bit_identical(n, f, lam):
+    """Bray-Curtis / Jaccard on integer tables: the sparse intersection kernels and the dense
+    kernels give the same bits, and both equal SciPy's definitions (oracle)."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    indptr, cols, vals = synthetic.poisson_csr(n, f, lam, seed=17)
+    # a few empty samples and a large count
+    vals = vals.copy()
+    if len(vals):
+        vals[0] = 100000
+    dense = synthetic.csr_to_dense(indptr, cols, vals, f)
+    exp_bc, exp_j = oracle_fast.braycurtis(dense), oracle_fast.jaccard(dense)
+    total = n * (n - 1) // 2
+    res = {}
+    try:
+        for mode in (0, 1):
+            _capi.set_option("sparse_features", mode)
+            with _capi.Problem.features(indptr, cols, vals.astype(np.float64), n, f) as prob:
+                for key in ("braycurtis", "jaccard"):
+                    prob.compute(key)
+                    t = prob.timings()
+                    if mode == 0 or lam < 0.1:   # very dense buckets legitimately fall back
+                        assert (t["nodes_resident"] == 0) == (mode == 1)
+                    res[(mode, key)] = prob.fetch(np.empty(total))
+    finally:
+        _capi.set_option("sparse_features", -1)
+    for key, exp in (("braycurtis", exp_bc), ("jaccard", exp_j)):
+        assert np.array_equal(res[(0, key)], exp, equal_nan=True), key + " dense"
+        assert np.array_equal(res[(1, key)], exp, equal_nan=True), key + " sparse"
+
+
+def test_sparse_path_falls_back_for_non_integer_counts():
+    _skbio_b200()
+    from skbio_b200 import _capi, synthetic
+
+    n, f = 200, 4000
+    indptr, cols, vals = synthetic.poisson_csr(n, f, 0.01, seed=3)
+    fv = vals.astype(np.float64) * 0.5
+    dense = synthetic.csr_to_dense(indptr, cols, fv, f)
+    from oracle import oracle_fast
+    with _capi.Problem.features(indptr, cols, fv, n, f) as prob:
+        prob.compute("braycurtis")
+        assert prob.timings()["nodes_resident"] > 0      # dense fp64 path
+        got = prob.fetch(np.empty(n * (n - 1) // 2))
+    assert_close_rel(got, oracle_fast.braycurtis(dense), 1e-13, "float braycurtis")

@@ -28,7 +28,7 @@ def run(n, tips, lam, keys, feat_keys=()):
                 t = prob.timings()
                 print(f"{key}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "e2e"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("e2e", "sparse")):
     print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), "lds64 gathers/s", _capi.microbench(2), flush=True)
     run(4096, 20000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"], ["braycurtis", "jaccard"])
     if len(sys.argv) > 1 and sys.argv[1] == "big":
@@ -59,3 +59,21 @@ def e2e_breakdown(n=10000, tips=100000, lam=0.02, key="weighted_unifrac_normaliz
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "e2e":
     e2e_breakdown()
+
+
+def sparse_probe(n=20000, f=50000, lam=0.01):
+    indptr, cols, vals = synthetic.poisson_csr(n, f, lam, seed=0)
+    P = n * (n - 1) // 2
+    for mode in (1, 0):
+        _capi.set_option("sparse_features", mode)
+        with _capi.Problem.features(indptr, cols, vals.astype(np.float64), n, f) as prob:
+            for key in ("braycurtis", "jaccard"):
+                for rep in range(2):
+                    t0 = time.perf_counter(); prob.compute(key); wall = time.perf_counter() - t0
+                t = prob.timings()
+                print(f"sparse={mode} {key}: wall {wall*1e3:.1f} ms embed {t['embed_ms']:.2f} pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
+    _capi.set_option("sparse_features", -1)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sparse":
+    sparse_probe()
