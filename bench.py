@@ -438,10 +438,13 @@ def run_ours(args):
                            "int32 tile, all SMs, measured in this run")
             alg_units = matches
             units_per_term = matches / max(P_shard * nodes_per_launch, 1)
+            sparse_bytes = P_shard * 24.0 + 2.0 * len(inp["cols"]) * 8.0  # result write + finalize r/w, buckets
         achieved = alg_units / (avg_launch_ms * 1e-3) / 1e12
         elem_bytes = 8.0 if workload in ("weighted", "weighted_unnorm", "braycurtis") else 1.0 / 8.0
         # unique embedding bytes a launch must read at least once
         alg_bytes = n * nodes_per_launch * elem_bytes
+        if sparse_path:
+            alg_bytes = sparse_bytes
         roofline = {
             "kernel": kernel, "bound": bound, "achieved": achieved,
             "peak": peak / 1e12, "unit": unit,
