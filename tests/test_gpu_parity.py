@@ -317,3 +317,38 @@ def test_sparse_path_falls_back_for_non_integer_counts():
         assert prob.timings()["nodes_resident"] > 0      # dense fp64 path
         got = prob.fetch(np.empty(n * (n - 1) // 2))
     assert_close_rel(got, oracle_fast.braycurtis(dense), 1e-13, "float braycurtis")
+
+
+def test_config1_full_size_through_the_api():
+    """BASELINE config 1 in full (1,000 samples x 10,000 tips, 19,999 nodes, Poisson 0.1) through
+    the public API with a tree OBJECT and shuffled taxa, every pair compared with the oracle."""
+    import time
+
+    sb = _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import synthetic
+
+    n, tips = 1000, 10000
+    parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=1)
+    indptr, cols, vals = synthetic.poisson_csr(n, tips, 0.1, seed=0)
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    perm = np.random.default_rng(5).permutation(tips)          # taxa in shuffled order
+    taxa = [f"T{i}" for i in perm]
+    table = np.ascontiguousarray(dense[:, perm])
+    tree = synthetic.to_nodes(parent, length, names)
+    ids = [f"S{i}" for i in range(n)]
+    exp = oracle_fast.unifrac_all(dense, tip_node, parent, length)
+    timings = {}
+    for key, metric, kw in KEYS:
+        kwargs = dict(kw)
+        if "unifrac" in metric:
+            kwargs.update(tree=tree, taxa=taxa)
+        t0 = time.perf_counter()
+        dm = sb.beta_diversity(metric, table, ids, **kwargs)
+        timings[key] = time.perf_counter() - t0
+        got = dm.condensed_form()
+        if key in ("jaccard", "braycurtis"):
+            assert np.array_equal(got, exp[key], equal_nan=True), key
+        else:
+            assert_close_rel(got, exp[key], UNIFRAC_RTOL, "config 1 " + key)
+    print("config-1 full API wall seconds:", {k: round(v, 3) for k, v in timings.items()})
