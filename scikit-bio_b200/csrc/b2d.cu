@@ -26,6 +26,7 @@ static int64_t g_chunk_nodes = 8192;           // nodes per pair-kernel launch
 static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
 static int g_weighted_variant = 3;             // 2 = 128x128 tiles / 8x4 threads, 3 = ILP variant
+static int g_walk_decomposed = 1;              // 0 = always the sequential weighted walk
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 
 static bool plain_kernels() {
@@ -129,6 +130,10 @@ struct b2d_problem {
     uint32_t* d_fold = nullptr;
     double* d_len = nullptr;
     double* d_tipdist = nullptr;
+    uint8_t* d_flags1 = nullptr;      // subtree decomposition of the weighted walk
+    int64_t* d_spans = nullptr;
+    int32_t* d_top_pos = nullptr;
+    uint8_t* d_top_flags = nullptr;
     // shard geometry
     std::vector<int64_t> owned;      // owned row stripes
     std::vector<int64_t> row_base;   // [nb] offset in d_out or -1
@@ -169,6 +174,7 @@ static void free_problem(b2d_problem* p) {
     cudaFree(p->d_tiles); cudaFree(p->d_row_base); cudaFree(p->d_out); cudaFree(p->d_total);
     cudaFree(p->d_svec); cudaFree(p->d_emb); cudaFree(p->d_state);
     cudaFree(p->d_out2); cudaFree(p->d_owned);
+    cudaFree(p->d_flags1); cudaFree(p->d_spans); cudaFree(p->d_top_pos); cudaFree(p->d_top_flags);
     cudaFree(p->d_sp_entries); cudaFree(p->d_sp_ptr); cudaFree(p->d_sp_rowchunk);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
@@ -209,6 +215,12 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     if ((rc = upload(&p->d_fold, o.fold_mask.data(), o.fold_mask.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_len, o.len_q.data(), o.len_q.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_tipdist, o.tipdist_q.data(), o.tipdist_q.size(), p->stream))) return rc;
+    if (o.decomposed) {
+        if ((rc = upload(&p->d_flags1, o.flags1.data(), o.flags1.size(), p->stream))) return rc;
+        if ((rc = upload(&p->d_spans, o.spans.data(), o.spans.size(), p->stream))) return rc;
+        if ((rc = upload(&p->d_top_pos, o.top_pos.data(), o.top_pos.size(), p->stream))) return rc;
+        if ((rc = upload(&p->d_top_flags, o.top_flags.data(), o.top_flags.size(), p->stream))) return rc;
+    }
     // node id -> engine position, on the device
     {
         int32_t* d_qof = nullptr;
@@ -327,6 +339,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_chunk_nodes = value <= 0 ? 8192 : (value + 127) / 128 * 128;
     } else if (s == "emb_budget_bytes") {
         g_emb_budget_bytes = value < 0 ? 0 : value;
+    } else if (s == "walk_decomposed") {
+        g_walk_decomposed = value ? 1 : 0;
     } else if (s == "sparse_features") {
         g_sparse_features = value < 0 ? -1 : (value ? 1 : 0);
     } else if (s == "weighted_variant") {
@@ -548,6 +562,18 @@ static int compute_dense(b2d_problem* p, int metric) {
                 k_scatter_dense<int64_t><<<sblocks, wpb * 32, 0, p->stream>>>(
                     p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->n, q0, q1, QR,
                     (unsigned long long*)p->d_emb, 0);
+                if (p->order.decomposed && QR == p->mpad && g_walk_decomposed) {
+                    // whole tree resident: independent small subtrees in parallel, then the top
+                    const int64_t nspans = (int64_t)p->order.spans.size() / 2;
+                    if (nspans) {
+                        dim3 grid((unsigned)(p->npad / 128), (unsigned)nspans);
+                        k_propagate_weighted_spans<<<grid, 128, 0, p->stream>>>(
+                            (unsigned long long*)p->d_emb, p->d_flags1, p->d_spans, p->npad, QR);
+                    }
+                    k_propagate_weighted_top<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
+                        (unsigned long long*)p->d_emb, p->d_top_pos, p->d_top_flags,
+                        (int64_t)p->order.top_pos.size(), p->npad, QR);
+                } else
                 k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
                     (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR,
                     p->d_state, p->order.depth_at[q0 / NODE_STRIPE]);

@@ -149,13 +149,14 @@ k_propagate_weighted(unsigned long long* __restrict__ emb, const uint8_t* __rest
     long long T = d > 0 ? S[d - 1] : 0;
     // Software pipeline: the counts of group g+PF are requested before group g is processed
     // (the buffer is updated in place, so the compiler cannot hoist these loads itself).
+    // Streaming (evict-first) accesses keep L1 for the per-lane stack in local memory.
     constexpr int G = 8, PF = 3;
     long long own[PF + 1][G];
 #pragma unroll
     for (int g = 0; g < PF; ++g)
 #pragma unroll
         for (int u = 0; u < G; ++u)
-            own[g][u] = (q0 + (int64_t)g * G < q1) ? (long long)p[((int64_t)g * G + u) * TILE] : 0;
+            own[g][u] = (q0 + (int64_t)g * G < q1) ? (long long)__ldcs(p + ((int64_t)g * G + u) * TILE) : 0;
     for (int64_t qg = q0; qg < q1; qg += (PF + 1) * G) {
 #pragma unroll
         for (int ph = 0; ph <= PF; ++ph) {
@@ -166,7 +167,7 @@ k_propagate_weighted(unsigned long long* __restrict__ emb, const uint8_t* __rest
                 if (qn < q1) {
 #pragma unroll
                     for (int u = 0; u < G; ++u)
-                        own[(ph + PF) % (PF + 1)][u] = (long long)p[(qn - q0 + u) * TILE];
+                        own[(ph + PF) % (PF + 1)][u] = (long long)__ldcs(p + (qn - q0 + u) * TILE);
                 }
             }
             const unsigned long long f8 = *reinterpret_cast<const unsigned long long*>(flags + q);
@@ -179,7 +180,7 @@ k_propagate_weighted(unsigned long long* __restrict__ emb, const uint8_t* __rest
                     v += T;
                     d -= 1;
                     if (d > 0) T = S[d - 1];
-                    p[(q - q0 + u) * TILE] = (unsigned long long)v;  // tips keep their own count
+                    __stcs(p + (q - q0 + u) * TILE, (unsigned long long)v);  // tips keep their own count
                 }
                 if (f & NF_FOLD) {
                     T += v;
@@ -193,6 +194,89 @@ k_propagate_weighted(unsigned long long* __restrict__ emb, const uint8_t* __rest
     }
     if (d > 0) S[d - 1] = T;
     for (int i = 0; i < d; ++i) state[(int64_t)i * npad + s] = S[i];
+}
+
+// Subtree decomposition, phase 1: thread = (sample, span); walks one span of whole small
+// subtrees with an empty stack.  At a subtree root (NF_CUT) the value is final and the stack
+// is reset instead of pushed.  Plenty of independent warps -> no software prefetch needed.
+constexpr uint8_t NF_CUT = 8;
+__global__ void __launch_bounds__(128)
+k_propagate_weighted_spans(unsigned long long* __restrict__ emb, const uint8_t* __restrict__ flags1,
+                           const int64_t* __restrict__ spans, int64_t npad, int64_t QR) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad) return;
+    const int64_t qa = spans[2 * (int64_t)blockIdx.y], qb = spans[2 * (int64_t)blockIdx.y + 1];
+    const int64_t blk = s / TILE, sl = s % TILE;
+    unsigned long long* p = emb + (blk * QR) * TILE + sl;
+    long long S[MAX_STACK];
+    int d = 0;
+    long long T = 0;
+    for (int64_t q = qa; q < qb; ++q) {
+        const unsigned f = flags1[q];
+        long long v = (long long)p[q * TILE];
+        if (f & NF_HAS_CHILDREN) {
+            v += T;
+            d -= 1;
+            if (d > 0) T = S[d - 1];
+            p[q * TILE] = (unsigned long long)v;
+        }
+        if (f & NF_CUT) {
+            d = 0;
+        } else if (f & NF_FOLD) {
+            T += v;
+        } else {
+            if (d > 0) S[d - 1] = T;
+            T = v;
+            d += 1;
+        }
+    }
+}
+
+// Phase 2: lane = sample, sequential over the (short) list of top positions; subtree roots
+// computed in phase 1 enter as leaves.
+__global__ void __launch_bounds__(128)
+k_propagate_weighted_top(unsigned long long* __restrict__ emb, const int32_t* __restrict__ top_pos,
+                         const uint8_t* __restrict__ top_flags, int64_t ntop, int64_t npad,
+                         int64_t QR) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad) return;
+    const int64_t blk = s / TILE, sl = s % TILE;
+    unsigned long long* p = emb + (blk * QR) * TILE + sl;
+    long long S[MAX_STACK];
+    int d = 0;
+    long long T = 0;
+    constexpr int PF = 8;
+    long long own[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) own[u] = u < ntop ? (long long)p[(int64_t)top_pos[u] * TILE] : 0;
+    for (int64_t k0 = 0; k0 < ntop; k0 += PF) {
+        long long cur[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) cur[u] = own[u];
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            own[u] = (k0 + PF + u < ntop) ? (long long)p[(int64_t)top_pos[k0 + PF + u] * TILE] : 0;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int64_t k = k0 + u;
+            if (k >= ntop) break;
+            const unsigned f = top_flags[k];
+            long long v = cur[u];
+            if (f & NF_HAS_CHILDREN) {
+                v += T;
+                d -= 1;
+                if (d > 0) T = S[d - 1];
+                p[(int64_t)top_pos[k] * TILE] = (unsigned long long)v;
+            }
+            if (f & NF_FOLD) {
+                T += v;
+            } else {
+                if (d > 0) S[d - 1] = T;
+                T = v;
+                d += 1;
+            }
+        }
+    }
 }
 
 // int64 subtree counts -> fp64 proportions count/total (the count itself when total == 0,

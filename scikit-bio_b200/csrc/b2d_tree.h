@@ -27,6 +27,16 @@ struct TreeOrder {
     std::vector<double> tipdist_q;  // [mpad] tip-to-root distance on tips, 0 elsewhere
     std::vector<int32_t> depth_at;  // [mpad/128 + 1] stack depth before each 128-node stripe
     int max_depth = 0;
+    // Subtree decomposition of the weighted walk (used when the whole tree is resident):
+    // phase 1 walks every maximal subtree of <= cut_size nodes independently (one span of
+    // consecutive positions each, empty stack), phase 2 walks only the remaining "top" nodes
+    // with those subtree roots acting as leaves.
+    bool decomposed = false;
+    int64_t cut_size = 0;
+    std::vector<uint8_t> flags1;     // [mpad] phase-1 flags: flags | NF_CUT (8) on subtree roots
+    std::vector<int64_t> spans;      // [2 * n_spans] {first position, end position}
+    std::vector<int32_t> top_pos;    // phase-2 positions, ascending
+    std::vector<uint8_t> top_flags;  // phase-2 flags (cut roots: no HAS_CHILDREN)
 };
 
 // Returns "" on success, else an error message.
@@ -125,6 +135,58 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
     if (m % 128 == 0) out.depth_at[m / 128] = depth;
     out.max_depth = max_depth;
     if (max_depth > 60) return "internal error: propagation stack deeper than 60";
+    // ---- subtree decomposition ----
+    {
+        const int64_t B = std::min<int64_t>(4096, std::max<int64_t>(64, m / 256));
+        out.cut_size = B;
+        out.flags1 = out.flags;
+        std::vector<int64_t> spans;
+        std::vector<int32_t> top_pos;
+        std::vector<uint8_t> top_flags;
+        // in q order a subtree rooted at position p with s nodes occupies [p - s + 1, p]
+        for (int64_t v = 0; v < m; ++v) {
+            const int64_t pq = out.q_of_id[v];
+            const bool big = size[v] > B;
+            const bool parent_big = parent[v] < 0 || size[parent[v]] > B;
+            if (big) {
+                top_pos.push_back((int32_t)pq);
+            } else if (parent_big) {  // root of a maximal small subtree
+                top_pos.push_back((int32_t)pq);
+                out.flags1[pq] |= 8;
+                if (size[v] >= 2) {
+                    spans.push_back(pq - size[v] + 1);
+                    spans.push_back(pq + 1);
+                }
+            }
+        }
+        std::sort(top_pos.begin(), top_pos.end());
+        top_flags.resize(top_pos.size());
+        for (size_t k = 0; k < top_pos.size(); ++k) {
+            uint8_t f = out.flags[top_pos[k]];
+            if (out.flags1[top_pos[k]] & 8) f &= (uint8_t)~1u;  // already summed: acts as a leaf
+            top_flags[k] = f;
+        }
+        // sort spans by start and merge neighbours that touch (no top node in between)
+        std::vector<std::pair<int64_t, int64_t>> sp;
+        for (size_t k = 0; k + 1 < spans.size(); k += 2) sp.push_back({spans[k], spans[k + 1]});
+        std::sort(sp.begin(), sp.end());
+        std::vector<int64_t> merged;
+        for (auto& x : sp) {
+            if (!merged.empty() && merged.back() == x.first &&
+                x.second - merged[merged.size() - 2] <= 2 * B)
+                merged.back() = x.second;
+            else {
+                merged.push_back(x.first);
+                merged.push_back(x.second);
+            }
+        }
+        out.spans.swap(merged);
+        out.top_pos.swap(top_pos);
+        out.top_flags.swap(top_flags);
+        // worthwhile only if the sequential part shrinks a lot (not for caterpillars)
+        out.decomposed = m >= 4096 && (int64_t)out.top_pos.size() * 8 <= m &&
+                         (int64_t)out.spans.size() / 2 <= 60000;
+    }
     return "";
 }
 

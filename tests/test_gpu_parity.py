@@ -352,3 +352,29 @@ def test_config1_full_size_through_the_api():
         else:
             assert_close_rel(got, exp[key], UNIFRAC_RTOL, "config 1 " + key)
     print("config-1 full API wall seconds:", {k: round(v, 3) for k, v in timings.items()})
+
+
+@pytest.mark.parametrize("cat", [False, True])
+def test_decomposed_and_sequential_walks_agree_bitwise(cat):
+    """The subtree-decomposed weighted propagation (parallel small subtrees + short top walk)
+    and the sequential per-lane walk produce identical distances; both match the oracle."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 130, 6000
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.02, 31, cat)
+    node_ids = tip_node[cols]
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    exp = oracle_fast.unifrac_all(dense, tip_node, parent, length)["weighted_unifrac_normalized"]
+    res = {}
+    try:
+        for mode in (1, 0):
+            _capi.set_option("walk_decomposed", mode)
+            with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+                prob.compute("weighted_unifrac_normalized")
+                res[mode] = prob.fetch(np.empty(n * (n - 1) // 2))
+    finally:
+        _capi.set_option("walk_decomposed", 1)
+    assert np.array_equal(res[0], res[1])
+    assert_close_rel(res[1], exp, UNIFRAC_RTOL, "decomposed walk")
