@@ -246,3 +246,23 @@ def test_partial_beta_diversity_host_contract():
         partial_beta_diversity("braycurtis", B1, ids, [("A", "B")])
     dm = partial_beta_diversity(lambda u, v: float(np.abs(u - v).sum()), np.asarray(B1), ids, [("B", "A")])
     assert dm["A", "B"] == 9.0 and dm["B", "A"] == 9.0
+
+
+def test_real_skbio_treenode_is_accepted_when_available():
+    """Duck typing against the real classes (only where scikit-bio is importable, e.g. the build
+    container with the out-of-tree reference build on PYTHONPATH): flatten_tree(TreeNode) equals
+    TreeNode.to_array, validation raises the reference's own exception types."""
+    skbio = pytest.importorskip("skbio")
+    from io import StringIO
+
+    case = [c for c in golden_cases() if c["name"] == "multifurcating_unary_rootlen"][0]
+    t = skbio.TreeNode.read(StringIO(case["newick"]))
+    p, l, nm = skbio_b200.flatten_tree(t)
+    arr = t.to_array(nan_length_value=0.0)
+    assert list(nm) == list(arr["name"]) and np.array_equal(l, arr["length"])
+    assert np.array_equal(p, np.array(case["tree_parent"]))
+    from skbio.tree import MissingNodeError
+
+    with pytest.raises(MissingNodeError):
+        skbio_b200.validate_taxa_and_tree(["a", "nope"], t)
+    assert skbio_b200.MissingNodeError is MissingNodeError
