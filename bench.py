@@ -445,12 +445,19 @@ def run_ours(args):
         alg_bytes = n * nodes_per_launch * elem_bytes
         if sparse_path:
             alg_bytes = sparse_bytes
+        # DRAM bytes of ONE launch of the dominant kernel from `ncu --set full` captures of this
+        # very configuration (profiles/r1_ncu_*_one_launch.txt); null for any other shape
+        traffic = None
+        if not (args.samples or args.tips or args.lam) and world == 1 and emulate == 1:
+            traffic = {"weighted": 9.319172e9 + 0.402809e9, "unweighted": 0.133509e9 + 0.346140e9}.get(workload)
         roofline = {
             "kernel": kernel, "bound": bound, "achieved": achieved,
             "peak": peak / 1e12, "unit": unit,
             "frac": achieved / (peak / 1e12),
             "peak_source": peak_source,
-            "traffic": None,
+            "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
+                              "profiles/r1_ncu_*_one_launch.txt" if traffic else None,
             "avg_launch_ms": avg_launch_ms, "launches_per_step": pair_launches_per_step,
             "algorithmic_terms_per_launch": P_shard * nodes_per_launch,
             "units_per_term": units_per_term,
