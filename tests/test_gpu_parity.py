@@ -378,3 +378,73 @@ def test_decomposed_and_sequential_walks_agree_bitwise(cat):
         _capi.set_option("walk_decomposed", 1)
     assert np.array_equal(res[0], res[1])
     assert_close_rel(res[1], exp, UNIFRAC_RTOL, "decomposed walk")
+
+
+def _random_nested_tree(rng, n_tips, max_children=5, p_unary=0.1):
+    """Random multifurcating tree as nested tuples (name, length, children); unary internal
+    nodes, zero-length branches and a root length included."""
+    nodes = [(f"t{i}", float(rng.choice([0.0, rng.uniform(0.01, 2.0)], p=[0.1, 0.9])), [])
+             for i in range(n_tips)]
+    k = 0
+    while len(nodes) > 1:
+        if rng.random() < p_unary:
+            arity = 1
+        else:
+            arity = int(rng.integers(2, max_children + 1))
+        arity = min(arity, len(nodes))
+        idx = sorted(rng.choice(len(nodes), size=arity, replace=False), reverse=True)
+        kids = [nodes.pop(i) for i in idx]
+        length = float(rng.choice([0.0, rng.uniform(0.01, 2.0)], p=[0.1, 0.9]))
+        nodes.append((f"n{k}" if rng.random() < 0.5 else None, length, kids))
+        k += 1
+        if arity == 1 and len(nodes) == 1:
+            break
+    name, _, kids = nodes[0]
+    return (name, float(rng.choice([0.0, 0.3])) if rng.random() < 0.5 else None, kids)
+
+
+def _nested_to_newick(node):
+    name, length, kids = node
+    s = ""
+    if kids:
+        s += "(" + ",".join(_nested_to_newick(c) for c in kids) + ")"
+    if name is not None:
+        s += "'" + name + "'"
+    if length is not None:
+        s += ":" + repr(length)
+    return s
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_multifurcating_trees_full_api_vs_numpy_oracle(seed):
+    """Random multifurcating trees with unary nodes, zero lengths and optional root length:
+    Newick -> product flattener -> GPU, against the NumPy oracle fed by its OWN, separate
+    implementation of the reference's id assignment."""
+    sb = _skbio_b200()
+    from oracle import oracle_np
+
+    rng = np.random.default_rng(100 + seed)
+    n_tips = int(rng.integers(5, 120))
+    nested = _random_nested_tree(rng, n_tips)
+    newick = _nested_to_newick(nested) + ";"
+    parent, length, names, child_index = oracle_np.tree_arrays_from_nested(nested)
+    n = int(rng.integers(2, 40))
+    tips = [f"t{i}" for i in rng.permutation(n_tips)]
+    taxa = tips[: max(1, int(n_tips * rng.uniform(0.5, 1.0)))]
+    counts = rng.poisson(rng.uniform(0.2, 2.0), size=(n, len(taxa)))
+    counts[rng.integers(0, n)] = 0
+    tree = sb.read_newick(newick)
+    p2, l2, n2 = sb.flatten_tree(tree)
+    assert np.array_equal(p2, parent) and np.array_equal(l2, length) and list(n2) == list(names)
+    for key, metric, kw in KEYS[:3]:
+        exp = oracle_np.unifrac_condensed(metric, counts, taxa, parent, length, names,
+                                          normalized=kw.get("normalized", False))
+        with np.errstate(all="ignore"):
+            # validate=False: the random root may have more than two children ("unrooted")
+            got = sb.beta_diversity(metric, counts, tree=tree, taxa=taxa, validate=False,
+                                    **kw).condensed_form()
+        assert_close_rel(got, exp, UNIFRAC_RTOL, f"seed {seed} {key}")
+    assert np.array_equal(sb.beta_diversity("jaccard", counts).condensed_form(),
+                          oracle_np.jaccard_condensed(counts))
+    assert np.array_equal(sb.beta_diversity("braycurtis", counts).condensed_form(),
+                          oracle_np.braycurtis_condensed(counts), equal_nan=True)
