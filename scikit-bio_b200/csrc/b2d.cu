@@ -550,6 +550,9 @@ static int compute_dense(b2d_problem* p, int metric) {
         k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(
             p->d_indptr, (const double*)p->d_values, p->n, p->d_svec);
     }
+    // the second raw-sum buffer must exist before the embedding takes its share of memory
+    if (p->ntiles && p->mpad > g_chunk_nodes && !p->d_out2)
+        B2D_CUDA(cudaMalloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
     // resident node range
     size_t free_b = 0, total_b = 0;
     B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
