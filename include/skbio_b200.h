@@ -167,6 +167,18 @@ int b2d_set_option(const char* name, int64_t value);
  * kind 3: shared-memory int32 atomicAdd/s on random cells (the sparse feature kernel's bound). */
 int b2d_microbench(int device, int kind, double* result);
 
+/* Host only: Newick text -> flat tree in the reference's node id order, without node objects
+ * (stands in for TreeNode.read + TreeNode.to_array, /root/reference/skbio/io/format/newick.py:270-336,
+ * /root/reference/skbio/tree/_tree.py:6235-6329).  length[k] is NaN where the text gave none;
+ * names are returned as one byte buffer with offsets (UTF-8 bytes as in the text). */
+typedef struct b2d_flat_tree b2d_flat_tree;
+int b2d_newick_parse(const char* text, int64_t len, b2d_flat_tree** out);
+int64_t b2d_flat_tree_nodes(const b2d_flat_tree* t);
+int64_t b2d_flat_tree_name_bytes(const b2d_flat_tree* t);
+int b2d_flat_tree_get(const b2d_flat_tree* t, int32_t* parent, double* length, int64_t* name_off,
+                      uint8_t* has_name, char* name_buf);
+void b2d_flat_tree_free(b2d_flat_tree* t);
+
 /* Host only (no GPU needed): which slices of the condensed vector shard `shard` of
  * `n_shards` owns: {first condensed index, count} per owned row stripe, ascending (at most
  * 2*ceil(n/128) int64), the number of stripes and the total element count.  This is the

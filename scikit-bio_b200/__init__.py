@@ -2,8 +2,8 @@
 
 Import as ``skbio_b200`` (see ``skbio_b200/__init__.py``).
 """
-from ._tree import (SimpleTreeNode, read_newick, flatten_tree, validate_taxa_and_tree,  # noqa: F401
-                    DuplicateNodeError, MissingNodeError)
+from ._tree import (SimpleTreeNode, FlatTree, read_newick, read_newick_flat, flatten_tree,  # noqa: F401
+                    validate_taxa_and_tree, DuplicateNodeError, MissingNodeError)
 from ._dm import DistanceMatrix, SimpleDistanceMatrix  # noqa: F401
 from ._capi import EngineError, available  # noqa: F401
 from ._driver import (alpha_diversity, beta_diversity, block_beta_diversity,  # noqa: F401

@@ -87,6 +87,17 @@ def _declare(lib):
     lib.b2d_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.b2d_microbench.restype = ctypes.c_int
     lib.b2d_microbench.argtypes = [ctypes.c_int, ctypes.c_int, _f64p]
+    lib.b2d_newick_parse.restype = ctypes.c_int
+    lib.b2d_newick_parse.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]
+    lib.b2d_flat_tree_nodes.restype = ctypes.c_int64
+    lib.b2d_flat_tree_nodes.argtypes = [ctypes.c_void_p]
+    lib.b2d_flat_tree_name_bytes.restype = ctypes.c_int64
+    lib.b2d_flat_tree_name_bytes.argtypes = [ctypes.c_void_p]
+    lib.b2d_flat_tree_get.restype = ctypes.c_int
+    lib.b2d_flat_tree_get.argtypes = [ctypes.c_void_p, _i32p, _f64p, _i64p,
+                                      ctypes.POINTER(ctypes.c_uint8), ctypes.c_char_p]
+    lib.b2d_flat_tree_free.restype = None
+    lib.b2d_flat_tree_free.argtypes = [ctypes.c_void_p]
     lib.b2d_shard_layout.restype = ctypes.c_int
     lib.b2d_shard_layout.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _i64p, _i64p, _i64p]
     lib.b2d_debug_tree_order.restype = ctypes.c_int
@@ -102,6 +113,8 @@ EXPORTED_SYMBOLS = [
     "b2d_problem_sample_vector", "b2d_problem_timings", "b2d_problem_destroy",
     "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
     "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout", "b2d_problem_select_tiles",
+    "b2d_newick_parse", "b2d_flat_tree_nodes", "b2d_flat_tree_name_bytes", "b2d_flat_tree_get",
+    "b2d_flat_tree_free",
 ]
 
 
@@ -151,6 +164,34 @@ def microbench(kind, device=0):
     out = ctypes.c_double(0.0)
     _check(load().b2d_microbench(int(device), int(kind), ctypes.byref(out)))
     return out.value
+
+
+def newick_to_flat(text):
+    """(parent int32[m], length float64[m] with NaN for 'no length', names object[m]) straight
+    from Newick text, in the reference's node id order - no node objects (host only)."""
+    lib = load()
+    raw = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+    h = ctypes.c_void_p()
+    _check(lib.b2d_newick_parse(raw, len(raw), ctypes.byref(h)))
+    try:
+        m = int(lib.b2d_flat_tree_nodes(h))
+        nb = int(lib.b2d_flat_tree_name_bytes(h))
+        parent = np.empty(m, dtype=np.int32)
+        length = np.empty(m, dtype=np.float64)
+        off = np.empty(m + 1, dtype=np.int64)
+        has = np.empty(m, dtype=np.uint8)
+        buf = ctypes.create_string_buffer(max(nb, 1))
+        _check(lib.b2d_flat_tree_get(h, _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(off, _i64p),
+                                     has.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), buf))
+    finally:
+        lib.b2d_flat_tree_free(h)
+    blob = buf.raw[:nb]
+    names = np.empty(m, dtype=object)
+    hasl = has.tolist()
+    offl = off.tolist()
+    for k in range(m):
+        names[k] = blob[offl[k]:offl[k + 1]].decode("utf-8") if hasl[k] else None
+    return parent, length, names
 
 
 def shard_layout(n_samples, shard, n_shards):

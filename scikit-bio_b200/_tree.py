@@ -198,6 +198,43 @@ def read_newick(text):
     return root
 
 
+class FlatTree:
+    """A tree as flat arrays in the reference's node id order (root last, ``parent[k] > k``).
+
+    Accepted wherever ``beta_diversity`` takes ``tree=``; skips node objects altogether.
+    ``length`` holds NaN where the source gave no branch length (``None`` on a TreeNode).
+    Build one with ``read_newick_flat`` (native parser) or from your own arrays.
+    """
+
+    __slots__ = ("parent", "length", "names")
+
+    def __init__(self, parent, length, names):
+        self.parent = np.ascontiguousarray(parent, dtype=np.int32)
+        self.length = np.ascontiguousarray(length, dtype=np.float64)
+        self.names = np.asarray(names, dtype=object)
+        if not (len(self.parent) == len(self.length) == len(self.names)):
+            raise ValueError("parent, length and names must have the same length")
+
+    def __len__(self):
+        return len(self.parent)
+
+    def tip_mask(self):
+        has_child = np.zeros(len(self.parent), dtype=bool)
+        has_child[self.parent[self.parent >= 0]] = True
+        return ~has_child
+
+
+def read_newick_flat(text):
+    """Newick text (or an open file / path-like ending in a Newick file) -> ``FlatTree``,
+    parsed natively (libskbb200) straight into reference id order."""
+    from . import _capi
+
+    if hasattr(text, "read"):
+        text = text.read()
+    parent, length, names = _capi.newick_to_flat(text)
+    return FlatTree(parent, length, names)
+
+
 def _root_of(tree):
     r = getattr(tree, "root", None)
     if callable(r):
@@ -217,6 +254,10 @@ def flatten_tree(tree, assign_ids=True):
     As in the reference, ``node.id`` is written on every node when ``assign_ids`` is true
     (/root/reference/skbio/tree/_tree.py:5353-5359).
     """
+    if isinstance(tree, FlatTree):
+        length = tree.length.copy()
+        length[np.isnan(length)] = 0.0  # to_array(nan_length_value=0.0)
+        return tree.parent, length, tree.names
     nodes = []  # nodes in id order
     parents = []  # parent *object index into ``order``* resolved afterwards
     # ids are handed out to the children of each node when the node is reached in postorder
@@ -259,6 +300,21 @@ def validate_taxa_and_tree(taxa, tree):
     taxon_set = set(taxa)
     if len(taxa) != len(taxon_set):
         raise ValueError("All taxa must be unique.")
+    if isinstance(tree, FlatTree):
+        m = len(tree)
+        if int(np.count_nonzero(tree.parent == m - 1)) > 2:
+            raise ValueError("The tree must be rooted.")
+        if np.isnan(tree.length[: m - 1]).any():
+            raise ValueError("All non-root nodes in the tree must have a branch length.")
+        tip_names = list(tree.names[:m][tree.tip_mask()]) if m > 1 else []
+        tip_name_set = set(tip_names)
+        if len(tip_names) != len(tip_name_set):
+            raise DuplicateNodeError("All tip names in the tree must be unique.")
+        missing = taxon_set - tip_name_set
+        if missing:
+            raise MissingNodeError(
+                f"{len(missing)} taxa are not present as tip names in the tree.")
+        return
     if len(_root_of(tree).children) > 2:
         raise ValueError("The tree must be rooted.")
     tip_names = []

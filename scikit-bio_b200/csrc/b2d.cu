@@ -18,6 +18,7 @@
 #include "b2d_pair.cuh"
 #include "b2d_sparse.cuh"
 #include "b2d_tree.h"
+#include "b2d_newick.h"
 
 namespace b2d {
 thread_local std::string g_last_error;
@@ -1051,6 +1052,40 @@ int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe
     if (total_out) *total_out = total;
     return B2D_OK;
 }
+
+struct b2d_flat_tree {
+    FlatTree t;
+};
+
+int b2d_newick_parse(const char* text, int64_t len, b2d_flat_tree** out) {
+    if (!text || !out || len < 0) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    b2d_flat_tree* h = new b2d_flat_tree();
+    std::string err = parse_newick(text, len, h->t);
+    if (!err.empty()) {
+        delete h;
+        *out = nullptr;
+        return fail(B2D_ERR_INVALID_ARGUMENT, err);
+    }
+    *out = h;
+    return B2D_OK;
+}
+
+int64_t b2d_flat_tree_nodes(const b2d_flat_tree* t) { return t ? (int64_t)t->t.parent.size() : 0; }
+int64_t b2d_flat_tree_name_bytes(const b2d_flat_tree* t) { return t ? (int64_t)t->t.name_buf.size() : 0; }
+
+int b2d_flat_tree_get(const b2d_flat_tree* t, int32_t* parent, double* length, int64_t* name_off,
+                      uint8_t* has_name, char* name_buf) {
+    if (!t) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL tree");
+    const FlatTree& f = t->t;
+    if (parent) memcpy(parent, f.parent.data(), f.parent.size() * sizeof(int32_t));
+    if (length) memcpy(length, f.length.data(), f.length.size() * sizeof(double));
+    if (name_off) memcpy(name_off, f.name_off.data(), f.name_off.size() * sizeof(int64_t));
+    if (has_name) memcpy(has_name, f.has_name.data(), f.has_name.size());
+    if (name_buf && !f.name_buf.empty()) memcpy(name_buf, f.name_buf.data(), f.name_buf.size());
+    return B2D_OK;
+}
+
+void b2d_flat_tree_free(b2d_flat_tree* t) { delete t; }
 
 int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* length,
                          int32_t* q_of_id, uint8_t* flags_mpad, double* len_q_mpad,

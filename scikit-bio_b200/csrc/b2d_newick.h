@@ -1,0 +1,200 @@
+// Native Newick -> flat arrays (host only).  Produces the tree directly in the reference's node
+// id order (TreeNode.assign_ids, /root/reference/skbio/tree/_tree.py:5337-5359) without ever
+// building node objects; behaviour follows the reference reader
+// (/root/reference/skbio/io/format/newick.py:270-336 and its tokenizer :380-470): nested
+// [comments] are skipped, 'quoted labels' are literal with '' for a quote, underscores in
+// unquoted labels become spaces, whitespace outside quotes is ignored between tokens and
+// rejected inside an unquoted label, an empty label is "no name", ':' introduces a length.
+#pragma once
+
+#include <stdint.h>
+#include <stdlib.h>
+
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace b2d {
+
+struct FlatTree {
+    std::vector<int32_t> parent;    // reference id order, root last, -1 for the root
+    std::vector<double> length;     // NaN = no length given
+    std::vector<int64_t> name_off;  // [n+1] offsets into name_buf
+    std::vector<uint8_t> has_name;
+    std::string name_buf;
+};
+
+inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
+    struct Node {
+        int32_t parent;
+        int32_t first_child, last_child, next_sibling;
+        double length;
+        int64_t name_b, name_e;  // into names
+        bool has_name;
+    };
+    std::vector<Node> nodes;
+    std::string names;
+    auto new_node = [&](int32_t parent) {
+        Node nd{parent, -1, -1, -1, std::nan(""), 0, 0, false};
+        nodes.push_back(nd);
+        int32_t id = (int32_t)nodes.size() - 1;
+        if (parent >= 0) {
+            if (nodes[parent].first_child < 0)
+                nodes[parent].first_child = id;
+            else
+                nodes[nodes[parent].last_child].next_sibling = id;
+            nodes[parent].last_child = id;
+        }
+        return id;
+    };
+    int32_t cur = new_node(-1);
+    std::vector<int32_t> stack;  // open parents
+    int64_t i = 0;
+    bool done = false;
+    bool closed_children = false;  // cur got its children by a ')' (no more '(' allowed for it)
+    auto skip_ws_comments = [&]() -> bool {
+        while (i < n) {
+            char c = s[i];
+            if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v') {
+                ++i;
+            } else if (c == '[') {
+                int depth = 0;
+                while (i < n) {
+                    if (s[i] == '[') ++depth;
+                    else if (s[i] == ']') { --depth; if (depth == 0) { ++i; break; } }
+                    ++i;
+                }
+                if (depth != 0) return false;
+            } else {
+                break;
+            }
+        }
+        return true;
+    };
+    // reads a label or a number token (quoted or not); returns false on malformed input
+    auto read_token = [&](std::string& tok, bool& quoted) -> bool {
+        tok.clear();
+        quoted = false;
+        if (i < n && s[i] == '\'') {
+            quoted = true;
+            ++i;
+            while (i < n) {
+                if (s[i] == '\'') {
+                    if (i + 1 < n && s[i + 1] == '\'') { tok.push_back('\''); i += 2; continue; }
+                    ++i;
+                    return true;
+                }
+                tok.push_back(s[i++]);
+            }
+            return false;  // unbalanced quote
+        }
+        bool seen_ws = false;
+        while (i < n) {
+            char c = s[i];
+            if (c == '(' || c == ')' || c == ',' || c == ':' || c == ';' || c == '\'') break;
+            if (c == '[') { if (!skip_ws_comments()) return false; continue; }
+            if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v') {
+                seen_ws = true;
+                ++i;
+                continue;
+            }
+            if (seen_ws && !tok.empty()) return false;  // unescaped whitespace inside a label
+            tok.push_back(c);
+            ++i;
+        }
+        return true;
+    };
+    while (!done) {
+        if (!skip_ws_comments()) return "unbalanced [comment] in Newick text";
+        if (i >= n) break;
+        char c = s[i];
+        if (c == '(') {
+            if (closed_children || nodes[cur].first_child >= 0 && false) return "could not parse Newick: unnested children";
+            stack.push_back(cur);
+            cur = new_node(cur);
+            closed_children = false;
+            ++i;
+        } else if (c == ',') {
+            if (stack.empty()) return "could not parse Newick: ',' outside parentheses";
+            cur = new_node(stack.back());
+            closed_children = false;
+            ++i;
+        } else if (c == ')') {
+            if (stack.empty()) return "could not parse Newick: parentheses are unbalanced";
+            cur = stack.back();
+            stack.pop_back();
+            closed_children = true;
+            ++i;
+        } else if (c == ';') {
+            done = true;
+            ++i;
+        } else if (c == ':') {
+            ++i;
+            if (!skip_ws_comments()) return "unbalanced [comment] in Newick text";
+            std::string tok;
+            bool quoted;
+            if (!read_token(tok, quoted)) return "could not parse Newick: malformed length";
+            char* endp = nullptr;
+            double v = strtod(tok.c_str(), &endp);
+            if (tok.empty() || endp == tok.c_str() || *endp != '\0')
+                return "Could not read length as numeric type: " + tok + ".";
+            nodes[cur].length = v;
+        } else {
+            std::string tok;
+            bool quoted;
+            if (!read_token(tok, quoted)) return "could not parse Newick: unbalanced quotes or whitespace in a label";
+            if (!quoted)
+                for (auto& ch : tok)
+                    if (ch == '_') ch = ' ';
+            if (!tok.empty()) {
+                nodes[cur].has_name = true;
+                nodes[cur].name_b = (int64_t)names.size();
+                names += tok;
+                nodes[cur].name_e = (int64_t)names.size();
+            }
+        }
+    }
+    if (!done || !stack.empty())
+        return "Could not parse file as newick. `(Parenthesis)`, `'single-quotes'`, `[comments]` may be "
+               "unbalanced, or tree may be missing its root.";
+    // reference ids: walk in postorder; when a node is reached its children get consecutive ids
+    const int64_t m = (int64_t)nodes.size();
+    std::vector<int32_t> new_id(m, -1);
+    int32_t counter = 0;
+    {
+        std::vector<std::pair<int32_t, int32_t>> st;  // (node, next child to descend into)
+        st.push_back({0, nodes[0].first_child});
+        while (!st.empty()) {
+            auto& top = st.back();
+            if (top.second >= 0) {
+                int32_t ch = top.second;
+                top.second = nodes[ch].next_sibling;
+                st.push_back({ch, nodes[ch].first_child});
+            } else {
+                int32_t v = top.first;
+                st.pop_back();
+                for (int32_t ch = nodes[v].first_child; ch >= 0; ch = nodes[ch].next_sibling) new_id[ch] = counter++;
+            }
+        }
+        new_id[0] = counter;
+    }
+    out.parent.assign(m, -1);
+    out.length.assign(m, std::nan(""));
+    out.has_name.assign(m, 0);
+    std::vector<int32_t> old_of(m);
+    for (int64_t v = 0; v < m; ++v) old_of[new_id[v]] = (int32_t)v;
+    out.name_off.assign(m + 1, 0);
+    out.name_buf.clear();
+    for (int64_t k = 0; k < m; ++k) {
+        const Node& nd = nodes[old_of[k]];
+        out.parent[k] = nd.parent >= 0 ? new_id[nd.parent] : -1;
+        out.length[k] = nd.length;
+        out.has_name[k] = nd.has_name ? 1 : 0;
+        out.name_off[k] = (int64_t)out.name_buf.size();
+        if (nd.has_name) out.name_buf.append(names, (size_t)nd.name_b, (size_t)(nd.name_e - nd.name_b));
+    }
+    out.name_off[m] = (int64_t)out.name_buf.size();
+    return "";
+}
+
+}  // namespace b2d

@@ -266,3 +266,47 @@ def test_real_skbio_treenode_is_accepted_when_available():
     with pytest.raises(MissingNodeError):
         skbio_b200.validate_taxa_and_tree(["a", "nope"], t)
     assert skbio_b200.MissingNodeError is MissingNodeError
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_native_newick_parser_matches_reference_to_array(case):
+    """libskbb200's Newick -> flat arrays equals TreeNode.read + to_array of the reference."""
+    _, parent, length, names = case_arrays(case)
+    ft = skbio_b200.read_newick_flat(case["newick"])
+    p, l, nm = skbio_b200.flatten_tree(ft)
+    assert np.array_equal(p, parent) and np.array_equal(l, length) and list(nm) == list(names)
+
+
+def test_native_newick_parser_details(qiime_tt):
+    ft = skbio_b200.read_newick_flat("(('a b':1,'it''s':2)x:0.5,c_d:3[comment [nested]])r;")
+    assert list(ft.names) == ["a b", "it's", "x", "c d", "r"]
+    assert np.isnan(ft.length[-1]) and list(ft.length[:-1]) == [1.0, 2.0, 0.5, 3.0]
+    ft = skbio_b200.read_newick_flat(" ( a : 1e-3 ,\n b:2 ) ; trailing junk")
+    assert list(ft.names) == ["a", "b", None] and ft.length[0] == 1e-3
+    py = skbio_b200.flatten_tree(skbio_b200.read_newick(qiime_tt["newick"]))
+    nat = skbio_b200.flatten_tree(skbio_b200.read_newick_flat(qiime_tt["newick"]))
+    assert all(np.array_equal(a, b) for a, b in zip(py[:2], nat[:2])) and list(py[2]) == list(nat[2])
+    for bad in ["((a,b);", "(a,b", "(a:x,b);", "('a,b);", "(a b,c);"]:
+        with pytest.raises(_capi.EngineError):
+            skbio_b200.read_newick_flat(bad)
+    # big random tree round trip
+    parent, length, names, _ = synthetic.random_join_tree(3000, seed=9)
+    ft = skbio_b200.read_newick_flat(synthetic.to_newick(parent, length, names))
+    assert np.array_equal(ft.parent, parent) and list(ft.names) == list(names)
+    assert np.array_equal(ft.length[:-1], length[:-1]) and np.isnan(ft.length[-1])
+
+
+def test_flat_tree_validation_messages():
+    t = skbio_b200.read_newick_flat(T1)
+    skbio_b200.validate_taxa_and_tree(OIDS, t)
+    with pytest.raises(skbio_b200.MissingNodeError, match="1 taxa are not present"):
+        skbio_b200.validate_taxa_and_tree(OIDS + ["nope"], t)
+    with pytest.raises(ValueError, match="The tree must be rooted"):
+        skbio_b200.validate_taxa_and_tree(OIDS, skbio_b200.read_newick_flat(
+            "((OTU1:0.1,OTU2:0.2):0.3,OTU3:0.5,(OTU4:0.7,OTU5:0.1):1.1);"))
+    with pytest.raises(ValueError, match="must have a branch length"):
+        skbio_b200.validate_taxa_and_tree(OIDS, skbio_b200.read_newick_flat(
+            "((OTU1:0.1,OTU2:0.2):0.3,((OTU3:0.5,OTU4:0.7),OTU5:1.1):1)root;"))
+    with pytest.raises(skbio_b200.DuplicateNodeError):
+        skbio_b200.validate_taxa_and_tree(OIDS, skbio_b200.read_newick_flat(
+            "((OTU1:0.1,OTU2:0.2):0.3,((OTU3:0.5,OTU4:0.7):1,(OTU5:1.1,OTU2:1):1):1)root;"))
