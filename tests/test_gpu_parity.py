@@ -48,6 +48,10 @@ def test_golden_full_api(case):
         dm = sb.beta_diversity(metric, counts, case["ids"], **kwargs)
         got = dm.condensed_form()
         assert list(dm.ids) == case["result_ids"]
+        if "unifrac" in metric:  # same call with the native flat tree instead of node objects
+            kwargs["tree"] = sb.read_newick_flat(case["newick"])
+            dm2 = sb.beta_diversity(metric, counts, case["ids"], **kwargs)
+            assert np.array_equal(dm2.condensed_form(), got, equal_nan=True)
         if key == "jaccard":
             assert np.array_equal(got, exp), f"{case['name']} jaccard not bit-exact"
         elif key == "braycurtis" and counts.dtype.kind in "iub":
