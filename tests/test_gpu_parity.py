@@ -452,3 +452,30 @@ def test_random_multifurcating_trees_full_api_vs_numpy_oracle(seed):
                           oracle_np.jaccard_condensed(counts))
     assert np.array_equal(sb.beta_diversity("braycurtis", counts).condensed_form(),
                           oracle_np.braycurtis_condensed(counts), equal_nan=True)
+
+
+def test_all_zero_table_and_degenerate_shapes():
+    """An all-zero table: UniFrac variants and Jaccard give 0.0, Bray-Curtis NaN (SciPy's 0/0),
+    exactly like the reference; 2-sample and 128/129-sample shapes hit the tile edges."""
+    sb = _skbio_b200()
+    from oracle import oracle_np
+
+    tree = sb.read_newick("((a:1,b:2):1,(c:1,d:3):2)r;")
+    taxa = list("abcd")
+    zero = np.zeros((3, 4), dtype=int)
+    assert not sb.beta_diversity("unweighted_unifrac", zero, tree=tree, taxa=taxa).condensed_form().any()
+    assert not sb.beta_diversity("weighted_unifrac", zero, tree=tree, taxa=taxa).condensed_form().any()
+    assert not sb.beta_diversity("weighted_unifrac", zero, tree=tree, taxa=taxa,
+                                 normalized=True).condensed_form().any()
+    assert not sb.beta_diversity("jaccard", zero).condensed_form().any()
+    assert np.isnan(sb.beta_diversity("braycurtis", zero).condensed_form()).all()
+    parent, length, names = sb.flatten_tree(tree)
+    rng = np.random.default_rng(2)
+    for n in (2, 128, 129):
+        counts = rng.poisson(1.0, size=(n, 4))
+        for metric, kw in (("unweighted_unifrac", {}), ("weighted_unifrac", {"normalized": True})):
+            exp = oracle_np.unifrac_condensed(metric, counts, taxa, parent, length, names,
+                                              normalized=kw.get("normalized", False))
+            with np.errstate(all="ignore"):
+                got = sb.beta_diversity(metric, counts, tree=tree, taxa=taxa, **kw).condensed_form()
+            assert_close_rel(got, exp, UNIFRAC_RTOL, f"n={n} {metric}")
