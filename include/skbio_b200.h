@@ -167,6 +167,17 @@ int b2d_set_option(const char* name, int64_t value);
  * kind 3: shared-memory int32 atomicAdd/s on random cells (the sparse feature kernel's bound). */
 int b2d_microbench(int device, int kind, double* result);
 
+/* PERMANOVA partial statistic for many groupings at once ("next" consumer of the distance
+ * matrix): s_w_out[g] = sum over pairs i<j with groupings[g][i] == groupings[g][j] of
+ * d_ij^2 * inv_group_size[group].  Replaces the per-permutation loop over
+ * permanova_f_stat_sW_condensed_cy (/root/reference/skbio/stats/distance/_cutils.pyx:418-470,
+ * /root/reference/skbio/stats/distance/_base.py:2340-2364); the optional accelerator the reference
+ * binds for the same job is skbb_permanova_fp64 (/root/reference/skbio/binaries/_distance.py:161-193).
+ * condensed: n(n-1)/2 distances (host); groupings: [n_groupings][n] int32 group ids. */
+int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_groupings,
+                     const int32_t* groupings, int32_t n_groups, const double* inv_group_size,
+                     double* s_w_out);
+
 /* Host only: Newick text -> flat tree in the reference's node id order, without node objects
  * (stands in for TreeNode.read + TreeNode.to_array, /root/reference/skbio/io/format/newick.py:270-336,
  * /root/reference/skbio/tree/_tree.py:6235-6329).  length[k] is NaN where the text gave none;

@@ -9,4 +9,6 @@ from ._capi import EngineError, available  # noqa: F401
 from ._driver import (alpha_diversity, beta_diversity, block_beta_diversity,  # noqa: F401
                       partial_beta_diversity, install)
 
+from ._stats import permanova  # noqa: F401
+
 __version__ = "0.1.0"

@@ -87,6 +87,9 @@ def _declare(lib):
     lib.b2d_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.b2d_microbench.restype = ctypes.c_int
     lib.b2d_microbench.argtypes = [ctypes.c_int, ctypes.c_int, _f64p]
+    lib.b2d_permanova_sw.restype = ctypes.c_int
+    lib.b2d_permanova_sw.argtypes = [ctypes.c_int, ctypes.c_int64, _f64p, ctypes.c_int64, _i32p,
+                                     ctypes.c_int32, _f64p, _f64p]
     lib.b2d_newick_parse.restype = ctypes.c_int
     lib.b2d_newick_parse.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]
     lib.b2d_flat_tree_nodes.restype = ctypes.c_int64
@@ -114,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
     "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout", "b2d_problem_select_tiles",
     "b2d_newick_parse", "b2d_flat_tree_nodes", "b2d_flat_tree_name_bytes", "b2d_flat_tree_get",
-    "b2d_flat_tree_free",
+    "b2d_flat_tree_free", "b2d_permanova_sw",
 ]
 
 
@@ -164,6 +167,19 @@ def microbench(kind, device=0):
     out = ctypes.c_double(0.0)
     _check(load().b2d_microbench(int(device), int(kind), ctypes.byref(out)))
     return out.value
+
+
+def permanova_sw(condensed, groupings, inv_group_size, device=0):
+    """s_W for every row of ``groupings`` ([k][n] int32) on a condensed distance vector."""
+    lib = load()
+    condensed = np.ascontiguousarray(condensed, dtype=np.float64)
+    groupings = np.ascontiguousarray(groupings, dtype=np.int32)
+    inv = np.ascontiguousarray(inv_group_size, dtype=np.float64)
+    k, n = groupings.shape
+    out = np.empty(k, dtype=np.float64)
+    _check(lib.b2d_permanova_sw(int(device), n, _ptr(condensed, _f64p), k, _ptr(groupings, _i32p),
+                                len(inv), _ptr(inv, _f64p), _ptr(out, _f64p)))
+    return out
 
 
 def newick_to_flat(text):

@@ -17,6 +17,7 @@
 #include "b2d_embed.cuh"
 #include "b2d_pair.cuh"
 #include "b2d_sparse.cuh"
+#include "b2d_permanova.cuh"
 #include "b2d_tree.h"
 #include "b2d_newick.h"
 
@@ -1050,6 +1051,43 @@ int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe
     }
     if (n_stripes_out) *n_stripes_out = k;
     if (total_out) *total_out = total;
+    return B2D_OK;
+}
+
+int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_groupings,
+                     const int32_t* groupings, int32_t n_groups, const double* inv_group_size,
+                     double* s_w_out) {
+    if (!condensed || !groupings || !inv_group_size || !s_w_out)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n < 2 || n_groupings < 1 || n_groups < 1 || n_groups > 4096)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "need n >= 2, n_groupings >= 1 and 1 <= n_groups <= 4096");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2D_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    B2D_CUDA(cudaSetDevice(device));
+    for (int64_t k = 0; k < n_groupings * n; ++k)
+        if (groupings[k] < 0 || groupings[k] >= n_groups)
+            return fail(B2D_ERR_INVALID_ARGUMENT, "group id out of range");
+    const int64_t P = n * (n - 1) / 2, nb = (n + TILE - 1) / TILE;
+    double *d_cond = nullptr, *d_w = nullptr, *d_partial = nullptr, *d_out = nullptr;
+    int32_t* d_g = nullptr;
+    B2D_CUDA(cudaMalloc(&d_cond, P * sizeof(double)));
+    B2D_CUDA(cudaMalloc(&d_g, n_groupings * n * sizeof(int32_t)));
+    B2D_CUDA(cudaMalloc(&d_w, n_groups * sizeof(double)));
+    B2D_CUDA(cudaMalloc(&d_partial, nb * n_groupings * sizeof(double)));
+    B2D_CUDA(cudaMalloc(&d_out, n_groupings * sizeof(double)));
+    B2D_CUDA(cudaMemcpy(d_cond, condensed, P * sizeof(double), cudaMemcpyHostToDevice));
+    B2D_CUDA(cudaMemcpy(d_g, groupings, n_groupings * n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    B2D_CUDA(cudaMemcpy(d_w, inv_group_size, n_groups * sizeof(double), cudaMemcpyHostToDevice));
+    dim3 grid((unsigned)nb, (unsigned)((n_groupings + PM_BATCH - 1) / PM_BATCH));
+    k_permanova_sw<<<grid, 256, n_groups * sizeof(double)>>>(d_cond, n, d_g, n_groupings, d_w, n_groups,
+                                                             d_partial);
+    k_permanova_reduce<<<(unsigned)((n_groupings + 255) / 256), 256>>>(d_partial, nb, n_groupings, d_out);
+    B2D_CUDA(cudaGetLastError());
+    B2D_CUDA(cudaMemcpy(s_w_out, d_out, n_groupings * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_cond); cudaFree(d_g); cudaFree(d_w); cudaFree(d_partial); cudaFree(d_out);
     return B2D_OK;
 }
 

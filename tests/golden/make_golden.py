@@ -183,6 +183,27 @@ def main():
         q["reference_run"][key] = [float(x) for x in dm.condensed_form()]
     with open(os.path.join(HERE, "qiime191tt.json"), "w") as f:
         json.dump(q, f)
+    # --- PERMANOVA (consumer of the distance matrix; reference: stats/distance/_permanova.py) ---
+    from scipy.spatial.distance import pdist
+    from skbio.stats.distance import DistanceMatrix, permanova
+    pm = []
+    for n, k, feats, perms, seed, effect in [(30, 3, 12, 99, 7, 2.0), (120, 4, 40, 199, 42, 0.05),
+                                             (150, 2, 30, 99, 3, 0.0), (40, 5, 8, 0, 1, 1.0),
+                                             (64, 3, 10, 499, 11, 0.0)]:
+        rng = np.random.default_rng(seed + 1000)
+        grouping = rng.integers(0, k, size=n)
+        x = rng.poisson(3.0 + effect * grouping[:, None] * rng.random(feats)[None, :], size=(n, feats))
+        vec = pdist(x, "braycurtis")
+        dm = DistanceMatrix(vec, [f"s{i}" for i in range(n)])
+        labels = [f"g{g}" for g in grouping]
+        res = permanova(dm, labels, permutations=perms, seed=seed)
+        pm.append({"n": n, "condensed": [float(v) for v in vec], "grouping": labels,
+                   "permutations": perms, "seed": seed,
+                   "stat": float(res["test statistic"]),
+                   "p_value": None if perms == 0 else float(res["p-value"]),
+                   "num_groups": int(res["number of groups"])})
+    with open(os.path.join(HERE, "permanova.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py", "cases": pm}, f)
     print("wrote", len(cases), "cases")
 
 

@@ -479,3 +479,34 @@ def test_all_zero_table_and_degenerate_shapes():
             with np.errstate(all="ignore"):
                 got = sb.beta_diversity(metric, counts, tree=tree, taxa=taxa, **kw).condensed_form()
             assert_close_rel(got, exp, UNIFRAC_RTOL, f"n={n} {metric}")
+
+
+def test_permanova_matches_reference():
+    """GPU PERMANOVA (one pass over all permutations) vs the reference's permanova on the same
+    distance matrices, groupings and seeds: pseudo-F to 1e-12, p-value identical (the
+    permutation stream is reproduced on the host with the same Generator calls)."""
+    import json
+
+    from conftest import GOLDEN
+
+    sb = _skbio_b200()
+    from skbio_b200._dm import SimpleDistanceMatrix
+
+    with open(os.path.join(GOLDEN, "permanova.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        n = c["n"]
+        dm = SimpleDistanceMatrix(np.array(c["condensed"]), [f"s{i}" for i in range(n)])
+        res = sb.permanova(dm, c["grouping"], permutations=c["permutations"], seed=c["seed"])
+        assert res["sample size"] == n and res["number of groups"] == c["num_groups"]
+        assert abs(res["test statistic"] - c["stat"]) <= 1e-12 * abs(c["stat"])
+        if c["permutations"] == 0:
+            assert np.isnan(res["p-value"])
+        else:
+            assert res["p-value"] == c["p_value"]
+    with pytest.raises(ValueError, match="All values in the grouping vector are the same"):
+        sb.permanova(dm, ["a"] * n)
+    with pytest.raises(ValueError, match="Grouping vector size must match"):
+        sb.permanova(dm, ["a", "b"])
+    with pytest.raises(TypeError, match="Input must be a DistanceMatrix"):
+        sb.permanova(np.zeros((3, 3)), ["a", "b", "a"])
