@@ -28,7 +28,7 @@ def run(n, tips, lam, keys, feat_keys=()):
                 t = prob.timings()
                 print(f"{key}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("e2e", "sparse")):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("e2e", "sparse", "permanova")):
     print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), "lds64 gathers/s", _capi.microbench(2), flush=True)
     run(4096, 20000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"], ["braycurtis", "jaccard"])
     if len(sys.argv) > 1 and sys.argv[1] == "big":
@@ -77,3 +77,27 @@ def sparse_probe(n=20000, f=50000, lam=0.01):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sparse":
     sparse_probe()
+
+
+def permanova_probe(n=10000, perms=999):
+    import skbio_b200
+    from skbio_b200._dm import SimpleDistanceMatrix
+    rng = np.random.default_rng(0)
+    vec = rng.random(n * (n - 1) // 2)
+    dm = SimpleDistanceMatrix(vec, [str(i) for i in range(n)], condensed=True)
+    grouping = rng.integers(0, 4, size=n)
+    for rep in range(2):
+        t0 = time.perf_counter()
+        res = skbio_b200.permanova(dm, grouping, permutations=perms, seed=1)
+        dt = time.perf_counter() - t0
+    print(f"permanova n={n} perms={perms}: {dt:.3f} s  F={res['test statistic']:.6f} p={res['p-value']}", flush=True)
+    # CPU cost of ONE permutation with the reference's algorithm restated in NumPy
+    t0 = time.perf_counter()
+    iu = np.triu_indices(n, k=1)
+    same = grouping[iu[0]] == grouping[iu[1]]
+    sw = (vec[same] ** 2 / np.bincount(grouping)[grouping[iu[0]][same]]).sum()
+    print(f"numpy one permutation: {time.perf_counter()-t0:.2f} s", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "permanova":
+    permanova_probe()
