@@ -120,7 +120,9 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_mhz_min": float(min(sm)) if sm else None,
                 "sm_max_mhz": float(max(smmax)) if smmax else None,
+                "power_w_median": float(np.median(power)) if power else None,
                 "power_w_max": float(max(power)) if power else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 

@@ -131,7 +131,6 @@ struct b2d_problem {
     uint32_t* d_hc = nullptr;
     uint32_t* d_fold = nullptr;
     double* d_len = nullptr;
-    double* d_len2 = nullptr;         // [2*(mpad+1)]: entries 2q, 2q+1 = length of node q-1 (0 for q = 0)
     double* d_tipdist = nullptr;
     uint8_t* d_flags1 = nullptr;      // subtree decomposition of the weighted walk
     int64_t* d_spans = nullptr;
@@ -172,7 +171,7 @@ static void free_problem(b2d_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->d_indptr); cudaFree(p->d_qidx); cudaFree(p->d_values); cudaFree(p->d_flags);
-    cudaFree(p->d_hc); cudaFree(p->d_fold); cudaFree(p->d_len); cudaFree(p->d_tipdist); cudaFree(p->d_len2);
+    cudaFree(p->d_hc); cudaFree(p->d_fold); cudaFree(p->d_len); cudaFree(p->d_tipdist);
     cudaFree(p->d_tiles); cudaFree(p->d_row_base); cudaFree(p->d_out); cudaFree(p->d_total);
     cudaFree(p->d_svec); cudaFree(p->d_emb); cudaFree(p->d_state);
     cudaFree(p->d_out2); cudaFree(p->d_owned);
@@ -216,12 +215,6 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     if ((rc = upload(&p->d_hc, o.hc_mask.data(), o.hc_mask.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_fold, o.fold_mask.data(), o.fold_mask.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_len, o.len_q.data(), o.len_q.size(), p->stream))) return rc;
-    {
-        std::vector<double> len2(2 * (o.len_q.size() + 1), 0.0);
-        for (size_t q = 0; q < o.len_q.size(); ++q) len2[2 * (q + 1)] = len2[2 * (q + 1) + 1] = o.len_q[q];
-        if ((rc = upload(&p->d_len2, len2.data(), len2.size(), p->stream))) return rc;
-        B2D_CUDA(cudaStreamSynchronize(p->stream));  // len2 is a local
-    }
     if ((rc = upload(&p->d_tipdist, o.tipdist_q.data(), o.tipdist_q.size(), p->stream))) return rc;
     if (o.decomposed) {
         if ((rc = upload(&p->d_flags1, o.flags1.data(), o.flags1.size(), p->stream))) return rc;
@@ -498,8 +491,7 @@ static int finalize(b2d_problem* p, int epilogue) {
 }
 
 static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* len_rel,
-                              const double* len2_rel, int64_t q0, int64_t q1, int64_t QR,
-                              int epilogue) {
+                              int64_t q0, int64_t q1, int64_t QR, int epilogue) {
     // node chunks [qa, qb) relative to the resident range; two-level fp64 summation:
     // registers within a chunk, `out` across chunks.
     B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -529,7 +521,7 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
         else if (g_weighted_variant == 2)
             k_pair_weighted<<<(unsigned)p->ntiles, WK_THREADS, WK_SMEM, st>>>(emb, len_rel, a);
         else
-            k_pair_weighted_v3<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, st>>>(emb, len_rel, len2_rel, a);
+            k_pair_weighted_v3<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, st>>>(emb, len_rel, a);
         p->n_launch += 1;
     }
     B2D_CUDA(cudaGetLastError());
@@ -618,8 +610,7 @@ static int compute_dense(b2d_problem* p, int metric) {
         B2D_CUDA(cudaEventRecord(eb, p->stream));
         if (p->ntiles) {
             if ((rc = fork_streams(p))) return rc;
-            rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, p->d_len2 + 2 * q0, q0, q1, QR,
-                                    epilogue);
+            rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue);
             if (rc) return rc;
             if ((rc = join_streams(p))) return rc;
             if (q1 == p->mpad && (rc = finalize(p, epilogue))) return rc;

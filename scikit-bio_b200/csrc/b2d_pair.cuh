@@ -248,18 +248,19 @@ k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q
 //     instructions per node and thread (A and B rows share one shared-memory pitch so one
 //     pointer addresses both).
 // 6-stage ring of {16 x 64 A values (pitch 128), 16 x 128 B values, 16 lengths}, bulk copies.
+// (Tried: lengths in the A-row padding, read at the top of the iteration instead of carried in
+//  a register - two instructions fewer per node but the exposed load latency cost 7 %.)
 // =========================================================================================
 constexpr int W3_KS = 16;
 constexpr int W3_STAGES = 6;
 constexpr int W3_ROWS = 64;
 constexpr int W3_CWARPS = 8;
 constexpr int W3_THREADS = W3_CWARPS * 32 + 32;
-constexpr int W3_STAGE_DOUBLES = 2 * W3_KS * TILE;  // A (pitch 128, lengths in the padding) + B
+constexpr int W3_STAGE_DOUBLES = 2 * W3_KS * TILE + W3_KS;  // A (pitch 128) + B + len
 constexpr size_t W3_SMEM = (size_t)W3_STAGES * W3_STAGE_DOUBLES * sizeof(double) + 2 * W3_STAGES * sizeof(uint64_t);
 
 __global__ void __launch_bounds__(W3_THREADS, 1)
-k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ len_q,
-                   const double* __restrict__ len2, PairArgs a) {
+k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ len_q, PairArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)W3_STAGES * W3_STAGE_DOUBLES * sizeof(double));
@@ -284,21 +285,20 @@ k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ le
         if (tid == W3_CWARPS * 32) {
             const double* Ag = emb + ((int64_t)bi * a.QR + a.qa) * TILE + half * W3_ROWS;
             const double* Bg = emb + ((int64_t)bj * a.QR + a.qa) * TILE;
-            const double* Lg = len2 + 2 * a.qa;   // len2[2q] = len2[2q+1] = length of node q-1
+            const double* Lg = len_q + a.qa;
             int s = 0;
             uint32_t ph = 0;
             for (int64_t it = 0; it < nstage; ++it) {
                 if (it >= W3_STAGES) mbar_wait(&empty[s], ph ^ 1u);
                 double* A = stage_base + (size_t)s * W3_STAGE_DOUBLES;
                 double* B = A + W3_KS * TILE;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)((W3_KS * W3_ROWS + W3_KS * TILE + 2 * W3_KS) * sizeof(double)));
+                double* L = B + W3_KS * TILE;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)((W3_KS * W3_ROWS + W3_KS * TILE + W3_KS) * sizeof(double)));
 #pragma unroll
-                for (int k = 0; k < W3_KS; ++k) {
+                for (int k = 0; k < W3_KS; ++k)
                     bulk_g2s(A + k * TILE, Ag + (it * W3_KS + k) * TILE, W3_ROWS * sizeof(double), &full[s]);
-                    // the length of the PREVIOUS node rides in the padding of this node's A row
-                    bulk_g2s(A + k * TILE + W3_ROWS, Lg + 2 * (it * W3_KS + k), 2 * sizeof(double), &full[s]);
-                }
                 bulk_g2s(B, Bg + it * W3_KS * TILE, W3_KS * TILE * sizeof(double), &full[s]);
+                bulk_g2s(L, Lg + it * W3_KS, W3_KS * sizeof(double), &full[s]);
                 if (++s == W3_STAGES) {
                     s = 0;
                     ph ^= 1u;
@@ -325,16 +325,18 @@ k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ le
             acc[r][c] = 0.0;
             d[r][c] = 0.0;
         }
+    double lc = 0.0;  // length of the node whose differences are held in d
+
     int s = 0;
     uint32_t ph = 0;
     for (int64_t it = 0; it < nstage; ++it) {
         mbar_wait(&full[s], ph);
         const double* P = stage_base + (size_t)s * W3_STAGE_DOUBLES;  // A row; B row at +16*TILE
+        const double* Lp = P + 2 * W3_KS * TILE;
         const double* Pend = P + W3_KS * TILE;
 #pragma unroll 1
-        for (; P != Pend; P += TILE) {
-            // length of the previous node (whose differences are in d), then this node's operands
-            const double lc = P[W3_ROWS];
+        for (; P != Pend; P += TILE, ++Lp) {
+            // operands of this node; the DFMAs below still work on the previous node
             double av[8], bv[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -348,6 +350,7 @@ k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ le
                 bv[2 * g] = t.x;
                 bv[2 * g + 1] = t.y;
             }
+            const double ln = *Lp;
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -355,6 +358,7 @@ k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ le
                     acc[r][c] = fma(fabs(d[r][c]), lc, acc[r][c]);
                     d[r][c] = av[r] - bv[c];
                 }
+            lc = ln;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -363,13 +367,10 @@ k_pair_weighted_v3(const double* __restrict__ emb, const double* __restrict__ le
             ph ^= 1u;
         }
     }
-    if (nstage > 0) {
-        const double lc = len_q[a.qb - 1];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fma(fabs(d[r][c]), lc, acc[r][c]);
-    }
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(fabs(d[r][c]), lc, acc[r][c]);
 
     // ---------------- epilogue ----------------
     const int64_t base = a.row_base[bi];
