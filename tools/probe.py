@@ -28,7 +28,7 @@ def run(n, tips, lam, keys, feat_keys=()):
                 t = prob.timings()
                 print(f"{key}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("e2e", "sparse", "permanova")):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("e2e", "sparse", "permanova", "e2ef")):
     print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), "lds64 gathers/s", _capi.microbench(2), flush=True)
     run(4096, 20000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"], ["braycurtis", "jaccard"])
     if len(sys.argv) > 1 and sys.argv[1] == "big":
@@ -101,3 +101,26 @@ def permanova_probe(n=10000, perms=999):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "permanova":
     permanova_probe()
+
+
+def e2e_features(n=10000, f=50000, lam=0.01):
+    indptr, cols, vals = synthetic.poisson_csr(n, f, lam, seed=0)
+    P = n * (n - 1) // 2
+    out = _capi.PinnedBuffer(P)
+    for key, v in (("braycurtis", vals.astype(np.float64)), ("jaccard", vals.astype(np.float64)), ("braycurtis", vals.astype(np.float64))):
+        for rep in range(2):
+            t0 = time.perf_counter()
+            prob = _capi.Problem.features(indptr, cols, v, n, f)
+            t1 = time.perf_counter()
+            prob.compute(key)
+            t2 = time.perf_counter()
+            prob.fetch(out.array)
+            t3 = time.perf_counter()
+            tm = prob.timings()
+            prob.destroy()
+            t4 = time.perf_counter()
+            print(f"{key} rep{rep}: create {1e3*(t1-t0):.1f} compute {1e3*(t2-t1):.1f} (dev {tm['compute_ms']:.1f}, resident {tm['nodes_resident']}) fetch {1e3*(t3-t2):.1f} destroy {1e3*(t4-t3):.1f} ms", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "e2ef":
+    e2e_features()
