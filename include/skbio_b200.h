@@ -135,6 +135,11 @@ int b2d_problem_fetch_compact(b2d_problem* p, double* out, int64_t* stripe_offse
  * _faith_pd, /root/reference/skbio/diversity/alpha/_pd.py:19-51). */
 int b2d_problem_sample_vector(b2d_problem* p, double* out_n);
 
+/* Generalised phylogenetic diversity per sample for a tree problem created WITH count values
+ * (replaces _phydiv, /root/reference/skbio/diversity/alpha/_pd.py:190-239): rooted 0/1,
+ * weight 0 (unweighted), 1 (abundance-weighted) or theta in (0,1).  out_n: n_samples doubles. */
+int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n);
+
 /* Device-side phase timings of the last compute, milliseconds (CUDA events on the
  * problem's stream): [0] embedding build, [1] pair kernels, [2] total compute,
  * [3] last fetch (D2H), [4] upload at create (H2D), [5] last pair-kernel launch count,

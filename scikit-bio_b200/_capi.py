@@ -71,6 +71,8 @@ def _declare(lib):
     lib.b2d_problem_fetch_compact.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _i64p, _i64p]
     lib.b2d_problem_sample_vector.restype = ctypes.c_int
     lib.b2d_problem_sample_vector.argtypes = [ctypes.c_void_p, _f64p]
+    lib.b2d_problem_phydiv.restype = ctypes.c_int
+    lib.b2d_problem_phydiv.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, _f64p]
     lib.b2d_problem_timings.restype = ctypes.c_int
     lib.b2d_problem_timings.argtypes = [ctypes.c_void_p, _f64p, ctypes.c_int]
     lib.b2d_problem_destroy.restype = ctypes.c_int
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
     "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout", "b2d_problem_select_tiles",
     "b2d_newick_parse", "b2d_flat_tree_nodes", "b2d_flat_tree_name_bytes", "b2d_flat_tree_get",
-    "b2d_flat_tree_free", "b2d_permanova_sw",
+    "b2d_flat_tree_free", "b2d_permanova_sw", "b2d_problem_phydiv",
 ]
 
 
@@ -340,6 +342,12 @@ class Problem:
         out = np.empty(self.n, dtype=np.float64)
         if self.n:
             _check(load().b2d_problem_sample_vector(self._h, _ptr(out, _f64p)))
+        return out
+
+    def phydiv(self, rooted, weight):
+        out = np.empty(self.n, dtype=np.float64)
+        if self.n:
+            _check(load().b2d_problem_phydiv(self._h, 1 if rooted else 0, float(weight), _ptr(out, _f64p)))
         return out
 
     def timings(self):

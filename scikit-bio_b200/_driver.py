@@ -28,7 +28,7 @@ import numpy as np
 from . import _capi
 from ._dm import make_distance_matrix
 from ._table import ingest_table, to_csr, validate_counts_matrix, _is_sparse
-from ._tree import flatten_tree, map_taxa_to_nodes, validate_taxa_and_tree
+from ._tree import FlatTree, flatten_tree, map_taxa_to_nodes, validate_taxa_and_tree
 
 # /root/reference/skbio/diversity/_driver.py:43-52
 _qualitative_metrics = {
@@ -349,6 +349,8 @@ def alpha_diversity(metric, counts, ids=None, validate=True, **kwargs):
     import pandas as pd
 
     device = _devices_arg(kwargs.pop("devices", None))[0]
+    if metric == "phydiv":
+        return _phydiv_engine(counts, ids, validate, device, kwargs)
     if metric != "faith_pd":
         from skbio.diversity import alpha_diversity as _skbio_alpha  # type: ignore
 
@@ -381,6 +383,53 @@ def alpha_diversity(metric, counts, ids=None, validate=True, **kwargs):
         prob.compute("faith_pd")
         vec = prob.sample_vector()
     return pd.Series(vec, index=ids)
+
+
+def _phydiv_engine(counts, ids, validate, device, kwargs):
+    """``alpha_diversity('phydiv', ..., rooted=None, weight=False)`` on the engine
+    (/root/reference/skbio/diversity/_driver.py:192-204, alpha/_pd.py:190-239, 242-420)."""
+    import pandas as pd
+
+    taxa = kwargs.pop("taxa", None)
+    counts, ids, taxa = ingest_table(counts, ids, taxa)
+    if 0 in counts.shape:
+        return pd.Series(np.zeros(len(ids)), index=ids)
+    if validate:
+        counts = validate_counts_matrix(counts)
+    taxa, tree, kwargs = _get_phylogenetic_kwargs(kwargs, taxa)
+    if isinstance(tree, FlatTree):
+        default_rooted = int(np.count_nonzero(tree.parent == len(tree) - 1)) == 2
+    else:
+        default_rooted = len(_root_children(tree)) == 2     # TreeNode._is_rooted, _tree.py:385
+    rooted = kwargs.pop("rooted", default_rooted)
+    weight = kwargs.pop("weight", False)
+    if kwargs:
+        raise TypeError(f"_phydiv() got an unexpected keyword argument '{next(iter(kwargs))}'")
+    if rooted is None:
+        rooted = default_rooted
+    if validate:
+        validate_taxa_and_tree(taxa, tree, rooted=False)
+    if isinstance(weight, bool):
+        w = 1.0 if weight else 0.0
+    else:
+        w = float(weight)
+        if not 0.0 <= w <= 1.0:
+            raise ValueError("`weight` must be a boolean or a number within [0, 1].")
+    if _capi.load().b2d_device_count() <= 0:
+        raise _capi.EngineError("no CUDA device visible: the B200 engine has no CPU fallback.")
+    parent, length, names = flatten_tree(tree)
+    indptr, cols, vals = to_csr(counts, "int64")
+    node_of_col = map_taxa_to_nodes(taxa, np.unique(cols), names)
+    with _capi.Problem.tree(parent, length, indptr, node_of_col[cols], vals, counts.shape[0],
+                            device=device) as prob:
+        vec = prob.phydiv(bool(rooted), w)
+    return pd.Series(vec, index=ids)
+
+
+def _root_children(tree):
+    r = getattr(tree, "root", None)
+    node = r() if callable(r) else tree
+    return node.children
 
 
 def _reference_route(metric, counts, ids, validate, pairwise_func, taxa, kwargs):

@@ -293,7 +293,7 @@ def flatten_tree(tree, assign_ids=True):
     return parent, length, names
 
 
-def validate_taxa_and_tree(taxa, tree):
+def validate_taxa_and_tree(taxa, tree, rooted=True):
     """Same checks, order, exception types and messages as the reference's
     ``_validate_taxa_and_tree(taxa, tree, rooted=True, lengths=True)``
     (/root/reference/skbio/tree/_utils.py:29-90)."""
@@ -302,7 +302,7 @@ def validate_taxa_and_tree(taxa, tree):
         raise ValueError("All taxa must be unique.")
     if isinstance(tree, FlatTree):
         m = len(tree)
-        if int(np.count_nonzero(tree.parent == m - 1)) > 2:
+        if rooted and int(np.count_nonzero(tree.parent == m - 1)) > 2:
             raise ValueError("The tree must be rooted.")
         if np.isnan(tree.length[: m - 1]).any():
             raise ValueError("All non-root nodes in the tree must have a branch length.")
@@ -315,7 +315,7 @@ def validate_taxa_and_tree(taxa, tree):
             raise MissingNodeError(
                 f"{len(missing)} taxa are not present as tip names in the tree.")
         return
-    if len(_root_of(tree).children) > 2:
+    if rooted and len(_root_of(tree).children) > 2:
         raise ValueError("The tree must be rooted.")
     tip_names = []
     for node in _postorder(tree, include_self=False):

@@ -917,6 +917,62 @@ int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_til
     return B2D_OK;
 }
 
+int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n) {
+    if (!p || !out_n) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (p->kind != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "phydiv needs a tree problem");
+    if (!(weight >= 0.0 && weight <= 1.0)) return fail(B2D_ERR_INVALID_ARGUMENT, "weight must be in [0, 1]");
+    B2D_CUDA(cudaSetDevice(p->device));
+    if (p->n == 0) return B2D_OK;
+    const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    B2D_CUDA(cudaMemsetAsync(p->d_total, 0, p->npad * sizeof(long long), p->stream));
+    k_sample_totals_all<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, (const int64_t*)p->d_values, p->n,
+                                                           p->d_total);
+    size_t free_b = 0, total_b = 0;
+    B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t nchunks = (p->mpad + 2047) / 2048;
+    double* d_partial = nullptr;
+    B2D_CUDA(cudaMalloc(&d_partial, (size_t)nchunks * p->npad * sizeof(double)));
+    B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t row_bytes = (size_t)p->nb * TILE * sizeof(double);
+    size_t budget = g_emb_budget_bytes ? (size_t)g_emb_budget_bytes
+                                       : (size_t)((double)(free_b + p->emb_bytes) * 0.85);
+    int64_t QR = (int64_t)(budget / std::max<size_t>(row_bytes, 1)) / 2048 * 2048;
+    if (QR < 2048) {
+        cudaFree(d_partial);
+        return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for 2048 node rows");
+    }
+    QR = std::min<int64_t>(QR, (p->mpad + 2047) / 2048 * 2048);
+    int rc = ensure_emb(p, (size_t)QR * row_bytes);
+    if (rc) {
+        cudaFree(d_partial);
+        return rc;
+    }
+    if (!p->d_state) B2D_CUDA(cudaMalloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
+    const int weighted = weight > 0.0 ? 1 : 0;
+    for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
+        const int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
+        B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, (size_t)QR * row_bytes, p->stream));
+        k_scatter_dense<int64_t><<<sblocks, wpb * 32, 0, p->stream>>>(
+            p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->n, q0, q1, QR,
+            (unsigned long long*)p->d_emb, 0);
+        k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
+            (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR, p->d_state,
+            p->order.depth_at[q0 / NODE_STRIPE]);
+        dim3 grid((unsigned)(p->npad / 128), (unsigned)((q1 - q0 + 2047) / 2048));
+        k_phydiv_partial<<<grid, 128, 0, p->stream>>>((const unsigned long long*)p->d_emb, p->d_len + q0,
+                                                       p->d_total, p->npad, q1 - q0, QR, rooted, weighted,
+                                                       weight, d_partial, q0 / 2048);
+    }
+    k_phydiv_reduce<<<(unsigned)((p->npad + 255) / 256), 256, 0, p->stream>>>(d_partial, nchunks, p->npad,
+                                                                              p->d_svec);
+    B2D_CUDA(cudaMemcpyAsync(out_n, p->d_svec, p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    B2D_CUDA(cudaGetLastError());
+    cudaFree(d_partial);
+    p->computed = false;  // d_total / d_svec no longer describe a distance computation
+    return B2D_OK;
+}
+
 int64_t b2d_problem_result_len(const b2d_problem* p) { return p ? p->out_len : 0; }
 
 static void stripe_range(const b2d_problem* p, int64_t b, int64_t* first, int64_t* count) {

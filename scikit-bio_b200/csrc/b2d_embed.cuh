@@ -279,6 +279,64 @@ k_propagate_weighted_top(unsigned long long* __restrict__ emb, const int32_t* __
     }
 }
 
+// Generalised phylogenetic diversity (_phydiv, /root/reference/skbio/diversity/alpha/_pd.py:190-239)
+// from int64 subtree counts: per sample  sum_q len_q * g(count_q)  with
+//   unweighted: g = [count > 0] (and count < total when unrooted)
+//   weighted  : f = count/total; unrooted: f = 2*min(f, 1-f); theta < 1: f = f^theta; g = f
+// thread = sample, grid.y = chunks of 2048 node rows -> partial[chunk][sample]; summed in chunk
+// order afterwards (two-level, deterministic).
+__global__ void __launch_bounds__(128)
+k_phydiv_partial(const unsigned long long* __restrict__ emb, const double* __restrict__ len_rel,
+                 const long long* __restrict__ total, int64_t npad, int64_t rows, int64_t QR,
+                 int rooted, int weighted, double theta, double* __restrict__ partial,
+                 int64_t chunk0) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad) return;
+    const int64_t blk = s / TILE, sl = s % TILE;
+    const unsigned long long* p = emb + (blk * QR) * TILE + sl;
+    const long long tot = total[s];
+    const double totd = (double)tot;
+    const int64_t qa = (int64_t)blockIdx.y * 2048, qb = (qa + 2048 < rows) ? qa + 2048 : rows;
+    double acc = 0.0;
+    if (tot > 0) {
+        for (int64_t q = qa; q < qb; ++q) {
+            const long long c = (long long)p[q * TILE];
+            if (c <= 0) continue;
+            if (!weighted) {
+                if (rooted || c < tot) acc += len_rel[q];
+            } else {
+                double f = (double)c / totd;
+                if (!rooted) f = 2.0 * fmin(f, 1.0 - f);
+                if (theta < 1.0) f = pow(f, theta);
+                acc += len_rel[q] * f;
+            }
+        }
+    }
+    partial[(chunk0 + blockIdx.y) * npad + s] = acc;
+}
+
+__global__ void k_phydiv_reduce(const double* __restrict__ partial, int64_t nchunks, int64_t npad,
+                                double* __restrict__ out) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad) return;
+    double v = 0.0;
+    for (int64_t c = 0; c < nchunks; ++c) v += partial[c * npad + s];
+    out[s] = v;
+}
+
+// every count of the sample, wherever it was placed (= the root's subtree count)
+__global__ void k_sample_totals_all(const int64_t* __restrict__ indptr, const int64_t* __restrict__ values,
+                                    int64_t n, long long* __restrict__ total) {
+    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (s >= n) return;
+    long long t = 0;
+    for (int64_t e = indptr[s] + lane; e < indptr[s + 1]; e += 32) t += values ? values[e] : 1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) total[s] = t;
+}
+
 // int64 subtree counts -> fp64 proportions count/total (the count itself when total == 0,
 // as _weighted_unifrac does, beta/_unifrac.py:399-410).  Elementwise, in place, two samples
 // (16 bytes) per thread; HBM-bound.

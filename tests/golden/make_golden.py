@@ -81,6 +81,13 @@ def run_case(name, newick, counts, taxa, ids=None, dtype="int"):
         fp = alpha_diversity("faith_pd", counts.astype(int) if counts.dtype != bool else counts,
                              ids, tree=tree, taxa=taxa)
     out["results"]["faith_pd"] = [float(x) for x in fp.values]
+    icounts = counts.astype(int) if counts.dtype != bool else counts
+    for rooted in (True, False):
+        for weight in (False, True, 0.5):
+            with np.errstate(all="ignore"):
+                pv = alpha_diversity("phydiv", icounts, ids, tree=tree, taxa=taxa, rooted=rooted,
+                                     weight=weight, validate=False)
+            out["results"][f"phydiv_r{int(rooted)}_w{float(weight)}"] = [float(x) for x in pv.values]
     return out
 
 

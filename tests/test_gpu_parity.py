@@ -70,6 +70,21 @@ def test_faith_pd_matches_reference(case):
     assert_close_rel(got.values, case["results"]["faith_pd"], UNIFRAC_RTOL, case["name"] + " faith_pd")
 
 
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_phydiv_matches_reference(case):
+    """alpha_diversity('phydiv') for rooted/unrooted x unweighted/weighted/theta=0.5."""
+    sb = _skbio_b200()
+    counts, parent, length, names = case_arrays(case)
+    tree = sb.read_newick_flat(case["newick"])
+    icounts = counts.astype(int) if counts.dtype != bool else counts
+    for rooted in (True, False):
+        for weight in (False, True, 0.5):
+            exp = case["results"][f"phydiv_r{int(rooted)}_w{float(weight)}"]
+            got = sb.alpha_diversity("phydiv", icounts, case["ids"], tree=tree, taxa=case["taxa"],
+                                     rooted=rooted, weight=weight, validate=False)
+            assert_close_rel(got.values, exp, 1e-12, f"{case['name']} phydiv r={rooted} w={weight}")
+
+
 def test_qiime_tiny_test(qiime_tt):
     sb = _skbio_b200()
     counts = np.array(qiime_tt["counts"])
