@@ -118,8 +118,6 @@ def read_newick(text):
     n = len(s)
     i = 0
     root = SimpleTreeNode()
-    cur = root
-    expect_label_for = root  # node whose label/length would be read next
 
     def skip_ws_comments(i):
         while i < n:

@@ -27,7 +27,6 @@ thread_local std::string g_last_error;
 static int64_t g_chunk_nodes = 8192;           // nodes per pair-kernel launch
 static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
-static int g_weighted_variant = 3;             // 2 = 128x128 tiles / 8x4 threads, 3 = ILP variant
 static int g_walk_decomposed = 1;              // 0 = always the sequential weighted walk
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 
@@ -357,8 +356,6 @@ int b2d_set_option(const char* name, int64_t value) {
         g_walk_decomposed = value ? 1 : 0;
     } else if (s == "sparse_features") {
         g_sparse_features = value < 0 ? -1 : (value ? 1 : 0);
-    } else if (s == "weighted_variant") {
-        g_weighted_variant = value == 2 ? 2 : 3;
     } else if (s == "plain_kernels") {
         g_plain_kernels = value ? 1 : 0;
     } else {
@@ -494,8 +491,6 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
                               int64_t q0, int64_t q1, int64_t QR, int epilogue) {
     // node chunks [qa, qb) relative to the resident range; two-level fp64 summation:
     // registers within a chunk, `out` across chunks.
-    B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)WK_SMEM));
     B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)W3_SMEM));
     for (int64_t qa = 0; qa < q1 - q0; qa += g_chunk_nodes) {
@@ -518,8 +513,6 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
         if (rc) return rc;
         if (plain_kernels())
             k_pair_weighted_plain<<<(unsigned)p->ntiles, 256, 0, st>>>(emb, len_rel, a);
-        else if (g_weighted_variant == 2)
-            k_pair_weighted<<<(unsigned)p->ntiles, WK_THREADS, WK_SMEM, st>>>(emb, len_rel, a);
         else
             k_pair_weighted_v3<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, st>>>(emb, len_rel, a);
         p->n_launch += 1;

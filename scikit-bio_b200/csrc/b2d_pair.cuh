@@ -96,145 +96,11 @@ k_finalize(double* __restrict__ out, const double* __restrict__ out2,
     }
 }
 
-// =========================================================================================
-// Weighted kernel: acc[i][j] += len_q * |p_q,i - p_q,j|   (also Bray-Curtis with len == 1)
-// 512 compute threads (16 row groups x 32 column groups, each thread an 8x4 register tile of
-// fp64 accumulators) + one producer warp that feeds a 4-stage ring of {A rows, B rows,
-// lengths} with bulk copies.  FP64-pipe bound: 2 FP64 instructions (DADD + DFMA) per
-// node-pair term.  Four compute warps per SM sub-partition hide the DADD->DFMA latency that
-// ptxas' schedule exposes (ncu round 1: 2 warps/SMSP gave 67 % FP64 pipe utilisation with
-// "wait" as the top stall).
-// =========================================================================================
-#define WK_DSUB(d, x, y) asm volatile("sub.f64 %0, %1, %2;" : "=d"(d) : "d"(x), "d"(y))
-#define WK_DFMA_ABS(acc, d, l)                                                       \
-    asm volatile("{\n\t.reg .f64 t;\n\tabs.f64 t, %1;\n\tfma.rn.f64 %0, t, %2, %0;\n\t}" \
-                 : "+d"(acc)                                                         \
-                 : "d"(d), "d"(l))
-
-constexpr int WK_KS = 16;      // nodes per stage
-constexpr int WK_STAGES = 4;
-constexpr int WK_CWARPS = 16;  // compute warps
-constexpr int WK_THREADS = WK_CWARPS * 32 + 32;
-constexpr int WK_STAGE_DOUBLES = 2 * WK_KS * TILE + WK_KS;  // A + B + len
-constexpr size_t WK_SMEM = (size_t)WK_STAGES * WK_STAGE_DOUBLES * sizeof(double) + 2 * WK_STAGES * sizeof(uint64_t);
-
-__global__ void __launch_bounds__(WK_THREADS, 1)
-k_pair_weighted(const double* __restrict__ emb, const double* __restrict__ len_q, PairArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* stage_base = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WK_STAGES * WK_STAGE_DOUBLES * sizeof(double));
-    uint64_t* empty = full + WK_STAGES;
-
-    const int tid = threadIdx.x;
-    const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
-    const int64_t niter = (a.qb - a.qa) / WK_KS;
-
-    if (tid == 0) {
-        for (int s = 0; s < WK_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], WK_CWARPS);  // one arrive per compute warp
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if (tid >= WK_CWARPS * 32) {
-        // ---------------- producer warp ----------------
-        if (tid == WK_CWARPS * 32) {
-            const double* Ag = emb + ((int64_t)bi * a.QR + a.qa) * TILE;
-            const double* Bg = emb + ((int64_t)bj * a.QR + a.qa) * TILE;
-            const double* Lg = len_q + a.qa;
-            for (int64_t it = 0; it < niter; ++it) {
-                int s = (int)(it % WK_STAGES);
-                uint32_t ph = (uint32_t)((it / WK_STAGES) & 1);
-                if (it >= WK_STAGES) mbar_wait(&empty[s], ph ^ 1u);
-                double* A = stage_base + (size_t)s * WK_STAGE_DOUBLES;
-                double* B = A + WK_KS * TILE;
-                double* L = B + WK_KS * TILE;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)(WK_STAGE_DOUBLES * sizeof(double)));
-                bulk_g2s(A, Ag + it * WK_KS * TILE, WK_KS * TILE * sizeof(double), &full[s]);
-                bulk_g2s(B, Bg + it * WK_KS * TILE, WK_KS * TILE * sizeof(double), &full[s]);
-                bulk_g2s(L, Lg + it * WK_KS, WK_KS * sizeof(double), &full[s]);
-            }
-        }
-        return;
-    }
-
-    // ---------------- compute warps ----------------
-    // thread (ty, tx): rows ty*8 .. ty*8+7 ; columns {tx*2, tx*2+1, 64+tx*2, 64+tx*2+1}
-    const int tx = tid & 31, ty = tid >> 5;
-    double acc[8][4];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-
-    for (int64_t it = 0; it < niter; ++it) {
-        int s = (int)(it % WK_STAGES);
-        uint32_t ph = (uint32_t)((it / WK_STAGES) & 1);
-        mbar_wait(&full[s], ph);
-        const double* A = stage_base + (size_t)s * WK_STAGE_DOUBLES;
-        const double* B = A + WK_KS * TILE;
-        const double* L = B + WK_KS * TILE;
-#pragma unroll 4
-        for (int k = 0; k < WK_KS; ++k) {
-            double av[8], bv[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                double2 t = *reinterpret_cast<const double2*>(A + k * TILE + ty * 8 + h * 2);
-                av[2 * h] = t.x;
-                av[2 * h + 1] = t.y;
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double2 u = *reinterpret_cast<const double2*>(B + k * TILE + h * 64 + tx * 2);
-                bv[2 * h] = u.x;
-                bv[2 * h + 1] = u.y;
-            }
-            const double l = L[k];
-            // Software-pipelined in batches of 8 terms (2 rows x 4 columns): the DADDs of
-            // batch b+1 are interleaved with the DFMAs of batch b, so a DFMA never issues
-            // right behind the DADD it depends on.  The volatile asm pins this order in the
-            // PTX (nvcc otherwise emits sub/fma back to back and ptxas keeps them so).
-            double d0[8], d1[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) WK_DSUB(d0[j], av[j >> 2], bv[j & 3]);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (b & 1) {
-                        WK_DFMA_ABS(acc[2 * b + (j >> 2)][j & 3], d1[j], l);
-                        if (b < 3) WK_DSUB(d0[j], av[2 * (b + 1) + (j >> 2)], bv[j & 3]);
-                    } else {
-                        WK_DFMA_ABS(acc[2 * b + (j >> 2)][j & 3], d0[j], l);
-                        if (b < 3) WK_DSUB(d1[j], av[2 * (b + 1) + (j >> 2)], bv[j & 3]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
-    }
-
-    // ---------------- epilogue ----------------
-    const int64_t base = a.row_base[bi];
-    const int64_t i0 = (int64_t)bi * TILE;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        int64_t i = i0 + ty * 8 + r;
-        if (i >= a.n) continue;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int64_t j = (int64_t)bj * TILE + (c >> 1) * 64 + tx * 2 + (c & 1);
-            emit(a, base, i0, i, j, acc[r][c]);
-        }
-    }
-}
+constexpr int WK_KS = 16;  // nodes per staging step of the plain cross-check kernel
 
 // =========================================================================================
-// Weighted kernel, variant 3 (default): same arithmetic, scheduled for instruction-level
-// parallelism instead of relying on many warps.
+// Weighted kernel (default):  acc[i][j] += len_q * |p_q,i - p_q,j|  (also dense Bray-Curtis
+// with len == 1), scheduled for instruction-level parallelism instead of relying on many warps.
 //   * one CTA owns a 64x128 half tile (grid = 2 x tiles); 8 compute warps, each a 32x32
 //     patch of pairs, each thread an 8x4 register tile; thread patches are 2-D inside the warp
 //     (4 row groups x 8 column groups) so one node costs 6 shared-memory wavefronts per warp;
