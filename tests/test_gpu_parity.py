@@ -525,3 +525,50 @@ def test_permanova_matches_reference():
         sb.permanova(dm, ["a", "b"])
     with pytest.raises(TypeError, match="Input must be a DistanceMatrix"):
         sb.permanova(np.zeros((3, 3)), ["a", "b", "a"])
+
+
+def test_reference_driver_known_answers():
+    """The reference's own beta_diversity tests, on the engine
+    (/root/reference/skbio/diversity/tests/test_driver.py:364-385, 625-713): hand-computed UniFrac
+    values to 6 places, Bray-Curtis goldens, DataFrame index -> ids, counts vs presence/absence
+    equality for qualitative metrics."""
+    import pandas as pd
+
+    sb = _skbio_b200()
+    table1 = [[1, 5], [2, 3], [0, 1]]
+    sids1 = list("ABC")
+    tree1 = sb.read_newick("((O1:0.25, O2:0.50):0.25, O3:0.75)root;")
+    oids1 = ["O1", "O2"]
+    dm = sb.beta_diversity("unweighted_unifrac", table1, sids1, taxa=oids1, tree=tree1)
+    assert dm.shape == (3, 3)
+    np.testing.assert_almost_equal(np.asarray(dm.data), [[0, 0, 0.25], [0, 0, 0.25], [0.25, 0.25, 0]], 6)
+    dm = sb.beta_diversity("weighted_unifrac", table1, sids1, taxa=oids1, tree=tree1)
+    np.testing.assert_almost_equal(np.asarray(dm.data),
+                                   [[0, 0.175, 0.12499999], [0.175, 0, 0.3], [0.12499999, 0.3, 0]], 6)
+    dm = sb.beta_diversity("weighted_unifrac", table1, sids1, taxa=oids1, tree=tree1, normalized=True)
+    np.testing.assert_almost_equal(np.asarray(dm.data),
+                                   [[0, 0.128834, 0.085714], [0.128834, 0, 0.2142857], [0.085714, 0.2142857, 0]], 6)
+    dm = sb.beta_diversity("braycurtis", table1, sids1)
+    np.testing.assert_almost_equal(dm.condensed_form(), [0.27272727, 0.71428571, 0.66666667], 6)
+    table2 = [[23, 64, 14, 0, 0, 3, 1], [0, 3, 35, 42, 0, 12, 1], [0, 5, 5, 0, 40, 40, 0],
+              [44, 35, 9, 0, 1, 0, 0], [0, 2, 8, 0, 35, 45, 1], [0, 0, 25, 35, 0, 19, 0]]
+    sids2 = list("ABCDEF")
+    dm = sb.beta_diversity("braycurtis", table2, sids2)
+    exp = [[0, 0.78787879, 0.86666667, 0.30927835, 0.85714286, 0.81521739],
+           [0.78787879, 0, 0.78142077, 0.86813187, 0.75, 0.1627907],
+           [0.86666667, 0.78142077, 0, 0.87709497, 0.09392265, 0.71597633],
+           [0.30927835, 0.86813187, 0.87709497, 0, 0.87777778, 0.89285714],
+           [0.85714286, 0.75, 0.09392265, 0.87777778, 0, 0.68235294],
+           [0.81521739, 0.1627907, 0.71597633, 0.89285714, 0.68235294, 0]]
+    np.testing.assert_almost_equal(np.asarray(dm.data), exp, 6)
+    # DataFrame index becomes the ids (issue 1808)
+    df = pd.DataFrame(table2, index=sids2)
+    assert list(sb.beta_diversity("jaccard", df).ids) == sids2
+    # qualitative metrics: counts and presence/absence give the same matrix (issue 1549)
+    table3 = table2 + [[88, 31, 0, 5, 5, 5, 5], [44, 39, 0, 0, 0, 0, 0]]
+    pa = np.asarray(table3) > 0
+    a = sb.beta_diversity("jaccard", table3).condensed_form()
+    b = sb.beta_diversity("jaccard", pa).condensed_form()
+    assert np.array_equal(a, b)
+    assert not np.array_equal(sb.beta_diversity("braycurtis", table3).condensed_form(),
+                              sb.beta_diversity("braycurtis", pa.astype(int)).condensed_form())
