@@ -143,7 +143,10 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
 /* Device-side phase timings of the last compute, milliseconds (CUDA events on the
  * problem's stream): [0] embedding build, [1] pair kernels, [2] total compute,
  * [3] last fetch (D2H), [4] upload at create (H2D), [5] last pair-kernel launch count,
- * [6] nodes resident per pass, [7] number of passes. */
+ * [6] nodes resident per pass, [7] number of passes, [8] node visits the weighted pair
+ * kernel executed (per 32x32 sample patch) and [9] the visits a kernel without zero-block
+ * skipping would make (both 0 when skipping was not used), [10] the part of [1] spent on
+ * the skipping bitmaps and closed-form sums.  n: slots to fill (<= 11). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);

@@ -16,6 +16,7 @@
 #include "b2d_common.cuh"
 #include "b2d_embed.cuh"
 #include "b2d_pair.cuh"
+#include "b2d_skip.cuh"
 #include "b2d_sparse.cuh"
 #include "b2d_permanova.cuh"
 #include "b2d_tree.h"
@@ -28,6 +29,7 @@ static int64_t g_chunk_nodes = 8192;           // nodes per pair-kernel launch
 static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
 static int g_walk_decomposed = 1;              // 0 = always the sequential weighted walk
+static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 
 static bool plain_kernels() {
@@ -119,7 +121,7 @@ struct b2d_problem {
     bool has_values = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // odd node chunks run here, into d_out2 (tails overlap)
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_sync[2] = {nullptr, nullptr};
     TreeOrder order;
     // device inputs
@@ -153,6 +155,15 @@ struct b2d_problem {
     void* d_emb = nullptr;
     size_t emb_bytes = 0;
     long long* d_state = nullptr;
+    // zero-block skipping (weighted pair kernel)
+    uint32_t* d_nz = nullptr;         // [npad/32][QR/32] group x node-row bitmaps
+    size_t nz_bytes = 0;
+    double* d_skipsum = nullptr;      // [npad/32][npad]
+    int32_t* d_glist[2] = {nullptr, nullptr};
+    int32_t* d_sblist[2] = {nullptr, nullptr};
+    int n_glist[2] = {0, 0}, n_sblist[2] = {0, 0};
+    unsigned long long* d_exec = nullptr;
+    double skip_executed = 0, skip_dense = 0, t_skip_prep = 0;
     // sparse feature-table path
     SpEntry* d_sp_entries = nullptr;
     int64_t* d_sp_ptr = nullptr;
@@ -176,6 +187,8 @@ static void free_problem(b2d_problem* p) {
     cudaFree(p->d_out2); cudaFree(p->d_owned);
     cudaFree(p->d_flags1); cudaFree(p->d_spans); cudaFree(p->d_top_pos); cudaFree(p->d_top_flags);
     cudaFree(p->d_sp_entries); cudaFree(p->d_sp_ptr);
+    cudaFree(p->d_nz); cudaFree(p->d_skipsum); cudaFree(p->d_exec);
+    for (int k = 0; k < 2; ++k) { cudaFree(p->d_glist[k]); cudaFree(p->d_sblist[k]); }
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -358,6 +371,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_sparse_features = value < 0 ? -1 : (value ? 1 : 0);
     } else if (s == "plain_kernels") {
         g_plain_kernels = value ? 1 : 0;
+    } else if (s == "weighted_skip") {
+        g_weighted_skip = value ? 1 : 0;
     } else {
         return fail(B2D_ERR_INVALID_ARGUMENT, "unknown option " + s);
     }
@@ -487,11 +502,62 @@ static int finalize(b2d_problem* p, int epilogue) {
     return B2D_OK;
 }
 
+// Zero-block skipping: device buffers that do not depend on the resident node range.
+static int skip_setup(b2d_problem* p) {
+    if (!p->d_skipsum) {
+        const int64_t ng = p->npad / 32;
+        B2D_CUDA(cudaMalloc(&p->d_skipsum, (size_t)ng * p->npad * sizeof(double)));
+        B2D_CUDA(cudaMalloc(&p->d_exec, sizeof(unsigned long long)));
+        // launch 0: groups of the owned row stripes x every sample block;
+        // launch 1: all other groups x the samples of the owned stripes
+        std::vector<int32_t> gl[2], sl[2];
+        std::vector<char> is_owned(p->nb, 0);
+        for (int64_t b : p->owned) is_owned[b] = 1;
+        for (int64_t b = 0; b < p->nb; ++b) {
+            for (int g = 0; g < 4; ++g) gl[is_owned[b] ? 0 : 1].push_back((int32_t)(4 * b + g));
+            sl[0].push_back((int32_t)b);
+            if (is_owned[b]) sl[1].push_back((int32_t)b);
+        }
+        for (int k = 0; k < 2; ++k) {
+            int rc;
+            if ((rc = upload(&p->d_glist[k], gl[k].data(), gl[k].size(), p->stream))) return rc;
+            if ((rc = upload(&p->d_sblist[k], sl[k].data(), sl[k].size(), p->stream))) return rc;
+            p->n_glist[k] = (int)gl[k].size();
+            p->n_sblist[k] = (int)sl[k].size();
+        }
+        B2D_CUDA(cudaStreamSynchronize(p->stream));  // host vectors go out of scope
+    }
+    B2D_CUDA(cudaMemsetAsync(p->d_skipsum, 0, (size_t)(p->npad / 32) * p->npad * sizeof(double), p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_exec, 0, sizeof(unsigned long long), p->stream));
+    return B2D_OK;
+}
+
+// bitmaps + skip sums of the resident rows [0, rows)
+static int skip_prepare_pass(b2d_problem* p, const double* len_rel, int64_t rows, int64_t QR) {
+    const int64_t ng = p->npad / 32, words = QR / 32;
+    const int64_t warps = ng * words;
+    k_group_nonzero<<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
+        (const double*)p->d_emb, ng, rows, QR, p->d_nz);
+    B2D_CUDA(cudaFuncSetAttribute(k_group_skipsums, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)SS_SMEM));
+    for (int k = 0; k < 2; ++k) {
+        if (!p->n_glist[k] || !p->n_sblist[k]) continue;
+        dim3 grid((unsigned)p->n_sblist[k], (unsigned)((p->n_glist[k] + 31) / 32));
+        k_group_skipsums<<<grid, SS_WARPS * 32, SS_SMEM, p->stream>>>(
+            (const double*)p->d_emb, len_rel, p->d_nz, p->d_glist[k], p->n_glist[k],
+            p->d_sblist[k], p->npad, rows, QR, p->d_skipsum);
+    }
+    B2D_CUDA(cudaGetLastError());
+    return B2D_OK;
+}
+
 static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* len_rel,
-                              int64_t q0, int64_t q1, int64_t QR, int epilogue) {
+                              int64_t q0, int64_t q1, int64_t QR, int epilogue, bool skip) {
     // node chunks [qa, qb) relative to the resident range; two-level fp64 summation:
     // registers within a chunk, `out` across chunks.
     B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)W3_SMEM));
+    B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_mask, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)W3_SMEM));
     for (int64_t qa = 0; qa < q1 - q0; qa += g_chunk_nodes) {
         int64_t qb = std::min<int64_t>(q1 - q0, qa + g_chunk_nodes);
@@ -511,7 +577,10 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
         cudaStream_t st;
         int rc = chunk_target(p, &st, &a.out, &a.first);
         if (rc) return rc;
-        if (plain_kernels())
+        if (skip)
+            k_pair_weighted_mask<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, st>>>(
+                emb, len_rel, p->d_nz, p->d_exec, a);
+        else if (plain_kernels())
             k_pair_weighted_plain<<<(unsigned)p->ntiles, 256, 0, st>>>(emb, len_rel, a);
         else
             k_pair_weighted_v3<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, st>>>(emb, len_rel, a);
@@ -540,9 +609,16 @@ static int compute_dense(b2d_problem* p, int metric) {
     // the second raw-sum buffer must exist before the embedding takes its share of memory
     if (p->ntiles && p->mpad > g_chunk_nodes && !p->d_out2)
         B2D_CUDA(cudaMalloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+    const bool skip = g_weighted_skip && !plain_kernels() && !p->custom_tiles && p->ntiles > 0;
+    p->skip_executed = p->skip_dense = 0;
+    if (skip) {
+        int rc0 = skip_setup(p);
+        if (rc0) return rc0;
+    }
     // resident node range
     size_t free_b = 0, total_b = 0;
     B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // one node row: 8 B per sample (+ 1 bit per 32-sample group for the skipping bitmaps)
     size_t row_bytes = (size_t)p->nb * TILE * sizeof(double);
     size_t budget = g_emb_budget_bytes ? (size_t)g_emb_budget_bytes
                                        : (size_t)((double)(free_b + p->emb_bytes) * 0.85);
@@ -550,7 +626,18 @@ static int compute_dense(b2d_problem* p, int metric) {
     QR = QR / NODE_STRIPE * NODE_STRIPE;
     if (QR < NODE_STRIPE) return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for one node stripe");
     QR = std::min<int64_t>(QR, p->mpad);
-    int rc = ensure_emb(p, (size_t)QR * row_bytes);
+    int rc = B2D_OK;
+    if (skip) {
+        const size_t need = (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t);
+        if (p->nz_bytes < need) {
+            cudaFree(p->d_nz);
+            p->d_nz = nullptr;
+            p->nz_bytes = 0;
+            B2D_CUDA(cudaMalloc(&p->d_nz, need));
+            p->nz_bytes = need;
+        }
+    }
+    rc = ensure_emb(p, (size_t)QR * row_bytes);
     if (rc) return rc;
     if (tree && !p->d_state)
         B2D_CUDA(cudaMalloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
@@ -561,7 +648,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     p->n_pass = 0;
     p->chunk_counter = 0;
     p->nodes_resident = (double)QR;
-    double t_embed = 0, t_pair = 0;
+    double t_embed = 0, t_pair = 0, t_prep = 0;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
         int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
@@ -602,11 +689,21 @@ static int compute_dense(b2d_problem* p, int metric) {
         }
         B2D_CUDA(cudaEventRecord(eb, p->stream));
         if (p->ntiles) {
+            if (skip) {
+                if ((rc = skip_prepare_pass(p, p->d_len + q0, q1 - q0, QR))) return rc;
+                B2D_CUDA(cudaEventRecord(p->ev[4], p->stream));
+            }
             if ((rc = fork_streams(p))) return rc;
-            rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue);
+            rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue, skip);
             if (rc) return rc;
             if ((rc = join_streams(p))) return rc;
-            if (q1 == p->mpad && (rc = finalize(p, epilogue))) return rc;
+            if (q1 == p->mpad) {
+                if (skip && p->out_len && !p->owned.empty()) {
+                    k_add_skipsums<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
+                        p->d_out, p->d_owned, p->d_row_base, p->n, p->npad, p->d_skipsum);
+                }
+                if ((rc = finalize(p, epilogue))) return rc;
+            }
         }
         B2D_CUDA(cudaEventRecord(ec, p->stream));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
@@ -614,11 +711,22 @@ static int compute_dense(b2d_problem* p, int metric) {
         t_embed += ms;
         cudaEventElapsedTime(&ms, eb, ec);
         t_pair += ms;
+        if (skip && p->ntiles) {
+            cudaEventElapsedTime(&ms, eb, p->ev[4]);
+            t_prep += ms;
+        }
         p->n_pass += 1;
     }
     B2D_CUDA(cudaGetLastError());
+    if (skip) {
+        unsigned long long ex = 0;
+        B2D_CUDA(cudaMemcpy(&ex, p->d_exec, sizeof(ex), cudaMemcpyDeviceToHost));
+        p->skip_executed = (double)ex;                                   // warp-patch x node visits
+        p->skip_dense = (double)p->ntiles * 16.0 * (double)p->m;         // without skipping
+    }
     p->t_embed = t_embed;
     p->t_pair = t_pair;
+    p->t_skip_prep = t_prep;
     return B2D_OK;
 }
 
@@ -640,6 +748,7 @@ static int compute_bits(b2d_problem* p, int metric) {
     }
     B2D_CUDA(cudaEventRecord(eb, p->stream));
     p->n_launch = 0;
+    p->skip_executed = p->skip_dense = p->t_skip_prep = 0;
     B2D_CUDA(cudaFuncSetAttribute(k_pair_unweighted_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)UL_SMEM));
     p->chunk_counter = 0;
@@ -762,6 +871,7 @@ static int compute_sparse(b2d_problem* p, int metric) {
         p->d_svec);
     B2D_CUDA(cudaEventRecord(eb, p->stream));
     p->n_launch = 0;
+    p->skip_executed = p->skip_dense = p->t_skip_prep = 0;
     p->chunk_counter = 0;
     if (p->ntiles) {
         B2D_CUDA(cudaFuncSetAttribute(k_pair_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM2));
@@ -1031,9 +1141,10 @@ int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[8] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
-                   p->n_launch, p->nodes_resident, p->n_pass};
-    for (int i = 0; i < n && i < 8; ++i) ms[i] = v[i];
+    double v[11] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+                    p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
+                    p->t_skip_prep};
+    for (int i = 0; i < n && i < 11; ++i) ms[i] = v[i];
     return B2D_OK;
 }
 

@@ -145,13 +145,67 @@ def test_plain_and_bulk_copy_kernels_agree_bitwise():
     parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.05, 9)
     node_ids = tip_node[cols]
     res = {}
-    for plain in (0, 1):
-        _capi.set_option("plain_kernels", plain)
-        with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
-            prob.compute("weighted_unifrac_normalized")
-            res[plain] = prob.fetch(np.empty(n * (n - 1) // 2))
-    _capi.set_option("plain_kernels", 0)
+    _capi.set_option("weighted_skip", 0)   # same node set and order in both kernels
+    try:
+        for plain in (0, 1):
+            _capi.set_option("plain_kernels", plain)
+            with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+                prob.compute("weighted_unifrac_normalized")
+                res[plain] = prob.fetch(np.empty(n * (n - 1) // 2))
+    finally:
+        _capi.set_option("plain_kernels", 0)
+        _capi.set_option("weighted_skip", 1)
     assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("n,tips,lam,cat", [(700, 500, 0.1, False), (300, 3000, 0.004, False),
+                                            (161, 2500, 0.01, True), (40, 64, 0.5, False)])
+def test_zero_block_skipping_matches_the_dense_kernel(n, tips, lam, cat):
+    """The default weighted kernel skips nodes at which a 32-sample group is all zero and adds
+    their closed-form contribution afterwards; it must agree with the kernel that visits every
+    node (1e-13: summation order only) and with the oracle, also with several node passes,
+    small launch chunks and shards."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, lam, 21, caterpillar=cat)
+    node_ids = tip_node[cols]
+    total = n * (n - 1) // 2
+    res = {}
+    try:
+        for skip in (0, 1):
+            _capi.set_option("weighted_skip", skip)
+            with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+                for key in ("weighted_unifrac", "weighted_unifrac_normalized"):
+                    prob.compute(key)
+                    t = prob.timings()
+                    if skip:
+                        assert 0 < t["visits_executed"] <= t["visits_dense"]
+                    else:
+                        assert t["visits_dense"] == 0
+                    res[(skip, key)] = prob.fetch(np.empty(total))
+        _capi.set_option("chunk_nodes", 128)
+        _capi.set_option("emb_budget_bytes", ((n + 127) // 128) * 128 * 8 * 256)  # 256 node rows resident
+        out = np.full(total, -1.0)
+        for shard in range(2):
+            with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, shard=shard, n_shards=2) as prob:
+                prob.compute("weighted_unifrac")
+                if len(parent) > 256:
+                    assert prob.timings()["passes"] > 1
+                prob.fetch(out)
+        res["multi"] = out
+    finally:
+        _capi.set_option("weighted_skip", 1)
+        _capi.set_option("chunk_nodes", 0)
+        _capi.set_option("emb_budget_bytes", 0)
+    for key in ("weighted_unifrac", "weighted_unifrac_normalized"):
+        assert_close_rel(res[(1, key)], res[(0, key)], 1e-13, key + " skip vs dense")
+    assert_close_rel(res["multi"], res[(0, "weighted_unifrac")], 1e-13, "skip multi-pass shards")
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    exp = oracle_fast.unifrac_all(dense, tip_node, parent, length)
+    for key in ("weighted_unifrac", "weighted_unifrac_normalized"):
+        assert_close_rel(res[(1, key)], exp[key], UNIFRAC_RTOL, key + " skip vs oracle")
 
 
 def test_shards_and_passes_reassemble_the_same_vector():

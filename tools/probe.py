@@ -28,7 +28,7 @@ def run(n, tips, lam, keys, feat_keys=()):
                 t = prob.timings()
                 print(f"{key}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("e2e", "sparse", "permanova", "e2ef")):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("e2e", "sparse", "permanova", "e2ef", "skip", "skip1")):
     print("dfma peak inst/s", _capi.microbench(0), "copy B/s", _capi.microbench(1), "lds64 gathers/s", _capi.microbench(2), flush=True)
     run(4096, 20000, 0.02, ["weighted_unifrac_normalized", "unweighted_unifrac"], ["braycurtis", "jaccard"])
     if len(sys.argv) > 1 and sys.argv[1] == "big":
@@ -124,3 +124,41 @@ def e2e_features(n=10000, f=50000, lam=0.01):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "e2ef":
     e2e_features()
+
+
+def skip_probe(n=10000, tips=100000, lam=0.02):
+    """weighted kernel with and without zero-block skipping (same problem, same box)"""
+    parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=1)
+    indptr, cols, vals = synthetic.poisson_csr(n, tips, lam, seed=0)
+    P = n * (n - 1) // 2
+    res = {}
+    for skip in (0, 1):
+        _capi.set_option("weighted_skip", skip)
+        with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+            for rep in range(2):
+                prob.compute("weighted_unifrac_normalized")
+            t = prob.timings()
+            res[skip] = prob.fetch(np.empty(P))
+            frac = t["visits_executed"] / t["visits_dense"] if t["visits_dense"] else 1.0
+            print(f"n={n} tips={tips} lam={lam} skip={skip}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms "
+                  f"launches {t['pair_launches']} visits {frac:.3f} of dense -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
+    _capi.set_option("weighted_skip", 1)
+    for k in (1,):
+        d = np.abs(res[0] - res[k]) / np.maximum(np.abs(res[0]), 1e-300)
+        print(f"max rel diff skip={k} vs dense:", float(d.max()), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "skip":
+    skip_probe(4096, 20000, 0.02)
+    skip_probe()
+    skip_probe(10000, 100000, 0.005)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "skip1":
+    # one compute of the skipping path, for an ncu launch list
+    n, tips, lam = 4096, 20000, 0.02
+    parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=1)
+    indptr, cols, vals = synthetic.poisson_csr(n, tips, lam, seed=0)
+    with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+        prob.compute("weighted_unifrac_normalized")
+        print(prob.timings())
