@@ -159,9 +159,12 @@ struct b2d_problem {
     uint32_t* d_nz = nullptr;         // [npad/32][QR/32] group x node-row bitmaps
     size_t nz_bytes = 0;
     double* d_skipsum = nullptr;      // [npad/32][npad]
-    int32_t* d_glist[2] = {nullptr, nullptr};
+    uint32_t* d_zt = nullptr;         // [QR][ngw] transposed zero bitmaps (permuted groups)
+    size_t zt_bytes = 0;
+    int32_t* d_gperm = nullptr;       // [32 * ngw] groups of the owned stripes first; -1 = padding
+    int64_t ngw = 0, ngw_owned = 0;
     int32_t* d_sblist[2] = {nullptr, nullptr};
-    int n_glist[2] = {0, 0}, n_sblist[2] = {0, 0};
+    int n_sblist[2] = {0, 0};
     unsigned long long* d_exec = nullptr;
     double skip_executed = 0, skip_dense = 0, t_skip_prep = 0;
     // sparse feature-table path
@@ -188,7 +191,8 @@ static void free_problem(b2d_problem* p) {
     cudaFree(p->d_flags1); cudaFree(p->d_spans); cudaFree(p->d_top_pos); cudaFree(p->d_top_flags);
     cudaFree(p->d_sp_entries); cudaFree(p->d_sp_ptr);
     cudaFree(p->d_nz); cudaFree(p->d_skipsum); cudaFree(p->d_exec);
-    for (int k = 0; k < 2; ++k) { cudaFree(p->d_glist[k]); cudaFree(p->d_sblist[k]); }
+    for (int k = 0; k < 2; ++k) cudaFree(p->d_sblist[k]);
+    cudaFree(p->d_zt); cudaFree(p->d_gperm);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -508,21 +512,27 @@ static int skip_setup(b2d_problem* p) {
         const int64_t ng = p->npad / 32;
         B2D_CUDA(cudaMalloc(&p->d_skipsum, (size_t)ng * p->npad * sizeof(double)));
         B2D_CUDA(cudaMalloc(&p->d_exec, sizeof(unsigned long long)));
-        // launch 0: groups of the owned row stripes x every sample block;
-        // launch 1: all other groups x the samples of the owned stripes
-        std::vector<int32_t> gl[2], sl[2];
+        // group order of the transposed bitmaps: groups of the owned row stripes first.
+        // launch 0: those groups x every sample; launch 1: all other groups x owned samples
+        std::vector<int32_t> gperm, sl[2];
         std::vector<char> is_owned(p->nb, 0);
         for (int64_t b : p->owned) is_owned[b] = 1;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int64_t b = 0; b < p->nb; ++b)
+                if ((is_owned[b] != 0) == (pass == 0))
+                    for (int g = 0; g < 4; ++g) gperm.push_back((int32_t)(4 * b + g));
+            while (gperm.size() % 32) gperm.push_back(-1);
+            if (pass == 0) p->ngw_owned = (int64_t)gperm.size() / 32;
+        }
+        p->ngw = (int64_t)gperm.size() / 32;
         for (int64_t b = 0; b < p->nb; ++b) {
-            for (int g = 0; g < 4; ++g) gl[is_owned[b] ? 0 : 1].push_back((int32_t)(4 * b + g));
             sl[0].push_back((int32_t)b);
             if (is_owned[b]) sl[1].push_back((int32_t)b);
         }
+        int rc;
+        if ((rc = upload(&p->d_gperm, gperm.data(), gperm.size(), p->stream))) return rc;
         for (int k = 0; k < 2; ++k) {
-            int rc;
-            if ((rc = upload(&p->d_glist[k], gl[k].data(), gl[k].size(), p->stream))) return rc;
             if ((rc = upload(&p->d_sblist[k], sl[k].data(), sl[k].size(), p->stream))) return rc;
-            p->n_glist[k] = (int)gl[k].size();
             p->n_sblist[k] = (int)sl[k].size();
         }
         B2D_CUDA(cudaStreamSynchronize(p->stream));  // host vectors go out of scope
@@ -538,13 +548,19 @@ static int skip_prepare_pass(b2d_problem* p, const double* len_rel, int64_t rows
     const int64_t warps = ng * words;
     k_group_nonzero<<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
         (const double*)p->d_emb, ng, rows, QR, p->d_nz);
-    B2D_CUDA(cudaFuncSetAttribute(k_group_skipsums, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)SS_SMEM));
+    if (p->ngw) {
+        const int64_t tw = p->ngw * words;
+        k_transpose_bitmaps<<<(unsigned)((tw + 7) / 8), 256, 0, p->stream>>>(p->d_nz, p->d_gperm, p->ngw,
+                                                                           words, p->d_zt);
+    }
+    constexpr int KW = 16;
     for (int k = 0; k < 2; ++k) {
-        if (!p->n_glist[k] || !p->n_sblist[k]) continue;
-        dim3 grid((unsigned)p->n_sblist[k], (unsigned)((p->n_glist[k] + 31) / 32));
-        k_group_skipsums<<<grid, SS_WARPS * 32, SS_SMEM, p->stream>>>(
-            (const double*)p->d_emb, len_rel, p->d_nz, p->d_glist[k], p->n_glist[k],
+        const int kw0 = k == 0 ? 0 : (int)p->ngw_owned;
+        const int kwn = k == 0 ? (int)p->ngw_owned : (int)(p->ngw - p->ngw_owned);
+        if (!kwn || !p->n_sblist[k]) continue;
+        dim3 grid((unsigned)p->n_sblist[k] * 32, (unsigned)((kwn + KW - 1) / KW));
+        k_sample_skipsums<KW><<<grid, 128, 0, p->stream>>>(
+            (const double*)p->d_emb, len_rel, p->d_zt, p->d_gperm, p->ngw, kw0, kwn,
             p->d_sblist[k], p->npad, rows, QR, p->d_skipsum);
     }
     B2D_CUDA(cudaGetLastError());
@@ -557,10 +573,12 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
     // registers within a chunk, `out` across chunks.
     B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)W3_SMEM));
-    B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_mask, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)W3_SMEM));
-    for (int64_t qa = 0; qa < q1 - q0; qa += g_chunk_nodes) {
-        int64_t qb = std::min<int64_t>(q1 - q0, qa + g_chunk_nodes);
+B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_mask, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)MK_SMEM));
+    // launches of the skipping kernel are about half as long per node: twice the nodes each
+    const int64_t chunk = skip ? 2 * g_chunk_nodes : g_chunk_nodes;
+    for (int64_t qa = 0; qa < q1 - q0; qa += chunk) {
+        int64_t qb = std::min<int64_t>(q1 - q0, qa + chunk);
         PairArgs a;
         a.tiles = p->d_tiles;
         a.row_base = p->d_row_base;
@@ -578,7 +596,7 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
         int rc = chunk_target(p, &st, &a.out, &a.first);
         if (rc) return rc;
         if (skip)
-            k_pair_weighted_mask<<<(unsigned)(2 * p->ntiles), W3_THREADS, W3_SMEM, st>>>(
+            k_pair_weighted_mask<<<(unsigned)(2 * p->ntiles), W3_THREADS, MK_SMEM, st>>>(
                 emb, len_rel, p->d_nz, p->d_exec, a);
         else if (plain_kernels())
             k_pair_weighted_plain<<<(unsigned)p->ntiles, 256, 0, st>>>(emb, len_rel, a);
@@ -635,6 +653,14 @@ static int compute_dense(b2d_problem* p, int metric) {
             p->nz_bytes = 0;
             B2D_CUDA(cudaMalloc(&p->d_nz, need));
             p->nz_bytes = need;
+        }
+        const size_t need_t = (size_t)QR * p->ngw * sizeof(uint32_t);
+        if (p->zt_bytes < need_t) {
+            cudaFree(p->d_zt);
+            p->d_zt = nullptr;
+            p->zt_bytes = 0;
+            B2D_CUDA(cudaMalloc(&p->d_zt, need_t));
+            p->zt_bytes = need_t;
         }
     }
     rc = ensure_emb(p, (size_t)QR * row_bytes);

@@ -35,98 +35,93 @@ k_group_nonzero(const double* __restrict__ emb, int64_t ngroups, int64_t rows, i
     if (lane == 0) nz[g * words + w] = bits;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
-// S[g][s] += sum over resident rows q with z[g][q] = 1 of len_q * p_qs.
-// One warp = 32 groups (lane g: group glist[blockIdx.y*32 + g]) x the 32 samples of one sample
-// group (4 warps of a CTA = the 4 sample groups of block sblist[blockIdx.x]); the warp walks
-// the node rows, skips rows at which its samples are all zero (their own bitmap) or at which no
-// lane's group is all zero, and does acc[s] = fma(z ? len : 0, p_qs, acc[s]) with the 32 values
-// of the row read as shared-memory broadcasts (rows are staged 32 at a time with cp.async,
-// double buffered, live rows only).
-constexpr int SS_WARPS = 4;
-constexpr size_t SS_SMEM = (size_t)SS_WARPS * 2 * 32 * 32 * sizeof(double);
-
-__global__ void __launch_bounds__(SS_WARPS * 32)
-k_group_skipsums(const double* __restrict__ emb, const double* __restrict__ len_rel,
-                 const uint32_t* __restrict__ nz, const int32_t* __restrict__ glist, int n_g,
-                 const int32_t* __restrict__ sblist, int64_t npad, int64_t rows, int64_t QR,
-                 double* __restrict__ S /*[npad/32][npad]*/) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* buf = reinterpret_cast<double*>(smem_raw) + warp * 2 * 1024;
-    const int64_t sb = sblist[blockIdx.x];
-    const int64_t words = QR / 32;
-    const int gi = blockIdx.y * 32 + lane;
-    const int gid = gi < n_g ? glist[gi] : -1;
-    const uint32_t* own_row = nz + (4 * sb + warp) * words;
-    const uint32_t* z_row = gid >= 0 ? nz + (int64_t)gid * words : nullptr;
-    const double* src = emb + (sb * QR) * TILE + warp * 32 + (lane & 15) * 2;
-    const int rsel = lane >> 4;  // lanes 0-15 copy even rows, 16-31 odd rows
-    const int nwords = (int)((rows + 31) / 32);
-
-    double acc[32];
+// Transposed zero bitmaps: zt[q][w] bit j = 1 when group gperm[32w + j] is all zero at resident
+// row q (0 for padding entries gperm = -1).  One warp per (32 groups, 32 rows): a 32 x 32 bit
+// transpose by ballots.
+__global__ void __launch_bounds__(256)
+k_transpose_bitmaps(const uint32_t* __restrict__ nz, const int32_t* __restrict__ gperm, int64_t ngw,
+                    int64_t words, uint32_t* __restrict__ zt /*[words * 32][ngw]*/) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= ngw * words) return;
+    const int64_t gw = warp % ngw, w = warp / ngw;
+    const int g = gperm[32 * gw + lane];
+    const uint32_t zero_rows = g >= 0 ? ~nz[(int64_t)g * words + w] : 0u;
+    uint32_t mine = 0;
 #pragma unroll
-    for (int s = 0; s < 32; ++s) acc[s] = 0.0;
-
-    uint32_t own_next = nwords > 0 ? own_row[0] : 0u;
-    {
-        double* dst = buf + (lane & 15) * 2;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int r = 2 * i + rsel;
-            if ((own_next >> r) & 1u) cp_async16(dst + r * 32, src + (int64_t)r * TILE);
-        }
-        cp_async_commit();
+    for (int b = 0; b < 32; ++b) {
+        const uint32_t m = __ballot_sync(0xffffffffu, (zero_rows >> b) & 1u);
+        if (lane == b) mine = m;
     }
-    for (int w = 0; w < nwords; ++w) {
-        const uint32_t own = own_next;
-        own_next = w + 1 < nwords ? own_row[w + 1] : 0u;
-        {
-            double* dst = buf + ((w + 1) & 1) * 1024 + (lane & 15) * 2;
-            const double* sp = src + (int64_t)(w + 1) * 32 * TILE;
+    zt[(w * 32 + lane) * ngw + gw] = mine;
+}
+
+// S[g][s] += sum over resident rows q with z[g][q] = 1 of len_q * p_qs, sample-major and sparse:
+// one warp per sample walks the sample's embedding column 32 rows at a time (lane = row), and for
+// every row where the sample is non-zero adds len*p to the accumulators of the groups that are
+// all zero there (lane = group within a word of zt, KW words per thread).  Work is proportional
+// to the non-zeros of the embedding times the number of groups, not to its size.
+//   samples: the 128 samples of block sblist[blockIdx.x / 32], four per CTA (one 32-byte sector)
+//   groups : words [kw0 + blockIdx.y * KW, ...) of the permuted group list, at most kw0 + kwn
+template <int KW>
+__global__ void __launch_bounds__(128)
+k_sample_skipsums(const double* __restrict__ emb, const double* __restrict__ len_rel,
+                  const uint32_t* __restrict__ zt, const int32_t* __restrict__ gperm, int64_t ngw,
+                  int kw0, int kwn, const int32_t* __restrict__ sblist, int64_t npad, int64_t rows,
+                  int64_t QR, double* __restrict__ S /*[npad/32][npad]*/) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t sb = sblist[blockIdx.x >> 5];
+    const int sidx = (blockIdx.x & 31) * 4 + warp;
+    const int kbeg = kw0 + blockIdx.y * KW;
+    const int kcnt = min(KW, kw0 + kwn - kbeg);
+    const double* col = emb + (sb * QR) * TILE + sidx;
+    double acc[KW];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int r = 2 * i + rsel;
-                if ((own_next >> r) & 1u) cp_async16(dst + r * 32, sp + (int64_t)r * TILE);
-            }
-            cp_async_commit();
+    for (int k = 0; k < KW; ++k) acc[k] = 0.0;
+    constexpr int U = 8;  // row blocks in flight
+    for (int64_t q0 = 0; q0 < rows; q0 += 32 * U) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + 32 * u + lane;
+            v[u] = q < rows ? col[q * TILE] : 0.0;
         }
-        cp_async_wait1();
-        __syncwarp();
-        if (own != 0u) {
-            const uint32_t zw = z_row ? ~z_row[w] : 0u;  // set bit = this lane's group is all zero
-            uint32_t todo = own & __reduce_or_sync(0xffffffffu, zw);
-            if (todo != 0u) {
-                const double lenw = len_rel[(int64_t)w * 32 + lane];
-                const double* B = buf + (w & 1) * 1024;
-#pragma unroll 1
-                while (todo != 0u) {
-                    const int b = __ffs(todo) - 1;
-                    todo &= todo - 1u;
-                    const double lb = __shfl_sync(0xffffffffu, lenw, b);
-                    const double zl = ((zw >> b) & 1u) ? lb : 0.0;
-                    const double2* row = reinterpret_cast<const double2*>(B + b * 32);
+        // lane b fetches the zero-group words of ITS row (only where the sample is non-zero), one
+        // block ahead of the block being accumulated; the accumulation loop gets them by shuffle
+        uint32_t zw[KW];
 #pragma unroll
-                    for (int h = 0; h < 16; ++h) {
-                        const double2 v = row[h];
-                        acc[2 * h] = fma(zl, v.x, acc[2 * h]);
-                        acc[2 * h + 1] = fma(zl, v.y, acc[2 * h + 1]);
+        for (int k = 0; k < KW; ++k)
+            zw[k] = (v[0] != 0.0 && k < kcnt) ? zt[(q0 + lane) * ngw + kbeg + k] : 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t zn[KW];
+#pragma unroll
+            for (int k = 0; k < KW; ++k)
+                zn[k] = (u + 1 < U && v[(u + 1) % U] != 0.0 && k < kcnt)
+                            ? zt[(q0 + 32 * (u + 1) + lane) * ngw + kbeg + k] : 0u;
+            uint32_t nzm = __ballot_sync(0xffffffffu, v[u] != 0.0);
+            if (nzm != 0u) {
+                const double lv = v[u] != 0.0 ? v[u] * len_rel[q0 + 32 * u + lane] : 0.0;
+                while (nzm != 0u) {
+                    const int b = __ffs(nzm) - 1;
+                    nzm &= nzm - 1u;
+                    const double x = __shfl_sync(0xffffffffu, lv, b);
+#pragma unroll
+                    for (int k = 0; k < KW; ++k) {
+                        const uint32_t w = __shfl_sync(0xffffffffu, zw[k], b);
+                        if ((w >> lane) & 1u) acc[k] += x;
                     }
                 }
             }
-        }
-        __syncwarp();
-    }
-    if (gid >= 0) {
-        double* o = S + (int64_t)gid * npad + sb * TILE + warp * 32;
 #pragma unroll
-        for (int s = 0; s < 32; ++s) o[s] += acc[s];
+            for (int k = 0; k < KW; ++k) zw[k] = zn[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+        if (k >= kcnt) continue;
+        const int g = gperm[32 * (kbeg + k) + lane];
+        if (g >= 0) S[(int64_t)g * npad + sb * TILE + sidx] += acc[k];
     }
 }
 
@@ -148,10 +143,10 @@ k_add_skipsums(double* __restrict__ out, const int64_t* __restrict__ owned,
 }
 
 // ---------------------------------------------------------------------------------------
-// Pair kernel.  Producer, ring and arithmetic loop are k_pair_weighted_v3's: every node row of
-// the chunk is staged (18 bulk copies per 16 rows).  Each consumer warp takes the two bitmap
-// words of its own row / column group straight from global memory (one word covers two stages,
-// the next one is prefetched) and visits only the staged rows that are live for its 32 x 32
+// Pair kernel.  Producer and arithmetic loop are k_pair_weighted_v3's: every node row of the
+// chunk is staged (34 bulk copies per 32 rows).  Each consumer warp takes the two bitmap
+// words of its own row / column group straight from global memory (one word per stage, the
+// next one is prefetched) and visits only the staged rows that are live for its 32 x 32
 // patch; the slot of the next visit is found while the current one computes, so the
 // shared-memory loads of an iteration depend on nothing computed in it.
 // (Tried: a gathering producer that stages only rows live for the half tile - lane b owns bit
@@ -159,22 +154,29 @@ k_add_skipsums(double* __restrict__ out, const int64_t* __restrict__ owned,
 //  takes uniform registers, so per-lane copies serialise into an ELECT/R2UR loop of ~9
 //  instructions each; 982 ms against 776 ms for this kernel at 10 000 x 100 000 tips.)
 // ---------------------------------------------------------------------------------------
+// Stage = 32 node rows = one bitmap word: A rows compact (64 values), B rows (128 values),
+// 32 lengths; 4 stages (193 KB).  (Tried: 8 stages of 16 rows - 3 % slower.)
+constexpr int MK_KS = 32;
+constexpr int MK_STAGES = 4;
+constexpr int MK_STAGE_DOUBLES = MK_KS * W3_ROWS + MK_KS * TILE + MK_KS;
+constexpr size_t MK_SMEM = (size_t)MK_STAGES * MK_STAGE_DOUBLES * sizeof(double) + 2 * MK_STAGES * sizeof(uint64_t);
+
 __global__ void __launch_bounds__(W3_THREADS, 1)
 k_pair_weighted_mask(const double* __restrict__ emb, const double* __restrict__ len_q,
                      const uint32_t* __restrict__ nz, unsigned long long* __restrict__ executed,
                      PairArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)W3_STAGES * W3_STAGE_DOUBLES * sizeof(double));
-    uint64_t* empty = full + W3_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)MK_STAGES * MK_STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + MK_STAGES;
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
     const int bi = a.tiles[2 * tile], bj = a.tiles[2 * tile + 1];
-    const int nstage = (int)((a.qb - a.qa) / W3_KS);
+    const int nstage = (int)((a.qb - a.qa) / MK_KS);   // chunks are multiples of 128 rows
 
     if (tid == 0) {
-        for (int s = 0; s < W3_STAGES; ++s) {
+        for (int s = 0; s < MK_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], W3_CWARPS);
         }
@@ -190,17 +192,17 @@ k_pair_weighted_mask(const double* __restrict__ emb, const double* __restrict__ 
             int s = 0;
             uint32_t ph = 0;
             for (int it = 0; it < nstage; ++it) {
-                if (it >= W3_STAGES) mbar_wait(&empty[s], ph ^ 1u);
-                double* A = stage_base + (size_t)s * W3_STAGE_DOUBLES;
-                double* B = A + W3_KS * TILE;
-                double* L = B + W3_KS * TILE;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)((W3_KS * W3_ROWS + W3_KS * TILE + W3_KS) * sizeof(double)));
-#pragma unroll
-                for (int k = 0; k < W3_KS; ++k)
-                    bulk_g2s(A + k * TILE, Ag + ((int64_t)it * W3_KS + k) * TILE, W3_ROWS * sizeof(double), &full[s]);
-                bulk_g2s(B, Bg + (int64_t)it * W3_KS * TILE, W3_KS * TILE * sizeof(double), &full[s]);
-                bulk_g2s(L, Lg + it * W3_KS, W3_KS * sizeof(double), &full[s]);
-                if (++s == W3_STAGES) {
+                if (it >= MK_STAGES) mbar_wait(&empty[s], ph ^ 1u);
+                double* A = stage_base + (size_t)s * MK_STAGE_DOUBLES;
+                double* B = A + MK_KS * W3_ROWS;
+                double* L = B + MK_KS * TILE;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(MK_STAGE_DOUBLES * sizeof(double)));
+#pragma unroll 8
+                for (int k = 0; k < MK_KS; ++k)
+                    bulk_g2s(A + k * W3_ROWS, Ag + ((int64_t)it * MK_KS + k) * TILE, W3_ROWS * sizeof(double), &full[s]);
+                bulk_g2s(B, Bg + (int64_t)it * MK_KS * TILE, MK_KS * TILE * sizeof(double), &full[s]);
+                bulk_g2s(L, Lg + it * MK_KS, MK_KS * sizeof(double), &full[s]);
+                if (++s == MK_STAGES) {
                     s = 0;
                     ph ^= 1u;
                 }
@@ -210,14 +212,15 @@ k_pair_weighted_mask(const double* __restrict__ emb, const double* __restrict__ 
     }
 
     const int warp = tid >> 5, lane = tid & 31;
-    const int pr = warp >> 2, pc = warp & 3;
+    // the two warps of a sub-partition (warp & 3) take different column groups, so its load is
+    // the sum of two less correlated visit counts
+    const int pr = warp >> 2, pc = (warp + 2 * pr) & 3;
     const int ty = lane >> 3, tx = lane & 7;
     const int aoff = pr * 32 + ty * 2;
-    const int boff = pc * 32 + tx * 2;
+    const int boff = MK_KS * W3_ROWS + pc * 32 + tx * 2;
     const int64_t words = a.QR / 32;
     const uint32_t* gA = nz + (int64_t)(4 * bi + 2 * half + pr) * words + a.qa / 32;
     const uint32_t* gB = nz + (int64_t)(4 * bj + pc) * words + a.qa / 32;
-    const int nwords = (nstage + 1) / 2;
 
     double acc[8][4], d[8][4];
 #pragma unroll
@@ -230,36 +233,33 @@ k_pair_weighted_mask(const double* __restrict__ emb, const double* __restrict__ 
     double lc = 0.0;
     unsigned nexec = 0;
 
-    uint32_t live = 0, live_next = nwords > 0 ? (gA[0] & gB[0]) : 0u;
+    uint32_t live_next = nstage > 0 ? (gA[0] & gB[0]) : 0u;
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nstage; ++it) {
-        if ((it & 1) == 0) {
-            live = live_next;
-            const int wn = (it >> 1) + 1;
-            live_next = wn < nwords ? (gA[wn] & gB[wn]) : 0u;
-            nexec += __popc(live);
-        }
-        uint32_t mask = (it & 1) ? (live >> 16) : (live & 0xffffu);
+        uint32_t mask = live_next;
+        live_next = it + 1 < nstage ? (gA[it + 1] & gB[it + 1]) : 0u;
+        nexec += __popc(mask);
         int k = __ffs(mask) - 1;
         mbar_wait(&full[s], ph);
-        const double* S0 = stage_base + (size_t)s * W3_STAGE_DOUBLES;
+        const double* S0 = stage_base + (size_t)s * MK_STAGE_DOUBLES;
 #pragma unroll 1
         while (k >= 0) {
-            const double* P = S0 + k * TILE;
-            const double* Lp = S0 + 2 * W3_KS * TILE + k;
+            const double* PA = S0 + k * W3_ROWS + aoff;
+            const double* PB = S0 + k * TILE + boff;
+            const double* Lp = S0 + MK_KS * (W3_ROWS + TILE) + k;
             mask &= mask - 1u;
             k = __ffs(mask) - 1;
             double av[8], bv[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const double2 t = *reinterpret_cast<const double2*>(P + aoff + h * 8);
+                const double2 t = *reinterpret_cast<const double2*>(PA + h * 8);
                 av[2 * h] = t.x;
                 av[2 * h + 1] = t.y;
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                const double2 t = *reinterpret_cast<const double2*>(P + W3_KS * TILE + boff + g * 16);
+                const double2 t = *reinterpret_cast<const double2*>(PB + g * 16);
                 bv[2 * g] = t.x;
                 bv[2 * g + 1] = t.y;
             }
@@ -275,7 +275,7 @@ k_pair_weighted_mask(const double* __restrict__ emb, const double* __restrict__ 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == W3_STAGES) {
+        if (++s == MK_STAGES) {
             s = 0;
             ph ^= 1u;
         }
@@ -286,6 +286,7 @@ k_pair_weighted_mask(const double* __restrict__ emb, const double* __restrict__ 
         for (int c = 0; c < 4; ++c) acc[r][c] = fma(fabs(d[r][c]), lc, acc[r][c]);
     if (executed && lane == 0 && nexec) atomicAdd(executed, (unsigned long long)nexec);
 
+    const int boff0 = pc * 32 + tx * 2;
     const int64_t base = a.row_base[bi];
     const int64_t i0 = (int64_t)bi * TILE;
 #pragma unroll
@@ -294,7 +295,7 @@ k_pair_weighted_mask(const double* __restrict__ emb, const double* __restrict__ 
         if (i >= a.n) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            int64_t j = (int64_t)bj * TILE + boff + (c >> 1) * 16 + (c & 1);
+            int64_t j = (int64_t)bj * TILE + boff0 + (c >> 1) * 16 + (c & 1);
             emit(a, base, i0, i, j, acc[r][c]);
         }
     }

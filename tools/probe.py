@@ -126,13 +126,16 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "e2ef":
     e2e_features()
 
 
+SKIPS = (0, 1)
+
+
 def skip_probe(n=10000, tips=100000, lam=0.02):
     """weighted kernel with and without zero-block skipping (same problem, same box)"""
     parent, length, names, tip_node = synthetic.random_join_tree(tips, seed=1)
     indptr, cols, vals = synthetic.poisson_csr(n, tips, lam, seed=0)
     P = n * (n - 1) // 2
     res = {}
-    for skip in (0, 1):
+    for skip in SKIPS:
         _capi.set_option("weighted_skip", skip)
         with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
             for rep in range(2):
@@ -141,14 +144,19 @@ def skip_probe(n=10000, tips=100000, lam=0.02):
             res[skip] = prob.fetch(np.empty(P))
             frac = t["visits_executed"] / t["visits_dense"] if t["visits_dense"] else 1.0
             print(f"n={n} tips={tips} lam={lam} skip={skip}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms "
-                  f"launches {t['pair_launches']} visits {frac:.3f} of dense -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
+                  f"(prep {t['skip_prep_ms']:.2f}) launches {t['pair_launches']} visits {frac:.3f} of dense -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
     _capi.set_option("weighted_skip", 1)
-    for k in (1,):
+    for k in SKIPS[1:]:
         d = np.abs(res[0] - res[k]) / np.maximum(np.abs(res[0]), 1e-300)
         print(f"max rel diff skip={k} vs dense:", float(d.max()), flush=True)
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "skip":
+    if len(sys.argv) > 2:
+        SKIPS = tuple(int(x) for x in sys.argv[2].split(","))
+    if len(sys.argv) > 3:
+        _capi.set_option("chunk_nodes", int(sys.argv[3]))
+        print("chunk_nodes", sys.argv[3])
     skip_probe(4096, 20000, 0.02)
     skip_probe()
     skip_probe(10000, 100000, 0.005)
