@@ -29,6 +29,7 @@ static int64_t g_chunk_nodes = 8192;           // nodes per pair-kernel launch
 static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
 static int g_walk_decomposed = 1;              // 0 = always the sequential weighted walk
+constexpr int SKIP_GW = 8;                     // group words per zero-path table (256 groups)
 static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 
@@ -121,7 +122,7 @@ struct b2d_problem {
     bool has_values = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // odd node chunks run here, into d_out2 (tails overlap)
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_sync[2] = {nullptr, nullptr};
     TreeOrder order;
     // device inputs
@@ -159,8 +160,12 @@ struct b2d_problem {
     uint32_t* d_nz = nullptr;         // [npad/32][QR/32] group x node-row bitmaps
     size_t nz_bytes = 0;
     double* d_skipsum = nullptr;      // [npad/32][npad]
-    uint32_t* d_zt = nullptr;         // [QR][ngw] transposed zero bitmaps (permuted groups)
-    size_t zt_bytes = 0;
+    uint32_t* d_zt = nullptr;         // [mpad][ngw] transposed zero bitmaps (permuted groups)
+    double* d_zpath = nullptr;        // [mpad][32 * SKIP_GW] zero-path lengths of one group chunk
+    int32_t* d_parent_q = nullptr;
+    int32_t* d_size_q = nullptr;
+    double* d_rd_hi = nullptr;
+    double* d_rd_lo = nullptr;
     int32_t* d_gperm = nullptr;       // [32 * ngw] groups of the owned stripes first; -1 = padding
     int64_t ngw = 0, ngw_owned = 0;
     int32_t* d_sblist[2] = {nullptr, nullptr};
@@ -192,7 +197,8 @@ static void free_problem(b2d_problem* p) {
     cudaFree(p->d_sp_entries); cudaFree(p->d_sp_ptr);
     cudaFree(p->d_nz); cudaFree(p->d_skipsum); cudaFree(p->d_exec);
     for (int k = 0; k < 2; ++k) cudaFree(p->d_sblist[k]);
-    cudaFree(p->d_zt); cudaFree(p->d_gperm);
+    cudaFree(p->d_zt); cudaFree(p->d_gperm); cudaFree(p->d_zpath);
+    cudaFree(p->d_parent_q); cudaFree(p->d_size_q); cudaFree(p->d_rd_hi); cudaFree(p->d_rd_lo);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -445,6 +451,10 @@ int b2d_problem_create_features(b2d_problem** out, int device, int64_t n_samples
     for (int64_t k = 0; k < n_features; ++k) o.len_q[k] = 1.0;
     o.tipdist_q.assign(1, 0.0);
     o.depth_at.assign(o.mpad / 128 + 1, 0);
+    o.parent_q.assign(o.mpad, -1);  // flat: every feature is its own root
+    o.size_q.assign(o.mpad, 1);
+    o.rd_hi = o.len_q;
+    o.rd_lo.assign(o.mpad, 0.0);
     p->mpad = o.mpad;
     p->NS = p->mpad / NODE_STRIPE;
     rc = setup_common(p, indptr, feature_ids, values, sizeof(double));
@@ -530,6 +540,13 @@ static int skip_setup(b2d_problem* p) {
             if (is_owned[b]) sl[1].push_back((int32_t)b);
         }
         int rc;
+        const TreeOrder& o = p->order;
+        if ((rc = upload(&p->d_parent_q, o.parent_q.data(), o.parent_q.size(), p->stream))) return rc;
+        if ((rc = upload(&p->d_size_q, o.size_q.data(), o.size_q.size(), p->stream))) return rc;
+        if ((rc = upload(&p->d_rd_hi, o.rd_hi.data(), o.rd_hi.size(), p->stream))) return rc;
+        if ((rc = upload(&p->d_rd_lo, o.rd_lo.data(), o.rd_lo.size(), p->stream))) return rc;
+        B2D_CUDA(cudaMalloc(&p->d_zt, (size_t)p->mpad * p->ngw * sizeof(uint32_t)));
+        B2D_CUDA(cudaMalloc(&p->d_zpath, (size_t)p->mpad * 32 * SKIP_GW * sizeof(double)));
         if ((rc = upload(&p->d_gperm, gperm.data(), gperm.size(), p->stream))) return rc;
         for (int k = 0; k < 2; ++k) {
             if ((rc = upload(&p->d_sblist[k], sl[k].data(), sl[k].size(), p->stream))) return rc;
@@ -542,27 +559,48 @@ static int skip_setup(b2d_problem* p) {
     return B2D_OK;
 }
 
-// bitmaps + skip sums of the resident rows [0, rows)
-static int skip_prepare_pass(b2d_problem* p, const double* len_rel, int64_t rows, int64_t QR) {
-    const int64_t ng = p->npad / 32, words = QR / 32;
+// Closed-form sums S[g][s] from the bitmaps of ALL node rows (after the last pass), the tree
+// arrays and the CSR input; groups in chunks of 32 * SKIP_GW (one zero-path table at a time).
+static int skip_closed_form(b2d_problem* p) {
+    const bool tree = p->kind == 0;
+    for (int part = 0; part < 2; ++part) {
+        // part 0: groups of the owned stripes x every sample; part 1: other groups x owned samples
+        const int w0 = part == 0 ? 0 : (int)p->ngw_owned;
+        const int w1 = part == 0 ? (int)p->ngw_owned : (int)p->ngw;
+        if (w1 <= w0 || !p->n_sblist[part]) continue;
+        for (int kbeg = w0; kbeg < w1; kbeg += SKIP_GW) {
+            const int kcnt = std::min(SKIP_GW, w1 - kbeg);
+            B2D_CUDA(cudaMemsetAsync(p->d_zpath, 0, (size_t)p->mpad * 32 * SKIP_GW * sizeof(double), p->stream));
+            const int64_t warps = p->m * kcnt;
+            k_fill_zero_paths<SKIP_GW><<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
+                p->d_zt, p->ngw, kbeg, kcnt, p->d_parent_q, p->d_size_q, p->d_rd_hi, p->d_rd_lo,
+                p->m, p->d_zpath);
+            const unsigned grid = (unsigned)p->n_sblist[part] * 16;
+            if (tree)
+                k_sample_pathsums<SKIP_GW, int64_t><<<grid, 256, 0, p->stream>>>(
+                    p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->d_total, p->d_zpath,
+                    p->d_gperm, kbeg, kcnt, p->d_sblist[part], p->n, p->npad, p->d_skipsum);
+            else
+                k_sample_pathsums<SKIP_GW, double><<<grid, 256, 0, p->stream>>>(
+                    p->d_indptr, p->d_qidx, (const double*)p->d_values, nullptr, p->d_zpath,
+                    p->d_gperm, kbeg, kcnt, p->d_sblist[part], p->n, p->npad, p->d_skipsum);
+        }
+    }
+    B2D_CUDA(cudaGetLastError());
+    return B2D_OK;
+}
+
+// group x node bitmaps of the resident rows [q0, q0 + rows): row-major for the pair kernel
+// (this pass only), transposed for the closed-form sums (all passes)
+static int skip_prepare_pass(b2d_problem* p, int64_t q0, int64_t rows, int64_t QR) {
+    const int64_t ng = p->npad / 32, words = QR / 32, nwords = (rows + 31) / 32;
     const int64_t warps = ng * words;
     k_group_nonzero<<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
         (const double*)p->d_emb, ng, rows, QR, p->d_nz);
-    if (p->ngw) {
-        const int64_t tw = p->ngw * words;
-        k_transpose_bitmaps<<<(unsigned)((tw + 7) / 8), 256, 0, p->stream>>>(p->d_nz, p->d_gperm, p->ngw,
-                                                                           words, p->d_zt);
-    }
-    constexpr int KW = 16;
-    for (int k = 0; k < 2; ++k) {
-        const int kw0 = k == 0 ? 0 : (int)p->ngw_owned;
-        const int kwn = k == 0 ? (int)p->ngw_owned : (int)(p->ngw - p->ngw_owned);
-        if (!kwn || !p->n_sblist[k]) continue;
-        dim3 grid((unsigned)p->n_sblist[k] * 32, (unsigned)((kwn + KW - 1) / KW));
-        k_sample_skipsums<KW><<<grid, 128, 0, p->stream>>>(
-            (const double*)p->d_emb, len_rel, p->d_zt, p->d_gperm, p->ngw, kw0, kwn,
-            p->d_sblist[k], p->npad, rows, QR, p->d_skipsum);
-    }
+    const int64_t tw = p->ngw * nwords;
+    if (tw)
+        k_transpose_bitmaps<<<(unsigned)((tw + 7) / 8), 256, 0, p->stream>>>(
+            p->d_nz, p->d_gperm, p->ngw, words, nwords, q0, p->d_zt);
     B2D_CUDA(cudaGetLastError());
     return B2D_OK;
 }
@@ -654,14 +692,6 @@ static int compute_dense(b2d_problem* p, int metric) {
             B2D_CUDA(cudaMalloc(&p->d_nz, need));
             p->nz_bytes = need;
         }
-        const size_t need_t = (size_t)QR * p->ngw * sizeof(uint32_t);
-        if (p->zt_bytes < need_t) {
-            cudaFree(p->d_zt);
-            p->d_zt = nullptr;
-            p->zt_bytes = 0;
-            B2D_CUDA(cudaMalloc(&p->d_zt, need_t));
-            p->zt_bytes = need_t;
-        }
     }
     rc = ensure_emb(p, (size_t)QR * row_bytes);
     if (rc) return rc;
@@ -675,6 +705,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     p->chunk_counter = 0;
     p->nodes_resident = (double)QR;
     double t_embed = 0, t_pair = 0, t_prep = 0;
+    bool closed_form_timed = false;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
         int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
@@ -716,7 +747,7 @@ static int compute_dense(b2d_problem* p, int metric) {
         B2D_CUDA(cudaEventRecord(eb, p->stream));
         if (p->ntiles) {
             if (skip) {
-                if ((rc = skip_prepare_pass(p, p->d_len + q0, q1 - q0, QR))) return rc;
+                if ((rc = skip_prepare_pass(p, q0, q1 - q0, QR))) return rc;
                 B2D_CUDA(cudaEventRecord(p->ev[4], p->stream));
             }
             if ((rc = fork_streams(p))) return rc;
@@ -725,6 +756,10 @@ static int compute_dense(b2d_problem* p, int metric) {
             if ((rc = join_streams(p))) return rc;
             if (q1 == p->mpad) {
                 if (skip && p->out_len && !p->owned.empty()) {
+                    B2D_CUDA(cudaEventRecord(p->ev[5], p->stream));
+                    if ((rc = skip_closed_form(p))) return rc;
+                    B2D_CUDA(cudaEventRecord(p->ev[6], p->stream));
+                    closed_form_timed = true;
                     k_add_skipsums<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                         p->d_out, p->d_owned, p->d_row_base, p->n, p->npad, p->d_skipsum);
                 }
@@ -740,6 +775,10 @@ static int compute_dense(b2d_problem* p, int metric) {
         if (skip && p->ntiles) {
             cudaEventElapsedTime(&ms, eb, p->ev[4]);
             t_prep += ms;
+            if (closed_form_timed) {
+                cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]);
+                t_prep += ms;
+            }
         }
         p->n_pass += 1;
     }

@@ -8,6 +8,17 @@
 //   x(i,j)  = sum_{q: z[g(i)][q] = 0 and z[g(j)][q] = 0} len_q |p_qi - p_qj|  +  S[g(i)][j] + S[g(j)][i]
 // exactly (same non-negative terms, another summation order).  The pair kernel only visits the
 // nodes of the first sum, decided per consumer warp (32 x 32 patch) from the bitmaps z.
+//
+// S is not summed over the embedding.  The nodes at which a group is all zero form whole
+// subtrees (a zero node has only zero descendants), and p_qs is the sum of the sample's entries
+// below q, so
+//   S[g][s] = sum over the CSR entries (node t, proportion p_ts) of sample s of p_ts * E[g][t],
+//   E[g][t] = sum of len over the path from t up to, not including, its first ancestor at which
+//             g is non-zero (0 when g is non-zero at t itself)
+// E is filled from the roots of the maximal zero subtrees (zero node with a non-zero parent):
+// every node x below such a root c gets rd(x) - rd(parent(c)), rd = distance to the root kept
+// as a double-double so that the difference is exact to the last bit of E.  Work: one bit test
+// per (group, node) + one multiply-add per (group, CSR entry) - no pass over the embedding.
 #pragma once
 
 #include "b2d_common.cuh"
@@ -35,15 +46,15 @@ k_group_nonzero(const double* __restrict__ emb, int64_t ngroups, int64_t rows, i
     if (lane == 0) nz[g * words + w] = bits;
 }
 
-// Transposed zero bitmaps: zt[q][w] bit j = 1 when group gperm[32w + j] is all zero at resident
-// row q (0 for padding entries gperm = -1).  One warp per (32 groups, 32 rows): a 32 x 32 bit
-// transpose by ballots.
+// Transposed zero bitmaps: zt[q0 + q][w] bit j = 1 when group gperm[32w + j] is all zero at
+// resident row q (0 for padding entries gperm = -1).  One warp per (32 groups, 32 rows): a
+// 32 x 32 bit transpose by ballots.
 __global__ void __launch_bounds__(256)
 k_transpose_bitmaps(const uint32_t* __restrict__ nz, const int32_t* __restrict__ gperm, int64_t ngw,
-                    int64_t words, uint32_t* __restrict__ zt /*[words * 32][ngw]*/) {
+                    int64_t words, int64_t nwords, int64_t q0, uint32_t* __restrict__ zt /*[mpad][ngw]*/) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= ngw * words) return;
+    if (warp >= ngw * nwords) return;
     const int64_t gw = warp % ngw, w = warp / ngw;
     const int g = gperm[32 * gw + lane];
     const uint32_t zero_rows = g >= 0 ? ~nz[(int64_t)g * words + w] : 0u;
@@ -53,75 +64,83 @@ k_transpose_bitmaps(const uint32_t* __restrict__ nz, const int32_t* __restrict__
         const uint32_t m = __ballot_sync(0xffffffffu, (zero_rows >> b) & 1u);
         if (lane == b) mine = m;
     }
-    zt[(w * 32 + lane) * ngw + gw] = mine;
+    zt[(q0 + w * 32 + lane) * ngw + gw] = mine;
 }
 
-// S[g][s] += sum over resident rows q with z[g][q] = 1 of len_q * p_qs, sample-major and sparse:
-// one warp per sample walks the sample's embedding column 32 rows at a time (lane = row), and for
-// every row where the sample is non-zero adds len*p to the accumulators of the groups that are
-// all zero there (lane = group within a word of zt, KW words per thread).  Work is proportional
-// to the non-zeros of the embedding times the number of groups, not to its size.
-//   samples: the 128 samples of block sblist[blockIdx.x / 32], four per CTA (one 32-byte sector)
-//   groups : words [kw0 + blockIdx.y * KW, ...) of the permuted group list, at most kw0 + kwn
-template <int KW>
-__global__ void __launch_bounds__(128)
-k_sample_skipsums(const double* __restrict__ emb, const double* __restrict__ len_rel,
-                  const uint32_t* __restrict__ zt, const int32_t* __restrict__ gperm, int64_t ngw,
-                  int kw0, int kwn, const int32_t* __restrict__ sblist, int64_t npad, int64_t rows,
-                  int64_t QR, double* __restrict__ S /*[npad/32][npad]*/) {
+// E[x][gl] for the GW words [kbeg, kbeg + GW) of the permuted group list (gl = 32 * word + lane);
+// E is zero-initialised.  One warp per (node q, word): lanes whose group has a maximal zero
+// subtree rooted at q fill the subtree's position range.
+template <int GW>
+__global__ void __launch_bounds__(256)
+k_fill_zero_paths(const uint32_t* __restrict__ zt, int64_t ngw, int kbeg, int kcnt,
+                  const int32_t* __restrict__ parent_q, const int32_t* __restrict__ size_q,
+                  const double* __restrict__ rd_hi, const double* __restrict__ rd_lo, int64_t m,
+                  double* __restrict__ E /*[mpad][32 * GW]*/) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= m * kcnt) return;
+    const int64_t q = warp / kcnt;
+    const int k = (int)(warp % kcnt);
+    const uint32_t zq = zt[q * ngw + kbeg + k];
+    if (zq == 0u) return;
+    const int32_t par = parent_q[q];
+    const uint32_t roots = par >= 0 ? (zq & ~zt[(int64_t)par * ngw + kbeg + k]) : zq;
+    if (!((roots >> lane) & 1u)) return;
+    const double bh = par >= 0 ? rd_hi[par] : 0.0, bl = par >= 0 ? rd_lo[par] : 0.0;
+    double* e = E + 32 * k + lane;
+    for (int64_t x = q - size_q[q] + 1; x <= q; ++x)
+        e[x * (32 * GW)] = (rd_hi[x] - bh) + (rd_lo[x] - bl);
+}
+
+// S[g][s] = sum over the CSR entries of sample s of p * E[node][g]; one warp per sample, lane =
+// group within a word, GW words per thread.  V = int64 counts (divided by the sample total, as
+// k_counts_to_proportions does) or double values (features, taken as they are).
+template <int GW, typename V>
+__global__ void __launch_bounds__(256)
+k_sample_pathsums(const int64_t* __restrict__ indptr, const int32_t* __restrict__ qidx,
+                  const V* __restrict__ values, const long long* __restrict__ total,
+                  const double* __restrict__ E, const int32_t* __restrict__ gperm, int kbeg, int kcnt,
+                  const int32_t* __restrict__ sblist, int64_t n, int64_t npad,
+                  double* __restrict__ S /*[npad/32][npad]*/) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t sb = sblist[blockIdx.x >> 5];
-    const int sidx = (blockIdx.x & 31) * 4 + warp;
-    const int kbeg = kw0 + blockIdx.y * KW;
-    const int kcnt = min(KW, kw0 + kwn - kbeg);
-    const double* col = emb + (sb * QR) * TILE + sidx;
-    double acc[KW];
+    const int64_t s = (int64_t)sblist[blockIdx.x >> 4] * TILE + (blockIdx.x & 15) * 8 + warp;
+    if (s >= n) return;
+    double acc[GW];
 #pragma unroll
-    for (int k = 0; k < KW; ++k) acc[k] = 0.0;
-    constexpr int U = 8;  // row blocks in flight
-    for (int64_t q0 = 0; q0 < rows; q0 += 32 * U) {
-        double v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t q = q0 + 32 * u + lane;
-            v[u] = q < rows ? col[q * TILE] : 0.0;
+    for (int k = 0; k < GW; ++k) acc[k] = 0.0;
+    const int64_t e0 = indptr[s], e1 = indptr[s + 1];
+    double inv_by = 1.0;
+    bool divide = false;
+    if (total) {
+        const long long t = total[s];
+        divide = t > 0;
+        inv_by = (double)t;
+    }
+    for (int64_t eb = e0; eb < e1; eb += 32) {
+        const int64_t e = eb + lane;
+        int32_t q = 0;
+        double pv = 0.0;
+        if (e < e1) {
+            q = qidx[e];
+            pv = values ? (double)values[e] : 1.0;
+            if (divide) pv = pv / inv_by;
         }
-        // lane b fetches the zero-group words of ITS row (only where the sample is non-zero), one
-        // block ahead of the block being accumulated; the accumulation loop gets them by shuffle
-        uint32_t zw[KW];
+        const int cnt = (int)min((int64_t)32, e1 - eb);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const int32_t qj = __shfl_sync(0xffffffffu, q, j);
+            const double pj = __shfl_sync(0xffffffffu, pv, j);
+            const double* row = E + (int64_t)qj * (32 * GW) + lane;
 #pragma unroll
-        for (int k = 0; k < KW; ++k)
-            zw[k] = (v[0] != 0.0 && k < kcnt) ? zt[(q0 + lane) * ngw + kbeg + k] : 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            uint32_t zn[KW];
-#pragma unroll
-            for (int k = 0; k < KW; ++k)
-                zn[k] = (u + 1 < U && v[(u + 1) % U] != 0.0 && k < kcnt)
-                            ? zt[(q0 + 32 * (u + 1) + lane) * ngw + kbeg + k] : 0u;
-            uint32_t nzm = __ballot_sync(0xffffffffu, v[u] != 0.0);
-            if (nzm != 0u) {
-                const double lv = v[u] != 0.0 ? v[u] * len_rel[q0 + 32 * u + lane] : 0.0;
-                while (nzm != 0u) {
-                    const int b = __ffs(nzm) - 1;
-                    nzm &= nzm - 1u;
-                    const double x = __shfl_sync(0xffffffffu, lv, b);
-#pragma unroll
-                    for (int k = 0; k < KW; ++k) {
-                        const uint32_t w = __shfl_sync(0xffffffffu, zw[k], b);
-                        if ((w >> lane) & 1u) acc[k] += x;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < KW; ++k) zw[k] = zn[k];
+            for (int k = 0; k < GW; ++k)
+                if (k < kcnt) acc[k] = fma(pj, row[32 * k], acc[k]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < KW; ++k) {
+    for (int k = 0; k < GW; ++k) {
         if (k >= kcnt) continue;
         const int g = gperm[32 * (kbeg + k) + lane];
-        if (g >= 0) S[(int64_t)g * npad + sb * TILE + sidx] += acc[k];
+        if (g >= 0) S[(int64_t)g * npad + s] = acc[k];
     }
 }
 

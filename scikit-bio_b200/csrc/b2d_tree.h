@@ -27,6 +27,12 @@ struct TreeOrder {
     std::vector<double> tipdist_q;  // [mpad] tip-to-root distance on tips, 0 elsewhere
     std::vector<int32_t> depth_at;  // [mpad/128 + 1] stack depth before each 128-node stripe
     int max_depth = 0;
+    // per position, for the closed-form part of zero-block skipping (b2d_skip.cuh): parent
+    // position (-1: root / padding), subtree size (a subtree is the position range
+    // [q - size + 1, q]) and the root distance sum(len) over q .. root as an unevaluated
+    // double-double sum hi + lo, so that differences along a path lose nothing to cancellation
+    std::vector<int32_t> parent_q, size_q;
+    std::vector<double> rd_hi, rd_lo;
     // Subtree decomposition of the weighted walk (used when the whole tree is resident):
     // phase 1 walks every maximal subtree of <= cut_size nodes independently (one span of
     // consecutive positions each, empty stack), phase 2 walks only the remaining "top" nodes
@@ -130,6 +136,28 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
         out.len_q[q] = length[v];
         out.tipdist_q[q] = has_children ? 0.0 : d[v];
         ++q;
+    }
+    out.parent_q.assign(out.mpad, -1);
+    out.size_q.assign(out.mpad, 1);
+    out.rd_hi.assign(out.mpad, 0.0);
+    out.rd_lo.assign(out.mpad, 0.0);
+    {
+        std::vector<double> hi(m), lo(m);
+        for (int64_t k = m - 1; k >= 0; --k) {  // parents before children
+            const double ph = parent[k] >= 0 ? hi[parent[k]] : 0.0, pl = parent[k] >= 0 ? lo[parent[k]] : 0.0;
+            const double a = ph, b = length[k];
+            const double sum = a + b, bb = sum - a;
+            const double err = (a - (sum - bb)) + (b - bb);  // TwoSum
+            const double l2 = pl + err;
+            const double h = sum + l2;
+            hi[k] = h;
+            lo[k] = l2 - (h - sum);
+            const int64_t pq = out.q_of_id[k];
+            out.rd_hi[pq] = hi[k];
+            out.rd_lo[pq] = lo[k];
+            out.size_q[pq] = (int32_t)size[k];
+            out.parent_q[pq] = parent[k] >= 0 ? out.q_of_id[parent[k]] : -1;
+        }
     }
     for (int64_t s = (m + 127) / 128; s <= out.mpad / 128; ++s) out.depth_at[s] = depth;
     if (m % 128 == 0) out.depth_at[m / 128] = depth;
