@@ -165,8 +165,20 @@ int b2d_beta_diversity_features(int metric, int device,
                                 const double* values,
                                 int shard, int n_shards, double* out_condensed);
 
-/* Tuning knobs (0 keeps the default): nodes per pair-kernel launch (two-level fp64
- * summation granularity) and a cap on the embedding bytes resident per pass. */
+/* Process-wide tuning knobs:
+ *   "chunk_nodes"       nodes per pair-kernel launch = granularity of the two-level fp64
+ *                       summation (0: default 8192; the zero-skipping kernel runs twice that)
+ *   "emb_budget_bytes"  cap on the embedding bytes resident per pass (0: 85 % of free memory)
+ *   "weighted_skip"     1 (default): the weighted / dense Bray-Curtis pair kernel skips nodes at
+ *                       which a 32-sample group is all zero and adds their closed-form
+ *                       contribution; 0: every node is visited
+ *   "cache_embedding"   1 (default): the embedding buffer of a destroyed problem is kept, one
+ *                       per device, for the next problem (cudaMalloc / cudaFree of tens of GB
+ *                       cost 0.1 - 0.6 s); 0: free it now and stop keeping it
+ *   "sparse_features"   -1 auto, 0 never, 1 whenever legal: intersection kernel for integer
+ *                       feature tables (Bray-Curtis / Jaccard)
+ *   "walk_decomposed"   0: always the sequential tree walk;  "plain_kernels" 1: cross-check
+ *                       kernels without bulk copies. */
 int b2d_set_option(const char* name, int64_t value);
 
 /* On-device micro-benchmarks used by bench.py for the roofline denominators:

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,6 +31,7 @@ static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
 static int g_walk_decomposed = 1;              // 0 = always the sequential weighted walk
 constexpr int SKIP_GW = 8;                     // group words per zero-path table (256 groups)
+static int g_cache_embedding = 1;              // keep the embedding buffer of a destroyed problem
 static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 
@@ -112,6 +114,80 @@ __global__ void k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ 
 
 using namespace b2d;
 
+// The embedding buffer is by far the largest allocation (up to 85 % of the device) and
+// cudaMalloc / cudaFree of it cost tens to hundreds of milliseconds, so the buffer of a
+// destroyed problem is parked here, one per device, for the next problem on that device.
+struct EmbCache {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+static std::mutex g_emb_cache_mu;
+static EmbCache g_emb_cache[64];
+
+static size_t emb_cache_bytes(int device) {
+    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
+    return device >= 0 && device < 64 ? g_emb_cache[device].bytes : 0;
+}
+// take the parked buffer if it is large enough, else release it (the caller allocates)
+static void* emb_cache_take(int device, size_t need, size_t* got) {
+    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
+    *got = 0;
+    if (device < 0 || device >= 64) return nullptr;
+    EmbCache& c = g_emb_cache[device];
+    if (!c.ptr) return nullptr;
+    void* ptr = c.ptr;
+    const size_t bytes = c.bytes;
+    c.ptr = nullptr;
+    c.bytes = 0;
+    if (bytes >= need) {
+        *got = bytes;
+        return ptr;
+    }
+    cudaFree(ptr);
+    return nullptr;
+}
+static void emb_cache_put(int device, void* ptr, size_t bytes) {
+    if (!ptr) return;
+    if (!g_cache_embedding || device < 0 || device >= 64) {
+        cudaFree(ptr);
+        return;
+    }
+    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
+    EmbCache& c = g_emb_cache[device];
+    if (c.ptr && c.bytes >= bytes) {
+        cudaFree(ptr);
+        return;
+    }
+    if (c.ptr) cudaFree(c.ptr);
+    c.ptr = ptr;
+    c.bytes = bytes;
+}
+static void emb_cache_clear();
+// cudaMalloc that gives the parked embedding buffer back to the driver before giving up
+template <typename T>
+static cudaError_t b2d_malloc(T** ptr, size_t bytes) {
+    cudaError_t e = cudaMalloc((void**)ptr, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        emb_cache_clear();
+        e = cudaMalloc((void**)ptr, bytes);
+    }
+    return e;
+}
+static void emb_cache_clear() {
+    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d)
+        if (g_emb_cache[d].ptr) {
+            cudaSetDevice(d);
+            cudaFree(g_emb_cache[d].ptr);
+            g_emb_cache[d].ptr = nullptr;
+            g_emb_cache[d].bytes = 0;
+        }
+    cudaSetDevice(cur);
+}
+
 struct b2d_problem {
     int device = 0;
     int kind = 0;  // 0 tree, 1 features
@@ -191,7 +267,7 @@ static void free_problem(b2d_problem* p) {
     cudaFree(p->d_indptr); cudaFree(p->d_qidx); cudaFree(p->d_values); cudaFree(p->d_flags);
     cudaFree(p->d_hc); cudaFree(p->d_fold); cudaFree(p->d_len); cudaFree(p->d_tipdist);
     cudaFree(p->d_tiles); cudaFree(p->d_row_base); cudaFree(p->d_out); cudaFree(p->d_total);
-    cudaFree(p->d_svec); cudaFree(p->d_emb); cudaFree(p->d_state);
+    cudaFree(p->d_svec); emb_cache_put(p->device, p->d_emb, p->emb_bytes); cudaFree(p->d_state);
     cudaFree(p->d_out2); cudaFree(p->d_owned);
     cudaFree(p->d_flags1); cudaFree(p->d_spans); cudaFree(p->d_top_pos); cudaFree(p->d_top_flags);
     cudaFree(p->d_sp_entries); cudaFree(p->d_sp_ptr);
@@ -208,7 +284,7 @@ static void free_problem(b2d_problem* p) {
 
 template <typename T>
 static int upload(T** dst, const T* src, size_t count, cudaStream_t s) {
-    B2D_CUDA(cudaMalloc((void**)dst, std::max<size_t>(count, 1) * sizeof(T)));
+    B2D_CUDA(b2d_malloc(dst, std::max<size_t>(count, 1) * sizeof(T)));
     if (count) B2D_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     return B2D_OK;
 }
@@ -228,7 +304,7 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     if ((rc = upload(&p->d_indptr, indptr, (size_t)p->n + 1, p->stream))) return rc;
     if ((rc = upload(&p->d_qidx, ids, (size_t)p->nnz, p->stream))) return rc;
     if (values) {
-        B2D_CUDA(cudaMalloc(&p->d_values, std::max<size_t>(p->nnz, 1) * value_size));
+        B2D_CUDA(b2d_malloc(&p->d_values, std::max<size_t>(p->nnz, 1) * value_size));
         if (p->nnz)
             B2D_CUDA(cudaMemcpyAsync(p->d_values, values, p->nnz * value_size,
                                      cudaMemcpyHostToDevice, p->stream));
@@ -251,7 +327,7 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
         if (p->kind == 0) {
             if ((rc = upload(&d_qof, o.q_of_id.data(), o.q_of_id.size(), p->stream))) return rc;
         }
-        B2D_CUDA(cudaMalloc(&d_err, sizeof(int)));
+        B2D_CUDA(b2d_malloc(&d_err, sizeof(int)));
         B2D_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), p->stream));
         if (p->nnz) {
             int64_t blocks = (p->nnz + 255) / 256;
@@ -300,10 +376,10 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     p->ntiles = (int64_t)tiles.size() / 2;
     if ((rc = upload(&p->d_tiles, tiles.data(), tiles.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_row_base, p->row_base.data(), p->row_base.size(), p->stream))) return rc;
-    B2D_CUDA(cudaMalloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
     if ((rc = upload(&p->d_owned, p->owned.data(), p->owned.size(), p->stream))) return rc;
-    B2D_CUDA(cudaMalloc(&p->d_total, p->npad * sizeof(long long)));
-    B2D_CUDA(cudaMalloc(&p->d_svec, p->npad * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&p->d_total, p->npad * sizeof(long long)));
+    B2D_CUDA(b2d_malloc(&p->d_svec, p->npad * sizeof(double)));
     B2D_CUDA(cudaMemsetAsync(p->d_total, 0, p->npad * sizeof(long long), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_svec, 0, p->npad * sizeof(double), p->stream));
     B2D_CUDA(cudaEventRecord(e1, p->stream));
@@ -381,6 +457,9 @@ int b2d_set_option(const char* name, int64_t value) {
         g_sparse_features = value < 0 ? -1 : (value ? 1 : 0);
     } else if (s == "plain_kernels") {
         g_plain_kernels = value ? 1 : 0;
+    } else if (s == "cache_embedding") {
+        g_cache_embedding = value ? 1 : 0;
+        if (!value) emb_cache_clear();
     } else if (s == "weighted_skip") {
         g_weighted_skip = value ? 1 : 0;
     } else {
@@ -473,7 +552,13 @@ static int ensure_emb(b2d_problem* p, size_t bytes) {
         p->d_emb = nullptr;
         p->emb_bytes = 0;
     }
-    B2D_CUDA(cudaMalloc(&p->d_emb, bytes));
+    size_t got = 0;
+    if (void* cached = emb_cache_take(p->device, bytes, &got)) {
+        p->d_emb = cached;
+        p->emb_bytes = got;
+        return B2D_OK;
+    }
+    B2D_CUDA(b2d_malloc(&p->d_emb, bytes));
     p->emb_bytes = bytes;
     return B2D_OK;
 }
@@ -485,7 +570,7 @@ static int chunk_target(b2d_problem* p, cudaStream_t* st, double** out, int* fir
     const int64_t ci = p->chunk_counter++;
     const int side = (int)(ci & 1);
     if (side == 1 && !p->d_out2)
-        B2D_CUDA(cudaMalloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
     if (side == 1 && ci == 1 && p->custom_tiles && p->out_len)
         B2D_CUDA(cudaMemsetAsync(p->d_out2, 0, p->out_len * sizeof(double), p->stream2));
     *st = side ? p->stream2 : p->stream;
@@ -520,8 +605,8 @@ static int finalize(b2d_problem* p, int epilogue) {
 static int skip_setup(b2d_problem* p) {
     if (!p->d_skipsum) {
         const int64_t ng = p->npad / 32;
-        B2D_CUDA(cudaMalloc(&p->d_skipsum, (size_t)ng * p->npad * sizeof(double)));
-        B2D_CUDA(cudaMalloc(&p->d_exec, sizeof(unsigned long long)));
+        B2D_CUDA(b2d_malloc(&p->d_skipsum, (size_t)ng * p->npad * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_exec, sizeof(unsigned long long)));
         // group order of the transposed bitmaps: groups of the owned row stripes first.
         // launch 0: those groups x every sample; launch 1: all other groups x owned samples
         std::vector<int32_t> gperm, sl[2];
@@ -545,8 +630,8 @@ static int skip_setup(b2d_problem* p) {
         if ((rc = upload(&p->d_size_q, o.size_q.data(), o.size_q.size(), p->stream))) return rc;
         if ((rc = upload(&p->d_rd_hi, o.rd_hi.data(), o.rd_hi.size(), p->stream))) return rc;
         if ((rc = upload(&p->d_rd_lo, o.rd_lo.data(), o.rd_lo.size(), p->stream))) return rc;
-        B2D_CUDA(cudaMalloc(&p->d_zt, (size_t)p->mpad * p->ngw * sizeof(uint32_t)));
-        B2D_CUDA(cudaMalloc(&p->d_zpath, (size_t)p->mpad * 32 * SKIP_GW * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_zt, (size_t)p->mpad * p->ngw * sizeof(uint32_t)));
+        B2D_CUDA(b2d_malloc(&p->d_zpath, (size_t)p->mpad * 32 * SKIP_GW * sizeof(double)));
         if ((rc = upload(&p->d_gperm, gperm.data(), gperm.size(), p->stream))) return rc;
         for (int k = 0; k < 2; ++k) {
             if ((rc = upload(&p->d_sblist[k], sl[k].data(), sl[k].size(), p->stream))) return rc;
@@ -664,7 +749,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     }
     // the second raw-sum buffer must exist before the embedding takes its share of memory
     if (p->ntiles && p->mpad > g_chunk_nodes && !p->d_out2)
-        B2D_CUDA(cudaMalloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
     const bool skip = g_weighted_skip && !plain_kernels() && !p->custom_tiles && p->ntiles > 0;
     p->skip_executed = p->skip_dense = 0;
     if (skip) {
@@ -677,7 +762,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     // one node row: 8 B per sample (+ 1 bit per 32-sample group for the skipping bitmaps)
     size_t row_bytes = (size_t)p->nb * TILE * sizeof(double);
     size_t budget = g_emb_budget_bytes ? (size_t)g_emb_budget_bytes
-                                       : (size_t)((double)(free_b + p->emb_bytes) * 0.85);
+                                       : (size_t)((double)(free_b + p->emb_bytes + emb_cache_bytes(p->device)) * 0.85);
     int64_t QR = (int64_t)(budget / std::max<size_t>(row_bytes, 1));
     QR = QR / NODE_STRIPE * NODE_STRIPE;
     if (QR < NODE_STRIPE) return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for one node stripe");
@@ -689,14 +774,14 @@ static int compute_dense(b2d_problem* p, int metric) {
             cudaFree(p->d_nz);
             p->d_nz = nullptr;
             p->nz_bytes = 0;
-            B2D_CUDA(cudaMalloc(&p->d_nz, need));
+            B2D_CUDA(b2d_malloc(&p->d_nz, need));
             p->nz_bytes = need;
         }
     }
     rc = ensure_emb(p, (size_t)QR * row_bytes);
     if (rc) return rc;
     if (tree && !p->d_state)
-        B2D_CUDA(cudaMalloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
+        B2D_CUDA(b2d_malloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
     int epilogue = metric == B2D_WEIGHTED_UNIFRAC_NORMALIZED ? EPI_WEIGHTED_NORM
                    : metric == B2D_BRAYCURTIS               ? EPI_BRAYCURTIS
                                                              : EPI_RAW;
@@ -872,7 +957,7 @@ static int build_sparse(b2d_problem* p) {
     if (p->has_values) {  // integer counts with row sums below 2^31 only
         int* d_bad = nullptr;
         int bad = 0;
-        B2D_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+        B2D_CUDA(b2d_malloc(&d_bad, sizeof(int)));
         B2D_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
         k_sp_check<<<(unsigned)((p->nnz + 255) / 256), 256, 0, p->stream>>>((const double*)p->d_values,
                                                                              p->nnz, d_bad);
@@ -890,7 +975,7 @@ static int build_sparse(b2d_problem* p) {
     const int64_t nch = (p->m + SP_CHUNK - 1) / SP_CHUNK;
     const int64_t nbuckets = p->nb * nch;
     unsigned* d_counts = nullptr;
-    B2D_CUDA(cudaMalloc(&d_counts, (nbuckets + 1) * sizeof(unsigned)));
+    B2D_CUDA(b2d_malloc(&d_counts, (nbuckets + 1) * sizeof(unsigned)));
     B2D_CUDA(cudaMemsetAsync(d_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
     k_sp_count<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->n, nch, d_counts);
     std::vector<unsigned> counts(nbuckets);
@@ -904,9 +989,9 @@ static int build_sparse(b2d_problem* p) {
         }
         ptr[b + 1] = ptr[b] + counts[b];
     }
-    B2D_CUDA(cudaMalloc(&p->d_sp_ptr, (nbuckets + 1) * sizeof(int64_t)));
+    B2D_CUDA(b2d_malloc(&p->d_sp_ptr, (nbuckets + 1) * sizeof(int64_t)));
     B2D_CUDA(cudaMemcpyAsync(p->d_sp_ptr, ptr.data(), (nbuckets + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
-    B2D_CUDA(cudaMalloc(&p->d_sp_entries, std::max<int64_t>(p->nnz, 1) * sizeof(SpEntry)));
+    B2D_CUDA(b2d_malloc(&p->d_sp_entries, std::max<int64_t>(p->nnz, 1) * sizeof(SpEntry)));
     B2D_CUDA(cudaMemsetAsync(d_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
     if (p->has_values)
         k_sp_scatter<double><<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, (const double*)p->d_values,
@@ -1078,7 +1163,7 @@ int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_til
     if ((rc = upload(&p->d_owned, p->owned.data(), p->owned.size(), p->stream))) return rc;
     B2D_CUDA(cudaMemcpyAsync(p->d_row_base, p->row_base.data(), p->nb * sizeof(int64_t),
                              cudaMemcpyHostToDevice, p->stream));
-    B2D_CUDA(cudaMalloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&p->d_out, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     p->custom_tiles = true;
     p->computed = false;
@@ -1099,11 +1184,11 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
     B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const int64_t nchunks = (p->mpad + 2047) / 2048;
     double* d_partial = nullptr;
-    B2D_CUDA(cudaMalloc(&d_partial, (size_t)nchunks * p->npad * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&d_partial, (size_t)nchunks * p->npad * sizeof(double)));
     B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t row_bytes = (size_t)p->nb * TILE * sizeof(double);
     size_t budget = g_emb_budget_bytes ? (size_t)g_emb_budget_bytes
-                                       : (size_t)((double)(free_b + p->emb_bytes) * 0.85);
+                                       : (size_t)((double)(free_b + p->emb_bytes + emb_cache_bytes(p->device)) * 0.85);
     int64_t QR = (int64_t)(budget / std::max<size_t>(row_bytes, 1)) / 2048 * 2048;
     if (QR < 2048) {
         cudaFree(d_partial);
@@ -1115,7 +1200,7 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
         cudaFree(d_partial);
         return rc;
     }
-    if (!p->d_state) B2D_CUDA(cudaMalloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
+    if (!p->d_state) B2D_CUDA(b2d_malloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
     const int weighted = weight > 0.0 ? 1 : 0;
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
         const int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
@@ -1289,11 +1374,11 @@ int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_g
     const int64_t P = n * (n - 1) / 2, nb = (n + TILE - 1) / TILE;
     double *d_cond = nullptr, *d_w = nullptr, *d_partial = nullptr, *d_out = nullptr;
     int32_t* d_g = nullptr;
-    B2D_CUDA(cudaMalloc(&d_cond, P * sizeof(double)));
-    B2D_CUDA(cudaMalloc(&d_g, n_groupings * n * sizeof(int32_t)));
-    B2D_CUDA(cudaMalloc(&d_w, n_groups * sizeof(double)));
-    B2D_CUDA(cudaMalloc(&d_partial, nb * n_groupings * sizeof(double)));
-    B2D_CUDA(cudaMalloc(&d_out, n_groupings * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&d_cond, P * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&d_g, n_groupings * n * sizeof(int32_t)));
+    B2D_CUDA(b2d_malloc(&d_w, n_groups * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&d_partial, nb * n_groupings * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&d_out, n_groupings * sizeof(double)));
     B2D_CUDA(cudaMemcpy(d_cond, condensed, P * sizeof(double), cudaMemcpyHostToDevice));
     B2D_CUDA(cudaMemcpy(d_g, groupings, n_groupings * n * sizeof(int32_t), cudaMemcpyHostToDevice));
     B2D_CUDA(cudaMemcpy(d_w, inv_group_size, n_groups * sizeof(double), cudaMemcpyHostToDevice));
@@ -1373,7 +1458,7 @@ int b2d_microbench(int device, int kind, double* result) {
         B2D_CUDA(cudaGetDeviceProperties(&prop, device));
         const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 14;
         double* d = nullptr;
-        B2D_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&d, (size_t)blocks * threads * sizeof(double)));
         for (int rep = 0; rep < 6; ++rep) {
             B2D_CUDA(cudaEventRecord(e0));
             k_bench_dfma<<<blocks, threads>>>(d, iters);
@@ -1388,8 +1473,8 @@ int b2d_microbench(int device, int kind, double* result) {
     } else if (kind == 1) {
         const int64_t bytes = (int64_t)2 << 30;
         uint4 *a = nullptr, *b = nullptr;
-        B2D_CUDA(cudaMalloc(&a, bytes));
-        B2D_CUDA(cudaMalloc(&b, bytes));
+        B2D_CUDA(b2d_malloc(&a, bytes));
+        B2D_CUDA(b2d_malloc(&b, bytes));
         B2D_CUDA(cudaMemset(a, 1, bytes));
         for (int rep = 0; rep < 6; ++rep) {
             B2D_CUDA(cudaEventRecord(e0));
@@ -1410,7 +1495,7 @@ int b2d_microbench(int device, int kind, double* result) {
         const int smem = 256 * 32 * sizeof(double);
         B2D_CUDA(cudaFuncSetAttribute(k_bench_lds64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         double* d = nullptr;
-        B2D_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&d, (size_t)blocks * threads * sizeof(double)));
         for (int rep = 0; rep < 6; ++rep) {
             B2D_CUDA(cudaEventRecord(e0));
             k_bench_lds64<<<blocks, threads, smem>>>(d, iters);
@@ -1429,7 +1514,7 @@ int b2d_microbench(int device, int kind, double* result) {
         const int smem = 128 * 128 * sizeof(int);
         B2D_CUDA(cudaFuncSetAttribute(k_bench_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int* d = nullptr;
-        B2D_CUDA(cudaMalloc(&d, (size_t)blocks * sizeof(int)));
+        B2D_CUDA(b2d_malloc(&d, (size_t)blocks * sizeof(int)));
         for (int rep = 0; rep < 6; ++rep) {
             B2D_CUDA(cudaEventRecord(e0));
             k_bench_atoms<<<blocks, threads, smem>>>(d, iters);
