@@ -615,7 +615,9 @@ static int skip_setup(b2d_problem* p) {
         for (int pass = 0; pass < 2; ++pass) {
             for (int64_t b = 0; b < p->nb; ++b)
                 if ((is_owned[b] != 0) == (pass == 0))
-                    for (int g = 0; g < 4; ++g) gperm.push_back((int32_t)(4 * b + g));
+                    for (int g = 0; g < 4; ++g)
+                        if ((4 * b + g) * 32 < p->n)  // groups made of padding samples only: never read
+                            gperm.push_back((int32_t)(4 * b + g));
             while (gperm.size() % 32) gperm.push_back(-1);
             if (pass == 0) p->ngw_owned = (int64_t)gperm.size() / 32;
         }

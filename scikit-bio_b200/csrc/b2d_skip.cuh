@@ -69,7 +69,7 @@ k_transpose_bitmaps(const uint32_t* __restrict__ nz, const int32_t* __restrict__
 
 // E[x][gl] for the GW words [kbeg, kbeg + GW) of the permuted group list (gl = 32 * word + lane);
 // E is zero-initialised.  One warp per (node q, word): lanes whose group has a maximal zero
-// subtree rooted at q fill the subtree's position range.
+// subtree rooted at q fill the subtree's position range [q - size + 1, q].
 template <int GW>
 __global__ void __launch_bounds__(256)
 k_fill_zero_paths(const uint32_t* __restrict__ zt, int64_t ngw, int kbeg, int kcnt,
@@ -85,11 +85,20 @@ k_fill_zero_paths(const uint32_t* __restrict__ zt, int64_t ngw, int kbeg, int kc
     if (zq == 0u) return;
     const int32_t par = parent_q[q];
     const uint32_t roots = par >= 0 ? (zq & ~zt[(int64_t)par * ngw + kbeg + k]) : zq;
-    if (!((roots >> lane) & 1u)) return;
+    if (roots == 0u) return;
     const double bh = par >= 0 ? rd_hi[par] : 0.0, bl = par >= 0 ? rd_lo[par] : 0.0;
-    double* e = E + 32 * k + lane;
-    for (int64_t x = q - size_q[q] + 1; x <= q; ++x)
-        e[x * (32 * GW)] = (rd_hi[x] - bh) + (rd_lo[x] - bl);
+    const int64_t lo = q - size_q[q] + 1;
+    if (q - lo < 32) {  // the usual case: a handful of nodes, one lane per group
+        if (!((roots >> lane) & 1u)) return;
+        double* e = E + 32 * k + lane;
+        for (int64_t x = lo; x <= q; ++x) e[x * (32 * GW)] = (rd_hi[x] - bh) + (rd_lo[x] - bl);
+    } else {            // a whole clade without the group: lanes share the position range
+        for (int64_t x = lo + lane; x <= q; x += 32) {
+            const double v = (rd_hi[x] - bh) + (rd_lo[x] - bl);
+            double* e = E + x * (32 * GW) + 32 * k;
+            for (uint32_t r = roots; r != 0u; r &= r - 1u) e[__ffs(r) - 1] = v;
+        }
+    }
 }
 
 // S[g][s] = sum over the CSR entries of sample s of p * E[node][g]; one warp per sample, lane =

@@ -158,9 +158,10 @@ def test_plain_and_bulk_copy_kernels_agree_bitwise():
     assert np.array_equal(res[0], res[1])
 
 
-@pytest.mark.parametrize("n,tips,lam,cat", [(700, 500, 0.1, False), (300, 3000, 0.004, False),
-                                            (161, 2500, 0.01, True), (40, 64, 0.5, False)])
-def test_zero_block_skipping_matches_the_dense_kernel(n, tips, lam, cat):
+@pytest.mark.parametrize("n,tips,lam,cat,clade", [(700, 500, 0.1, False, False), (300, 3000, 0.004, False, False),
+                                                  (161, 2500, 0.01, True, False), (40, 64, 0.5, False, False),
+                                                  (300, 4000, 0.05, False, True), (200, 3000, 0.05, True, True)])
+def test_zero_block_skipping_matches_the_dense_kernel(n, tips, lam, cat, clade):
     """The default weighted kernel skips nodes at which a 32-sample group is all zero and adds
     their closed-form contribution afterwards; it must agree with the kernel that visits every
     node (1e-13: summation order only) and with the oracle, also with several node passes,
@@ -170,6 +171,18 @@ def test_zero_block_skipping_matches_the_dense_kernel(n, tips, lam, cat):
     from skbio_b200 import _capi, synthetic
 
     parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, lam, 21, caterpillar=cat)
+    if clade:
+        # the first 96 samples (three whole groups) see only the first 40 % of the tips, and two
+        # samples are empty: whole clades / the whole tree without a group (long zero paths)
+        keep = np.ones(len(cols), dtype=bool)
+        for s in range(min(96, n)):
+            sl = slice(indptr[s], indptr[s + 1])
+            keep[sl] = cols[sl] < int(0.4 * tips)
+        for s in (100, 101):
+            keep[indptr[s]:indptr[s + 1]] = False
+        counts = np.add.reduceat(keep, indptr[:-1]) * (np.diff(indptr) > 0)
+        cols, vals = cols[keep], vals[keep]
+        indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     node_ids = tip_node[cols]
     total = n * (n - 1) // 2
     res = {}
