@@ -357,8 +357,7 @@ def run_ours(args):
         pair_ms.append(t["pair_ms"])
         embed_ms.append(t["embed_ms"])
         prep_ms.append(t["skip_prep_ms"])
-        # per pass: scatter/propagate/normalise (3) and, with zero-block skipping, bitmaps + sums (2)
-        launches += t["pair_launches"] + (5 if t["visits_dense"] else 3) * t["passes"]
+        launches += t["kernels"]   # every kernel the library launched for this step
         pair_launches_per_step = t["pair_launches"]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -380,6 +379,13 @@ def run_ours(args):
     # (rank r's page-locked buffer holds only what rank r computed)
     compact = world > 1 or emulate > 1
     out = _capi.PinnedBuffer(P_shard if compact else P_total)
+    # inputs in page-locked host memory as well: the H2D copies inside the timed region are DMA
+    pinned_inputs = {k: _capi.PinnedBuffer.like(inp[k]) for k in ("parent", "length", "indptr", "ids", "vals")
+                     if inp.get(k) is not None}
+    inp_pageable = inp
+    inp = dict(inp)
+    for k, b in pinned_inputs.items():
+        inp[k] = b.array
     e2e_times = []
     for it in range(3):
         barrier()
@@ -392,6 +398,7 @@ def run_ours(args):
                 p2.fetch(out.array)
         torch.cuda.synchronize(device)
         e2e_times.append(time.perf_counter() - t0)
+    inp = inp_pageable
     e2e_s = min(e2e_times)
     if rank == 0:
         print("e2e repetitions (s):", [round(x, 4) for x in e2e_times], file=sys.stderr)
@@ -520,7 +527,9 @@ def run_ours(args):
             "wall_ms_per_step": wall_step_ms_max,
             "embed_ms": float(np.mean(embed_ms)), "pair_ms": float(np.mean(pair_ms)),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "seconds": float(te[0])},
+                    "d2h_bytes_per_step": int(d2h), "seconds": float(te[0]),
+                    "host_buffers": "page-locked (b2d_host_alloc) for inputs and result",
+                    "timed": "create (H2D) + compute + fetch (D2H) + destroy, best of 3"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -528,6 +537,8 @@ def run_ours(args):
             "checksum_first_1M": checksum,
         }
     out.free()
+    for b in pinned_inputs.values():
+        b.free()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -146,7 +146,8 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * [6] nodes resident per pass, [7] number of passes, [8] node visits the weighted pair
  * kernel executed (per 32x32 sample patch) and [9] the visits a kernel without zero-block
  * skipping would make (both 0 when skipping was not used), [10] the part of [1] spent on
- * the skipping bitmaps and closed-form sums.  n: slots to fill (<= 11). */
+ * the skipping bitmaps and closed-form sums, [11] kernels launched by the last compute (all
+ * of them: embedding, bitmaps, pair launches, closed form, finalize).  n: slots to fill (<= 12). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);

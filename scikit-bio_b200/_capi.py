@@ -242,16 +242,26 @@ def debug_tree_order(parent, length):
 
 
 class PinnedBuffer:
-    """fp64 vector in page-locked host memory owned by the native library."""
+    """Vector (fp64 by default) in page-locked host memory owned by the native library."""
 
-    def __init__(self, n):
+    def __init__(self, n, dtype=np.float64):
         self._lib = load()
         self.n = int(n)
-        self.ptr = self._lib.b2d_host_alloc(max(self.n, 1) * 8)
+        dt = np.dtype(dtype)
+        nbytes = max(self.n, 1) * dt.itemsize
+        self.ptr = self._lib.b2d_host_alloc(nbytes)
         if not self.ptr:
             raise MemoryError("b2d_host_alloc failed")
-        buf = (ctypes.c_double * max(self.n, 1)).from_address(self.ptr)
-        self.array = np.frombuffer(buf, dtype=np.float64, count=self.n)
+        buf = (ctypes.c_char * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dt, count=self.n)
+
+    @classmethod
+    def like(cls, a):
+        """Page-locked copy of a host array (so that its upload is a plain DMA)."""
+        a = np.ascontiguousarray(a)
+        b = cls(a.size, a.dtype)
+        b.array[:] = a.ravel()
+        return b
 
     def free(self):
         if self.ptr:
@@ -351,12 +361,12 @@ class Problem:
         return out
 
     def timings(self):
-        t = np.zeros(11, dtype=np.float64)
-        _check(load().b2d_problem_timings(self._h, _ptr(t, _f64p), 11))
+        t = np.zeros(12, dtype=np.float64)
+        _check(load().b2d_problem_timings(self._h, _ptr(t, _f64p), 12))
         return {"embed_ms": t[0], "pair_ms": t[1], "compute_ms": t[2], "fetch_ms": t[3],
                 "upload_ms": t[4], "pair_launches": int(t[5]), "nodes_resident": int(t[6]),
                 "passes": int(t[7]), "visits_executed": float(t[8]), "visits_dense": float(t[9]),
-                "skip_prep_ms": t[10]}
+                "skip_prep_ms": t[10], "kernels": int(t[11])}
 
     def destroy(self):
         if self._h is not None:

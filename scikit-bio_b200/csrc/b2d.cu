@@ -259,6 +259,7 @@ struct b2d_problem {
     int last_metric = -1;
     double t_embed = 0, t_pair = 0, t_total = 0, t_fetch = 0, t_upload = 0;
     double n_launch = 0, nodes_resident = 0, n_pass = 0;
+    double n_kernels = 0;             // kernels launched by the last compute (all of them)
 };
 
 static void free_problem(b2d_problem* p) {
@@ -595,6 +596,7 @@ static int join_streams(b2d_problem* p) {
 static int finalize(b2d_problem* p, int epilogue) {
     if (!p->out_len || p->owned.empty()) return B2D_OK;
     const double* out2 = p->chunk_counter >= 2 ? p->d_out2 : nullptr;
+    p->n_kernels += 1;
     k_finalize<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
         p->d_out, out2, p->d_owned, p->d_row_base, p->n, epilogue, p->d_svec, p->d_total);
     B2D_CUDA(cudaGetLastError());
@@ -659,10 +661,12 @@ static int skip_closed_form(b2d_problem* p) {
             const int kcnt = std::min(SKIP_GW, w1 - kbeg);
             B2D_CUDA(cudaMemsetAsync(p->d_zpath, 0, (size_t)p->mpad * 32 * SKIP_GW * sizeof(double), p->stream));
             const int64_t warps = p->m * kcnt;
+            p->n_kernels += 1;
             k_fill_zero_paths<SKIP_GW><<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
                 p->d_zt, p->ngw, kbeg, kcnt, p->d_parent_q, p->d_size_q, p->d_rd_hi, p->d_rd_lo,
                 p->m, p->d_zpath);
             const unsigned grid = (unsigned)p->n_sblist[part] * 16;
+            p->n_kernels += 1;
             if (tree)
                 k_sample_pathsums<SKIP_GW, int64_t><<<grid, 256, 0, p->stream>>>(
                     p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->d_total, p->d_zpath,
@@ -682,9 +686,11 @@ static int skip_closed_form(b2d_problem* p) {
 static int skip_prepare_pass(b2d_problem* p, int64_t q0, int64_t rows, int64_t QR) {
     const int64_t ng = p->npad / 32, words = QR / 32, nwords = (rows + 31) / 32;
     const int64_t warps = ng * words;
+    p->n_kernels += 1;
     k_group_nonzero<<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
         (const double*)p->d_emb, ng, rows, QR, p->d_nz);
     const int64_t tw = p->ngw * nwords;
+    p->n_kernels += tw ? 1 : 0;
     if (tw)
         k_transpose_bitmaps<<<(unsigned)((tw + 7) / 8), 256, 0, p->stream>>>(
             p->d_nz, p->d_gperm, p->ngw, words, nwords, q0, p->d_zt);
@@ -741,11 +747,13 @@ static int compute_dense(b2d_problem* p, int metric) {
     float ms;
     B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
     if (tree) {
+        p->n_kernels += 1;
         k_sample_totals_tree<<<sblocks, wpb * 32, 0, p->stream>>>(
             p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->d_flags,
             metric == B2D_WEIGHTED_UNIFRAC_NORMALIZED ? p->d_tipdist : nullptr, p->n, p->d_total,
             p->d_svec);
     } else {
+        p->n_kernels += 1;
         k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(
             p->d_indptr, (const double*)p->d_values, p->n, p->d_svec);
     }
@@ -800,6 +808,7 @@ static int compute_dense(b2d_problem* p, int metric) {
         B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, (size_t)QR * row_bytes, p->stream));
         if (p->n) {
             if (tree) {
+                p->n_kernels += 1;
                 k_scatter_dense<int64_t><<<sblocks, wpb * 32, 0, p->stream>>>(
                     p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->n, q0, q1, QR,
                     (unsigned long long*)p->d_emb, 0);
@@ -808,24 +817,30 @@ static int compute_dense(b2d_problem* p, int metric) {
                     const int64_t nspans = (int64_t)p->order.spans.size() / 2;
                     if (nspans) {
                         dim3 grid((unsigned)(p->npad / 128), (unsigned)nspans);
+                        p->n_kernels += 1;
                         k_propagate_weighted_spans<<<grid, 128, 0, p->stream>>>(
                             (unsigned long long*)p->d_emb, p->d_flags1, p->d_spans, p->npad, QR);
                     }
+                    p->n_kernels += 1;
                     k_propagate_weighted_top<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
                         (unsigned long long*)p->d_emb, p->d_top_pos, p->d_top_flags,
                         (int64_t)p->order.top_pos.size(), p->npad, QR);
-                } else
-                k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
-                    (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR,
-                    p->d_state, p->order.depth_at[q0 / NODE_STRIPE]);
+                } else {
+                    p->n_kernels += 1;
+                    k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
+                        (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR,
+                        p->d_state, p->order.depth_at[q0 / NODE_STRIPE]);
+                }
                 {
                     const int64_t threads = p->nb * (TILE / 2);
                     dim3 grid((unsigned)((threads + 255) / 256),
                               (unsigned)std::min<int64_t>(q1 - q0, 2048));
+                    p->n_kernels += 1;
                     k_counts_to_proportions<<<grid, 256, 0, p->stream>>>(
                         (unsigned long long*)p->d_emb, p->d_total, p->nb, q1 - q0, QR);
                 }
             } else {
+                p->n_kernels += 1;
                 k_scatter_dense<double><<<sblocks, wpb * 32, 0, p->stream>>>(
                     p->d_indptr, p->d_qidx, (const double*)p->d_values, p->n, q0, q1, QR,
                     (unsigned long long*)p->d_emb, 1);
@@ -847,6 +862,7 @@ static int compute_dense(b2d_problem* p, int metric) {
                     if ((rc = skip_closed_form(p))) return rc;
                     B2D_CUDA(cudaEventRecord(p->ev[6], p->stream));
                     closed_form_timed = true;
+                    p->n_kernels += 1;
                     k_add_skipsums<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                         p->d_out, p->d_owned, p->d_row_base, p->n, p->npad, p->d_skipsum);
                 }
@@ -893,8 +909,10 @@ static int compute_bits(b2d_problem* p, int metric) {
     B2D_CUDA(cudaEventRecord(ea, p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, bytes, p->stream));
     if (p->n) {
+        p->n_kernels += 1;
         k_scatter_bits<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->n, p->NS,
                                                            (uint32_t*)p->d_emb);
+        p->n_kernels += 1;
         k_propagate_bits<<<(unsigned)p->nb, TILE, 0, p->stream>>>(
             (uint4*)p->d_emb, p->d_hc, p->d_fold, p->d_len, p->NS, p->d_svec);
     }
@@ -961,8 +979,10 @@ static int build_sparse(b2d_problem* p) {
         int bad = 0;
         B2D_CUDA(b2d_malloc(&d_bad, sizeof(int)));
         B2D_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
+        p->n_kernels += 1;
         k_sp_check<<<(unsigned)((p->nnz + 255) / 256), 256, 0, p->stream>>>((const double*)p->d_values,
                                                                              p->nnz, d_bad);
+        p->n_kernels += 1;
         k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, (const double*)p->d_values,
                                                                     p->n, p->d_svec);
         std::vector<double> sums(p->n);
@@ -979,6 +999,7 @@ static int build_sparse(b2d_problem* p) {
     unsigned* d_counts = nullptr;
     B2D_CUDA(b2d_malloc(&d_counts, (nbuckets + 1) * sizeof(unsigned)));
     B2D_CUDA(cudaMemsetAsync(d_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+    p->n_kernels += 1;
     k_sp_count<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->n, nch, d_counts);
     std::vector<unsigned> counts(nbuckets);
     B2D_CUDA(cudaMemcpyAsync(counts.data(), d_counts, nbuckets * sizeof(unsigned), cudaMemcpyDeviceToHost, p->stream));
@@ -995,6 +1016,7 @@ static int build_sparse(b2d_problem* p) {
     B2D_CUDA(cudaMemcpyAsync(p->d_sp_ptr, ptr.data(), (nbuckets + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
     B2D_CUDA(b2d_malloc(&p->d_sp_entries, std::max<int64_t>(p->nnz, 1) * sizeof(SpEntry)));
     B2D_CUDA(cudaMemsetAsync(d_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+    p->n_kernels += 1;
     if (p->has_values)
         k_sp_scatter<double><<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, (const double*)p->d_values,
                                                                   p->n, nch, p->d_sp_ptr, d_counts, p->d_sp_entries);
@@ -1002,6 +1024,7 @@ static int build_sparse(b2d_problem* p) {
         k_sp_scatter<double><<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, (const double*)nullptr,
                                                                   p->n, nch, p->d_sp_ptr, d_counts, p->d_sp_entries);
     B2D_CUDA(cudaFuncSetAttribute(k_sp_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SORT_SMEM));
+    p->n_kernels += 1;
     k_sp_sort<<<(unsigned)nbuckets, 256, SP_SORT_SMEM, p->stream>>>(p->d_sp_entries, p->d_sp_ptr);
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     B2D_CUDA(cudaGetLastError());
@@ -1018,6 +1041,7 @@ static int compute_sparse(b2d_problem* p, int metric) {
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     B2D_CUDA(cudaEventRecord(ea, p->stream));
     // per-sample sums (Bray-Curtis) or feature counts (Jaccard: values ignored)
+    p->n_kernels += 1;
     k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(
         p->d_indptr, metric == B2D_BRAYCURTIS ? (const double*)p->d_values : (const double*)nullptr, p->n,
         p->d_svec);
@@ -1071,6 +1095,7 @@ int b2d_problem_compute(b2d_problem* p, int metric) {
     B2D_CUDA(cudaSetDevice(p->device));
     if (p->custom_tiles && p->out_len)
         B2D_CUDA(cudaMemsetAsync(p->d_out, 0, p->out_len * sizeof(double), p->stream));
+    p->n_kernels = 0;
     int rc;
     switch (metric) {
         case B2D_UNWEIGHTED_UNIFRAC:
@@ -1115,6 +1140,7 @@ int b2d_problem_compute(b2d_problem* p, int metric) {
             return fail(B2D_ERR_INVALID_ARGUMENT, "unknown metric id");
     }
     if (rc) return rc;
+    p->n_kernels += p->n_launch;  // the pair-kernel launches
     p->t_total = p->t_embed + p->t_pair;
     p->computed = true;
     p->last_metric = metric;
@@ -1293,10 +1319,10 @@ int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[11] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+    double v[12] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
-                    p->t_skip_prep};
-    for (int i = 0; i < n && i < 11; ++i) ms[i] = v[i];
+                    p->t_skip_prep, p->n_kernels};
+    for (int i = 0; i < n && i < 12; ++i) ms[i] = v[i];
     return B2D_OK;
 }
 
