@@ -226,6 +226,14 @@ int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* l
                          int32_t* q_of_id, uint8_t* flags_mpad, double* len_q_mpad,
                          double* tipdist_q_mpad, int32_t* max_depth);
 
+/* Test hook (host only): the per-position arrays behind the closed-form part of zero-block
+ * skipping, all sized n_nodes rounded up to 128: parent position (-1 root / padding), subtree
+ * size (the subtree of position q is the range [q - size + 1, q]) and the distance to the
+ * root (sum of lengths over q .. root) as an unevaluated double-double sum hi + lo. */
+int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* length,
+                         int32_t* parent_q_mpad, int32_t* size_q_mpad, double* rd_hi_mpad,
+                         double* rd_lo_mpad);
+
 #ifdef __cplusplus
 }
 #endif

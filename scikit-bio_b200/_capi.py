@@ -115,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "b2d_api_version", "b2d_device_count", "b2d_last_error", "b2d_host_alloc", "b2d_host_free",
     "b2d_problem_create_tree", "b2d_problem_create_features", "b2d_problem_compute",
     "b2d_problem_result_len", "b2d_problem_fetch", "b2d_problem_fetch_compact",
-    "b2d_problem_sample_vector", "b2d_problem_timings", "b2d_problem_destroy",
+    "b2d_problem_sample_vector", "b2d_problem_timings", "b2d_problem_destroy", "b2d_debug_tree_paths",
     "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
     "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout", "b2d_problem_select_tiles",
     "b2d_newick_parse", "b2d_flat_tree_nodes", "b2d_flat_tree_name_bytes", "b2d_flat_tree_get",
@@ -239,6 +239,24 @@ def debug_tree_order(parent, length):
                                     flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
                                     _ptr(lq, _f64p), _ptr(td, _f64p), ctypes.byref(depth)))
     return {"q_of_id": q, "flags": flags, "len_q": lq, "tipdist_q": td, "max_depth": depth.value}
+
+
+def debug_tree_paths(parent, length):
+    """Per-position parent / subtree size / double-double root distance (host-only test hook)."""
+    lib = load()
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    length = np.ascontiguousarray(length, dtype=np.float64)
+    m = len(parent)
+    mpad = (m + 127) // 128 * 128
+    pq = np.empty(mpad, dtype=np.int32)
+    sz = np.empty(mpad, dtype=np.int32)
+    hi = np.empty(mpad, dtype=np.float64)
+    lo = np.empty(mpad, dtype=np.float64)
+    lib.b2d_debug_tree_paths.restype = ctypes.c_int
+    lib.b2d_debug_tree_paths.argtypes = [ctypes.c_int64, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p]
+    _check(lib.b2d_debug_tree_paths(m, _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(pq, _i32p),
+                                    _ptr(sz, _i32p), _ptr(hi, _f64p), _ptr(lo, _f64p)))
+    return {"parent_q": pq, "size_q": sz, "rd_hi": hi, "rd_lo": lo}
 
 
 class PinnedBuffer:

@@ -1469,6 +1469,20 @@ int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* l
     return B2D_OK;
 }
 
+int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* length,
+                         int32_t* parent_q_mpad, int32_t* size_q_mpad, double* rd_hi_mpad,
+                         double* rd_lo_mpad) {
+    if (!parent || !length) return fail(B2D_ERR_INVALID_ARGUMENT, "parent/length is NULL");
+    TreeOrder o;
+    std::string err = build_tree_order(n_nodes, parent, length, o);
+    if (!err.empty()) return fail(B2D_ERR_INVALID_ARGUMENT, err);
+    if (parent_q_mpad) memcpy(parent_q_mpad, o.parent_q.data(), o.parent_q.size() * sizeof(int32_t));
+    if (size_q_mpad) memcpy(size_q_mpad, o.size_q.data(), o.size_q.size() * sizeof(int32_t));
+    if (rd_hi_mpad) memcpy(rd_hi_mpad, o.rd_hi.data(), o.rd_hi.size() * sizeof(double));
+    if (rd_lo_mpad) memcpy(rd_lo_mpad, o.rd_lo.data(), o.rd_lo.size() * sizeof(double));
+    return B2D_OK;
+}
+
 int b2d_microbench(int device, int kind, double* result) {
     if (!result) return fail(B2D_ERR_INVALID_ARGUMENT, "result is NULL");
     int ndev = 0;

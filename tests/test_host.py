@@ -193,6 +193,43 @@ def test_engine_node_order_propagates_like_traverse_reduce(gen, tips):
     assert np.array_equal(t["len_q"][t["q_of_id"]], length)
 
 
+@pytest.mark.parametrize("gen,tips", [("random_join_tree", 300), ("caterpillar_tree", 3000),
+                                      ("random_join_tree", 1)])
+def test_subtree_ranges_and_double_double_root_distances(gen, tips):
+    """Arrays behind the closed-form part of zero-block skipping: the subtree of position q is
+    the position range [q - size + 1, q], and hi + lo is the root distance to ~2^-100."""
+    from fractions import Fraction
+
+    parent, length, names, tip_node = getattr(synthetic, gen)(tips, seed=11)
+    rng = np.random.default_rng(3)
+    length = length * rng.uniform(1e-6, 1e3, size=len(length))  # lengths of very different size
+    t = _capi.debug_tree_order(parent, length)
+    pth = _capi.debug_tree_paths(parent, length)
+    q_of = t["q_of_id"]
+    m = len(parent)
+    exact = [None] * m
+    size = np.ones(m, dtype=np.int64)
+    for k in range(m - 1, -1, -1):   # parents before children
+        exact[k] = Fraction(float(length[k])) + (exact[parent[k]] if parent[k] >= 0 else 0)
+    for k in range(m):
+        if parent[k] >= 0:
+            size[parent[k]] += size[k]
+    lo_pos = np.full(m, m, dtype=np.int64)   # smallest position inside each node's subtree
+    for k in range(m):
+        lo_pos[k] = min(lo_pos[k], q_of[k])
+        if parent[k] >= 0:
+            lo_pos[parent[k]] = min(lo_pos[parent[k]], lo_pos[k])
+    for k in range(m):
+        q = q_of[k]
+        assert pth["size_q"][q] == size[k]
+        assert lo_pos[k] == q - size[k] + 1          # contiguous range ending at q
+        assert pth["parent_q"][q] == (q_of[parent[k]] if parent[k] >= 0 else -1)
+        dd = Fraction(float(pth["rd_hi"][q])) + Fraction(float(pth["rd_lo"][q]))
+        assert abs(dd - exact[k]) <= exact[k] * Fraction(1, 2 ** 95)
+        assert abs(pth["rd_lo"][q]) <= abs(pth["rd_hi"][q]) * 2.0 ** -52
+    assert np.all(pth["parent_q"][m:] == -1)
+
+
 def test_engine_rejects_bad_trees():
     with pytest.raises(_capi.EngineError, match="parent"):
         _capi.debug_tree_order(np.array([0, -1]), np.zeros(2))
