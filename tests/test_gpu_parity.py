@@ -6,6 +6,7 @@ Tolerances (BASELINE.json north_star): integer/bit work is bit-exact (Jaccard, i
 Bray-Curtis, presence logic); UniFrac distances within 1e-12 relative in fp64.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -14,6 +15,7 @@ from conftest import assert_close_rel, case_arrays, golden_cases
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIFRAC_RTOL = 1e-12
 
 
@@ -639,3 +641,16 @@ def test_reference_driver_known_answers():
     assert np.array_equal(a, b)
     assert not np.array_equal(sb.beta_diversity("braycurtis", table3).condensed_form(),
                               sb.beta_diversity("braycurtis", pa.astype(int)).condensed_form())
+
+
+def test_randomised_sweep_weighted_and_dense_braycurtis():
+    """Random shapes (n = 2 .. 700, 2 .. 4000 tips, both tree kinds, scaled branch lengths), shards,
+    node passes and launch chunks through the C ABI: weighted UniFrac within 1e-12 of the oracle,
+    dense Bray-Curtis bit-exact (tools/fuzz_gpu.py, 16 cases)."""
+    _skbio_b200()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_gpu
+
+    worst, failures = fuzz_gpu.main(16, seed=5, verbose=False)
+    assert not failures, failures
+    assert worst <= UNIFRAC_RTOL
