@@ -177,10 +177,16 @@ k_add_skipsums(double* __restrict__ out, const int64_t* __restrict__ owned,
 // next one is prefetched) and visits only the staged rows that are live for its 32 x 32
 // patch; the slot of the next visit is found while the current one computes, so the
 // shared-memory loads of an iteration depend on nothing computed in it.
-// (Tried: a gathering producer that stages only rows live for the half tile - lane b owns bit
-//  b of the bitmap word, slots by prefix popcount, one bulk copy per row and operand.  UBLKCP
-//  takes uniform registers, so per-lane copies serialise into an ELECT/R2UR loop of ~9
-//  instructions each; 982 ms against 776 ms for this kernel at 10 000 x 100 000 tips.)
+// (Tried, twice: a gathering producer that stages only rows live for the half tile.  (1) A whole
+//  warp, lane b owning bit b of the bitmap word, slots by prefix popcount, one bulk copy per row
+//  and operand: UBLKCP takes uniform registers, so per-lane copies serialise into an ELECT/R2UR
+//  loop of ~9 instructions each - 982 ms against 776 ms for this kernel at 10 000 x 100 000
+//  tips.  (2) One lane walking the set bits, B rows and lengths copied per RUN of live rows,
+//  consumers compacting their masks with a lane-parallel bit-extract: 813 ms against 700 ms,
+//  and 577 against 349 ms at lambda = 0.005 - the data-dependent FLO/branch chain per run
+//  cannot feed eight consumer warps.  Also tried: 64 x 64 quadrants with two CTAs per SM so
+//  that one ring's waits are filled by the other's work - 748 ms, the doubled operand traffic
+//  and copy count cost more than the waits.)
 // ---------------------------------------------------------------------------------------
 // Stage = 32 node rows = one bitmap word: A rows compact (64 values), B rows (128 values),
 // 32 lengths; 4 stages (193 KB).  (Tried: 8 stages of 16 rows - 3 % slower.)
