@@ -147,7 +147,10 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * kernel executed (per 32x32 sample patch) and [9] the visits a kernel without zero-block
  * skipping would make (both 0 when skipping was not used), [10] the part of [1] spent on
  * the skipping bitmaps and closed-form sums, [11] kernels launched by the last compute (all
- * of them: embedding, bitmaps, pair launches, closed form, finalize).  n: slots to fill (<= 12). */
+ * of them: embedding, bitmaps, pair launches, closed form, finalize), [12] duration of the
+ * sparse tip-row kernel (0 when the tips went through the dense kernel), [13] number of
+ * near-duplicate pairs that made the last compute redo the tips densely (normally 0).
+ * n: slots to fill (<= 14). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);
@@ -173,6 +176,10 @@ int b2d_beta_diversity_features(int metric, int device,
  *   "weighted_skip"     1 (default): the weighted / dense Bray-Curtis pair kernel skips nodes at
  *                       which a 32-sample group is all zero and adds their closed-form
  *                       contribution; 0: every node is visited
+ *   "tips_sparse"       1 (default): with weighted_skip, the tip rows of a tree problem go through a
+ *                       sparse intersection kernel in exact fixed point instead of the dense
+ *                       kernel; 0: dense.  Falls back by itself for very dense tables and when
+ *                       near-duplicate samples are found.
  *   "cache_embedding"   1 (default): the embedding buffer of a destroyed problem is kept, one
  *                       per device, for the next problem (cudaMalloc / cudaFree of tens of GB
  *                       cost 0.1 - 0.6 s); 0: free it now and stop keeping it

@@ -18,6 +18,7 @@
 #include "b2d_embed.cuh"
 #include "b2d_pair.cuh"
 #include "b2d_skip.cuh"
+#include "b2d_tips.cuh"
 #include "b2d_sparse.cuh"
 #include "b2d_permanova.cuh"
 #include "b2d_tree.h"
@@ -31,6 +32,7 @@ static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
 static int g_walk_decomposed = 1;              // 0 = always the sequential weighted walk
 constexpr int SKIP_GW = 8;                     // group words per zero-path table (256 groups)
+static int g_tips_sparse = 1;                  // tip rows of the weighted kernel as a sparse intersection
 static int g_cache_embedding = 1;              // keep the embedding buffer of a destroyed problem
 static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
@@ -198,7 +200,7 @@ struct b2d_problem {
     bool has_values = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // odd node chunks run here, into d_out2 (tails overlap)
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_sync[2] = {nullptr, nullptr};
     TreeOrder order;
     // device inputs
@@ -248,6 +250,21 @@ struct b2d_problem {
     int n_sblist[2] = {0, 0};
     unsigned long long* d_exec = nullptr;
     double skip_executed = 0, skip_dense = 0, t_skip_prep = 0;
+    // tip rows as a sparse intersection (b2d_tips.cuh)
+    int tips_mode = 0;                // 0 undecided, 1 usable, -1 not usable for this problem
+    bool tips_active = false;         // the current compute handles the tip rows sparsely
+    double* d_rd_hi_int = nullptr;
+    double* d_rd_lo_int = nullptr;
+    double* d_tip_u = nullptr;        // [npad] U_i (double, for the scale and the guard)
+    long long* d_tip_ufx = nullptr;   // [npad] U_i in fixed point
+    double* d_tip_scale = nullptr;    // {2^(61-e), 2^(e-61)}
+    unsigned long long* d_tip_word = nullptr;  // [0] max U bits, [1] flagged pairs
+    int* d_tip_status = nullptr;
+    unsigned* d_tip_counts = nullptr;
+    int64_t* d_tip_ptr = nullptr;
+    TipEntry* d_tip_entries = nullptr;
+    int64_t tip_nch = 0;
+    double tips_flagged = 0, t_tips = 0;
     // sparse feature-table path
     SpEntry* d_sp_entries = nullptr;
     int64_t* d_sp_ptr = nullptr;
@@ -276,6 +293,9 @@ static void free_problem(b2d_problem* p) {
     for (int k = 0; k < 2; ++k) cudaFree(p->d_sblist[k]);
     cudaFree(p->d_zt); cudaFree(p->d_gperm); cudaFree(p->d_zpath);
     cudaFree(p->d_parent_q); cudaFree(p->d_size_q); cudaFree(p->d_rd_hi); cudaFree(p->d_rd_lo);
+    cudaFree(p->d_rd_hi_int); cudaFree(p->d_rd_lo_int); cudaFree(p->d_tip_u); cudaFree(p->d_tip_ufx);
+    cudaFree(p->d_tip_scale); cudaFree(p->d_tip_word); cudaFree(p->d_tip_status); cudaFree(p->d_tip_counts);
+    cudaFree(p->d_tip_ptr); cudaFree(p->d_tip_entries);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -458,6 +478,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_sparse_features = value < 0 ? -1 : (value ? 1 : 0);
     } else if (s == "plain_kernels") {
         g_plain_kernels = value ? 1 : 0;
+    } else if (s == "tips_sparse") {
+        g_tips_sparse = value ? 1 : 0;
     } else if (s == "cache_embedding") {
         g_cache_embedding = value ? 1 : 0;
         if (!value) emb_cache_clear();
@@ -648,6 +670,56 @@ static int skip_setup(b2d_problem* p) {
     return B2D_OK;
 }
 
+// Tip rows as a sparse intersection: buffers, fixed-point scale, buckets sorted by node position.
+// Rebuilt by every compute (like the embedding); tips_mode becomes -1 when a bucket is too large
+// for the shared-memory sort (very dense tables).
+static int tips_build(b2d_problem* p) {
+    const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    const int64_t nch = (p->mpad + TP_CHUNK - 1) / TP_CHUNK;
+    const int64_t nbuckets = p->nb * nch;
+    p->tip_nch = nch;
+    if (!p->d_tip_u) {
+        const TreeOrder& o = p->order;
+        int rc;
+        if ((rc = upload(&p->d_rd_hi_int, o.rd_hi_int.data(), o.rd_hi_int.size(), p->stream))) return rc;
+        if ((rc = upload(&p->d_rd_lo_int, o.rd_lo_int.data(), o.rd_lo_int.size(), p->stream))) return rc;
+        B2D_CUDA(b2d_malloc(&p->d_tip_u, p->npad * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_ufx, p->npad * sizeof(long long)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_scale, 2 * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_word, 2 * sizeof(unsigned long long)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_status, sizeof(int)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_counts, (nbuckets + 1) * sizeof(unsigned)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_ptr, (nbuckets + 1) * sizeof(int64_t)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_entries, std::max<int64_t>(p->nnz, 1) * sizeof(TipEntry)));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_u, 0, p->npad * sizeof(double), p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_ufx, 0, p->npad * sizeof(long long), p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 2 * sizeof(unsigned long long), p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+    const int64_t* vals = (const int64_t*)p->d_values;
+    p->n_kernels += 6;
+    k_tip_usum<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, vals, p->d_total, p->d_flags,
+                                                    p->d_len, p->n, p->d_tip_u, p->d_tip_word);
+    k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
+    k_tip_count<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->d_flags, p->n, nch,
+                                                     p->d_tip_counts);
+    k_tip_scan<<<1, 1024, 0, p->stream>>>(p->d_tip_counts, nbuckets, p->d_tip_ptr, p->d_tip_status);
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+    k_tip_scatter<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, vals, p->d_total, p->d_flags,
+                                                       p->d_len, p->d_tip_scale, p->n, nch, p->d_tip_ptr,
+                                                       p->d_tip_counts, p->d_tip_entries, p->d_tip_ufx);
+    B2D_CUDA(cudaFuncSetAttribute(k_tip_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SORT_SMEM));
+    k_tip_sort<<<(unsigned)nbuckets, 256, TP_SORT_SMEM, p->stream>>>(p->d_tip_entries, p->d_tip_ptr);
+    int status = 0;
+    B2D_CUDA(cudaMemcpyAsync(&status, p->d_tip_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    B2D_CUDA(cudaGetLastError());
+    p->tips_mode = status ? -1 : 1;
+    return B2D_OK;
+}
+
 // Closed-form sums S[g][s] from the bitmaps of ALL node rows (after the last pass), the tree
 // arrays and the CSR input; groups in chunks of 32 * SKIP_GW (one zero-path table at a time).
 static int skip_closed_form(b2d_problem* p) {
@@ -663,8 +735,9 @@ static int skip_closed_form(b2d_problem* p) {
             const int64_t warps = p->m * kcnt;
             p->n_kernels += 1;
             k_fill_zero_paths<SKIP_GW><<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
-                p->d_zt, p->ngw, kbeg, kcnt, p->d_parent_q, p->d_size_q, p->d_rd_hi, p->d_rd_lo,
-                p->m, p->d_zpath);
+                p->d_zt, p->ngw, kbeg, kcnt, p->d_parent_q, p->d_size_q,
+                p->tips_active ? p->d_rd_hi_int : p->d_rd_hi,
+                p->tips_active ? p->d_rd_lo_int : p->d_rd_lo, p->m, p->d_zpath);
             const unsigned grid = (unsigned)p->n_sblist[part] * 16;
             p->n_kernels += 1;
             if (tree)
@@ -762,9 +835,15 @@ static int compute_dense(b2d_problem* p, int metric) {
         B2D_CUDA(b2d_malloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
     const bool skip = g_weighted_skip && !plain_kernels() && !p->custom_tiles && p->ntiles > 0;
     p->skip_executed = p->skip_dense = 0;
+    p->tips_active = false;
+    p->t_tips = 0;
     if (skip) {
         int rc0 = skip_setup(p);
         if (rc0) return rc0;
+        if (tree && g_tips_sparse && p->tips_mode >= 0 && p->n > 0) {
+            if ((rc0 = tips_build(p))) return rc0;
+            p->tips_active = p->tips_mode == 1;
+        }
     }
     // resident node range
     size_t free_b = 0, total_b = 0;
@@ -800,7 +879,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     p->chunk_counter = 0;
     p->nodes_resident = (double)QR;
     double t_embed = 0, t_pair = 0, t_prep = 0;
-    bool closed_form_timed = false;
+    bool closed_form_timed = false, tips_timed = false;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
         int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
@@ -850,9 +929,39 @@ static int compute_dense(b2d_problem* p, int metric) {
         if (p->ntiles) {
             if (skip) {
                 if ((rc = skip_prepare_pass(p, q0, q1 - q0, QR))) return rc;
+                if (p->tips_active) {  // the pair kernel never visits a tip row
+                    const int64_t ng = p->npad / 32, nwords = (q1 - q0 + 31) / 32;
+                    p->n_kernels += 1;
+                    k_mask_tip_rows<<<(unsigned)((ng * nwords + 255) / 256), 256, 0, p->stream>>>(
+                        p->d_nz, p->d_hc + q0 / 32, ng, QR / 32, nwords);
+                }
                 B2D_CUDA(cudaEventRecord(p->ev[4], p->stream));
             }
             if ((rc = fork_streams(p))) return rc;
+            if (p->tips_active && q0 == 0) {  // all tip rows at once: sparse intersection
+                PairArgs a;
+                a.tiles = p->d_tiles;
+                a.row_base = p->d_row_base;
+                a.out = p->d_out;
+                a.svec = p->d_svec;
+                a.total = p->d_total;
+                a.n = p->n;
+                a.qa = 0;
+                a.qb = 0;
+                a.QR = QR;
+                a.NS = p->NS;
+                a.last = 0;
+                a.epilogue = epilogue;
+                cudaStream_t st;
+                if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
+                B2D_CUDA(cudaFuncSetAttribute(k_pair_tips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
+                B2D_CUDA(cudaEventRecord(p->ev[7], st));
+                k_pair_tips<<<(unsigned)p->ntiles, TP_THREADS, TP_SMEM, st>>>(
+                    p->d_tip_entries, p->d_tip_ptr, p->tip_nch, p->d_tip_ufx, p->d_tip_scale, a);
+                B2D_CUDA(cudaEventRecord(p->ev[8], st));
+                tips_timed = true;
+                p->n_kernels += 1;
+            }
             rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue, skip);
             if (rc) return rc;
             if ((rc = join_streams(p))) return rc;
@@ -865,6 +974,12 @@ static int compute_dense(b2d_problem* p, int metric) {
                     p->n_kernels += 1;
                     k_add_skipsums<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                         p->d_out, p->d_owned, p->d_row_base, p->n, p->npad, p->d_skipsum);
+                    if (p->tips_active) {  // near-duplicate pairs: see b2d_tips.cuh
+                        p->n_kernels += 1;
+                        k_tip_guard<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
+                            p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, p->d_owned,
+                            p->d_row_base, p->n, p->d_tip_u, p->d_tip_word + 1);
+                    }
                 }
                 if ((rc = finalize(p, epilogue))) return rc;
             }
@@ -882,10 +997,23 @@ static int compute_dense(b2d_problem* p, int metric) {
                 cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]);
                 t_prep += ms;
             }
+            if (tips_timed && q0 == 0) {
+                cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]);
+                p->t_tips = ms;
+            }
         }
         p->n_pass += 1;
     }
     B2D_CUDA(cudaGetLastError());
+    if (p->tips_active) {
+        unsigned long long flagged = 0;
+        B2D_CUDA(cudaMemcpy(&flagged, p->d_tip_word + 1, sizeof(flagged), cudaMemcpyDeviceToHost));
+        if (flagged) {  // near-duplicate samples: redo with the tips in the dense kernel
+            p->tips_mode = -1;
+            p->tips_flagged = (double)flagged;
+            return compute_dense(p, metric);
+        }
+    }
     if (skip) {
         unsigned long long ex = 0;
         B2D_CUDA(cudaMemcpy(&ex, p->d_exec, sizeof(ex), cudaMemcpyDeviceToHost));
@@ -1096,6 +1224,7 @@ int b2d_problem_compute(b2d_problem* p, int metric) {
     if (p->custom_tiles && p->out_len)
         B2D_CUDA(cudaMemsetAsync(p->d_out, 0, p->out_len * sizeof(double), p->stream));
     p->n_kernels = 0;
+    p->tips_flagged = 0;
     int rc;
     switch (metric) {
         case B2D_UNWEIGHTED_UNIFRAC:
@@ -1319,10 +1448,10 @@ int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[12] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+    double v[14] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
-                    p->t_skip_prep, p->n_kernels};
-    for (int i = 0; i < n && i < 12; ++i) ms[i] = v[i];
+                    p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged};
+    for (int i = 0; i < n && i < 14; ++i) ms[i] = v[i];
     return B2D_OK;
 }
 

@@ -33,6 +33,9 @@ struct TreeOrder {
     // double-double sum hi + lo, so that differences along a path lose nothing to cancellation
     std::vector<int32_t> parent_q, size_q;
     std::vector<double> rd_hi, rd_lo;
+    // the same with the tips' own branches left out (a tip gets its parent's distance): used
+    // when the tip rows are handled by the sparse intersection kernel (b2d_tips.cuh)
+    std::vector<double> rd_hi_int, rd_lo_int;
     // Subtree decomposition of the weighted walk (used when the whole tree is resident):
     // phase 1 walks every maximal subtree of <= cut_size nodes independently (one span of
     // consecutive positions each, empty stack), phase 2 walks only the remaining "top" nodes
@@ -158,6 +161,14 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
             out.size_q[pq] = (int32_t)size[k];
             out.parent_q[pq] = parent[k] >= 0 ? out.q_of_id[parent[k]] : -1;
         }
+        out.rd_hi_int = out.rd_hi;
+        out.rd_lo_int = out.rd_lo;
+        for (int64_t k = 0; k < m; ++k)
+            if (coff[k + 1] == coff[k]) {  // tip
+                const int64_t pq = out.q_of_id[k];
+                out.rd_hi_int[pq] = parent[k] >= 0 ? hi[parent[k]] : 0.0;
+                out.rd_lo_int[pq] = parent[k] >= 0 ? lo[parent[k]] : 0.0;
+            }
     }
     for (int64_t s = (m + 127) / 128; s <= out.mpad / 128; ++s) out.depth_at[s] = depth;
     if (m % 128 == 0) out.depth_at[m / 128] = depth;

@@ -654,3 +654,60 @@ def test_randomised_sweep_weighted_and_dense_braycurtis():
     worst, failures = fuzz_gpu.main(16, seed=5, verbose=False)
     assert not failures, failures
     assert worst <= UNIFRAC_RTOL
+
+
+def test_sparse_tip_rows_agree_with_the_dense_kernel_and_fall_back_when_they_must():
+    """Tip rows as a fixed-point sparse intersection (default) vs the dense kernel; the two
+    fall-backs: a table too dense for the position buckets, and near-duplicate samples (where
+    U_i + U_j - 2 * intersection would cancel) which make the engine redo the tips densely."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    def run(parent, length, indptr, cols, vals, tip_node, n, key, tips_sparse):
+        _capi.set_option("tips_sparse", tips_sparse)
+        try:
+            with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+                prob.compute(key)
+                return prob.fetch(np.empty(n * (n - 1) // 2)), prob.timings()
+        finally:
+            _capi.set_option("tips_sparse", 1)
+
+    # 1. ordinary sparse table: sparse tips used, no pair flagged, agrees with dense tips and oracle
+    n, tips = 300, 3000
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.02, 31)
+    exp = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr, cols, vals, tips), tip_node, parent, length)
+    for key in ("weighted_unifrac", "weighted_unifrac_normalized"):
+        a, ta = run(parent, length, indptr, cols, vals, tip_node, n, key, 1)
+        b, tb = run(parent, length, indptr, cols, vals, tip_node, n, key, 0)
+        assert ta["tips_ms"] > 0 and ta["tips_flagged"] == 0 and tb["tips_ms"] == 0
+        assert_close_rel(a, b, 1e-13, key + " sparse vs dense tips")
+        assert_close_rel(a, exp[key], UNIFRAC_RTOL, key + " sparse tips vs oracle")
+
+    # 2. identical samples stay at exactly 0; a near-duplicate pair triggers the dense redo
+    vals2, cols2, indptr2 = vals.copy(), cols.copy(), indptr.copy()
+    s0, s1 = slice(indptr[0], indptr[1]), None
+    # sample 1 := sample 0 (exact copy), sample 2 := sample 0 with one count changed by 1 in ~1e6
+    rows = [(cols[s0], vals[s0] * 100000), (cols[s0], vals[s0] * 100000)]
+    v3 = vals[s0] * 100000
+    v3 = v3.copy()
+    v3[0] += 1
+    rows.append((cols[s0], v3))
+    for s in range(3, n):
+        rows.append((cols[indptr[s]:indptr[s + 1]], vals[indptr[s]:indptr[s + 1]]))
+    cols2 = np.concatenate([r[0] for r in rows])
+    vals2 = np.concatenate([r[1] for r in rows])
+    indptr2 = np.concatenate([[0], np.cumsum([len(r[0]) for r in rows])]).astype(np.int64)
+    exp2 = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr2, cols2, vals2, tips), tip_node, parent, length)
+    got, t = run(parent, length, indptr2, cols2, vals2, tip_node, n, "weighted_unifrac", 1)
+    assert t["tips_flagged"] > 0 and t["tips_ms"] == 0          # redone with dense tips
+    assert got[0] == 0.0                                          # pair (0, 1): identical samples
+    assert_close_rel(got, exp2["weighted_unifrac"], UNIFRAC_RTOL, "near-duplicates")
+
+    # 3. every sample holds every tip: position buckets overflow, the dense kernel takes the tips
+    n3, tips3 = 260, 4500
+    parent3, length3, names3, tip_node3, indptr3, cols3, vals3 = _random_problem(n3, tips3, 3.0, 32)
+    exp3 = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr3, cols3, vals3, tips3), tip_node3, parent3, length3)
+    got3, t3 = run(parent3, length3, indptr3, cols3, vals3, tip_node3, n3, "weighted_unifrac_normalized", 1)
+    assert t3["tips_ms"] == 0 and t3["tips_flagged"] == 0
+    assert_close_rel(got3, exp3["weighted_unifrac_normalized"], UNIFRAC_RTOL, "dense table")

@@ -144,7 +144,7 @@ def skip_probe(n=10000, tips=100000, lam=0.02):
             res[skip] = prob.fetch(np.empty(P))
             frac = t["visits_executed"] / t["visits_dense"] if t["visits_dense"] else 1.0
             print(f"n={n} tips={tips} lam={lam} skip={skip}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms "
-                  f"(prep {t['skip_prep_ms']:.2f}) launches {t['pair_launches']} visits {frac:.3f} of dense -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
+                  f"(prep {t['skip_prep_ms']:.2f} tips {t['tips_ms']:.2f} flagged {t['tips_flagged']}) launches {t['pair_launches']} visits {frac:.3f} of dense -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
     _capi.set_option("weighted_skip", 1)
     for k in SKIPS[1:]:
         d = np.abs(res[0] - res[k]) / np.maximum(np.abs(res[0]), 1e-300)
