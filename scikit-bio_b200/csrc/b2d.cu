@@ -10,7 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -116,78 +118,134 @@ __global__ void k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ 
 
 using namespace b2d;
 
-// The embedding buffer is by far the largest allocation (up to 85 % of the device) and
-// cudaMalloc / cudaFree of it cost tens to hundreds of milliseconds, so the buffer of a
-// destroyed problem is parked here, one per device, for the next problem on that device.
-struct EmbCache {
-    void* ptr = nullptr;
-    size_t bytes = 0;
+// Device memory is kept across problems.  cudaMalloc / cudaFree of the large buffers (the
+// embedding: up to 85 % of the device; results, zero-path table, tip buckets: 0.3 - 0.4 GB each)
+// cost tens to hundreds of milliseconds per call, so freed blocks of 1 MB and more are parked in a
+// per-device pool and handed to the next request of about the same size (the embedding, whose
+// size follows the free memory, has its own slot: any parked buffer that is large enough).
+// Everything parked is given back to the driver when an allocation fails, and by
+// b2d_set_option("cache_embedding", 0).
+struct DevPool {
+    std::unordered_map<void*, size_t> live;   // blocks handed out by b2d_malloc
+    std::multimap<size_t, void*> idle;        // parked blocks by size
+    void* emb = nullptr;                      // parked embedding buffer
+    size_t emb_bytes = 0;
 };
-static std::mutex g_emb_cache_mu;
-static EmbCache g_emb_cache[64];
+static std::mutex g_pool_mu;
+static DevPool g_pool[64];
+constexpr size_t POOL_MIN_BYTES = (size_t)1 << 20;
 
-static size_t emb_cache_bytes(int device) {
-    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
-    return device >= 0 && device < 64 ? g_emb_cache[device].bytes : 0;
+static int pool_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d >= 0 && d < 64 ? d : 0;
 }
-// take the parked buffer if it is large enough, else release it (the caller allocates)
+// give every parked block of every device back to the driver
+static void pool_clear() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) {
+        DevPool& pl = g_pool[d];
+        if (pl.idle.empty() && !pl.emb) continue;
+        cudaSetDevice(d);
+        for (auto& kv : pl.idle) cudaFree(kv.second);
+        pl.idle.clear();
+        if (pl.emb) {
+            pl.live.erase(pl.emb);
+            cudaFree(pl.emb);
+            pl.emb = nullptr;
+            pl.emb_bytes = 0;
+        }
+    }
+    cudaSetDevice(cur);
+}
+template <typename T>
+static cudaError_t b2d_malloc(T** ptr, size_t bytes) {
+    const int d = pool_device();
+    if (g_cache_embedding && bytes >= POOL_MIN_BYTES) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        DevPool& pl = g_pool[d];
+        auto it = pl.idle.lower_bound(bytes);
+        if (it != pl.idle.end() && it->first <= bytes + bytes / 4) {
+            *ptr = (T*)it->second;
+            pl.live[it->second] = it->first;
+            pl.idle.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc((void**)ptr, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_clear();
+        e = cudaMalloc((void**)ptr, bytes);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool[d].live[(void*)*ptr] = bytes;
+    }
+    return e;
+}
+static void b2d_free(void* ptr) {
+    if (!ptr) return;
+    const int d = pool_device();
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        DevPool& pl = g_pool[d];
+        auto it = pl.live.find(ptr);
+        if (it != pl.live.end()) {
+            const size_t bytes = it->second;
+            pl.live.erase(it);
+            if (g_cache_embedding && bytes >= POOL_MIN_BYTES) {
+                pl.idle.insert({bytes, ptr});
+                return;
+            }
+        }
+    }
+    cudaFree(ptr);
+}
+// bytes parked on a device (they count as free memory when the embedding is sized)
+static size_t emb_cache_bytes(int device) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (device < 0 || device >= 64) return 0;
+    size_t b = g_pool[device].emb_bytes;
+    for (auto& kv : g_pool[device].idle) b += kv.first;
+    return b;
+}
+// take the parked embedding buffer if it is large enough, else release it (the caller allocates)
 static void* emb_cache_take(int device, size_t need, size_t* got) {
-    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
     *got = 0;
     if (device < 0 || device >= 64) return nullptr;
-    EmbCache& c = g_emb_cache[device];
-    if (!c.ptr) return nullptr;
-    void* ptr = c.ptr;
-    const size_t bytes = c.bytes;
-    c.ptr = nullptr;
-    c.bytes = 0;
+    DevPool& pl = g_pool[device];
+    if (!pl.emb) return nullptr;
+    void* ptr = pl.emb;
+    const size_t bytes = pl.emb_bytes;
+    pl.emb = nullptr;
+    pl.emb_bytes = 0;
     if (bytes >= need) {
         *got = bytes;
         return ptr;
     }
+    pl.live.erase(ptr);
     cudaFree(ptr);
     return nullptr;
 }
 static void emb_cache_put(int device, void* ptr, size_t bytes) {
     if (!ptr) return;
-    if (!g_cache_embedding || device < 0 || device >= 64) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    DevPool& pl = g_pool[device >= 0 && device < 64 ? device : 0];
+    if (!g_cache_embedding || device < 0 || device >= 64 || (pl.emb && pl.emb_bytes >= bytes)) {
+        pl.live.erase(ptr);
         cudaFree(ptr);
         return;
     }
-    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
-    EmbCache& c = g_emb_cache[device];
-    if (c.ptr && c.bytes >= bytes) {
-        cudaFree(ptr);
-        return;
+    if (pl.emb) {
+        pl.live.erase(pl.emb);
+        cudaFree(pl.emb);
     }
-    if (c.ptr) cudaFree(c.ptr);
-    c.ptr = ptr;
-    c.bytes = bytes;
-}
-static void emb_cache_clear();
-// cudaMalloc that gives the parked embedding buffer back to the driver before giving up
-template <typename T>
-static cudaError_t b2d_malloc(T** ptr, size_t bytes) {
-    cudaError_t e = cudaMalloc((void**)ptr, bytes);
-    if (e == cudaErrorMemoryAllocation) {
-        cudaGetLastError();
-        emb_cache_clear();
-        e = cudaMalloc((void**)ptr, bytes);
-    }
-    return e;
-}
-static void emb_cache_clear() {
-    std::lock_guard<std::mutex> lk(g_emb_cache_mu);
-    int cur = 0;
-    cudaGetDevice(&cur);
-    for (int d = 0; d < 64; ++d)
-        if (g_emb_cache[d].ptr) {
-            cudaSetDevice(d);
-            cudaFree(g_emb_cache[d].ptr);
-            g_emb_cache[d].ptr = nullptr;
-            g_emb_cache[d].bytes = 0;
-        }
-    cudaSetDevice(cur);
+    pl.emb = ptr;
+    pl.emb_bytes = bytes;
 }
 
 struct b2d_problem {
@@ -282,20 +340,20 @@ struct b2d_problem {
 static void free_problem(b2d_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->d_indptr); cudaFree(p->d_qidx); cudaFree(p->d_values); cudaFree(p->d_flags);
-    cudaFree(p->d_hc); cudaFree(p->d_fold); cudaFree(p->d_len); cudaFree(p->d_tipdist);
-    cudaFree(p->d_tiles); cudaFree(p->d_row_base); cudaFree(p->d_out); cudaFree(p->d_total);
-    cudaFree(p->d_svec); emb_cache_put(p->device, p->d_emb, p->emb_bytes); cudaFree(p->d_state);
-    cudaFree(p->d_out2); cudaFree(p->d_owned);
-    cudaFree(p->d_flags1); cudaFree(p->d_spans); cudaFree(p->d_top_pos); cudaFree(p->d_top_flags);
-    cudaFree(p->d_sp_entries); cudaFree(p->d_sp_ptr);
-    cudaFree(p->d_nz); cudaFree(p->d_skipsum); cudaFree(p->d_exec);
-    for (int k = 0; k < 2; ++k) cudaFree(p->d_sblist[k]);
-    cudaFree(p->d_zt); cudaFree(p->d_gperm); cudaFree(p->d_zpath);
-    cudaFree(p->d_parent_q); cudaFree(p->d_size_q); cudaFree(p->d_rd_hi); cudaFree(p->d_rd_lo);
-    cudaFree(p->d_rd_hi_int); cudaFree(p->d_rd_lo_int); cudaFree(p->d_tip_u); cudaFree(p->d_tip_ufx);
-    cudaFree(p->d_tip_scale); cudaFree(p->d_tip_word); cudaFree(p->d_tip_status); cudaFree(p->d_tip_counts);
-    cudaFree(p->d_tip_ptr); cudaFree(p->d_tip_entries);
+    b2d_free(p->d_indptr); b2d_free(p->d_qidx); b2d_free(p->d_values); b2d_free(p->d_flags);
+    b2d_free(p->d_hc); b2d_free(p->d_fold); b2d_free(p->d_len); b2d_free(p->d_tipdist);
+    b2d_free(p->d_tiles); b2d_free(p->d_row_base); b2d_free(p->d_out); b2d_free(p->d_total);
+    b2d_free(p->d_svec); emb_cache_put(p->device, p->d_emb, p->emb_bytes); b2d_free(p->d_state);
+    b2d_free(p->d_out2); b2d_free(p->d_owned);
+    b2d_free(p->d_flags1); b2d_free(p->d_spans); b2d_free(p->d_top_pos); b2d_free(p->d_top_flags);
+    b2d_free(p->d_sp_entries); b2d_free(p->d_sp_ptr);
+    b2d_free(p->d_nz); b2d_free(p->d_skipsum); b2d_free(p->d_exec);
+    for (int k = 0; k < 2; ++k) b2d_free(p->d_sblist[k]);
+    b2d_free(p->d_zt); b2d_free(p->d_gperm); b2d_free(p->d_zpath);
+    b2d_free(p->d_parent_q); b2d_free(p->d_size_q); b2d_free(p->d_rd_hi); b2d_free(p->d_rd_lo);
+    b2d_free(p->d_rd_hi_int); b2d_free(p->d_rd_lo_int); b2d_free(p->d_tip_u); b2d_free(p->d_tip_ufx);
+    b2d_free(p->d_tip_scale); b2d_free(p->d_tip_word); b2d_free(p->d_tip_status); b2d_free(p->d_tip_counts);
+    b2d_free(p->d_tip_ptr); b2d_free(p->d_tip_entries);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -358,8 +416,8 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
         int herr = 0;
         B2D_CUDA(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
-        cudaFree(d_qof);
-        cudaFree(d_err);
+        b2d_free(d_qof);
+        b2d_free(d_err);
         if (herr) return fail(B2D_ERR_INVALID_ARGUMENT, "node/feature id out of range in CSR indices");
     }
     // shard geometry: owned row stripes, tiles, compact output offsets
@@ -482,7 +540,7 @@ int b2d_set_option(const char* name, int64_t value) {
         g_tips_sparse = value ? 1 : 0;
     } else if (s == "cache_embedding") {
         g_cache_embedding = value ? 1 : 0;
-        if (!value) emb_cache_clear();
+        if (!value) pool_clear();
     } else if (s == "weighted_skip") {
         g_weighted_skip = value ? 1 : 0;
     } else {
@@ -571,7 +629,7 @@ int b2d_problem_create_features(b2d_problem** out, int device, int64_t n_samples
 static int ensure_emb(b2d_problem* p, size_t bytes) {
     if (p->emb_bytes >= bytes) return B2D_OK;
     if (p->d_emb) {
-        cudaFree(p->d_emb);
+        b2d_free(p->d_emb);
         p->d_emb = nullptr;
         p->emb_bytes = 0;
     }
@@ -860,7 +918,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     if (skip) {
         const size_t need = (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t);
         if (p->nz_bytes < need) {
-            cudaFree(p->d_nz);
+            b2d_free(p->d_nz);
             p->d_nz = nullptr;
             p->nz_bytes = 0;
             B2D_CUDA(b2d_malloc(&p->d_nz, need));
@@ -1117,7 +1175,7 @@ static int build_sparse(b2d_problem* p) {
         B2D_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaMemcpyAsync(sums.data(), p->d_svec, p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
-        cudaFree(d_bad);
+        b2d_free(d_bad);
         if (bad) return B2D_OK;
         for (double v : sums)
             if (v >= 2147483648.0) return B2D_OK;
@@ -1135,7 +1193,7 @@ static int build_sparse(b2d_problem* p) {
     std::vector<int64_t> ptr(nbuckets + 1, 0);
     for (int64_t b = 0; b < nbuckets; ++b) {
         if (counts[b] > (unsigned)SP_SORT_MAX) {  // too dense for the shared-memory sort
-            cudaFree(d_counts);
+            b2d_free(d_counts);
             return B2D_OK;
         }
         ptr[b + 1] = ptr[b] + counts[b];
@@ -1156,7 +1214,7 @@ static int build_sparse(b2d_problem* p) {
     k_sp_sort<<<(unsigned)nbuckets, 256, SP_SORT_SMEM, p->stream>>>(p->d_sp_entries, p->d_sp_ptr);
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     B2D_CUDA(cudaGetLastError());
-    cudaFree(d_counts);
+    b2d_free(d_counts);
     p->sp_nch = nch;
     p->sp_ready = 1;
     return B2D_OK;
@@ -1305,10 +1363,10 @@ int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_til
             keep.push_back(tiles[2 * t]);
             keep.push_back(tiles[2 * t + 1]);
         }
-    cudaFree(p->d_tiles);
-    cudaFree(p->d_out);
-    cudaFree(p->d_out2);
-    cudaFree(p->d_owned);
+    b2d_free(p->d_tiles);
+    b2d_free(p->d_out);
+    b2d_free(p->d_out2);
+    b2d_free(p->d_owned);
     p->d_tiles = nullptr;
     p->d_out = nullptr;
     p->d_out2 = nullptr;
@@ -1348,13 +1406,13 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
                                        : (size_t)((double)(free_b + p->emb_bytes + emb_cache_bytes(p->device)) * 0.85);
     int64_t QR = (int64_t)(budget / std::max<size_t>(row_bytes, 1)) / 2048 * 2048;
     if (QR < 2048) {
-        cudaFree(d_partial);
+        b2d_free(d_partial);
         return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for 2048 node rows");
     }
     QR = std::min<int64_t>(QR, (p->mpad + 2047) / 2048 * 2048);
     int rc = ensure_emb(p, (size_t)QR * row_bytes);
     if (rc) {
-        cudaFree(d_partial);
+        b2d_free(d_partial);
         return rc;
     }
     if (!p->d_state) B2D_CUDA(b2d_malloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
@@ -1378,7 +1436,7 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
     B2D_CUDA(cudaMemcpyAsync(out_n, p->d_svec, p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     B2D_CUDA(cudaGetLastError());
-    cudaFree(d_partial);
+    b2d_free(d_partial);
     p->computed = false;  // d_total / d_svec no longer describe a distance computation
     return B2D_OK;
 }
@@ -1545,7 +1603,7 @@ int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_g
     k_permanova_reduce<<<(unsigned)((n_groupings + 255) / 256), 256>>>(d_partial, nb, n_groupings, d_out);
     B2D_CUDA(cudaGetLastError());
     B2D_CUDA(cudaMemcpy(s_w_out, d_out, n_groupings * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_cond); cudaFree(d_g); cudaFree(d_w); cudaFree(d_partial); cudaFree(d_out);
+    b2d_free(d_cond); b2d_free(d_g); b2d_free(d_w); b2d_free(d_partial); b2d_free(d_out);
     return B2D_OK;
 }
 
@@ -1639,7 +1697,7 @@ int b2d_microbench(int device, int kind, double* result) {
             cudaEventElapsedTime(&ms, e0, e1);
             if (rep > 0 && ms < best) best = ms;
         }
-        cudaFree(d);
+        b2d_free(d);
         *result = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
     } else if (kind == 1) {
         const int64_t bytes = (int64_t)2 << 30;
@@ -1656,8 +1714,8 @@ int b2d_microbench(int device, int kind, double* result) {
             cudaEventElapsedTime(&ms, e0, e1);
             if (rep > 0 && ms < best) best = ms;
         }
-        cudaFree(a);
-        cudaFree(b);
+        b2d_free(a);
+        b2d_free(b);
         *result = 2.0 * (double)bytes / (best * 1e-3);
     } else if (kind == 2) {
         cudaDeviceProp prop;
@@ -1676,7 +1734,7 @@ int b2d_microbench(int device, int kind, double* result) {
             cudaEventElapsedTime(&ms, e0, e1);
             if (rep > 0 && ms < best) best = ms;
         }
-        cudaFree(d);
+        b2d_free(d);
         *result = (double)blocks * threads * 4.0 * iters / (best * 1e-3);
     } else if (kind == 3) {
         cudaDeviceProp prop;
@@ -1695,7 +1753,7 @@ int b2d_microbench(int device, int kind, double* result) {
             cudaEventElapsedTime(&ms, e0, e1);
             if (rep > 0 && ms < best) best = ms;
         }
-        cudaFree(d);
+        b2d_free(d);
         *result = (double)blocks * threads * (double)iters / (best * 1e-3);
     } else {
         return fail(B2D_ERR_INVALID_ARGUMENT, "unknown microbench kind");
