@@ -180,9 +180,10 @@ int b2d_beta_diversity_features(int metric, int device,
  *                       sparse intersection kernel in exact fixed point instead of the dense
  *                       kernel; 0: dense.  Falls back by itself for very dense tables and when
  *                       near-duplicate samples are found.
- *   "cache_embedding"   1 (default): the embedding buffer of a destroyed problem is kept, one
- *                       per device, for the next problem (cudaMalloc / cudaFree of tens of GB
- *                       cost 0.1 - 0.6 s); 0: free it now and stop keeping it
+ *   "cache_embedding"   1 (default): device buffers of 1 MB and more (the embedding above all)
+ *                       are parked per device when a problem is destroyed and reused by the
+ *                       next one (cudaMalloc / cudaFree of tens of GB cost 0.1 - 0.7 s); they
+ *                       are released when an allocation fails; 0: release now, stop parking
  *   "sparse_features"   -1 auto, 0 never, 1 whenever legal: intersection kernel for integer
  *                       feature tables (Bray-Curtis / Jaccard)
  *   "walk_decomposed"   0: always the sequential tree walk;  "plain_kernels" 1: cross-check
