@@ -149,8 +149,9 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * the skipping bitmaps and closed-form sums, [11] kernels launched by the last compute (all
  * of them: embedding, bitmaps, pair launches, closed form, finalize), [12] duration of the
  * sparse tip-row kernel (0 when the tips went through the dense kernel), [13] number of
- * near-duplicate pairs that made the last compute redo the tips densely (normally 0).
- * n: slots to fill (<= 14). */
+ * near-duplicate pairs that made the last compute redo the tips densely (normally 0),
+ * [14] largest number of tips below a node whose row went through the sparse intersection
+ * kernel (0: none, 1: tip rows only), [15] entries of those rows.  n: slots to fill (<= 16). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);
@@ -180,6 +181,9 @@ int b2d_beta_diversity_features(int metric, int device,
  *                       sparse intersection kernel in exact fixed point instead of the dense
  *                       kernel; 0: dense.  Falls back by itself for very dense tables and when
  *                       near-duplicate samples are found.
+ *   "sparse_rows_max_tips"  0 (default): when the whole embedding is resident, rows of nodes with
+ *                       up to about 0.1 / (table density) tips below them join the tips in the
+ *                       intersection kernel; k > 0: up to k tips (1 = tip rows only)
  *   "cache_embedding"   1 (default): device buffers of 1 MB and more (the embedding above all)
  *                       are parked per device when a problem is destroyed and reused by the
  *                       next one (cudaMalloc / cudaFree of tens of GB cost 0.1 - 0.7 s); they

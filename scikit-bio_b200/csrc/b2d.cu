@@ -34,6 +34,7 @@ static int64_t g_emb_budget_bytes = 0;         // 0 = 85 % of free memory
 static int g_plain_kernels = -1;               // -1 = read env B2D_PLAIN_KERNELS
 static int g_walk_decomposed = 1;              // 0 = always the sequential weighted walk
 constexpr int SKIP_GW = 8;                     // group words per zero-path table (256 groups)
+static int g_sparse_rows_max_tips = 0;         // 0 = from the table's density; 1 = tips only
 static int g_tips_sparse = 1;                  // tip rows of the weighted kernel as a sparse intersection
 static int g_cache_embedding = 1;              // keep the embedding buffer of a destroyed problem
 static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
@@ -321,6 +322,23 @@ struct b2d_problem {
     unsigned* d_tip_counts = nullptr;
     int64_t* d_tip_ptr = nullptr;
     TipEntry* d_tip_entries = nullptr;
+    unsigned short* d_tip_runs = nullptr;   // [nbuckets][TP_CHUNK + 8] run starts per position
+    int64_t tip_entries_cap = 0;            // entries d_tip_entries can hold
+    // sparse rows beyond the tips (whole embedding resident): nodes with <= rows_S0 tips below
+    bool rows_general = false;
+    int rows_S0 = 0, rows_S0_uploaded = 0;
+    double rows_entries = 0;
+    uint32_t* d_rows_sparse = nullptr;      // [mpad/32] bit = row goes through the intersection kernel
+    uint32_t* d_rows_dense = nullptr;       // complement (what the pair kernel may visit)
+    double* d_rdR_hi = nullptr;             // root distances without the sparse rows' branches
+    double* d_rdR_lo = nullptr;
+    int32_t* d_dense_pos = nullptr;         // positions of the rows left to the dense pair kernel
+    int64_t n_dense = 0, n_dense_pad = 0;
+    double* d_embd = nullptr;               // [nb][n_dense_pad][128] those rows, packed
+    double* d_lend = nullptr;
+    size_t embd_bytes = 0;
+    unsigned* d_rows_qcount = nullptr;      // [nbuckets][4]
+    double* d_rows_upart = nullptr;         // [nch * 4][npad]
     int64_t tip_nch = 0;
     double tips_flagged = 0, t_tips = 0;
     // sparse feature-table path
@@ -353,7 +371,10 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_parent_q); b2d_free(p->d_size_q); b2d_free(p->d_rd_hi); b2d_free(p->d_rd_lo);
     b2d_free(p->d_rd_hi_int); b2d_free(p->d_rd_lo_int); b2d_free(p->d_tip_u); b2d_free(p->d_tip_ufx);
     b2d_free(p->d_tip_scale); b2d_free(p->d_tip_word); b2d_free(p->d_tip_status); b2d_free(p->d_tip_counts);
-    b2d_free(p->d_tip_ptr); b2d_free(p->d_tip_entries);
+    b2d_free(p->d_tip_ptr); b2d_free(p->d_tip_entries); b2d_free(p->d_tip_runs);
+    b2d_free(p->d_rows_sparse); b2d_free(p->d_rows_dense); b2d_free(p->d_rdR_hi); b2d_free(p->d_rdR_lo);
+    b2d_free(p->d_rows_qcount); b2d_free(p->d_rows_upart);
+    b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -536,6 +557,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_sparse_features = value < 0 ? -1 : (value ? 1 : 0);
     } else if (s == "plain_kernels") {
         g_plain_kernels = value ? 1 : 0;
+    } else if (s == "sparse_rows_max_tips") {
+        g_sparse_rows_max_tips = value < 0 ? 0 : (int)std::min<int64_t>(value, 1 << 20);
     } else if (s == "tips_sparse") {
         g_tips_sparse = value ? 1 : 0;
     } else if (s == "cache_embedding") {
@@ -731,8 +754,7 @@ static int skip_setup(b2d_problem* p) {
 // Tip rows as a sparse intersection: buffers, fixed-point scale, buckets sorted by node position.
 // Rebuilt by every compute (like the embedding); tips_mode becomes -1 when a bucket is too large
 // for the shared-memory sort (very dense tables).
-static int tips_build(b2d_problem* p) {
-    const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+static int tips_buffers(b2d_problem* p) {
     const int64_t nch = (p->mpad + TP_CHUNK - 1) / TP_CHUNK;
     const int64_t nbuckets = p->nb * nch;
     p->tip_nch = nch;
@@ -748,7 +770,7 @@ static int tips_build(b2d_problem* p) {
         B2D_CUDA(b2d_malloc(&p->d_tip_status, sizeof(int)));
         B2D_CUDA(b2d_malloc(&p->d_tip_counts, (nbuckets + 1) * sizeof(unsigned)));
         B2D_CUDA(b2d_malloc(&p->d_tip_ptr, (nbuckets + 1) * sizeof(int64_t)));
-        B2D_CUDA(b2d_malloc(&p->d_tip_entries, std::max<int64_t>(p->nnz, 1) * sizeof(TipEntry)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_runs, (size_t)nbuckets * (TP_CHUNK + 8) * sizeof(unsigned short)));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
     }
     B2D_CUDA(cudaMemsetAsync(p->d_tip_u, 0, p->npad * sizeof(double), p->stream));
@@ -756,6 +778,29 @@ static int tips_build(b2d_problem* p) {
     B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 2 * sizeof(unsigned long long), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+    return B2D_OK;
+}
+
+static int tips_entries_reserve(b2d_problem* p, int64_t count) {
+    if (p->tip_entries_cap >= count && p->d_tip_entries) return B2D_OK;
+    b2d_free(p->d_tip_entries);
+    p->d_tip_entries = nullptr;
+    p->tip_entries_cap = 0;
+    B2D_CUDA(b2d_malloc(&p->d_tip_entries, std::max<int64_t>(count, 1) * sizeof(TipEntry)));
+    p->tip_entries_cap = count;
+    return B2D_OK;
+}
+
+// Tip rows as a sparse intersection, entries from the CSR input (used when the embedding is built
+// in several passes): fixed-point scale, buckets sorted by node position.  Rebuilt by every
+// compute (like the embedding); tips_mode becomes -1 when a bucket is too large for the
+// shared-memory sort (very dense tables).
+static int tips_build(b2d_problem* p) {
+    const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    int rc;
+    if ((rc = tips_buffers(p))) return rc;
+    if ((rc = tips_entries_reserve(p, p->nnz))) return rc;
+    const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
     const int64_t* vals = (const int64_t*)p->d_values;
     p->n_kernels += 6;
     k_tip_usum<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, vals, p->d_total, p->d_flags,
@@ -763,19 +808,133 @@ static int tips_build(b2d_problem* p) {
     k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
     k_tip_count<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->d_flags, p->n, nch,
                                                      p->d_tip_counts);
-    k_tip_scan<<<1, 1024, 0, p->stream>>>(p->d_tip_counts, nbuckets, p->d_tip_ptr, p->d_tip_status);
+    k_tip_scan<<<1, 1024, 0, p->stream>>>(p->d_tip_counts, nbuckets, p->d_tip_ptr, p->d_tip_status,
+                                          (unsigned)TP_SORT_MAX);
     B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
     k_tip_scatter<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, vals, p->d_total, p->d_flags,
                                                        p->d_len, p->d_tip_scale, p->n, nch, p->d_tip_ptr,
                                                        p->d_tip_counts, p->d_tip_entries, p->d_tip_ufx);
     B2D_CUDA(cudaFuncSetAttribute(k_tip_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SORT_SMEM));
-    k_tip_sort<<<(unsigned)nbuckets, 256, TP_SORT_SMEM, p->stream>>>(p->d_tip_entries, p->d_tip_ptr);
+    k_tip_sort<<<(unsigned)nbuckets, 256, TP_SORT_SMEM, p->stream>>>(p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs);
     int status = 0;
     B2D_CUDA(cudaMemcpyAsync(&status, p->d_tip_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     B2D_CUDA(cudaGetLastError());
     p->tips_mode = status ? -1 : 1;
     return B2D_OK;
+}
+
+// Sparse rows (nodes with at most S0 tips below) taken from the resident embedding.  S0 follows the
+// table's density (a node with s tips below is non-zero for about s * nnz / (n * tips) of the
+// samples; the intersection kernel wins up to ~10 %) and is halved while a bucket overflows.
+static int rows_build(b2d_problem* p, int64_t QR) {
+    const TreeOrder& o = p->order;
+    int rc;
+    if ((rc = tips_buffers(p))) return rc;
+    const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
+    if (!p->rows_S0) {
+        int64_t ntips = 0;
+        for (int64_t q = 0; q < p->mpad; ++q) ntips = std::max<int64_t>(ntips, o.tips_q[q]);
+        const double dens = (double)p->nnz / std::max(1.0, (double)p->n * (double)std::max<int64_t>(ntips, 1));
+        int s0 = g_sparse_rows_max_tips ? g_sparse_rows_max_tips : (int)std::min(32.0, std::max(1.0, 0.1 / std::max(dens, 1e-9)));
+        p->rows_S0 = std::max(1, s0);
+    }
+    if (!p->d_rows_qcount) {
+        B2D_CUDA(b2d_malloc(&p->d_rows_sparse, (p->mpad / 32) * sizeof(uint32_t)));
+        B2D_CUDA(b2d_malloc(&p->d_rows_dense, (p->mpad / 32) * sizeof(uint32_t)));
+        B2D_CUDA(b2d_malloc(&p->d_rdR_hi, p->mpad * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_rdR_lo, p->mpad * sizeof(double)));
+        B2D_CUDA(b2d_malloc(&p->d_rows_qcount, nbuckets * 4 * sizeof(unsigned)));
+        B2D_CUDA(b2d_malloc(&p->d_rows_upart, (size_t)nch * 4 * p->npad * sizeof(double)));
+    }
+    for (;;) {
+        if (p->rows_S0_uploaded != p->rows_S0) {
+            const int S0 = p->rows_S0;
+            std::vector<uint32_t> sp(p->mpad / 32, 0u), de(p->mpad / 32, 0u);
+            std::vector<double> hi(p->mpad, 0.0), lo(p->mpad, 0.0);
+            for (int64_t q = p->mpad - 1; q >= 0; --q) {  // parents (higher positions) first
+                const bool real = o.tips_q[q] > 0;
+                const bool inR = real && o.tips_q[q] <= S0;
+                if (inR) sp[q >> 5] |= 1u << (q & 31);
+                else if (real) de[q >> 5] |= 1u << (q & 31);
+                const int32_t par = o.parent_q[q];
+                if (inR) {
+                    hi[q] = par >= 0 ? hi[par] : 0.0;
+                    lo[q] = par >= 0 ? lo[par] : 0.0;
+                } else {
+                    hi[q] = o.rd_hi[q];
+                    lo[q] = o.rd_lo[q];
+                }
+            }
+            B2D_CUDA(cudaMemcpyAsync(p->d_rows_sparse, sp.data(), sp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+            B2D_CUDA(cudaMemcpyAsync(p->d_rows_dense, de.data(), de.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+            B2D_CUDA(cudaMemcpyAsync(p->d_rdR_hi, hi.data(), hi.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            B2D_CUDA(cudaMemcpyAsync(p->d_rdR_lo, lo.data(), lo.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            std::vector<int32_t> dpos;
+            for (int64_t q = 0; q < p->mpad; ++q)
+                if ((de[q >> 5] >> (q & 31)) & 1u) dpos.push_back((int32_t)q);
+            p->n_dense = (int64_t)dpos.size();
+            p->n_dense_pad = std::max<int64_t>(128, (p->n_dense + 127) / 128 * 128);
+            b2d_free(p->d_dense_pos);
+            p->d_dense_pos = nullptr;
+            if ((rc = upload(&p->d_dense_pos, dpos.data(), dpos.size(), p->stream))) return rc;
+            B2D_CUDA(cudaStreamSynchronize(p->stream));
+            p->rows_S0_uploaded = S0;
+        }
+        const int64_t rows = p->mpad;
+        p->n_kernels += 5;
+        k_rows_count<<<dim3((unsigned)p->nb, (unsigned)nch), 128, 0, p->stream>>>(
+            (const double*)p->d_emb, p->d_len, p->d_rows_sparse, rows, QR, nch, p->npad, p->d_rows_qcount,
+            p->d_rows_upart);
+        k_rows_bucket_counts<<<(unsigned)((nbuckets + 255) / 256), 256, 0, p->stream>>>(p->d_rows_qcount, nbuckets,
+                                                                                      p->d_tip_counts);
+        k_tip_scan<<<1, 1024, 0, p->stream>>>(p->d_tip_counts, nbuckets, p->d_tip_ptr, p->d_tip_status, 65535u);
+        k_rows_ureduce<<<(unsigned)((p->npad + 255) / 256), 256, 0, p->stream>>>(p->d_rows_upart, nch * 4, p->npad,
+                                                                               p->d_tip_u, p->d_tip_word);
+        k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
+        int status = 0;
+        int64_t total = 0;
+        B2D_CUDA(cudaMemcpyAsync(&status, p->d_tip_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaMemcpyAsync(&total, p->d_tip_ptr + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        B2D_CUDA(cudaGetLastError());
+        if (status) {  // a bucket holds more than 65535 entries: fewer rows
+            if (p->rows_S0 == 1) {
+                p->tips_mode = -1;
+                return B2D_OK;
+            }
+            p->rows_S0 /= 2;
+            B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 2 * sizeof(unsigned long long), p->stream));
+            B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
+            continue;
+        }
+        if ((rc = tips_entries_reserve(p, total))) return rc;
+        p->rows_entries = (double)total;
+        p->n_kernels += 1;
+        k_rows_scatter<<<dim3((unsigned)p->nb, (unsigned)nch), 128, 0, p->stream>>>(
+            (const double*)p->d_emb, p->d_len, p->d_rows_sparse, p->d_tip_scale, rows, QR, nch,
+            p->d_rows_qcount, p->d_tip_ptr, p->d_tip_entries, p->d_tip_runs,
+            (unsigned long long*)p->d_tip_ufx);
+        // the rows left to the dense pair kernel, packed
+        const size_t need = (size_t)p->nb * p->n_dense_pad * TILE * sizeof(double);
+        if (p->embd_bytes < need) {
+            b2d_free(p->d_embd);
+            b2d_free(p->d_lend);
+            p->d_embd = nullptr;
+            p->d_lend = nullptr;
+            p->embd_bytes = 0;
+            B2D_CUDA(b2d_malloc(&p->d_embd, need));
+            B2D_CUDA(b2d_malloc(&p->d_lend, p->n_dense_pad * sizeof(double)));
+            p->embd_bytes = need;
+        }
+        p->n_kernels += 1;
+        k_compact_rows<<<dim3((unsigned)p->n_dense_pad, (unsigned)p->nb), 128, 0, p->stream>>>(
+            (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, p->d_embd,
+            p->d_lend);
+        B2D_CUDA(cudaGetLastError());
+        p->tips_mode = 1;
+        return B2D_OK;
+    }
 }
 
 // Closed-form sums S[g][s] from the bitmaps of ALL node rows (after the last pass), the tree
@@ -794,8 +953,8 @@ static int skip_closed_form(b2d_problem* p) {
             p->n_kernels += 1;
             k_fill_zero_paths<SKIP_GW><<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
                 p->d_zt, p->ngw, kbeg, kcnt, p->d_parent_q, p->d_size_q,
-                p->tips_active ? p->d_rd_hi_int : p->d_rd_hi,
-                p->tips_active ? p->d_rd_lo_int : p->d_rd_lo, p->m, p->d_zpath);
+                p->tips_active ? (p->rows_general ? p->d_rdR_hi : p->d_rd_hi_int) : p->d_rd_hi,
+                p->tips_active ? (p->rows_general ? p->d_rdR_lo : p->d_rd_lo_int) : p->d_rd_lo, p->m, p->d_zpath);
             const unsigned grid = (unsigned)p->n_sblist[part] * 16;
             p->n_kernels += 1;
             if (tree)
@@ -835,7 +994,7 @@ static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* l
     // registers within a chunk, `out` across chunks.
     B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)W3_SMEM));
-B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_mask, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2D_CUDA(cudaFuncSetAttribute(k_pair_weighted_mask, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)MK_SMEM));
     // launches of the skipping kernel are about half as long per node: twice the nodes each
     const int64_t chunk = skip ? 2 * g_chunk_nodes : g_chunk_nodes;
@@ -898,11 +1057,8 @@ static int compute_dense(b2d_problem* p, int metric) {
     if (skip) {
         int rc0 = skip_setup(p);
         if (rc0) return rc0;
-        if (tree && g_tips_sparse && p->tips_mode >= 0 && p->n > 0) {
-            if ((rc0 = tips_build(p))) return rc0;
-            p->tips_active = p->tips_mode == 1;
-        }
     }
+    const bool want_tips = skip && tree && g_tips_sparse && p->tips_mode >= 0 && p->n > 0;
     // resident node range
     size_t free_b = 0, total_b = 0;
     B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -915,6 +1071,12 @@ static int compute_dense(b2d_problem* p, int metric) {
     if (QR < NODE_STRIPE) return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for one node stripe");
     QR = std::min<int64_t>(QR, p->mpad);
     int rc = B2D_OK;
+    // whole tree resident: sparse rows from the embedding (inside the pass); else tips from the CSR
+    p->rows_general = want_tips && QR == p->mpad;
+    if (want_tips && !p->rows_general) {
+        if ((rc = tips_build(p))) return rc;
+        p->tips_active = p->tips_mode == 1;
+    }
     if (skip) {
         const size_t need = (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t);
         if (p->nz_bytes < need) {
@@ -986,8 +1148,18 @@ static int compute_dense(b2d_problem* p, int metric) {
         B2D_CUDA(cudaEventRecord(eb, p->stream));
         if (p->ntiles) {
             if (skip) {
+                if (p->rows_general) {
+                    if ((rc = rows_build(p, QR))) return rc;
+                    p->tips_active = p->tips_mode == 1;
+                }
                 if ((rc = skip_prepare_pass(p, q0, q1 - q0, QR))) return rc;
-                if (p->tips_active) {  // the pair kernel never visits a tip row
+                if (p->tips_active && p->rows_general) {
+                    // the pair kernel streams the packed dense rows only: their own bitmaps
+                    const int64_t ng = p->npad / 32, wd = p->n_dense_pad / 32;
+                    p->n_kernels += 1;
+                    k_group_nonzero<<<(unsigned)((ng * wd + 7) / 8), 256, 0, p->stream>>>(
+                        p->d_embd, ng, p->n_dense_pad, p->n_dense_pad, p->d_nz);
+                } else if (p->tips_active) {  // the pair kernel never visits a tip row
                     const int64_t ng = p->npad / 32, nwords = (q1 - q0 + 31) / 32;
                     p->n_kernels += 1;
                     k_mask_tip_rows<<<(unsigned)((ng * nwords + 255) / 256), 256, 0, p->stream>>>(
@@ -1015,12 +1187,15 @@ static int compute_dense(b2d_problem* p, int metric) {
                 B2D_CUDA(cudaFuncSetAttribute(k_pair_tips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
                 B2D_CUDA(cudaEventRecord(p->ev[7], st));
                 k_pair_tips<<<(unsigned)p->ntiles, TP_THREADS, TP_SMEM, st>>>(
-                    p->d_tip_entries, p->d_tip_ptr, p->tip_nch, p->d_tip_ufx, p->d_tip_scale, a);
+                    p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, p->tip_nch, p->d_tip_ufx, p->d_tip_scale, a);
                 B2D_CUDA(cudaEventRecord(p->ev[8], st));
                 tips_timed = true;
                 p->n_kernels += 1;
             }
-            rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue, skip);
+            if (p->tips_active && p->rows_general)
+                rc = launch_pairs_dense(p, p->d_embd, p->d_lend, 0, p->n_dense_pad, p->n_dense_pad, epilogue, skip);
+            else
+                rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue, skip);
             if (rc) return rc;
             if ((rc = join_streams(p))) return rc;
             if (q1 == p->mpad) {
@@ -1506,10 +1681,12 @@ int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[14] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+    double v[16] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
-                    p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged};
-    for (int i = 0; i < n && i < 14; ++i) ms[i] = v[i];
+                    p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged,
+                    p->tips_active ? (p->rows_general ? (double)p->rows_S0 : 1.0) : 0.0,
+                    p->tips_active && p->rows_general ? p->rows_entries : 0.0};
+    for (int i = 0; i < n && i < 16; ++i) ms[i] = v[i];
     return B2D_OK;
 }
 

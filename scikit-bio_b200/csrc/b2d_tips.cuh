@@ -16,10 +16,11 @@
 // The pair kernel then never visits a tip row (its bits are cleared in the row-major bitmaps)
 // and the closed form of b2d_skip.cuh uses root distances that leave the tips' own branches out.
 //
-// Layout and kernel follow b2d_sparse.cuh: CSR entries on tips are bucketed by (sample block of
-// 128, chunk of 4096 node positions), sorted by position inside a bucket; a CTA owns one tile,
-// stages the column block's bucket with its per-position run boundaries and lets every lane walk
-// the run of one row entry, adding min(w, w') into a 128 x 128 int64 tile in shared memory.
+// Layout: CSR entries on tips are bucketed by (sample block of 128, chunk of 2048 node positions)
+// and sorted by position inside a bucket, with the start of every position's run kept beside
+// them; a CTA owns one tile, stages the column block's bucket and run starts in shared memory
+// and lets every thread walk the run of one row entry (read from global memory), adding
+// min(w, w') into a 128 x 128 int64 tile in shared memory.
 #pragma once
 
 #include <cuda_pipeline.h>
@@ -29,9 +30,8 @@
 
 namespace b2d {
 
-constexpr int TP_CHUNK = 4096;
-constexpr int TP_MAXE = 2048;      // column entries resident per batch
-constexpr int TP_MAXR = 2048;      // row entries resident per batch
+constexpr int TP_CHUNK = 2048;     // node positions per bucket
+constexpr int TP_MAXE = 5120;      // column entries resident per batch (normally a whole bucket)
 constexpr int TP_SORT_MAX = 8192;  // largest bucket the shared-memory counting sort accepts
 constexpr int TP_THREADS = 512;
 struct TipEntry {
@@ -39,8 +39,8 @@ struct TipEntry {
     uint32_t pad;
     long long val; // fixed-point len * proportion
 };
-constexpr size_t TP_SMEM = (size_t)TILE * TILE * sizeof(long long) + 2 * TP_CHUNK * sizeof(unsigned short) +
-                           (size_t)(TP_MAXE + TP_MAXR) * sizeof(TipEntry);
+constexpr size_t TP_SMEM = (size_t)TILE * TILE * sizeof(long long) + (size_t)TP_MAXE * sizeof(TipEntry) +
+                           (TP_CHUNK + 8) * sizeof(unsigned short);
 constexpr size_t TP_SORT_SMEM = (size_t)TP_SORT_MAX * sizeof(TipEntry) + (TP_CHUNK + 1) * sizeof(int);
 
 __device__ __forceinline__ double tip_weight(const int64_t* values, const long long tot, const double* len,
@@ -102,7 +102,7 @@ __global__ void k_tip_count(const int64_t* __restrict__ indptr, const int32_t* _
 // 4. exclusive scan of the bucket sizes (one CTA) + "a bucket is too large" flag
 __global__ void __launch_bounds__(1024)
 k_tip_scan(const unsigned* __restrict__ counts, int64_t nbuckets, int64_t* __restrict__ ptr,
-           int* __restrict__ status) {
+           int* __restrict__ status, unsigned limit) {
     __shared__ long long part[1024];
     const int tid = threadIdx.x;
     const int64_t per = (nbuckets + 1023) / 1024;
@@ -111,7 +111,7 @@ k_tip_scan(const unsigned* __restrict__ counts, int64_t nbuckets, int64_t* __res
     bool big = false;
     for (int64_t b = b0; b < b1; ++b) {
         sum += counts[b];
-        big |= counts[b] > (unsigned)TP_SORT_MAX;
+        big |= counts[b] > limit;
     }
     if (big) atomicOr(status, 1);
     part[tid] = sum;
@@ -163,26 +163,29 @@ __global__ void k_tip_scatter(const int64_t* __restrict__ indptr, const int32_t*
     if (lane == 0) Ufx[s] = u;
 }
 
-// 6. sort every bucket by position (counting sort in shared memory, one CTA per bucket)
+// 6. sort every bucket by position (counting sort in shared memory, one CTA per bucket) and keep
+// the run starts: runs[bucket][f] = first entry of position f, runs[bucket][TP_CHUNK] = size
 __global__ void __launch_bounds__(256)
-k_tip_sort(TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr) {
+k_tip_sort(TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr,
+           unsigned short* __restrict__ runs /*[nbuckets][TP_CHUNK + 8]*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TipEntry* buf = reinterpret_cast<TipEntry*>(smem_raw);
     int* cnt = reinterpret_cast<int*>(buf + TP_SORT_MAX);  // [TP_CHUNK + 1]
     const int64_t b0 = bucket_ptr[blockIdx.x];
     const int nb = (int)(bucket_ptr[blockIdx.x + 1] - b0);
-    if (nb <= 1 || nb > TP_SORT_MAX) return;
+    if (nb == 0 || nb > TP_SORT_MAX) return;
     const int tid = threadIdx.x;
+    constexpr int PER = TP_CHUNK / 256;
     for (int x = tid; x <= TP_CHUNK; x += 256) cnt[x] = 0;
     for (int x = tid; x < nb; x += 256) buf[x] = entries[b0 + x];
     __syncthreads();
     for (int x = tid; x < nb; x += 256) atomicAdd(&cnt[(buf[x].key >> 7) + 1], 1);
     __syncthreads();
     __shared__ int part[256];
-    int local[16], sum = 0;
+    int local[PER], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        local[k] = cnt[1 + tid * 16 + k];
+    for (int k = 0; k < PER; ++k) {
+        local[k] = cnt[1 + tid * PER + k];
         sum += local[k];
     }
     part[tid] = sum;
@@ -194,11 +197,14 @@ k_tip_sort(TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_pt
         __syncthreads();
     }
     int run = part[tid] - sum;
+    unsigned short* rs = runs + (size_t)blockIdx.x * (TP_CHUNK + 8);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        cnt[1 + tid * 16 + k] = run;
+    for (int k = 0; k < PER; ++k) {
+        cnt[1 + tid * PER + k] = run;
+        rs[tid * PER + k] = (unsigned short)run;
         run += local[k];
     }
+    if (tid == 255) rs[TP_CHUNK] = (unsigned short)nb;
     __syncthreads();
     for (int x = tid; x < nb; x += 256) {
         const TipEntry e = buf[x];
@@ -207,58 +213,65 @@ k_tip_sort(TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_pt
     }
 }
 
-// 7. the tile kernel: T(i,j) = U_i + U_j - 2 * sum_{t in both} min(w_ti, w_tj), exact in fixed point
+// 7. the tile kernel: T(i,j) = U_i + U_j - 2 * sum_{t in both} min(w_ti, w_tj), exact in fixed point.
+// Per position chunk the column block's bucket and its run starts are staged in shared memory
+// (one batch unless the bucket is larger than TP_MAXE); the row block's entries are read straight
+// from global memory, one per thread, and each walks the run of its position.
 __global__ void __launch_bounds__(TP_THREADS, 1)
-k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr, int64_t nch,
-            const long long* __restrict__ Ufx, const double* __restrict__ scale, PairArgs a) {
+k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr,
+            const unsigned short* __restrict__ runs, int64_t nch, const long long* __restrict__ Ufx,
+            const double* __restrict__ scale, PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem_raw);  // [128][128]
-    unsigned short* fstart = reinterpret_cast<unsigned short*>(smem_raw + (size_t)TILE * TILE * sizeof(long long));
-    unsigned short* fend = fstart + TP_CHUNK;
-    TipEntry* centry = reinterpret_cast<TipEntry*>(fend + TP_CHUNK);
-    TipEntry* rentry = centry + TP_MAXE;
+    // 64-bit sums as two 32-bit halves: shared memory has native 32-bit atomic adds only (a 64-bit
+    // atomicAdd is a compare-and-swap loop); the add that wraps the low half carries into the high
+    uint32_t* acc_lo = reinterpret_cast<uint32_t*>(smem_raw);   // [128][128]
+    uint32_t* acc_hi = acc_lo + TILE * TILE;                    // [128][128]
+    TipEntry* centry = reinterpret_cast<TipEntry*>(smem_raw + (size_t)TILE * TILE * sizeof(long long));
+    unsigned short* fstart = reinterpret_cast<unsigned short*>(centry + TP_MAXE);  // [TP_CHUNK + 1]
 
     const int tid = threadIdx.x;
     const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
-    for (int x = tid; x < TILE * TILE; x += TP_THREADS) acc[x] = 0ull;
+    for (int x = tid; x < 2 * TILE * TILE; x += TP_THREADS) acc_lo[x] = 0u;
 
     for (int64_t ch = 0; ch < nch; ++ch) {
-        const int64_t r0 = bucket_ptr[(int64_t)bi * nch + ch], r1 = bucket_ptr[(int64_t)bi * nch + ch + 1];
-        const int64_t c0 = bucket_ptr[(int64_t)bj * nch + ch], c1 = bucket_ptr[(int64_t)bj * nch + ch + 1];
+        const int64_t rbk = (int64_t)bi * nch + ch, cbk = (int64_t)bj * nch + ch;
+        const int64_t r0 = bucket_ptr[rbk], r1 = bucket_ptr[rbk + 1];
+        const int64_t c0 = bucket_ptr[cbk], c1 = bucket_ptr[cbk + 1];
         if (r1 == r0 || c1 == c0) continue;  // uniform across the CTA
+        const unsigned short* crun = runs + (size_t)cbk * (TP_CHUNK + 8);
         for (int64_t cb = c0; cb < c1; cb += TP_MAXE) {
             const int nc = (int)((c1 - cb) < TP_MAXE ? (c1 - cb) : TP_MAXE);
+            const int lo = (int)(cb - c0), hi = lo + nc;  // entry range of this batch within the bucket
             __syncthreads();  // previous batch fully consumed
-            for (int x = tid; x < TP_CHUNK; x += TP_THREADS) {
-                fstart[x] = 0;
-                fend[x] = 0;
-            }
             for (int x = tid; x < nc; x += TP_THREADS)
                 __pipeline_memcpy_async(&centry[x], &entries[cb + x], sizeof(TipEntry));
+            if (cb == c0)
+                for (int x = tid; x < (TP_CHUNK + 8) / 8; x += TP_THREADS)
+                    __pipeline_memcpy_async(fstart + 8 * x, crun + 8 * x, 16);
             __pipeline_commit();
             __pipeline_wait_prior(0);
             __syncthreads();
-            for (int x = tid; x < nc; x += TP_THREADS) {
-                const uint32_t f = centry[x].key >> 7;
-                if (x == 0 || (centry[x - 1].key >> 7) != f) fstart[f] = (unsigned short)x;
-                if (x == nc - 1 || (centry[x + 1].key >> 7) != f) fend[f] = (unsigned short)(x + 1);
-            }
-            for (int64_t rb = r0; rb < r1; rb += TP_MAXR) {
-                const int nr = (int)((r1 - rb) < TP_MAXR ? (r1 - rb) : TP_MAXR);
-                __syncthreads();  // boundaries complete / previous R batch consumed
-                for (int x = tid; x < nr; x += TP_THREADS)
-                    __pipeline_memcpy_async(&rentry[x], &entries[rb + x], sizeof(TipEntry));
-                __pipeline_commit();
-                __pipeline_wait_prior(0);
-                __syncthreads();
-                for (int x = tid; x < nr; x += TP_THREADS) {
-                    const TipEntry re = rentry[x];
-                    const uint32_t f = re.key >> 7, r = re.key & 127u;
-                    const int xe = fend[f];
-                    for (int e = fstart[f]; e < xe; ++e) {
-                        const TipEntry ce = centry[e];
-                        const long long add = re.val < ce.val ? re.val : ce.val;
-                        atomicAdd(&acc[r * TILE + (ce.key & 127u)], (unsigned long long)add);
+            constexpr int RU = 4;  // row entries in flight per thread
+            for (int64_t xb = r0 + tid; xb < r1; xb += (int64_t)RU * TP_THREADS) {
+                TipEntry re[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int64_t x = xb + (int64_t)u * TP_THREADS;
+                    if (x < r1) re[u] = entries[x];
+                    else re[u].key = 0xffffffffu;
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    if (re[u].key == 0xffffffffu) continue;
+                    const uint32_t f = re[u].key >> 7, r = re[u].key & 127u;
+                    const int e0 = max((int)fstart[f], lo), e1 = min((int)fstart[f + 1], hi);
+                    for (int e = e0; e < e1; ++e) {
+                        const TipEntry ce = centry[e - lo];
+                        const unsigned long long add = (unsigned long long)(re[u].val < ce.val ? re[u].val : ce.val);
+                        const uint32_t cell = r * TILE + (ce.key & 127u);
+                        const uint32_t alo = (uint32_t)add;
+                        const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                        atomicAdd(&acc_hi[cell], (uint32_t)(add >> 32) + (old + alo < old ? 1u : 0u));
                     }
                 }
             }
@@ -272,7 +285,8 @@ k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bu
         const int rr = x / TILE, c = x % TILE;
         const int64_t i = i0 + rr, j = (int64_t)bj * TILE + c;
         if (i >= j || j >= a.n) continue;
-        const long long t = Ufx[i] + Ufx[j] - 2 * (long long)acc[x];
+        const long long m = (long long)(((unsigned long long)acc_hi[x] << 32) | acc_lo[x]);
+        const long long t = Ufx[i] + Ufx[j] - 2 * m;
         emit(a, base, i0, i, j, (double)t * inv);
     }
 }
@@ -304,6 +318,118 @@ k_tip_guard(const double* __restrict__ out, const double* __restrict__ out2,
         if (x != 0.0 && x < 2.5e-4 * (ui + U[i + 1 + t])) ++c;
     }
     if (c) atomicAdd(flagged, (unsigned long long)c);
+}
+
+// ---------------------------------------------------------------------------------------
+// Sparse rows beyond the tips (whole embedding resident).  The rows of nodes with at most S0
+// tips below them (whole small subtrees; `sparse` = bitmap over node positions chosen by the
+// host) are as sparse as a few tips, so they go through the same intersection kernel.  Their
+// entries are the non-zeros of those embedding rows; one CTA owns one bucket (128-sample block b,
+// chunk of TP_CHUNK positions), its four warps a quarter of the chunk each, a lane four samples.
+// A warp walks its rows in position order, so the entries come out sorted by position and the
+// run starts are written on the way - no sort.
+// ---------------------------------------------------------------------------------------
+constexpr int TP_QROWS = TP_CHUNK / 4;
+
+// pass 1: entries per (bucket, quarter) and per-sample partial sums of len * p (double)
+__global__ void __launch_bounds__(128)
+k_rows_count(const double* __restrict__ emb, const double* __restrict__ len, const uint32_t* __restrict__ sparse,
+             int64_t rows, int64_t QR, int64_t nch, int64_t npad, unsigned* __restrict__ qcount /*[nb*nch][4]*/,
+             double* __restrict__ upart /*[nch*4][npad]*/) {
+    const int64_t b = blockIdx.x, ch = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t qa = ch * TP_CHUNK + (int64_t)warp * TP_QROWS, qb = min(rows, qa + TP_QROWS);
+    const double* p = emb + (b * QR) * TILE + lane;
+    double u[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned cnt = 0;
+    for (int64_t q = qa; q < qb; ++q) {
+        if (!((sparse[q >> 5] >> (q & 31)) & 1u)) continue;  // warp-uniform
+        const double l = len[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = p[q * TILE + 32 * k];
+            cnt += __popc(__ballot_sync(0xffffffffu, v != 0.0));
+            u[k] += l * v;
+        }
+    }
+    if (lane == 0) qcount[(b * nch + ch) * 4 + warp] = cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) upart[(ch * 4 + warp) * npad + b * TILE + 32 * k + lane] = u[k];
+}
+
+// bucket sizes from the quarter counts
+__global__ void k_rows_bucket_counts(const unsigned* __restrict__ qcount, int64_t nbuckets,
+                                     unsigned* __restrict__ counts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nbuckets) counts[t] = qcount[4 * t] + qcount[4 * t + 1] + qcount[4 * t + 2] + qcount[4 * t + 3];
+}
+
+// U_i = sum of the partials in a fixed order; maximum for the scale
+__global__ void k_rows_ureduce(const double* __restrict__ upart, int64_t nparts, int64_t npad,
+                               double* __restrict__ U, unsigned long long* __restrict__ maxbits) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad) return;
+    double u = 0.0;
+    for (int64_t k = 0; k < nparts; ++k) u += upart[k * npad + s];
+    U[s] = u;
+    atomicMax(maxbits, (unsigned long long)__double_as_longlong(u));
+}
+
+// pass 2: the entries (sorted by position by construction), run starts, U_i in fixed point
+__global__ void __launch_bounds__(128)
+k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, const uint32_t* __restrict__ sparse,
+               const double* __restrict__ scale, int64_t rows, int64_t QR, int64_t nch,
+               const unsigned* __restrict__ qcount, const int64_t* __restrict__ bucket_ptr,
+               TipEntry* __restrict__ entries, unsigned short* __restrict__ runs,
+               unsigned long long* __restrict__ Ufx) {
+    const int64_t b = blockIdx.x, ch = blockIdx.y;
+    const int64_t bucket = b * nch + ch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    unsigned run = 0;  // entries of the bucket before this warp's quarter
+    for (int w = 0; w < warp; ++w) run += qcount[bucket * 4 + w];
+    const int64_t qa = ch * TP_CHUNK + (int64_t)warp * TP_QROWS, qb = min(rows, qa + TP_QROWS);
+    const double* p = emb + (b * QR) * TILE + lane;
+    TipEntry* out = entries + bucket_ptr[bucket];
+    unsigned short* rs = runs + (size_t)bucket * (TP_CHUNK + 8);
+    const double sc = scale[0];
+    long long ufx[4] = {0, 0, 0, 0};
+    for (int64_t q = qa; q < qa + TP_QROWS; ++q) {
+        if (lane == 0) rs[q - ch * TP_CHUNK] = (unsigned short)run;
+        if (q >= qb || !((sparse[q >> 5] >> (q & 31)) & 1u)) continue;  // warp-uniform
+        const double l = len[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = p[q * TILE + 32 * k];
+            const uint32_t m = __ballot_sync(0xffffffffu, v != 0.0);
+            if (v != 0.0) {
+                const long long wv = __double2ll_rn(l * v * sc);
+                ufx[k] += wv;
+                TipEntry en;
+                en.key = ((uint32_t)(q - ch * TP_CHUNK) << 7) | (uint32_t)(32 * k + lane);
+                en.pad = 0;
+                en.val = wv;
+                out[run + __popc(m & lt)] = en;
+            }
+            run += __popc(m);
+        }
+    }
+    if (warp == 3 && lane == 0) rs[TP_CHUNK] = (unsigned short)run;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (ufx[k]) atomicAdd(&Ufx[b * TILE + 32 * k + lane], (unsigned long long)ufx[k]);
+}
+
+// The rows that stay with the dense pair kernel, packed: embd[block][r][128] = emb[block][pos[r]][128]
+// (zero rows and zero lengths in the padding), so that the pair kernel streams only them.
+__global__ void __launch_bounds__(128)
+k_compact_rows(const double* __restrict__ emb, const double* __restrict__ len, const int32_t* __restrict__ pos,
+               int64_t nd, int64_t nd_pad, int64_t QR, double* __restrict__ embd, double* __restrict__ lend) {
+    const int64_t r = blockIdx.x, b = blockIdx.y;
+    const bool real = r < nd;
+    const int64_t q = real ? pos[r] : 0;
+    embd[(b * nd_pad + r) * TILE + threadIdx.x] = real ? emb[(b * QR + q) * TILE + threadIdx.x] : 0.0;
+    if (b == 0 && threadIdx.x == 0) lend[r] = real ? len[q] : 0.0;
 }
 
 }  // namespace b2d

@@ -31,7 +31,7 @@ struct TreeOrder {
     // position (-1: root / padding), subtree size (a subtree is the position range
     // [q - size + 1, q]) and the root distance sum(len) over q .. root as an unevaluated
     // double-double sum hi + lo, so that differences along a path lose nothing to cancellation
-    std::vector<int32_t> parent_q, size_q;
+    std::vector<int32_t> parent_q, size_q, tips_q;  // tips_q: tips in the subtree (0 in the padding)
     std::vector<double> rd_hi, rd_lo;
     // the same with the tips' own branches left out (a tip gets its parent's distance): used
     // when the tip rows are handled by the sparse intersection kernel (b2d_tips.cuh)
@@ -142,6 +142,7 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
     }
     out.parent_q.assign(out.mpad, -1);
     out.size_q.assign(out.mpad, 1);
+    out.tips_q.assign(out.mpad, 0);
     out.rd_hi.assign(out.mpad, 0.0);
     out.rd_lo.assign(out.mpad, 0.0);
     {
@@ -160,6 +161,14 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
             out.rd_lo[pq] = lo[k];
             out.size_q[pq] = (int32_t)size[k];
             out.parent_q[pq] = parent[k] >= 0 ? out.q_of_id[parent[k]] : -1;
+        }
+        {
+            std::vector<int32_t> ntips(m, 0);
+            for (int64_t k = 0; k < m; ++k) {  // children precede parents
+                if (coff[k + 1] == coff[k]) ntips[k] = 1;
+                if (parent[k] >= 0) ntips[parent[k]] += ntips[k];
+                out.tips_q[out.q_of_id[k]] = ntips[k];
+            }
         }
         out.rd_hi_int = out.rd_hi;
         out.rd_lo_int = out.rd_lo;

@@ -144,7 +144,7 @@ def skip_probe(n=10000, tips=100000, lam=0.02):
             res[skip] = prob.fetch(np.empty(P))
             frac = t["visits_executed"] / t["visits_dense"] if t["visits_dense"] else 1.0
             print(f"n={n} tips={tips} lam={lam} skip={skip}: embed {t['embed_ms']:.2f} ms pair {t['pair_ms']:.2f} ms "
-                  f"(prep {t['skip_prep_ms']:.2f} tips {t['tips_ms']:.2f} flagged {t['tips_flagged']}) launches {t['pair_launches']} visits {frac:.3f} of dense -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
+                  f"(prep {t['skip_prep_ms']:.2f} tips {t['tips_ms']:.2f} flagged {t['tips_flagged']} S0 {t['sparse_rows_max_tips']} entries {t['sparse_row_entries']}) launches {t['pair_launches']} visits {frac:.3f} of dense -> {P/(t['compute_ms']*1e-3):.3e} pairs/s", flush=True)
     _capi.set_option("weighted_skip", 1)
     for k in SKIPS[1:]:
         d = np.abs(res[0] - res[k]) / np.maximum(np.abs(res[0]), 1e-300)
@@ -155,8 +155,8 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "skip":
     if len(sys.argv) > 2:
         SKIPS = tuple(int(x) for x in sys.argv[2].split(","))
     if len(sys.argv) > 3:
-        _capi.set_option("chunk_nodes", int(sys.argv[3]))
-        print("chunk_nodes", sys.argv[3])
+        _capi.set_option("sparse_rows_max_tips", int(sys.argv[3]))
+        print("sparse_rows_max_tips", sys.argv[3])
     skip_probe(4096, 20000, 0.02)
     skip_probe()
     skip_probe(10000, 100000, 0.005)
