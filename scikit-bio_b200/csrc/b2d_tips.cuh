@@ -268,7 +268,9 @@ k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bu
                     for (int e = e0; e < e1; ++e) {
                         const TipEntry ce = centry[e - lo];
                         const unsigned long long add = (unsigned long long)(re[u].val < ce.val ? re[u].val : ce.val);
-                        const uint32_t cell = r * TILE + (ce.key & 127u);
+                        // lanes of a warp mostly share the position and the column entry and differ
+                        // in the row sample: without the XOR they would all hit one bank
+                        const uint32_t cell = r * TILE + ((ce.key & 127u) ^ (r & 31u));
                         const uint32_t alo = (uint32_t)add;
                         const uint32_t old = atomicAdd(&acc_lo[cell], alo);
                         atomicAdd(&acc_hi[cell], (uint32_t)(add >> 32) + (old + alo < old ? 1u : 0u));
@@ -285,7 +287,8 @@ k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bu
         const int rr = x / TILE, c = x % TILE;
         const int64_t i = i0 + rr, j = (int64_t)bj * TILE + c;
         if (i >= j || j >= a.n) continue;
-        const long long m = (long long)(((unsigned long long)acc_hi[x] << 32) | acc_lo[x]);
+        const int xs = rr * TILE + (c ^ (rr & 31));
+        const long long m = (long long)(((unsigned long long)acc_hi[xs] << 32) | acc_lo[xs]);
         const long long t = Ufx[i] + Ufx[j] - 2 * m;
         emit(a, base, i0, i, j, (double)t * inv);
     }
