@@ -826,7 +826,7 @@ static int tips_build(b2d_problem* p) {
 
 // Sparse rows (nodes with at most S0 tips below) taken from the resident embedding.  S0 follows the
 // table's density (a node with s tips below is non-zero for about s * nnz / (n * tips) of the
-// samples; the intersection kernel wins up to ~10 %) and is halved while a bucket overflows.
+// samples; measured optimum: up to ~30 % of the samples) and is halved while a bucket overflows.
 static int rows_build(b2d_problem* p, int64_t QR) {
     const TreeOrder& o = p->order;
     int rc;
@@ -836,7 +836,7 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         int64_t ntips = 0;
         for (int64_t q = 0; q < p->mpad; ++q) ntips = std::max<int64_t>(ntips, o.tips_q[q]);
         const double dens = (double)p->nnz / std::max(1.0, (double)p->n * (double)std::max<int64_t>(ntips, 1));
-        int s0 = g_sparse_rows_max_tips ? g_sparse_rows_max_tips : (int)std::min(32.0, std::max(1.0, 0.1 / std::max(dens, 1e-9)));
+        int s0 = g_sparse_rows_max_tips ? g_sparse_rows_max_tips : (int)std::min(256.0, std::max(1.0, 0.32 / std::max(dens, 1e-9)));
         p->rows_S0 = std::max(1, s0);
     }
     if (!p->d_rows_qcount) {
