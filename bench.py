@@ -38,6 +38,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM bytes (read + write) of one launch at the default weighted configuration, from ncu captures
+NCU_TRAFFIC_WEIGHTED = {"k_pair_tips": 21.980974e9 + 0.402909e9, "k_pair_weighted_mask": 17.406591e9 + 0.437857e9}
 METRIC_NAME = "sample-pair distances/sec"
 UNIT = "pairs/s"
 
@@ -467,9 +469,12 @@ def run_ours(args):
             alg_bytes = sparse_bytes
         # DRAM bytes of ONE launch of the dominant kernel from `ncu --set full` captures of this
         # very configuration (profiles/r1_ncu_*_one_launch.txt); null for any other shape
-        traffic = None
-        if not (args.samples or args.tips or args.lam) and world == 1 and emulate == 1:
-            traffic = {"weighted": 38.739540e9 + 0.504003e9, "unweighted": 0.133509e9 + 0.346140e9}.get(workload)
+        # per-launch DRAM bytes from `ncu --set full` captures of this very configuration (default
+        # shapes only; profiles/r1_ncu_*): null for any other shape
+        default_shape = not (args.samples or args.tips or args.lam) and world == 1 and emulate == 1
+        TRAFFIC = {"k_pair_unweighted_lut": 0.133509e9 + 0.346140e9}
+        TRAFFIC.update(NCU_TRAFFIC_WEIGHTED)
+        traffic = TRAFFIC.get(kernel) if default_shape else None
         roofline = {
             "kernel": kernel, "bound": bound, "achieved": achieved,
             "peak": peak / 1e12, "unit": unit,
@@ -477,8 +482,7 @@ def run_ours(args):
             "peak_source": peak_source,
             "traffic": traffic,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
-                              "profiles/r1_ncu_*_one_launch.txt (weighted: every half tile streams all node "
-                              "rows of its launch from L2, 75 % L2 hits; 10 % of HBM peak)" if traffic else None,
+                              "profiles/r1_ncu_*_one_launch.txt" if traffic else None,
             "avg_launch_ms": avg_launch_ms, "launches_per_step": pair_launches_per_step,
             "algorithmic_terms_per_launch": P_shard * nodes_per_launch,
             "units_per_term": units_per_term,
@@ -492,6 +496,31 @@ def run_ours(args):
                     "note": "not the binding resource: a 128x128 pair tile does 16384 terms per "
                             "256 embedding elements read"},
         }
+        # Sparse rows (tips and nodes with few tips below) go through the intersection kernel; when it
+        # takes longer than the dense launches it is the dominant kernel and gets the roofline, with
+        # the dense kernel's numbers kept beside it.  Its unit of work: one (sample pair, row) match
+        # = two 32-bit shared-memory atomic adds.
+        if t.get("tips_ms", 0.0) > avg_launch_ms * pair_launches_per_step and t.get("sparse_row_matches", 0.0) > 0:
+            atom_peak = _capi.microbench(3, device)
+            atoms = 2.0 * t["sparse_row_matches"]
+            a_rate = atoms / (t["tips_ms"] * 1e-3) / 1e12
+            roofline = {
+                "kernel": "k_pair_tips", "bound": "smem-atomic", "achieved": a_rate,
+                "peak": atom_peak / 1e12, "unit": "Tatom/s (shared-memory int32 atomic adds)",
+                "frac": a_rate / (atom_peak / 1e12),
+                "peak_source": "b2d_microbench(3): shared-memory atomicAdd on random cells of a 128x128 int32 "
+                               "tile, all SMs, measured in this run",
+                "traffic": TRAFFIC.get("k_pair_tips") if default_shape else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the launch, ncu --set full, "
+                                  "profiles/r1_ncu_*_one_launch.txt" if default_shape and "k_pair_tips" in TRAFFIC else None,
+                "avg_launch_ms": float(t["tips_ms"]), "launches_per_step": 1,
+                "matches_per_launch": t["sparse_row_matches"], "units_per_match": 2.0,
+                "sparse_rows_max_tips": t["sparse_rows_max_tips"],
+                "sparse_row_entries": t["sparse_row_entries"],
+                # every bucket is read by about n/128 tiles (as row or as column block), 16 B per entry
+                "algorithmic_bytes_per_launch": 16.0 * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1),
+                "dense_kernel": roofline,
+            }
         cpu = None
         if not args.no_cpu and world == 1 and emulate == 1:
             n_sub = args.cpu_samples or (64 if inp["kind"] == "tree" else 1000)

@@ -151,7 +151,8 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * sparse tip-row kernel (0 when the tips went through the dense kernel), [13] number of
  * near-duplicate pairs that made the last compute redo the tips densely (normally 0),
  * [14] largest number of tips below a node whose row went through the sparse intersection
- * kernel (0: none, 1: tip rows only), [15] entries of those rows.  n: slots to fill (<= 16). */
+ * kernel (0: none, 1: tip rows only), [15] entries of those rows, [16] (sample pair, row) matches
+ * that kernel accumulated.  n: slots to fill (<= 17). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);

@@ -340,7 +340,7 @@ struct b2d_problem {
     unsigned* d_rows_qcount = nullptr;      // [nbuckets][4]
     double* d_rows_upart = nullptr;         // [nch * 4][npad]
     int64_t tip_nch = 0;
-    double tips_flagged = 0, t_tips = 0;
+    double tips_flagged = 0, t_tips = 0, tip_matches = 0;
     // sparse feature-table path
     SpEntry* d_sp_entries = nullptr;
     int64_t* d_sp_ptr = nullptr;
@@ -766,7 +766,7 @@ static int tips_buffers(b2d_problem* p) {
         B2D_CUDA(b2d_malloc(&p->d_tip_u, p->npad * sizeof(double)));
         B2D_CUDA(b2d_malloc(&p->d_tip_ufx, p->npad * sizeof(long long)));
         B2D_CUDA(b2d_malloc(&p->d_tip_scale, 2 * sizeof(double)));
-        B2D_CUDA(b2d_malloc(&p->d_tip_word, 2 * sizeof(unsigned long long)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_word, 4 * sizeof(unsigned long long)));
         B2D_CUDA(b2d_malloc(&p->d_tip_status, sizeof(int)));
         B2D_CUDA(b2d_malloc(&p->d_tip_counts, (nbuckets + 1) * sizeof(unsigned)));
         B2D_CUDA(b2d_malloc(&p->d_tip_ptr, (nbuckets + 1) * sizeof(int64_t)));
@@ -775,7 +775,7 @@ static int tips_buffers(b2d_problem* p) {
     }
     B2D_CUDA(cudaMemsetAsync(p->d_tip_u, 0, p->npad * sizeof(double), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_ufx, 0, p->npad * sizeof(long long), p->stream));
-    B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 2 * sizeof(unsigned long long), p->stream));
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 4 * sizeof(unsigned long long), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
     return B2D_OK;
@@ -1187,7 +1187,8 @@ static int compute_dense(b2d_problem* p, int metric) {
                 B2D_CUDA(cudaFuncSetAttribute(k_pair_tips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
                 B2D_CUDA(cudaEventRecord(p->ev[7], st));
                 k_pair_tips<<<(unsigned)p->ntiles, TP_THREADS, TP_SMEM, st>>>(
-                    p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, p->tip_nch, p->d_tip_ufx, p->d_tip_scale, a);
+                    p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
+                    p->d_tip_word + 2, a);
                 B2D_CUDA(cudaEventRecord(p->ev[8], st));
                 tips_timed = true;
                 p->n_kernels += 1;
@@ -1239,8 +1240,10 @@ static int compute_dense(b2d_problem* p, int metric) {
     }
     B2D_CUDA(cudaGetLastError());
     if (p->tips_active) {
-        unsigned long long flagged = 0;
-        B2D_CUDA(cudaMemcpy(&flagged, p->d_tip_word + 1, sizeof(flagged), cudaMemcpyDeviceToHost));
+        unsigned long long fm[2] = {0, 0};
+        B2D_CUDA(cudaMemcpy(fm, p->d_tip_word + 1, sizeof(fm), cudaMemcpyDeviceToHost));
+        const unsigned long long flagged = fm[0];
+        p->tip_matches = (double)fm[1];
         if (flagged) {  // near-duplicate samples: redo with the tips in the dense kernel
             p->tips_mode = -1;
             p->tips_flagged = (double)flagged;
@@ -1681,12 +1684,13 @@ int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[16] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+    double v[17] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
                     p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged,
                     p->tips_active ? (p->rows_general ? (double)p->rows_S0 : 1.0) : 0.0,
-                    p->tips_active && p->rows_general ? p->rows_entries : 0.0};
-    for (int i = 0; i < n && i < 16; ++i) ms[i] = v[i];
+                    p->tips_active && p->rows_general ? p->rows_entries : 0.0,
+                    p->tips_active ? p->tip_matches : 0.0};
+    for (int i = 0; i < n && i < 17; ++i) ms[i] = v[i];
     return B2D_OK;
 }
 

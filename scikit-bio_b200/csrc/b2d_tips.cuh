@@ -220,7 +220,7 @@ k_tip_sort(TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_pt
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr,
             const unsigned short* __restrict__ runs, int64_t nch, const long long* __restrict__ Ufx,
-            const double* __restrict__ scale, PairArgs a) {
+            const double* __restrict__ scale, unsigned long long* __restrict__ n_matches, PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // 64-bit sums as two 32-bit halves: shared memory has native 32-bit atomic adds only (a 64-bit
     // atomicAdd is a compare-and-swap loop); the add that wraps the low half carries into the high
@@ -232,6 +232,7 @@ k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bu
     const int tid = threadIdx.x;
     const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
     for (int x = tid; x < 2 * TILE * TILE; x += TP_THREADS) acc_lo[x] = 0u;
+    unsigned nm = 0;  // matches this thread accumulated
 
     for (int64_t ch = 0; ch < nch; ++ch) {
         const int64_t rbk = (int64_t)bi * nch + ch, cbk = (int64_t)bj * nch + ch;
@@ -265,6 +266,7 @@ k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bu
                     if (re[u].key == 0xffffffffu) continue;
                     const uint32_t f = re[u].key >> 7, r = re[u].key & 127u;
                     const int e0 = max((int)fstart[f], lo), e1 = min((int)fstart[f + 1], hi);
+                    nm += (unsigned)max(e1 - e0, 0);
                     for (int e = e0; e < e1; ++e) {
                         const TipEntry ce = centry[e - lo];
                         const unsigned long long add = (unsigned long long)(re[u].val < ce.val ? re[u].val : ce.val);
@@ -280,6 +282,11 @@ k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bu
         }
     }
     __syncthreads();
+    if (n_matches) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, o);
+        if ((tid & 31) == 0 && nm) atomicAdd(n_matches, (unsigned long long)nm);
+    }
     const double inv = scale[1];
     const int64_t base = a.row_base[bi];
     const int64_t i0 = (int64_t)bi * TILE;

@@ -711,3 +711,38 @@ def test_sparse_tip_rows_agree_with_the_dense_kernel_and_fall_back_when_they_mus
     got3, t3 = run(parent3, length3, indptr3, cols3, vals3, tip_node3, n3, "weighted_unifrac_normalized", 1)
     assert t3["tips_ms"] == 0 and t3["tips_flagged"] == 0
     assert_close_rel(got3, exp3["weighted_unifrac_normalized"], UNIFRAC_RTOL, "dense table")
+
+
+@pytest.mark.parametrize("cat", [False, True])
+def test_sparse_rows_threshold_does_not_change_the_result(cat):
+    """Rows of nodes with up to k tips below go through the intersection kernel (k from the table's
+    density by default): k = 1 (tips only), 2, 5, 40, automatic, and the all-dense kernel agree."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 390, 5000
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.01, 41, caterpillar=cat)
+    exp = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr, cols, vals, tips), tip_node, parent, length)
+    total = n * (n - 1) // 2
+    res = {}
+    try:
+        for k in (0, 1, 2, 5, 40):
+            _capi.set_option("sparse_rows_max_tips", k)
+            with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+                prob.compute("weighted_unifrac_normalized")
+                t = prob.timings()
+                assert t["tips_ms"] > 0 and t["tips_flagged"] == 0
+                assert t["sparse_rows_max_tips"] == (k if k else t["sparse_rows_max_tips"]) >= 1
+                assert t["sparse_row_matches"] > 0
+                res[k] = prob.fetch(np.empty(total))
+        _capi.set_option("tips_sparse", 0)
+        with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+            prob.compute("weighted_unifrac_normalized")
+            res["dense"] = prob.fetch(np.empty(total))
+    finally:
+        _capi.set_option("sparse_rows_max_tips", 0)
+        _capi.set_option("tips_sparse", 1)
+    for k, v in res.items():
+        assert_close_rel(v, exp["weighted_unifrac_normalized"], UNIFRAC_RTOL, f"sparse rows k={k}")
+        assert_close_rel(v, res["dense"], 1e-13, f"sparse rows k={k} vs dense")
