@@ -33,7 +33,7 @@ namespace b2d {
 constexpr int TP_CHUNK = 2048;     // node positions per bucket
 constexpr int TP_MAXE = 5120;      // column entries resident per batch (normally a whole bucket)
 constexpr int TP_SORT_MAX = 8192;  // largest bucket the shared-memory counting sort accepts
-constexpr int TP_THREADS = 512;
+constexpr int TP_THREADS = 1024;
 struct TipEntry {
     uint32_t key;  // position_in_chunk << 7 | sample_in_block
     uint32_t pad;
@@ -267,9 +267,12 @@ k_pair_tips(const TipEntry* __restrict__ entries, const int64_t* __restrict__ bu
                     const uint32_t f = re[u].key >> 7, r = re[u].key & 127u;
                     const int e0 = max((int)fstart[f], lo), e1 = min((int)fstart[f + 1], hi);
                     nm += (unsigned)max(e1 - e0, 0);
+#pragma unroll 4
                     for (int e = e0; e < e1; ++e) {
                         const TipEntry ce = centry[e - lo];
-                        const unsigned long long add = (unsigned long long)(re[u].val < ce.val ? re[u].val : ce.val);
+                        // min of two non-negative 61-bit integers: their bit patterns order like doubles
+                        const unsigned long long add = (unsigned long long)__double_as_longlong(
+                            fmin(__longlong_as_double(re[u].val), __longlong_as_double(ce.val)));
                         // lanes of a warp mostly share the position and the column entry and differ
                         // in the row sample: without the XOR they would all hit one bank
                         const uint32_t cell = r * TILE + ((ce.key & 127u) ^ (r & 31u));
