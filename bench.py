@@ -389,7 +389,7 @@ def run_ours(args):
     for k, b in pinned_inputs.items():
         inp[k] = b.array
     e2e_times = []
-    for it in range(3):
+    for it in range(5):
         barrier()
         t0 = time.perf_counter()
         with make_problem() as p2:
@@ -559,7 +559,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "seconds": float(te[0]),
                     "host_buffers": "page-locked (b2d_host_alloc) for inputs and result",
-                    "timed": "create (H2D) + compute + fetch (D2H) + destroy, best of 3"},
+                    "timed": "create (H2D) + compute + fetch (D2H) + destroy, best of 5"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
