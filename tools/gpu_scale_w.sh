@@ -7,5 +7,5 @@ python - <<PY
 import json
 for l in open("gpurun_out/bench_weighted_${N}gpu.json"):
     if l.startswith("{"):
-        d=json.loads(l); print(d["n_gpus"], d["config"]["samples"], d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["roofline"]["terms_visited_frac"])
+        d=json.loads(l); print(d["n_gpus"], d["config"]["samples"], d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["kernel"], d["roofline"]["frac"])
 PY
