@@ -329,7 +329,6 @@ struct b2d_problem {
     int rows_S0 = 0, rows_S0_uploaded = 0;
     double rows_entries = 0;
     uint32_t* d_rows_sparse = nullptr;      // [mpad/32] bit = row goes through the intersection kernel
-    uint32_t* d_rows_dense = nullptr;       // complement (what the pair kernel may visit)
     double* d_rdR_hi = nullptr;             // root distances without the sparse rows' branches
     double* d_rdR_lo = nullptr;
     int32_t* d_dense_pos = nullptr;         // positions of the rows left to the dense pair kernel
@@ -372,7 +371,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_rd_hi_int); b2d_free(p->d_rd_lo_int); b2d_free(p->d_tip_u); b2d_free(p->d_tip_ufx);
     b2d_free(p->d_tip_scale); b2d_free(p->d_tip_word); b2d_free(p->d_tip_status); b2d_free(p->d_tip_counts);
     b2d_free(p->d_tip_ptr); b2d_free(p->d_tip_entries); b2d_free(p->d_tip_runs);
-    b2d_free(p->d_rows_sparse); b2d_free(p->d_rows_dense); b2d_free(p->d_rdR_hi); b2d_free(p->d_rdR_lo);
+    b2d_free(p->d_rows_sparse); b2d_free(p->d_rdR_hi); b2d_free(p->d_rdR_lo);
     b2d_free(p->d_rows_qcount); b2d_free(p->d_rows_upart);
     b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -841,7 +840,6 @@ static int rows_build(b2d_problem* p, int64_t QR) {
     }
     if (!p->d_rows_qcount) {
         B2D_CUDA(b2d_malloc(&p->d_rows_sparse, (p->mpad / 32) * sizeof(uint32_t)));
-        B2D_CUDA(b2d_malloc(&p->d_rows_dense, (p->mpad / 32) * sizeof(uint32_t)));
         B2D_CUDA(b2d_malloc(&p->d_rdR_hi, p->mpad * sizeof(double)));
         B2D_CUDA(b2d_malloc(&p->d_rdR_lo, p->mpad * sizeof(double)));
         B2D_CUDA(b2d_malloc(&p->d_rows_qcount, nbuckets * 4 * sizeof(unsigned)));
@@ -867,7 +865,6 @@ static int rows_build(b2d_problem* p, int64_t QR) {
                 }
             }
             B2D_CUDA(cudaMemcpyAsync(p->d_rows_sparse, sp.data(), sp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
-            B2D_CUDA(cudaMemcpyAsync(p->d_rows_dense, de.data(), de.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
             B2D_CUDA(cudaMemcpyAsync(p->d_rdR_hi, hi.data(), hi.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
             B2D_CUDA(cudaMemcpyAsync(p->d_rdR_lo, lo.data(), lo.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
             std::vector<int32_t> dpos;

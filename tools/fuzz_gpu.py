@@ -33,6 +33,8 @@ def main(n_cases=40, seed=0, verbose=True):
         n_shards = int(rng.choice([1, 1, 2, 3]))
         chunk = int(rng.choice([0, 128, 256, 1024]))
         rows_res = int(rng.choice([0, 128, 384, 1024]))
+        max_tips = int(rng.choice([0, 0, 1, 3, 1 << 20]))   # sparse-row threshold (1 << 20: every row)
+        _capi.set_option("sparse_rows_max_tips", max_tips)
         _capi.set_option("chunk_nodes", chunk)
         _capi.set_option("emb_budget_bytes", ((n + 127) // 128) * 128 * 8 * rows_res)
         total = n * (n - 1) // 2
@@ -56,10 +58,11 @@ def main(n_cases=40, seed=0, verbose=True):
         if flag:
             failures.append((case, n, tips, lam, cat, n_shards, chunk, rows_res, errs, bc_ok))
         if verbose:
-            print(f"case {case}: n={n} tips={tips} lam={lam} cat={cat} shards={n_shards} chunk={chunk} rows={rows_res} "
+            print(f"case {case}: n={n} tips={tips} lam={lam} cat={cat} shards={n_shards} chunk={chunk} rows={rows_res} maxtips={max_tips} "
                   f"wu {errs['weighted_unifrac']:.2e} wun {errs['weighted_unifrac_normalized']:.2e} bc_exact {bc_ok}{flag}", flush=True)
     _capi.set_option("chunk_nodes", 0)
     _capi.set_option("emb_budget_bytes", 0)
+    _capi.set_option("sparse_rows_max_tips", 0)
     if verbose:
         print("worst relative error", worst)
     return worst, failures
