@@ -746,3 +746,31 @@ def test_sparse_rows_threshold_does_not_change_the_result(cat):
     for k, v in res.items():
         assert_close_rel(v, exp["weighted_unifrac_normalized"], UNIFRAC_RTOL, f"sparse rows k={k}")
         assert_close_rel(v, res["dense"], 1e-13, f"sparse rows k={k} vs dense")
+
+
+def test_one_problem_many_computes_in_any_order():
+    """A problem keeps its buffers (embedding, sparse-row entries, packed rows, bitmaps) between
+    computes; switching metrics back and forth must give what a fresh problem gives."""
+    _skbio_b200()
+    from skbio_b200 import _capi
+
+    n, tips = 260, 2500
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.02, 51)
+    node_ids = tip_node[cols]
+    total = n * (n - 1) // 2
+    fresh = {}
+    for key in ("weighted_unifrac", "unweighted_unifrac", "weighted_unifrac_normalized"):
+        with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+            prob.compute(key)
+            fresh[key] = prob.fetch(np.empty(total))
+    with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+        pd_fresh = prob.phydiv(True, 0.5)
+    order = ["weighted_unifrac", "unweighted_unifrac", "weighted_unifrac_normalized", "weighted_unifrac",
+             "unweighted_unifrac", "weighted_unifrac_normalized", "weighted_unifrac_normalized"]
+    with _capi.Problem.tree(parent, length, indptr, node_ids, vals, n) as prob:
+        for step, key in enumerate(order):
+            prob.compute(key)
+            got = prob.fetch(np.empty(total))
+            assert np.array_equal(got, fresh[key]), (step, key)
+            if step == 3:
+                assert np.array_equal(prob.phydiv(True, 0.5), pd_fresh)
