@@ -596,6 +596,13 @@ int b2d_problem_create_tree(b2d_problem** out, int device, int64_t n_samples, in
     }
     p->mpad = p->order.mpad;
     p->NS = p->mpad / NODE_STRIPE;
+    // min(len*p_i, len*p_j) = len*min(p_i, p_j) needs len >= 0: with a negative (or non-finite)
+    // branch length every row stays in the dense kernel
+    for (int64_t k = 0; k < n_nodes; ++k)
+        if (!(length[k] >= 0.0) || !std::isfinite(length[k])) {
+            p->tips_mode = -1;
+            break;
+        }
     rc = setup_common(p, indptr, node_ids, values, sizeof(int64_t));
     if (rc) {
         free_problem(p);

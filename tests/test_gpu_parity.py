@@ -774,3 +774,23 @@ def test_one_problem_many_computes_in_any_order():
             assert np.array_equal(got, fresh[key]), (step, key)
             if step == 3:
                 assert np.array_equal(prob.phydiv(True, 0.5), pd_fresh)
+
+
+def test_negative_branch_lengths_keep_every_row_in_the_dense_kernel():
+    """len * min(p_i, p_j) is only min(len p_i, len p_j) for len >= 0: a tree with a negative
+    branch length must not take the sparse-row path, and still matches the oracle."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 150, 900
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.03, 61)
+    length = length.copy()
+    length[tip_node[:50]] *= -1.0
+    exp = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr, cols, vals, tips), tip_node, parent, length)
+    with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+        prob.compute("weighted_unifrac")
+        t = prob.timings()
+        got = prob.fetch(np.empty(n * (n - 1) // 2))
+    assert t["tips_ms"] == 0 and t["sparse_rows_max_tips"] == 0
+    assert_close_rel(got, exp["weighted_unifrac"], 1e-9, "negative lengths")  # signed sums cancel
