@@ -185,8 +185,8 @@ int b2d_beta_diversity_features(int metric, int device,
  *   "sparse_rows_max_tips"  0 (default): when the whole embedding is resident, rows of nodes with
  *                       up to about 0.3 / (table density) tips below them join the tips in the
  *                       intersection kernel; k > 0: up to k tips (1 = tip rows only)
- *   "cache_embedding"   1 (default): device buffers of 1 MB and more (the embedding above all)
- *                       are parked per device when a problem is destroyed and reused by the
+ *   "cache_embedding"   1 (default): device buffers (the embedding above all) are parked per
+ *                       device when a problem is destroyed and reused by the
  *                       next one (cudaMalloc / cudaFree of tens of GB cost 0.1 - 0.7 s); they
  *                       are released when an allocation fails; 0: release now, stop parking
  *   "sparse_features"   -1 auto, 0 never, 1 whenever legal: intersection kernel for integer

@@ -121,8 +121,9 @@ using namespace b2d;
 
 // Device memory is kept across problems.  cudaMalloc / cudaFree of the large buffers (the
 // embedding: up to 85 % of the device; results, zero-path table, tip buckets: 0.3 - 0.4 GB each)
-// cost tens to hundreds of milliseconds per call, so freed blocks of 1 MB and more are parked in a
-// per-device pool and handed to the next request of about the same size (the embedding, whose
+// cost tens to hundreds of milliseconds per call (and now and then even a small cudaFree stalls for
+// 0.1 - 0.3 s), so freed blocks are parked in a per-device pool and handed to the next request of
+// about the same size (the embedding, whose
 // size follows the free memory, has its own slot: any parked buffer that is large enough).
 // Everything parked is given back to the driver when an allocation fails, and by
 // b2d_set_option("cache_embedding", 0).
@@ -161,10 +162,18 @@ static void pool_clear() {
     }
     cudaSetDevice(cur);
 }
+// small requests are rounded up to a power of two so that they are reused exactly
+static size_t pool_round(size_t bytes) {
+    if (bytes >= POOL_MIN_BYTES) return bytes;
+    size_t r = 256;
+    while (r < bytes) r <<= 1;
+    return r;
+}
 template <typename T>
 static cudaError_t b2d_malloc(T** ptr, size_t bytes) {
     const int d = pool_device();
-    if (g_cache_embedding && bytes >= POOL_MIN_BYTES) {
+    bytes = pool_round(bytes);
+    if (g_cache_embedding) {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         DevPool& pl = g_pool[d];
         auto it = pl.idle.lower_bound(bytes);
@@ -197,7 +206,7 @@ static void b2d_free(void* ptr) {
         if (it != pl.live.end()) {
             const size_t bytes = it->second;
             pl.live.erase(it);
-            if (g_cache_embedding && bytes >= POOL_MIN_BYTES) {
+            if (g_cache_embedding) {
                 pl.idle.insert({bytes, ptr});
                 return;
             }

@@ -41,7 +41,7 @@ def e2e_breakdown(n=10000, tips=100000, lam=0.02, key="weighted_unifrac_normaliz
     ids = tip_node[cols].astype(np.int32)
     P = n * (n - 1) // 2
     out = _capi.PinnedBuffer(P)
-    for rep in range(5):
+    for rep in range(12):
         t0 = time.perf_counter()
         prob = _capi.Problem.tree(parent, length, indptr, ids, vals, n)
         t1 = time.perf_counter()
