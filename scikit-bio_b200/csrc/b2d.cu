@@ -896,7 +896,7 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         }
         const int64_t rows = p->mpad;
         p->n_kernels += 5;
-        k_rows_count<<<dim3((unsigned)p->nb, (unsigned)nch), 128, 0, p->stream>>>(
+        k_rows_count<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
             (const double*)p->d_emb, p->d_len, p->d_rows_sparse, rows, QR, nch, p->npad, p->d_rows_qcount,
             p->d_rows_upart);
         k_rows_bucket_counts<<<(unsigned)((nbuckets + 255) / 256), 256, 0, p->stream>>>(p->d_rows_qcount, nbuckets,
@@ -924,7 +924,7 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         if ((rc = tips_entries_reserve(p, total))) return rc;
         p->rows_entries = (double)total;
         p->n_kernels += 1;
-        k_rows_scatter<<<dim3((unsigned)p->nb, (unsigned)nch), 128, 0, p->stream>>>(
+        k_rows_scatter<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
             (const double*)p->d_emb, p->d_len, p->d_rows_sparse, p->d_tip_scale, rows, QR, nch,
             p->d_rows_qcount, p->d_tip_ptr, p->d_tip_entries, p->d_tip_runs,
             (unsigned long long*)p->d_tip_ufx);

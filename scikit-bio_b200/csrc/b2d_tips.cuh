@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(128)
 k_rows_count(const double* __restrict__ emb, const double* __restrict__ len, const uint32_t* __restrict__ sparse,
              int64_t rows, int64_t QR, int64_t nch, int64_t npad, unsigned* __restrict__ qcount /*[nb*nch][4]*/,
              double* __restrict__ upart /*[nch*4][npad]*/) {
-    const int64_t b = blockIdx.x, ch = blockIdx.y;
+    const int64_t b = blockIdx.y, ch = blockIdx.x;  // chunks (up to 2^19) in x, sample blocks in y
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t qa = ch * TP_CHUNK + (int64_t)warp * TP_QROWS, qb = min(rows, qa + TP_QROWS);
     const double* p = emb + (b * QR) * TILE + lane;
@@ -395,7 +395,7 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
                const unsigned* __restrict__ qcount, const int64_t* __restrict__ bucket_ptr,
                TipEntry* __restrict__ entries, unsigned short* __restrict__ runs,
                unsigned long long* __restrict__ Ufx) {
-    const int64_t b = blockIdx.x, ch = blockIdx.y;
+    const int64_t b = blockIdx.y, ch = blockIdx.x;  // chunks (up to 2^19) in x, sample blocks in y
     const int64_t bucket = b * nch + ch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;

@@ -81,9 +81,22 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
     // heavy child first (stable for ties)
     for (int64_t k = 0; k < m; ++k) {
         int64_t b = coff[k], e = coff[k + 1];
-        if (e - b > 1)
+        if (e - b == 2) {  // the usual case: no temporary buffer, no call
+            if (size[child[b + 1]] > size[child[b]]) std::swap(child[b], child[b + 1]);
+        } else if (e - b > 2 && e - b <= 16) {  // stable insertion sort, descending size
+            for (int64_t i = b + 1; i < e; ++i) {
+                const int32_t x = child[i];
+                int64_t j = i;
+                while (j > b && size[child[j - 1]] < size[x]) {
+                    child[j] = child[j - 1];
+                    --j;
+                }
+                child[j] = x;
+            }
+        } else if (e - b > 16) {
             std::stable_sort(child.begin() + b, child.begin() + e,
                              [&](int32_t x, int32_t y) { return size[x] > size[y]; });
+        }
     }
     out.m = m;
     out.mpad = (m + 127) / 128 * 128;

@@ -64,7 +64,7 @@ def main(n_cases=40, seed=0, verbose=True):
     _capi.set_option("emb_budget_bytes", 0)
     _capi.set_option("sparse_rows_max_tips", 0)
     if verbose:
-        print("worst relative error", worst)
+        print("worst relative error", worst, "failures", len(failures))
     return worst, failures
 
 
