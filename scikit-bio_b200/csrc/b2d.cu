@@ -340,6 +340,10 @@ struct b2d_problem {
     uint32_t* d_rows_sparse = nullptr;      // [mpad/32] bit = row goes through the intersection kernel
     double* d_rdR_hi = nullptr;             // root distances without the sparse rows' branches
     double* d_rdR_lo = nullptr;
+    // several node passes with the tips handled sparsely: the other rows of a pass are packed too
+    bool pack_pass = false;
+    std::vector<int32_t> hc_pos;            // positions of the nodes with children, ascending
+    int32_t* d_hc_pos = nullptr;
     int32_t* d_dense_pos = nullptr;         // positions of the rows left to the dense pair kernel
     int64_t n_dense = 0, n_dense_pad = 0;
     double* d_embd = nullptr;               // [nb][n_dense_pad][128] those rows, packed
@@ -382,7 +386,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_tip_ptr); b2d_free(p->d_tip_entries); b2d_free(p->d_tip_runs);
     b2d_free(p->d_rows_sparse); b2d_free(p->d_rdR_hi); b2d_free(p->d_rdR_lo);
     b2d_free(p->d_rows_qcount); b2d_free(p->d_rows_upart);
-    b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend);
+    b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend); b2d_free(p->d_hc_pos);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -942,7 +946,7 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         }
         p->n_kernels += 1;
         k_compact_rows<<<dim3((unsigned)p->n_dense_pad, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, p->d_embd,
+            (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, p->d_embd,
             p->d_lend);
         B2D_CUDA(cudaGetLastError());
         p->tips_mode = 1;
@@ -1086,9 +1090,47 @@ static int compute_dense(b2d_problem* p, int metric) {
     int rc = B2D_OK;
     // whole tree resident: sparse rows from the embedding (inside the pass); else tips from the CSR
     p->rows_general = want_tips && QR == p->mpad;
+    p->pack_pass = false;
     if (want_tips && !p->rows_general) {
         if ((rc = tips_build(p))) return rc;
         p->tips_active = p->tips_mode == 1;
+        if (p->tips_active) {
+            // the rows with children of every pass are packed for the pair kernel (it is bound by
+            // streaming rows there): the resident range shrinks to leave room for the packed copy
+            if (p->hc_pos.empty()) {
+                for (int64_t q = 0; q < p->mpad; ++q)
+                    if ((p->order.flags[q] & (NF_HAS_CHILDREN | NF_PAD)) == NF_HAS_CHILDREN) p->hc_pos.push_back((int32_t)q);
+                if ((rc = upload(&p->d_hc_pos, p->hc_pos.data(), p->hc_pos.size(), p->stream))) return rc;
+                B2D_CUDA(cudaStreamSynchronize(p->stream));
+            }
+            const double fd = (double)p->hc_pos.size() / (double)std::max<int64_t>(p->m, 1);
+            int64_t QR2 = (int64_t)((double)QR / (1.0 + fd + 0.03)) / NODE_STRIPE * NODE_STRIPE;
+            if (QR2 >= NODE_STRIPE) {
+                QR = QR2;
+                // most rows with children in any pass of QR rows
+                int64_t most = 0;
+                size_t lo = 0;
+                for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
+                    size_t hi = lo;
+                    while (hi < p->hc_pos.size() && p->hc_pos[hi] < q0 + QR) ++hi;
+                    most = std::max<int64_t>(most, (int64_t)(hi - lo));
+                    lo = hi;
+                }
+                p->n_dense_pad = std::max<int64_t>(128, (most + 127) / 128 * 128);
+                const size_t need_d = (size_t)p->nb * p->n_dense_pad * TILE * sizeof(double);
+                if (p->embd_bytes < need_d) {
+                    b2d_free(p->d_embd);
+                    b2d_free(p->d_lend);
+                    p->d_embd = nullptr;
+                    p->d_lend = nullptr;
+                    p->embd_bytes = 0;
+                    B2D_CUDA(b2d_malloc(&p->d_embd, need_d));
+                    B2D_CUDA(b2d_malloc(&p->d_lend, p->n_dense_pad * sizeof(double)));
+                    p->embd_bytes = need_d;
+                }
+                p->pack_pass = true;
+            }
+        }
     }
     if (skip) {
         const size_t need = (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t);
@@ -1113,6 +1155,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     p->nodes_resident = (double)QR;
     double t_embed = 0, t_pair = 0, t_prep = 0;
     bool closed_form_timed = false, tips_timed = false;
+    int64_t pass_nd = 0, pass_nd_pad = 128;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
         int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
@@ -1172,6 +1215,19 @@ static int compute_dense(b2d_problem* p, int metric) {
                     p->n_kernels += 1;
                     k_group_nonzero<<<(unsigned)((ng * wd + 7) / 8), 256, 0, p->stream>>>(
                         p->d_embd, ng, p->n_dense_pad, p->n_dense_pad, p->d_nz);
+                } else if (p->tips_active && p->pack_pass) {
+                    // rows with children of this pass, packed, and their bitmaps
+                    const auto lo = std::lower_bound(p->hc_pos.begin(), p->hc_pos.end(), (int32_t)q0);
+                    const auto hi = std::lower_bound(p->hc_pos.begin(), p->hc_pos.end(), (int32_t)std::min<int64_t>(q1, INT32_MAX));
+                    pass_nd = (int64_t)(hi - lo);
+                    pass_nd_pad = std::max<int64_t>(128, (pass_nd + 127) / 128 * 128);
+                    const int64_t ng = p->npad / 32, wd = pass_nd_pad / 32;
+                    p->n_kernels += 2;
+                    k_compact_rows<<<dim3((unsigned)pass_nd_pad, (unsigned)p->nb), 128, 0, p->stream>>>(
+                        (const double*)p->d_emb, p->d_len, p->d_hc_pos + (lo - p->hc_pos.begin()), pass_nd,
+                        pass_nd_pad, QR, q0, p->d_embd, p->d_lend);
+                    k_group_nonzero<<<(unsigned)((ng * wd + 7) / 8), 256, 0, p->stream>>>(
+                        p->d_embd, ng, pass_nd_pad, pass_nd_pad, p->d_nz);
                 } else if (p->tips_active) {  // the pair kernel never visits a tip row
                     const int64_t ng = p->npad / 32, nwords = (q1 - q0 + 31) / 32;
                     p->n_kernels += 1;
@@ -1208,6 +1264,8 @@ static int compute_dense(b2d_problem* p, int metric) {
             }
             if (p->tips_active && p->rows_general)
                 rc = launch_pairs_dense(p, p->d_embd, p->d_lend, 0, p->n_dense_pad, p->n_dense_pad, epilogue, skip);
+            else if (p->tips_active && p->pack_pass)
+                rc = launch_pairs_dense(p, p->d_embd, p->d_lend, 0, pass_nd_pad, pass_nd_pad, epilogue, skip);
             else
                 rc = launch_pairs_dense(p, (const double*)p->d_emb, p->d_len + q0, q0, q1, QR, epilogue, skip);
             if (rc) return rc;
