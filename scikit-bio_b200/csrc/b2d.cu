@@ -946,8 +946,8 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         }
         p->n_kernels += 1;
         k_compact_rows<<<dim3((unsigned)p->n_dense_pad, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, p->d_embd,
-            p->d_lend);
+            (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, nullptr,
+            p->d_embd, p->d_lend);
         B2D_CUDA(cudaGetLastError());
         p->tips_mode = 1;
         return B2D_OK;
@@ -1186,7 +1186,9 @@ static int compute_dense(b2d_problem* p, int metric) {
                         (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR,
                         p->d_state, p->order.depth_at[q0 / NODE_STRIPE]);
                 }
-                {
+                // when the rows with children are packed per pass (and the tips come from the CSR)
+                // nothing reads the resident embedding as proportions: the packing divides
+                if (!p->pack_pass) {
                     const int64_t threads = p->nb * (TILE / 2);
                     dim3 grid((unsigned)((threads + 255) / 256),
                               (unsigned)std::min<int64_t>(q1 - q0, 2048));
@@ -1225,7 +1227,7 @@ static int compute_dense(b2d_problem* p, int metric) {
                     p->n_kernels += 2;
                     k_compact_rows<<<dim3((unsigned)pass_nd_pad, (unsigned)p->nb), 128, 0, p->stream>>>(
                         (const double*)p->d_emb, p->d_len, p->d_hc_pos + (lo - p->hc_pos.begin()), pass_nd,
-                        pass_nd_pad, QR, q0, p->d_embd, p->d_lend);
+                        pass_nd_pad, QR, q0, p->d_total, p->d_embd, p->d_lend);
                     k_group_nonzero<<<(unsigned)((ng * wd + 7) / 8), 256, 0, p->stream>>>(
                         p->d_embd, ng, pass_nd_pad, pass_nd_pad, p->d_nz);
                 } else if (p->tips_active) {  // the pair kernel never visits a tip row

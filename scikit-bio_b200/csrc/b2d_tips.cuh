@@ -436,14 +436,24 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
 // The rows that stay with the dense pair kernel, packed: embd[block][r][128] = emb[block][pos[r] - q0][128]
 // (zero rows and zero lengths in the padding), so that the pair kernel streams only them.  pos
 // holds absolute node positions, q0 is the first resident row of the pass.
+// With `total` given the embedding still holds the int64 subtree counts of the propagation and the
+// proportion count / total (the division k_counts_to_proportions does) is taken here, for the
+// packed rows only.
 __global__ void __launch_bounds__(128)
 k_compact_rows(const double* __restrict__ emb, const double* __restrict__ len, const int32_t* __restrict__ pos,
-               int64_t nd, int64_t nd_pad, int64_t QR, int64_t q0, double* __restrict__ embd,
-               double* __restrict__ lend) {
+               int64_t nd, int64_t nd_pad, int64_t QR, int64_t q0, const long long* __restrict__ total,
+               double* __restrict__ embd, double* __restrict__ lend) {
     const int64_t r = blockIdx.x, b = blockIdx.y;
     const bool real = r < nd;
     const int64_t q = real ? pos[r] : 0;
-    embd[(b * nd_pad + r) * TILE + threadIdx.x] = real ? emb[(b * QR + (q - q0)) * TILE + threadIdx.x] : 0.0;
+    double v = real ? emb[(b * QR + (q - q0)) * TILE + threadIdx.x] : 0.0;
+    if (total && real) {
+        const long long c = __double_as_longlong(v);
+        const long long t = total[b * TILE + threadIdx.x];
+        v = (double)c;
+        if (t > 0) v = v / (double)t;
+    }
+    embd[(b * nd_pad + r) * TILE + threadIdx.x] = v;
     if (b == 0 && threadIdx.x == 0) lend[r] = real ? len[q] : 0.0;
 }
 
