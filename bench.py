@@ -519,6 +519,12 @@ def run_ours(args):
                 "sparse_row_entries": t["sparse_row_entries"],
                 # every bucket is read by about n/128 tiles (as row or as column block), 16 B per entry
                 "algorithmic_bytes_per_launch": 16.0 * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1),
+                "hbm": {"algorithmic_bytes_per_launch": 16.0 * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1),
+                        "achieved_gbs": 16.0 * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1)
+                                        / (t["tips_ms"] * 1e-3) / 1e9,
+                        "peak_gbs": hbm_peak, "peak_source": peak_src,
+                        "note": "entries are re-read by every tile of their block row / column, mostly from L2; "
+                                "not the binding resource"},
                 "dense_kernel": roofline,
             }
         cpu = None
