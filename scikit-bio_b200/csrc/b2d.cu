@@ -349,6 +349,14 @@ struct b2d_problem {
     double* d_embd = nullptr;               // [nb][n_dense_pad][128] those rows, packed
     double* d_lend = nullptr;
     size_t embd_bytes = 0;
+    // unweighted UniFrac: sparse rows as bare keys, dense rows as packed bit stripes
+    bool urows_active = false;
+    uint32_t* d_ukeys = nullptr;
+    int64_t ukeys_cap = 0;
+    long long* d_lenfx = nullptr;           // [nch * TP_CHUNK] fixed-point lengths
+    uint32_t* d_bitsd = nullptr;            // [nb][n_dense_pad / 128][128][4]
+    size_t bitsd_bytes = 0;
+    double* d_ulend = nullptr;
     unsigned* d_rows_qcount = nullptr;      // [nbuckets][4]
     double* d_rows_upart = nullptr;         // [nch * 4][npad]
     int64_t tip_nch = 0;
@@ -387,6 +395,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_rows_sparse); b2d_free(p->d_rdR_hi); b2d_free(p->d_rdR_lo);
     b2d_free(p->d_rows_qcount); b2d_free(p->d_rows_upart);
     b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend); b2d_free(p->d_hc_pos);
+    b2d_free(p->d_ukeys); b2d_free(p->d_lenfx); b2d_free(p->d_bitsd); b2d_free(p->d_ulend);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -846,11 +855,11 @@ static int tips_build(b2d_problem* p) {
 // Sparse rows (nodes with at most S0 tips below) taken from the resident embedding.  S0 follows the
 // table's density (a node with s tips below is non-zero for about s * nnz / (n * tips) of the
 // samples; measured optimum: up to ~30 % of the samples) and is halved while a bucket overflows.
-static int rows_build(b2d_problem* p, int64_t QR) {
+// sparse-row threshold, masks, root distances and the list of dense positions for the current S0
+static int rows_masks(b2d_problem* p) {
     const TreeOrder& o = p->order;
-    int rc;
-    if ((rc = tips_buffers(p))) return rc;
     const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
+    int rc;
     if (!p->rows_S0) {
         int64_t ntips = 0;
         for (int64_t q = 0; q < p->mpad; ++q) ntips = std::max<int64_t>(ntips, o.tips_q[q]);
@@ -865,39 +874,47 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         B2D_CUDA(b2d_malloc(&p->d_rows_qcount, nbuckets * 4 * sizeof(unsigned)));
         B2D_CUDA(b2d_malloc(&p->d_rows_upart, (size_t)nch * 4 * p->npad * sizeof(double)));
     }
-    for (;;) {
-        if (p->rows_S0_uploaded != p->rows_S0) {
-            const int S0 = p->rows_S0;
-            std::vector<uint32_t> sp(p->mpad / 32, 0u), de(p->mpad / 32, 0u);
-            std::vector<double> hi(p->mpad, 0.0), lo(p->mpad, 0.0);
-            for (int64_t q = p->mpad - 1; q >= 0; --q) {  // parents (higher positions) first
-                const bool real = o.tips_q[q] > 0;
-                const bool inR = real && o.tips_q[q] <= S0;
-                if (inR) sp[q >> 5] |= 1u << (q & 31);
-                else if (real) de[q >> 5] |= 1u << (q & 31);
-                const int32_t par = o.parent_q[q];
-                if (inR) {
-                    hi[q] = par >= 0 ? hi[par] : 0.0;
-                    lo[q] = par >= 0 ? lo[par] : 0.0;
-                } else {
-                    hi[q] = o.rd_hi[q];
-                    lo[q] = o.rd_lo[q];
-                }
+    if (p->rows_S0_uploaded != p->rows_S0) {
+        const int S0 = p->rows_S0;
+        std::vector<uint32_t> sp(p->mpad / 32, 0u), de(p->mpad / 32, 0u);
+        std::vector<double> hi(p->mpad, 0.0), lo(p->mpad, 0.0);
+        for (int64_t q = p->mpad - 1; q >= 0; --q) {  // parents (higher positions) first
+            const bool real = o.tips_q[q] > 0;
+            const bool inR = real && o.tips_q[q] <= S0;
+            if (inR) sp[q >> 5] |= 1u << (q & 31);
+            else if (real) de[q >> 5] |= 1u << (q & 31);
+            const int32_t par = o.parent_q[q];
+            if (inR) {
+                hi[q] = par >= 0 ? hi[par] : 0.0;
+                lo[q] = par >= 0 ? lo[par] : 0.0;
+            } else {
+                hi[q] = o.rd_hi[q];
+                lo[q] = o.rd_lo[q];
             }
-            B2D_CUDA(cudaMemcpyAsync(p->d_rows_sparse, sp.data(), sp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
-            B2D_CUDA(cudaMemcpyAsync(p->d_rdR_hi, hi.data(), hi.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-            B2D_CUDA(cudaMemcpyAsync(p->d_rdR_lo, lo.data(), lo.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-            std::vector<int32_t> dpos;
-            for (int64_t q = 0; q < p->mpad; ++q)
-                if ((de[q >> 5] >> (q & 31)) & 1u) dpos.push_back((int32_t)q);
-            p->n_dense = (int64_t)dpos.size();
-            p->n_dense_pad = std::max<int64_t>(128, (p->n_dense + 127) / 128 * 128);
-            b2d_free(p->d_dense_pos);
-            p->d_dense_pos = nullptr;
-            if ((rc = upload(&p->d_dense_pos, dpos.data(), dpos.size(), p->stream))) return rc;
-            B2D_CUDA(cudaStreamSynchronize(p->stream));
-            p->rows_S0_uploaded = S0;
         }
+        B2D_CUDA(cudaMemcpyAsync(p->d_rows_sparse, sp.data(), sp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+        B2D_CUDA(cudaMemcpyAsync(p->d_rdR_hi, hi.data(), hi.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        B2D_CUDA(cudaMemcpyAsync(p->d_rdR_lo, lo.data(), lo.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        std::vector<int32_t> dpos;
+        for (int64_t q = 0; q < p->mpad; ++q)
+            if ((de[q >> 5] >> (q & 31)) & 1u) dpos.push_back((int32_t)q);
+        p->n_dense = (int64_t)dpos.size();
+        p->n_dense_pad = std::max<int64_t>(128, (p->n_dense + 127) / 128 * 128);
+        b2d_free(p->d_dense_pos);
+        p->d_dense_pos = nullptr;
+        if ((rc = upload(&p->d_dense_pos, dpos.data(), dpos.size(), p->stream))) return rc;
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        p->rows_S0_uploaded = S0;
+    }
+    return B2D_OK;
+}
+
+static int rows_build(b2d_problem* p, int64_t QR) {
+    int rc;
+    if ((rc = tips_buffers(p))) return rc;
+    const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
+    for (;;) {
+        if ((rc = rows_masks(p))) return rc;
         const int64_t rows = p->mpad;
         p->n_kernels += 5;
         k_rows_count<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
@@ -948,6 +965,75 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         k_compact_rows<<<dim3((unsigned)p->n_dense_pad, (unsigned)p->nb), 128, 0, p->stream>>>(
             (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, nullptr,
             p->d_embd, p->d_lend);
+        B2D_CUDA(cudaGetLastError());
+        p->tips_mode = 1;
+        return B2D_OK;
+    }
+}
+
+// Unweighted UniFrac: keys of the sparse rows from the presence bits, fixed-point lengths, packed
+// dense stripes.  Same threshold and fall-backs as rows_build.
+static int urows_build(b2d_problem* p) {
+    int rc;
+    if ((rc = tips_buffers(p))) return rc;
+    const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
+    if (!p->d_lenfx) B2D_CUDA(b2d_malloc(&p->d_lenfx, (size_t)nch * TP_CHUNK * sizeof(long long)));
+    for (;;) {
+        if ((rc = rows_masks(p))) return rc;
+        p->n_kernels += 5;
+        k_ubits_count<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
+            (const uint32_t*)p->d_emb, p->d_len, p->d_rows_sparse, p->mpad, p->NS, nch, p->npad,
+            p->d_rows_qcount, p->d_rows_upart);
+        k_rows_bucket_counts<<<(unsigned)((nbuckets + 255) / 256), 256, 0, p->stream>>>(p->d_rows_qcount, nbuckets,
+                                                                                      p->d_tip_counts);
+        k_tip_scan<<<1, 1024, 0, p->stream>>>(p->d_tip_counts, nbuckets, p->d_tip_ptr, p->d_tip_status, 65535u);
+        k_rows_ureduce<<<(unsigned)((p->npad + 255) / 256), 256, 0, p->stream>>>(p->d_rows_upart, nch * 4, p->npad,
+                                                                               p->d_tip_u, p->d_tip_word);
+        k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
+        int status = 0;
+        int64_t total = 0;
+        B2D_CUDA(cudaMemcpyAsync(&status, p->d_tip_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaMemcpyAsync(&total, p->d_tip_ptr + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        B2D_CUDA(cudaGetLastError());
+        if (status) {
+            if (p->rows_S0 == 1) {
+                p->tips_mode = -1;
+                return B2D_OK;
+            }
+            p->rows_S0 /= 2;
+            B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 4 * sizeof(unsigned long long), p->stream));
+            B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
+            continue;
+        }
+        if (p->ukeys_cap < total || !p->d_ukeys) {
+            b2d_free(p->d_ukeys);
+            p->d_ukeys = nullptr;
+            p->ukeys_cap = 0;
+            B2D_CUDA(b2d_malloc(&p->d_ukeys, std::max<int64_t>(total, 1) * sizeof(uint32_t)));
+            p->ukeys_cap = total;
+        }
+        p->rows_entries = (double)total;
+        const int64_t NSd = p->n_dense_pad / 128;
+        const size_t need = (size_t)p->nb * NSd * TILE * sizeof(uint4);
+        if (p->bitsd_bytes < need) {
+            b2d_free(p->d_bitsd);
+            b2d_free(p->d_ulend);
+            p->d_bitsd = nullptr;
+            p->d_ulend = nullptr;
+            p->bitsd_bytes = 0;
+            B2D_CUDA(b2d_malloc(&p->d_bitsd, need));
+            B2D_CUDA(b2d_malloc(&p->d_ulend, p->n_dense_pad * sizeof(double)));
+            p->bitsd_bytes = need;
+        }
+        p->n_kernels += 3;
+        k_make_lenfx<<<(unsigned)((nch * TP_CHUNK + 255) / 256), 256, 0, p->stream>>>(p->d_len, p->d_tip_scale,
+                                                                                    p->mpad, p->d_lenfx);
+        k_ubits_scatter<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
+            (const uint32_t*)p->d_emb, p->d_lenfx, p->d_rows_sparse, p->mpad, p->NS, nch, p->d_rows_qcount,
+            p->d_tip_ptr, p->d_ukeys, p->d_tip_runs, (unsigned long long*)p->d_tip_ufx);
+        k_pack_bits<<<dim3((unsigned)NSd, (unsigned)p->nb), 128, 0, p->stream>>>(
+            (const uint32_t*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->NS, NSd, p->d_bitsd, p->d_ulend);
         B2D_CUDA(cudaGetLastError());
         p->tips_mode = 1;
         return B2D_OK;
@@ -1070,6 +1156,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     const bool skip = g_weighted_skip && !plain_kernels() && !p->custom_tiles && p->ntiles > 0;
     p->skip_executed = p->skip_dense = 0;
     p->tips_active = false;
+    p->urows_active = false;
     p->t_tips = 0;
     if (skip) {
         int rc0 = skip_setup(p);
@@ -1359,12 +1446,51 @@ static int compute_bits(b2d_problem* p, int metric) {
     B2D_CUDA(cudaFuncSetAttribute(k_pair_unweighted_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)UL_SMEM));
     p->chunk_counter = 0;
+    p->urows_active = false;
+    p->tips_active = false;
+    p->t_tips = 0;
+    bool utips_timed = false;
+    if (p->ntiles && metric == B2D_UNWEIGHTED_UNIFRAC && p->kind == 0 && g_tips_sparse && g_weighted_skip &&
+        p->tips_mode >= 0 && !plain_kernels() && !p->custom_tiles && p->n > 0) {
+        // sparse rows through the intersection kernel, the others packed for the LUT kernel
+        if ((rc = urows_build(p))) return rc;
+        p->urows_active = p->tips_mode == 1;
+    }
     if (p->ntiles && metric != B2D_FAITH_PD) {
         if ((rc = fork_streams(p))) return rc;
+        if (p->urows_active) {
+            PairArgs a;
+            a.tiles = p->d_tiles;
+            a.row_base = p->d_row_base;
+            a.out = p->d_out;
+            a.svec = p->d_svec;
+            a.total = p->d_total;
+            a.n = p->n;
+            a.qa = 0;
+            a.qb = 0;
+            a.QR = 0;
+            a.NS = p->NS;
+            a.last = 0;
+            a.epilogue = EPI_UNWEIGHTED;
+            cudaStream_t st;
+            if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
+            B2D_CUDA(cudaFuncSetAttribute(k_pair_utips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UT_SMEM));
+            B2D_CUDA(cudaEventRecord(p->ev[7], st));
+            k_pair_utips<<<(unsigned)p->ntiles, TP_THREADS, UT_SMEM, st>>>(
+                p->d_ukeys, p->d_tip_ptr, p->d_tip_runs, p->d_lenfx, p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
+                p->d_tip_word + 2, a);
+            B2D_CUDA(cudaEventRecord(p->ev[8], st));
+            utips_timed = true;
+            p->n_kernels += 1;
+        }
         // bits kernels touch 8..32 nodes per instruction: use 4x longer node chunks per launch
         const int64_t chunk = 4 * g_chunk_nodes;
-        for (int64_t qa = 0; qa < p->mpad; qa += chunk) {
-            int64_t qb = std::min<int64_t>(p->mpad, qa + chunk);
+        const int64_t rows_total = p->urows_active ? p->n_dense_pad : p->mpad;
+        const int64_t NSx = p->urows_active ? p->n_dense_pad / 128 : p->NS;
+        const uint4* bits_x = p->urows_active ? (const uint4*)p->d_bitsd : (const uint4*)p->d_emb;
+        const double* len_x = p->urows_active ? p->d_ulend : p->d_len;
+        for (int64_t qa = 0; qa < rows_total; qa += chunk) {
+            int64_t qb = std::min<int64_t>(rows_total, qa + chunk);
             PairArgs a;
             a.tiles = p->d_tiles;
             a.row_base = p->d_row_base;
@@ -1375,7 +1501,7 @@ static int compute_bits(b2d_problem* p, int metric) {
             a.qa = qa;
             a.qb = qb;
             a.QR = 0;
-            a.NS = p->NS;
+            a.NS = NSx;
             a.last = 0;
             a.epilogue = metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED;
             cudaStream_t st;
@@ -1386,16 +1512,35 @@ static int compute_bits(b2d_problem* p, int metric) {
                 k_pair_unweighted<<<(unsigned)p->ntiles, 256, 0, st>>>((const uint4*)p->d_emb,
                                                                        p->d_len, a);
             else
-                k_pair_unweighted_lut<<<(unsigned)p->ntiles, 256, UL_SMEM, st>>>(
-                    (const uint4*)p->d_emb, p->d_len, a);
+                k_pair_unweighted_lut<<<(unsigned)p->ntiles, 256, UL_SMEM, st>>>(bits_x, len_x, a);
             p->n_launch += 1;
         }
         if ((rc = join_streams(p))) return rc;
+        if (p->urows_active && p->out_len && !p->owned.empty()) {  // near-duplicate pairs: see b2d_tips.cuh
+            p->n_kernels += 1;
+            k_tip_guard<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
+                p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, p->d_owned, p->d_row_base, p->n,
+                p->d_tip_u, p->d_tip_word + 1);
+        }
         if ((rc = finalize(p, metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED))) return rc;
     }
     B2D_CUDA(cudaEventRecord(ec, p->stream));
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     B2D_CUDA(cudaGetLastError());
+    if (p->urows_active) {
+        unsigned long long fm[2] = {0, 0};
+        B2D_CUDA(cudaMemcpy(fm, p->d_tip_word + 1, sizeof(fm), cudaMemcpyDeviceToHost));
+        p->tip_matches = (double)fm[1];
+        if (fm[0]) {  // near-duplicate samples: redo with every row in the look-up-table kernel
+            p->tips_mode = -1;
+            p->tips_flagged = (double)fm[0];
+            return compute_bits(p, metric);
+        }
+        if (utips_timed) {
+            cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]);
+            p->t_tips = ms;
+        }
+    }
     cudaEventElapsedTime(&ms, ea, eb);
     p->t_embed = ms;
     cudaEventElapsedTime(&ms, eb, ec);
@@ -1760,9 +1905,10 @@ int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     double v[17] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
                     p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged,
-                    p->tips_active ? (p->rows_general ? (double)p->rows_S0 : 1.0) : 0.0,
-                    p->tips_active && p->rows_general ? p->rows_entries : 0.0,
-                    p->tips_active ? p->tip_matches : 0.0};
+                    p->urows_active ? (double)p->rows_S0
+                                    : (p->tips_active ? (p->rows_general ? (double)p->rows_S0 : 1.0) : 0.0),
+                    p->urows_active || (p->tips_active && p->rows_general) ? p->rows_entries : 0.0,
+                    p->urows_active || p->tips_active ? p->tip_matches : 0.0};
     for (int i = 0; i < n && i < 17; ++i) ms[i] = v[i];
     return B2D_OK;
 }

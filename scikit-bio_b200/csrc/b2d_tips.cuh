@@ -457,4 +457,209 @@ k_compact_rows(const double* __restrict__ emb, const double* __restrict__ len, c
     if (b == 0 && threadIdx.x == 0) lend[r] = real ? len[q] : 0.0;
 }
 
+// =======================================================================================
+// Unweighted UniFrac: the same split on the presence bits.  sum_q len_q [u_q xor v_q] over the
+// sparse rows = U_i + U_j - 2 * sum_{q in both} len_q with U_i = sum_q len_q [u_q], and here the
+// weight of a match depends on the position only: entries are bare keys (4 bytes) and the
+// fixed-point lengths lenfx[q] = round(len_q * scale) live in a table.  The rows that stay with
+// the look-up-table kernel are packed into their own bit stripes.
+// bits layout (b2d_embed.cuh): word ((blk*NS + q/128)*128 + sample)*4 + (q%128)/32, bit q%32.
+// =======================================================================================
+constexpr int UT_MAXE = 16384;  // column keys resident per batch
+constexpr size_t UT_SMEM = (size_t)TILE * TILE * sizeof(long long) + (size_t)UT_MAXE * sizeof(uint32_t) +
+                           2 * (TP_CHUNK + 8) * sizeof(unsigned short) + (size_t)TP_CHUNK * sizeof(long long);
+
+// pass 1: entries per (bucket, quarter) and per-sample partial sums of the lengths (double)
+__global__ void __launch_bounds__(128)
+k_ubits_count(const uint32_t* __restrict__ bits, const double* __restrict__ len, const uint32_t* __restrict__ sparse,
+              int64_t mpad, int64_t NS, int64_t nch, int64_t npad, unsigned* __restrict__ qcount,
+              double* __restrict__ upart) {
+    const int64_t b = blockIdx.y, ch = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t w0 = (ch * TP_CHUNK + (int64_t)warp * TP_QROWS) / 32;
+    const int64_t w1 = min(mpad / 32, w0 + TP_QROWS / 32);
+    double u[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned cnt = 0;
+    for (int64_t W = w0; W < w1; ++W) {
+        const uint32_t mask = sparse[W];
+        if (mask == 0u) continue;  // warp-uniform
+        const uint32_t* src = bits + ((b * NS + W / 4) * TILE + lane) * 4 + (W & 3);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = src[(int64_t)32 * k * 4] & mask;
+            cnt += __popc(x);
+            while (x) {
+                const int bit = __ffs(x) - 1;
+                x &= x - 1u;
+                u[k] += len[W * 32 + bit];
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) qcount[(b * nch + ch) * 4 + warp] = cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) upart[(ch * 4 + warp) * npad + b * TILE + 32 * k + lane] = u[k];
+}
+
+__global__ void k_make_lenfx(const double* __restrict__ len, const double* __restrict__ scale, int64_t mpad,
+                             long long* __restrict__ lenfx) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < mpad) lenfx[q] = __double2ll_rn(len[q] * scale[0]);
+}
+
+// pass 2: the keys (sorted by position by construction), run starts, U_i in fixed point
+__global__ void __launch_bounds__(128)
+k_ubits_scatter(const uint32_t* __restrict__ bits, const long long* __restrict__ lenfx,
+                const uint32_t* __restrict__ sparse, int64_t mpad, int64_t NS, int64_t nch,
+                const unsigned* __restrict__ qcount, const int64_t* __restrict__ bucket_ptr,
+                uint32_t* __restrict__ keys, unsigned short* __restrict__ runs,
+                unsigned long long* __restrict__ Ufx) {
+    const int64_t b = blockIdx.y, ch = blockIdx.x;
+    const int64_t bucket = b * nch + ch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    unsigned run = 0;
+    for (int w = 0; w < warp; ++w) run += qcount[bucket * 4 + w];
+    const int64_t q0 = ch * TP_CHUNK + (int64_t)warp * TP_QROWS;
+    uint32_t* out = keys + bucket_ptr[bucket];
+    unsigned short* rs = runs + (size_t)bucket * (TP_CHUNK + 8);
+    long long ufx[4] = {0, 0, 0, 0};
+    for (int64_t W = q0 / 32; W < (q0 + TP_QROWS) / 32; ++W) {
+        const bool in = W < mpad / 32;
+        const uint32_t mask = in ? sparse[W] : 0u;
+        uint32_t x[4] = {0u, 0u, 0u, 0u};
+        if (mask != 0u) {
+            const uint32_t* src = bits + ((b * NS + W / 4) * TILE + lane) * 4 + (W & 3);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = src[(int64_t)32 * k * 4] & mask;
+        }
+        for (int bit = 0; bit < 32; ++bit) {
+            const int64_t q = W * 32 + bit;
+            if (lane == 0) rs[q - ch * TP_CHUNK] = (unsigned short)run;
+            if (!((mask >> bit) & 1u)) continue;  // warp-uniform
+            const long long lf = lenfx[q];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool on = (x[k] >> bit) & 1u;
+                const uint32_t m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    ufx[k] += lf;
+                    out[run + __popc(m & lt)] = ((uint32_t)(q - ch * TP_CHUNK) << 7) | (uint32_t)(32 * k + lane);
+                }
+                run += __popc(m);
+            }
+        }
+    }
+    if (warp == 3 && lane == 0) rs[TP_CHUNK] = (unsigned short)run;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (ufx[k]) atomicAdd(&Ufx[b * TILE + 32 * k + lane], (unsigned long long)ufx[k]);
+}
+
+// the tile kernel: T(i,j) = U_i + U_j - 2 * sum_{q in both} lenfx[q]
+__global__ void __launch_bounds__(TP_THREADS, 1)
+k_pair_utips(const uint32_t* __restrict__ keys, const int64_t* __restrict__ bucket_ptr,
+             const unsigned short* __restrict__ runs, const long long* __restrict__ lenfx, int64_t nch,
+             const long long* __restrict__ Ufx, const double* __restrict__ scale,
+             unsigned long long* __restrict__ n_matches, PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* acc_lo = reinterpret_cast<uint32_t*>(smem_raw);   // [128][128], see k_pair_tips
+    uint32_t* acc_hi = acc_lo + TILE * TILE;
+    uint32_t* ckey = reinterpret_cast<uint32_t*>(smem_raw + (size_t)TILE * TILE * sizeof(long long));
+    unsigned short* fstart = reinterpret_cast<unsigned short*>(ckey + UT_MAXE);
+    unsigned short* rstart = fstart + TP_CHUNK + 8;
+    long long* lf = reinterpret_cast<long long*>(rstart + TP_CHUNK + 8);  // [TP_CHUNK] lengths of the chunk
+
+    const int tid = threadIdx.x;
+    const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
+    for (int x = tid; x < 2 * TILE * TILE; x += TP_THREADS) acc_lo[x] = 0u;
+    unsigned nm = 0;
+
+    for (int64_t ch = 0; ch < nch; ++ch) {
+        const int64_t rbk = (int64_t)bi * nch + ch, cbk = (int64_t)bj * nch + ch;
+        const int64_t r0 = bucket_ptr[rbk], r1 = bucket_ptr[rbk + 1];
+        const int64_t c0 = bucket_ptr[cbk], c1 = bucket_ptr[cbk + 1];
+        if (r1 == r0 || c1 == c0) continue;  // uniform across the CTA
+        const unsigned short* crun = runs + (size_t)cbk * (TP_CHUNK + 8);
+        const unsigned short* rrun = runs + (size_t)rbk * (TP_CHUNK + 8);
+        for (int64_t cb = c0; cb < c1; cb += UT_MAXE) {
+            const int nc = (int)((c1 - cb) < UT_MAXE ? (c1 - cb) : UT_MAXE);
+            const int lo = (int)(cb - c0), hi = lo + nc;
+            __syncthreads();  // previous batch fully consumed
+            for (int x = tid; x < nc; x += TP_THREADS) ckey[x] = keys[cb + x];
+            if (cb == c0) {
+                for (int x = tid; x < (TP_CHUNK + 8) / 8; x += TP_THREADS) {
+                    reinterpret_cast<uint4*>(fstart)[x] = reinterpret_cast<const uint4*>(crun)[x];
+                    reinterpret_cast<uint4*>(rstart)[x] = reinterpret_cast<const uint4*>(rrun)[x];
+                }
+                for (int x = tid; x < TP_CHUNK; x += TP_THREADS) lf[x] = lenfx[ch * TP_CHUNK + x];
+            }
+            __syncthreads();
+            // one thread per (position, row sample) entry of the row bucket
+            for (int64_t x = r0 + tid; x < r1; x += TP_THREADS) {
+                const uint32_t rk = keys[x];
+                const uint32_t f = rk >> 7, r = rk & 127u;
+                const int e0 = max((int)fstart[f], lo), e1 = min((int)fstart[f + 1], hi);
+                if (e1 <= e0) continue;
+                nm += (unsigned)(e1 - e0);
+                const unsigned long long add = (unsigned long long)lf[f];
+                const uint32_t alo = (uint32_t)add, ahi = (uint32_t)(add >> 32);
+                const uint32_t rbase = r * TILE, rx = r & 31u;
+#pragma unroll 4
+                for (int e = e0; e < e1; ++e) {
+                    const uint32_t cell = rbase + ((ckey[e - lo] & 127u) ^ rx);
+                    const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                    atomicAdd(&acc_hi[cell], ahi + (old + alo < old ? 1u : 0u));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (n_matches) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, o);
+        if ((tid & 31) == 0 && nm) atomicAdd(n_matches, (unsigned long long)nm);
+    }
+    const double inv = scale[1];
+    const int64_t base = a.row_base[bi];
+    const int64_t i0 = (int64_t)bi * TILE;
+    for (int x = tid; x < TILE * TILE; x += TP_THREADS) {
+        const int rr = x / TILE, c = x % TILE;
+        const int64_t i = i0 + rr, j = (int64_t)bj * TILE + c;
+        if (i >= j || j >= a.n) continue;
+        const int xs = rr * TILE + (c ^ (rr & 31));
+        const long long m = (long long)(((unsigned long long)acc_hi[xs] << 32) | acc_lo[xs]);
+        const long long t = Ufx[i] + Ufx[j] - 2 * m;
+        emit(a, base, i0, i, j, (double)t * inv);
+    }
+}
+
+// the rows left to the look-up-table kernel, packed into their own stripes:
+// bit r of bitsd (same layout, NSd stripes) = bit pos[r] of bits; lend[r] = len[pos[r]]
+__global__ void __launch_bounds__(128)
+k_pack_bits(const uint32_t* __restrict__ bits, const double* __restrict__ len, const int32_t* __restrict__ pos,
+            int64_t nd, int64_t NS, int64_t NSd, uint32_t* __restrict__ bitsd, double* __restrict__ lend) {
+    const int64_t sd = blockIdx.x, b = blockIdx.y;
+    const int sample = threadIdx.x;
+    const uint32_t* src = bits + (b * NS * TILE + sample) * 4;
+    uint32_t wv[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t word = 0;
+        for (int bit = 0; bit < 32; ++bit) {
+            const int64_t r = sd * 128 + w * 32 + bit;
+            if (r >= nd) break;
+            const int64_t q = pos[r];
+            word |= ((src[(q / 128) * TILE * 4 + (q % 128) / 32] >> (q % 32)) & 1u) << bit;
+        }
+        wv[w] = word;
+    }
+    *reinterpret_cast<uint4*>(bitsd + ((b * NSd + sd) * TILE + sample) * 4) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    if (b == 0) {
+        const int64_t r = sd * 128 + sample;
+        lend[r] = r < nd ? len[pos[r]] : 0.0;
+    }
+}
+
 }  // namespace b2d
