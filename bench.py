@@ -502,25 +502,27 @@ def run_ours(args):
         # = two 32-bit shared-memory atomic adds.
         if t.get("tips_ms", 0.0) > avg_launch_ms * pair_launches_per_step and t.get("sparse_row_matches", 0.0) > 0:
             atom_peak = _capi.microbench(3, device)
+            entry_bytes = 4.0 if workload == "unweighted" else 16.0   # bare keys / {key, fixed-point weight}
             atoms = 2.0 * t["sparse_row_matches"]
             a_rate = atoms / (t["tips_ms"] * 1e-3) / 1e12
             roofline = {
-                "kernel": "k_pair_tips", "bound": "smem-atomic", "achieved": a_rate,
+                "kernel": "k_pair_utips" if workload == "unweighted" else "k_pair_tips", "bound": "smem-atomic",
+                "achieved": a_rate,
                 "peak": atom_peak / 1e12, "unit": "Tatom/s (shared-memory int32 atomic adds)",
                 "frac": a_rate / (atom_peak / 1e12),
                 "peak_source": "b2d_microbench(3): shared-memory atomicAdd on random cells of a 128x128 int32 "
                                "tile, all SMs, measured in this run",
-                "traffic": TRAFFIC.get("k_pair_tips") if default_shape else None,
+                "traffic": TRAFFIC.get("k_pair_tips") if default_shape and workload == "weighted" else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the launch, ncu --set full, "
-                                  "profiles/r1_ncu_*_one_launch.txt" if default_shape and "k_pair_tips" in TRAFFIC else None,
+                                  "profiles/r1_ncu_*_one_launch.txt" if default_shape and workload == "weighted" else None,
                 "avg_launch_ms": float(t["tips_ms"]), "launches_per_step": 1,
                 "matches_per_launch": t["sparse_row_matches"], "units_per_match": 2.0,
                 "sparse_rows_max_tips": t["sparse_rows_max_tips"],
                 "sparse_row_entries": t["sparse_row_entries"],
                 # every bucket is read by about n/128 tiles (as row or as column block), 16 B per entry
-                "algorithmic_bytes_per_launch": 16.0 * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1),
-                "hbm": {"algorithmic_bytes_per_launch": 16.0 * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1),
-                        "achieved_gbs": 16.0 * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1)
+                "algorithmic_bytes_per_launch": entry_bytes * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1),
+                "hbm": {"algorithmic_bytes_per_launch": entry_bytes * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1),
+                        "achieved_gbs": entry_bytes * t["sparse_row_entries"] * ((n + 127) // 128 + 1) / max(world * emulate, 1)
                                         / (t["tips_ms"] * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "peak_source": peak_src,
                         "note": "entries are re-read by every tile of their block row / column, mostly from L2; "

@@ -794,3 +794,87 @@ def test_negative_branch_lengths_keep_every_row_in_the_dense_kernel():
         got = prob.fetch(np.empty(n * (n - 1) // 2))
     assert t["tips_ms"] == 0 and t["sparse_rows_max_tips"] == 0
     assert_close_rel(got, exp["weighted_unifrac"], 1e-9, "negative lengths")  # signed sums cancel
+
+
+@pytest.mark.parametrize("cat", [False, True])
+def test_unweighted_sparse_rows_agree_with_the_lut_kernel_and_fall_back(cat):
+    """Unweighted UniFrac: sparse rows through the key-intersection kernel + packed dense stripes
+    (default) vs every row in the look-up-table kernel, for several thresholds; near-duplicate
+    samples make the engine redo the LUT way; Faith's PD is untouched."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 333, 4000
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.015, 71, caterpillar=cat)
+    exp = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr, cols, vals, tips), tip_node, parent, length)
+    total = n * (n - 1) // 2
+    res = {}
+    try:
+        for k in (0, 1, 4, 50, 1 << 20):
+            _capi.set_option("sparse_rows_max_tips", k)
+            for shards in (1, 2):
+                out = np.full(total, -1.0)
+                for sh in range(shards):
+                    with _capi.Problem.tree(parent, length, indptr, tip_node[cols], None, n, shard=sh, n_shards=shards) as prob:
+                        prob.compute("unweighted_unifrac")
+                        t = prob.timings()
+                        assert t["tips_ms"] > 0 and t["tips_flagged"] == 0 and t["sparse_row_matches"] > 0
+                        prob.fetch(out)
+                        if shards == 1:
+                            assert_close_rel(prob.sample_vector(), exp["faith_pd"], UNIFRAC_RTOL, "faith_pd")
+                res[(k, shards)] = out
+        _capi.set_option("tips_sparse", 0)
+        with _capi.Problem.tree(parent, length, indptr, tip_node[cols], None, n) as prob:
+            prob.compute("unweighted_unifrac")
+            assert prob.timings()["tips_ms"] == 0
+            res["lut"] = prob.fetch(np.empty(total))
+    finally:
+        _capi.set_option("sparse_rows_max_tips", 0)
+        _capi.set_option("tips_sparse", 1)
+    for k, v in res.items():
+        assert_close_rel(v, exp["unweighted_unifrac"], UNIFRAC_RTOL, f"unweighted sparse rows {k}")
+        assert_close_rel(v, res["lut"], 1e-13, f"unweighted sparse rows {k} vs LUT")
+
+    # an exact copy stays at exactly 0
+    rows = [cols[indptr[s]:indptr[s + 1]] for s in range(n)]
+    rows[1] = rows[0].copy()
+    cols2 = np.concatenate(rows)
+    indptr2 = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    dense2 = np.zeros((n, tips), dtype=np.int64)
+    for s in range(n):
+        dense2[s, rows[s]] = 1
+    exp2 = oracle_fast.unifrac_all(dense2, tip_node, parent, length)
+    with _capi.Problem.tree(parent, length, indptr2, tip_node[cols2], None, n) as prob:
+        prob.compute("unweighted_unifrac")
+        got = prob.fetch(np.empty(total))
+    assert got[0] == 0.0
+    assert_close_rel(got, exp2["unweighted_unifrac"], UNIFRAC_RTOL, "unweighted with a duplicate sample")
+
+    # a near-duplicate (one extra taxon on a 1e-9 branch whose parent the sample already reaches):
+    # the guard makes the engine redo the computation with every row in the LUT kernel
+    in0 = np.zeros(tips, dtype=bool)
+    in0[rows[0]] = True
+    par_of_tip = parent[tip_node]
+    extra = None
+    for t in np.flatnonzero(~in0):
+        sib = np.flatnonzero((par_of_tip == par_of_tip[t]) & in0)
+        if len(sib):
+            extra = int(t)
+            break
+    assert extra is not None
+    length3 = length.copy()
+    length3[tip_node[extra]] = 1e-9
+    rows[2] = np.concatenate([rows[0], [extra]])
+    cols3 = np.concatenate(rows)
+    indptr3 = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    dense3 = np.zeros((n, tips), dtype=np.int64)
+    for s in range(n):
+        dense3[s, rows[s]] = 1
+    exp3 = oracle_fast.unifrac_all(dense3, tip_node, parent, length3)
+    with _capi.Problem.tree(parent, length3, indptr3, tip_node[cols3], None, n) as prob:
+        prob.compute("unweighted_unifrac")
+        t = prob.timings()
+        got = prob.fetch(np.empty(total))
+    assert t["tips_flagged"] > 0 and t["tips_ms"] == 0
+    assert_close_rel(got, exp3["unweighted_unifrac"], UNIFRAC_RTOL, "unweighted near-duplicates")

@@ -39,7 +39,7 @@ def main(n_cases=40, seed=0, verbose=True):
         _capi.set_option("emb_budget_bytes", ((n + 127) // 128) * 128 * 8 * rows_res)
         total = n * (n - 1) // 2
         errs = {}
-        for key in ("weighted_unifrac", "weighted_unifrac_normalized"):
+        for key in ("weighted_unifrac", "weighted_unifrac_normalized", "unweighted_unifrac"):
             out = np.full(total, -7.0)
             for sh in range(n_shards):
                 with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n, shard=sh, n_shards=n_shards) as prob:
@@ -59,7 +59,8 @@ def main(n_cases=40, seed=0, verbose=True):
             failures.append((case, n, tips, lam, cat, n_shards, chunk, rows_res, errs, bc_ok))
         if verbose:
             print(f"case {case}: n={n} tips={tips} lam={lam} cat={cat} shards={n_shards} chunk={chunk} rows={rows_res} maxtips={max_tips} "
-                  f"wu {errs['weighted_unifrac']:.2e} wun {errs['weighted_unifrac_normalized']:.2e} bc_exact {bc_ok}{flag}", flush=True)
+                  f"wu {errs['weighted_unifrac']:.2e} wun {errs['weighted_unifrac_normalized']:.2e} "
+                  f"uu {errs['unweighted_unifrac']:.2e} bc_exact {bc_ok}{flag}", flush=True)
     _capi.set_option("chunk_nodes", 0)
     _capi.set_option("emb_budget_bytes", 0)
     _capi.set_option("sparse_rows_max_tips", 0)
