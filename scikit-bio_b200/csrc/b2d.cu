@@ -1540,6 +1540,9 @@ static int compute_bits(b2d_problem* p, int metric) {
             cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]);
             p->t_tips = ms;
         }
+        // share of the (tile, node row) work left to the look-up-table kernel
+        p->skip_executed = (double)p->ntiles * (double)p->n_dense_pad;
+        p->skip_dense = (double)p->ntiles * (double)p->mpad;
     }
     cudaEventElapsedTime(&ms, ea, eb);
     p->t_embed = ms;
