@@ -529,6 +529,12 @@ def run_ours(args):
                                 "not the binding resource"},
                 "dense_kernel": roofline,
             }
+            # the dense kernel's time is a difference of event times and overlaps with the tail of the
+            # intersection kernel on the other stream: a fraction above 1 only says the split is unreliable
+            if roofline["dense_kernel"]["frac"] > 1.0:
+                roofline["dense_kernel"]["frac"] = None
+                roofline["dense_kernel"]["note"] = ("time by difference (pair phase - preparation - intersection "
+                                                    "kernel), the two pair kernels overlap on two streams")
         cpu = None
         if not args.no_cpu and world == 1 and emulate == 1:
             n_sub = args.cpu_samples or (64 if inp["kind"] == "tree" else 1000)

@@ -1455,6 +1455,7 @@ static int compute_bits(b2d_problem* p, int metric) {
         // sparse rows through the intersection kernel, the others packed for the LUT kernel
         if ((rc = urows_build(p))) return rc;
         p->urows_active = p->tips_mode == 1;
+        B2D_CUDA(cudaEventRecord(p->ev[4], p->stream));
     }
     if (p->ntiles && metric != B2D_FAITH_PD) {
         if ((rc = fork_streams(p))) return rc;
@@ -1540,6 +1541,8 @@ static int compute_bits(b2d_problem* p, int metric) {
             cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]);
             p->t_tips = ms;
         }
+        cudaEventElapsedTime(&ms, eb, p->ev[4]);
+        p->t_skip_prep = ms;  // keys, run starts, packed stripes
         // share of the (tile, node row) work left to the look-up-table kernel
         p->skip_executed = (double)p->ntiles * (double)p->n_dense_pad;
         p->skip_dense = (double)p->ntiles * (double)p->mpad;
