@@ -183,8 +183,8 @@ int b2d_beta_diversity_features(int metric, int device,
  *                       kernel; 0: dense.  Falls back by itself for very dense tables and when
  *                       near-duplicate samples are found.
  *   "sparse_rows_max_tips"  0 (default): when the whole embedding is resident, rows of nodes with
- *                       up to about 0.3 / (table density) tips below them join the tips in the
- *                       intersection kernel; k > 0: up to k tips (1 = tip rows only)
+ *                       up to about 0.3 / (table density) tips below them (0.16 / density for
+ *                       unweighted UniFrac) join the tips in the intersection kernel; k > 0: up to k tips (1 = tip rows only)
  *   "cache_embedding"   1 (default): device buffers (the embedding above all) are parked per
  *                       device when a problem is destroyed and reused by the
  *                       next one (cudaMalloc / cudaFree of tens of GB cost 0.1 - 0.7 s); they

@@ -335,7 +335,8 @@ struct b2d_problem {
     int64_t tip_entries_cap = 0;            // entries d_tip_entries can hold
     // sparse rows beyond the tips (whole embedding resident): nodes with <= rows_S0 tips below
     bool rows_general = false;
-    int rows_S0 = 0, rows_S0_uploaded = 0;
+    int rows_S0 = 0, rows_S0_uploaded = 0;  // threshold in use / the one the device masks are for
+    int rows_S0_pref[2] = {0, 0};           // chosen threshold: [0] weighted, [1] unweighted
     double rows_entries = 0;
     uint32_t* d_rows_sparse = nullptr;      // [mpad/32] bit = row goes through the intersection kernel
     double* d_rdR_hi = nullptr;             // root distances without the sparse rows' branches
@@ -856,17 +857,21 @@ static int tips_build(b2d_problem* p) {
 // table's density (a node with s tips below is non-zero for about s * nnz / (n * tips) of the
 // samples; measured optimum: up to ~30 % of the samples) and is halved while a bucket overflows.
 // sparse-row threshold, masks, root distances and the list of dense positions for the current S0
-static int rows_masks(b2d_problem* p) {
+// which: 0 weighted (rows up to ~0.32 / density tips: the dense alternative is the FP64 kernel),
+// 1 unweighted (~0.16 / density: the look-up-table kernel is four times cheaper per row)
+static int rows_masks(b2d_problem* p, int which) {
     const TreeOrder& o = p->order;
     const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
     int rc;
-    if (!p->rows_S0) {
+    if (!p->rows_S0_pref[which]) {
         int64_t ntips = 0;
         for (int64_t q = 0; q < p->mpad; ++q) ntips = std::max<int64_t>(ntips, o.tips_q[q]);
         const double dens = (double)p->nnz / std::max(1.0, (double)p->n * (double)std::max<int64_t>(ntips, 1));
-        int s0 = g_sparse_rows_max_tips ? g_sparse_rows_max_tips : (int)std::min(256.0, std::max(1.0, 0.32 / std::max(dens, 1e-9)));
-        p->rows_S0 = std::max(1, s0);
+        const double factor = which == 0 ? 0.32 : 0.16;
+        int s0 = g_sparse_rows_max_tips ? g_sparse_rows_max_tips : (int)std::min(256.0, std::max(1.0, factor / std::max(dens, 1e-9)));
+        p->rows_S0_pref[which] = std::max(1, s0);
     }
+    p->rows_S0 = p->rows_S0_pref[which];
     if (!p->d_rows_qcount) {
         B2D_CUDA(b2d_malloc(&p->d_rows_sparse, (p->mpad / 32) * sizeof(uint32_t)));
         B2D_CUDA(b2d_malloc(&p->d_rdR_hi, p->mpad * sizeof(double)));
@@ -914,7 +919,7 @@ static int rows_build(b2d_problem* p, int64_t QR) {
     if ((rc = tips_buffers(p))) return rc;
     const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
     for (;;) {
-        if ((rc = rows_masks(p))) return rc;
+        if ((rc = rows_masks(p, 0))) return rc;
         const int64_t rows = p->mpad;
         p->n_kernels += 5;
         k_rows_count<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
@@ -937,7 +942,7 @@ static int rows_build(b2d_problem* p, int64_t QR) {
                 p->tips_mode = -1;
                 return B2D_OK;
             }
-            p->rows_S0 /= 2;
+            p->rows_S0_pref[0] = p->rows_S0 / 2;
             B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 2 * sizeof(unsigned long long), p->stream));
             B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
             continue;
@@ -979,7 +984,7 @@ static int urows_build(b2d_problem* p) {
     const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
     if (!p->d_lenfx) B2D_CUDA(b2d_malloc(&p->d_lenfx, (size_t)nch * TP_CHUNK * sizeof(long long)));
     for (;;) {
-        if ((rc = rows_masks(p))) return rc;
+        if ((rc = rows_masks(p, 1))) return rc;
         p->n_kernels += 5;
         k_ubits_count<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
             (const uint32_t*)p->d_emb, p->d_len, p->d_rows_sparse, p->mpad, p->NS, nch, p->npad,
@@ -1001,7 +1006,7 @@ static int urows_build(b2d_problem* p) {
                 p->tips_mode = -1;
                 return B2D_OK;
             }
-            p->rows_S0 /= 2;
+            p->rows_S0_pref[1] = p->rows_S0 / 2;
             B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 4 * sizeof(unsigned long long), p->stream));
             B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
             continue;
