@@ -1,26 +1,32 @@
-// Tip rows of the weighted kernel as a sparse intersection (tree problems, zero-block skipping on).
+// Sparse node rows as an intersection of sorted entry lists (tree problems, UniFrac).
 //
 // Half of the node rows are tips, and a tip row is the sparsest kind of row: sample i is
-// non-zero there only if it contains that very taxon.  With w_ti = len_t * p_ti,
-//   sum_t len_t |p_ti - p_tj| = U_i + U_j - 2 * sum_{t in both} min(w_ti, w_tj),   U_i = sum_t w_ti
-// and only tips present in BOTH samples need pair work (about 40 of 2 x 2000 per pair at config 2).
-// To keep the subtraction harmless the w are quantised once to 61-bit fixed point (scale = a
-// power of two from max_i U_i), after which U, the intersection sums and the combination are
-// exact integers: accumulation order does not matter (shared-memory integer atomics are
-// deterministic), identical samples give exactly 0, and the only error left is the rounding of
-// each w itself (2^-53 relative), i.e. at most 2.3e-16 * (U_i + U_j) absolute per pair.  Pairs
-// whose total weighted UniFrac is smaller than 2.5e-4 * (U_i + U_j) - near-duplicates, where that
-// absolute error could exceed 1e-12 relative - are counted by k_tip_guard, and the caller then
-// recomputes with the tips back in the dense kernel.
+// non-zero there only if it contains that very taxon; the rows of nodes with a few tips below
+// are hardly denser.  With w_qi = len_q * p_qi,
+//   sum_q len_q |p_qi - p_qj| = U_i + U_j - 2 * sum_{q in both} min(w_qi, w_qj),   U_i = sum_q w_qi
+// over those rows, and only rows non-zero in BOTH samples need pair work.  To keep the
+// subtraction harmless the w are quantised once to 61-bit fixed point (scale = a power of two
+// from max_i U_i), after which U, the intersection sums and the combination are exact integers:
+// accumulation order does not matter (shared-memory integer atomics are deterministic), identical
+// samples give exactly 0, and the only error left is the rounding of each w itself (2^-53
+// relative), i.e. at most 2.3e-16 * (U_i + U_j) absolute per pair.  Pairs whose whole distance is
+// smaller than 2.5e-4 * (U_i + U_j) - near-duplicates, where that absolute error could exceed
+// 1e-12 relative - are counted by k_tip_guard, and the caller then recomputes with every row in
+// the dense kernel.  Needs len >= 0 (the caller checks).
 //
-// The pair kernel then never visits a tip row (its bits are cleared in the row-major bitmaps)
-// and the closed form of b2d_skip.cuh uses root distances that leave the tips' own branches out.
-//
-// Layout: CSR entries on tips are bucketed by (sample block of 128, chunk of 2048 node positions)
-// and sorted by position inside a bucket, with the start of every position's run kept beside
-// them; a CTA owns one tile, stages the column block's bucket and run starts in shared memory
-// and lets every thread walk the run of one row entry (read from global memory), adding
-// min(w, w') into a 128 x 128 int64 tile in shared memory.
+// This file, in order:
+//   * tips only, entries from the CSR input (used when the embedding is built in several passes):
+//     k_tip_usum / k_tip_scale / k_tip_count / k_tip_scan / k_tip_scatter / k_tip_sort;
+//   * k_pair_tips: one CTA per tile, the column block's bucket and run starts staged in shared
+//     memory, one thread per row entry walking the run of its position, min(w, w') added into a
+//     128 x 128 tile of 64-bit sums (two 32-bit halves, XOR-swizzled cells); k_tip_guard;
+//   * rows of nodes with up to S0 tips below, entries = non-zeros of those embedding rows
+//     (whole embedding resident): k_rows_count / k_rows_ureduce / k_rows_scatter (position-sorted
+//     by construction, no sort), k_compact_rows (the rows left to the dense kernel, packed);
+//   * unweighted UniFrac on the presence bits: bare keys, fixed-point length table, packed bit
+//     stripes: k_ubits_count / k_make_lenfx / k_ubits_scatter / k_pair_utips / k_pack_bits.
+// Buckets: (sample block of 128, chunk of TP_CHUNK node positions), entries sorted by position,
+// the start of every position's run kept beside them.
 #pragma once
 
 #include <cuda_pipeline.h>
