@@ -242,10 +242,13 @@ int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* l
 /* Test hook (host only): the per-position arrays behind the closed-form part of zero-block
  * skipping, all sized n_nodes rounded up to 128: parent position (-1 root / padding), subtree
  * size (the subtree of position q is the range [q - size + 1, q]) and the distance to the
- * root (sum of lengths over q .. root) as an unevaluated double-double sum hi + lo. */
+ * root (sum of lengths over q .. root) as an unevaluated double-double sum hi + lo; the number
+ * of tips in the subtree (0 in the padding); and the root distance without the tips' own
+ * branches (a tip carries its parent's).  Any output may be NULL. */
 int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* length,
                          int32_t* parent_q_mpad, int32_t* size_q_mpad, double* rd_hi_mpad,
-                         double* rd_lo_mpad);
+                         double* rd_lo_mpad, int32_t* tips_q_mpad, double* rd_hi_int_mpad,
+                         double* rd_lo_int_mpad);
 
 #ifdef __cplusplus
 }

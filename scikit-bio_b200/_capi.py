@@ -252,11 +252,17 @@ def debug_tree_paths(parent, length):
     sz = np.empty(mpad, dtype=np.int32)
     hi = np.empty(mpad, dtype=np.float64)
     lo = np.empty(mpad, dtype=np.float64)
+    tq = np.empty(mpad, dtype=np.int32)
+    hi_int = np.empty(mpad, dtype=np.float64)
+    lo_int = np.empty(mpad, dtype=np.float64)
     lib.b2d_debug_tree_paths.restype = ctypes.c_int
-    lib.b2d_debug_tree_paths.argtypes = [ctypes.c_int64, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p]
+    lib.b2d_debug_tree_paths.argtypes = [ctypes.c_int64, _i32p, _f64p, _i32p, _i32p, _f64p, _f64p, _i32p,
+                                         _f64p, _f64p]
     _check(lib.b2d_debug_tree_paths(m, _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(pq, _i32p),
-                                    _ptr(sz, _i32p), _ptr(hi, _f64p), _ptr(lo, _f64p)))
-    return {"parent_q": pq, "size_q": sz, "rd_hi": hi, "rd_lo": lo}
+                                    _ptr(sz, _i32p), _ptr(hi, _f64p), _ptr(lo, _f64p), _ptr(tq, _i32p),
+                                    _ptr(hi_int, _f64p), _ptr(lo_int, _f64p)))
+    return {"parent_q": pq, "size_q": sz, "rd_hi": hi, "rd_lo": lo, "tips_q": tq, "rd_hi_int": hi_int,
+            "rd_lo_int": lo_int}
 
 
 class PinnedBuffer:

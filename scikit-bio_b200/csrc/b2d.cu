@@ -2069,7 +2069,8 @@ int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* l
 
 int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* length,
                          int32_t* parent_q_mpad, int32_t* size_q_mpad, double* rd_hi_mpad,
-                         double* rd_lo_mpad) {
+                         double* rd_lo_mpad, int32_t* tips_q_mpad, double* rd_hi_int_mpad,
+                         double* rd_lo_int_mpad) {
     if (!parent || !length) return fail(B2D_ERR_INVALID_ARGUMENT, "parent/length is NULL");
     TreeOrder o;
     std::string err = build_tree_order(n_nodes, parent, length, o);
@@ -2078,6 +2079,9 @@ int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* l
     if (size_q_mpad) memcpy(size_q_mpad, o.size_q.data(), o.size_q.size() * sizeof(int32_t));
     if (rd_hi_mpad) memcpy(rd_hi_mpad, o.rd_hi.data(), o.rd_hi.size() * sizeof(double));
     if (rd_lo_mpad) memcpy(rd_lo_mpad, o.rd_lo.data(), o.rd_lo.size() * sizeof(double));
+    if (tips_q_mpad) memcpy(tips_q_mpad, o.tips_q.data(), o.tips_q.size() * sizeof(int32_t));
+    if (rd_hi_int_mpad) memcpy(rd_hi_int_mpad, o.rd_hi_int.data(), o.rd_hi_int.size() * sizeof(double));
+    if (rd_lo_int_mpad) memcpy(rd_lo_int_mpad, o.rd_lo_int.data(), o.rd_lo_int.size() * sizeof(double));
     return B2D_OK;
 }
 

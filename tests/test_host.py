@@ -228,6 +228,24 @@ def test_subtree_ranges_and_double_double_root_distances(gen, tips):
         assert abs(dd - exact[k]) <= exact[k] * Fraction(1, 2 ** 95)
         assert abs(pth["rd_lo"][q]) <= abs(pth["rd_hi"][q]) * 2.0 ** -52
     assert np.all(pth["parent_q"][m:] == -1)
+    # tips below every node, and the root distance without the tips' own branches
+    ntips = np.zeros(m, dtype=np.int64)
+    has_child = np.zeros(m, dtype=bool)
+    has_child[parent[parent >= 0]] = True
+    ntips[~has_child] = 1
+    for k in range(m):
+        if parent[k] >= 0:
+            ntips[parent[k]] += ntips[k]
+    for k in range(m):
+        q = q_of[k]
+        assert pth["tips_q"][q] == ntips[k]
+        if has_child[k] or parent[k] < 0:
+            ref = (pth["rd_hi"][q], pth["rd_lo"][q]) if has_child[k] else (0.0, 0.0)
+        else:
+            pq = q_of[parent[k]]
+            ref = (pth["rd_hi"][pq], pth["rd_lo"][pq])
+        assert (pth["rd_hi_int"][q], pth["rd_lo_int"][q]) == ref
+    assert np.all(pth["tips_q"][m:] == 0)
 
 
 def test_engine_rejects_bad_trees():
