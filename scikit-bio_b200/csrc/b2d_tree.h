@@ -107,39 +107,66 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
     out.hc_mask.assign(out.mpad / 32, 0u);
     out.fold_mask.assign(out.mpad / 32, 0xffffffffu);
     out.depth_at.assign(out.mpad / 128 + 1, 0);
-    // tip-to-root distances exactly as _tip_distances accumulates them
-    // (/root/reference/skbio/diversity/_phylogenetic.pyx:52-56): d[i] = len[i] + d[parent]
-    std::vector<double> d(length, length + m);
-    for (int64_t k = m - 1; k >= 0; --k)
-        if (parent[k] >= 0) d[k] += d[parent[k]];
-    // iterative postorder, heavy child first
-    std::vector<int64_t> st_node, st_next;
-    st_node.push_back(root);
-    st_next.push_back(0);
+    // One iterative postorder (heavy child first) fills everything that is stored per position,
+    // in position order.  A frame carries what a node inherits from its parent, computed when the
+    // node is pushed:
+    //   * the tip-to-root distance exactly as _tip_distances accumulates it
+    //     (/root/reference/skbio/diversity/_phylogenetic.pyx:52-56): d[i] = len[i] + d[parent];
+    //   * the root distance sum(len) over node .. root as a double-double (TwoSum).
+    out.parent_q.assign(out.mpad, -1);
+    out.size_q.assign(out.mpad, 1);
+    out.tips_q.assign(out.mpad, 0);
+    out.rd_hi.assign(out.mpad, 0.0);
+    out.rd_lo.assign(out.mpad, 0.0);
+    out.rd_hi_int.assign(out.mpad, 0.0);
+    out.rd_lo_int.assign(out.mpad, 0.0);
+    struct Frame {
+        int64_t v, next;
+        double d, hi, lo;
+        int32_t tips;
+    };
+    std::vector<Frame> st;
+    st.reserve(1024);
+    st.push_back({root, 0, length[root], length[root], 0.0, 0});
     int64_t q = 0;
     int depth = 0, max_depth = 0;
-    while (!st_node.empty()) {
-        int64_t v = st_node.back();
-        int64_t i = st_next.back();
-        int64_t b = coff[v], e = coff[v + 1];
-        if (b + i < e) {
-            st_next.back() = i + 1;
-            st_node.push_back(child[b + i]);
-            st_next.push_back(0);
+    while (!st.empty()) {
+        Frame& fr = st.back();
+        const int64_t v = fr.v;
+        const int64_t b = coff[v], e = coff[v + 1];
+        if (b + fr.next < e) {
+            const int64_t c = child[b + fr.next];
+            fr.next += 1;
+            const double a = fr.hi, l = length[c];
+            const double sum = a + l, bb = sum - a;
+            const double err = (a - (sum - bb)) + (l - bb);  // TwoSum
+            const double l2 = fr.lo + err;
+            const double h = sum + l2;
+            const double dch = l + fr.d;
+            st.push_back({c, 0, dch, h, l2 - (h - sum), 0});  // invalidates fr
             continue;
         }
-        st_node.pop_back();
-        st_next.pop_back();
+        const bool has_children = e > b;
+        const int32_t tips = has_children ? fr.tips : 1;
+        const double dv = fr.d, hi = fr.hi, lo = fr.lo;
+        st.pop_back();
+        double phi = 0.0, plo = 0.0;
+        bool fold = false;
+        if (!st.empty()) {
+            Frame& pf = st.back();
+            pf.tips += tips;
+            phi = pf.hi;
+            plo = pf.lo;
+            fold = child[coff[pf.v]] != (int32_t)v;  // not the first visited
+        }
         if (q % 128 == 0) out.depth_at[q / 128] = depth;
         out.q_of_id[v] = (int32_t)q;
         uint8_t f = 0;
-        bool has_children = e > b;
-        bool fold = false;
-        if (parent[v] >= 0) fold = child[coff[parent[v]]] != (int32_t)v;  // not the first visited
         if (has_children) {
             f |= 1;
             depth -= 1;
             out.hc_mask[q >> 5] |= 1u << (q & 31);
+            for (int64_t i = b; i < e; ++i) out.parent_q[out.q_of_id[child[i]]] = (int32_t)q;
         }
         if (fold) {
             f |= 2;
@@ -150,47 +177,14 @@ inline std::string build_tree_order(int64_t m, const int32_t* parent, const doub
         if (depth > max_depth) max_depth = depth;
         out.flags[q] = f;
         out.len_q[q] = length[v];
-        out.tipdist_q[q] = has_children ? 0.0 : d[v];
+        out.tipdist_q[q] = has_children ? 0.0 : dv;
+        out.size_q[q] = (int32_t)size[v];
+        out.tips_q[q] = tips;
+        out.rd_hi[q] = hi;
+        out.rd_lo[q] = lo;
+        out.rd_hi_int[q] = has_children ? hi : phi;  // a tip carries its parent's distance
+        out.rd_lo_int[q] = has_children ? lo : plo;
         ++q;
-    }
-    out.parent_q.assign(out.mpad, -1);
-    out.size_q.assign(out.mpad, 1);
-    out.tips_q.assign(out.mpad, 0);
-    out.rd_hi.assign(out.mpad, 0.0);
-    out.rd_lo.assign(out.mpad, 0.0);
-    {
-        std::vector<double> hi(m), lo(m);
-        for (int64_t k = m - 1; k >= 0; --k) {  // parents before children
-            const double ph = parent[k] >= 0 ? hi[parent[k]] : 0.0, pl = parent[k] >= 0 ? lo[parent[k]] : 0.0;
-            const double a = ph, b = length[k];
-            const double sum = a + b, bb = sum - a;
-            const double err = (a - (sum - bb)) + (b - bb);  // TwoSum
-            const double l2 = pl + err;
-            const double h = sum + l2;
-            hi[k] = h;
-            lo[k] = l2 - (h - sum);
-            const int64_t pq = out.q_of_id[k];
-            out.rd_hi[pq] = hi[k];
-            out.rd_lo[pq] = lo[k];
-            out.size_q[pq] = (int32_t)size[k];
-            out.parent_q[pq] = parent[k] >= 0 ? out.q_of_id[parent[k]] : -1;
-        }
-        {
-            std::vector<int32_t> ntips(m, 0);
-            for (int64_t k = 0; k < m; ++k) {  // children precede parents
-                if (coff[k + 1] == coff[k]) ntips[k] = 1;
-                if (parent[k] >= 0) ntips[parent[k]] += ntips[k];
-                out.tips_q[out.q_of_id[k]] = ntips[k];
-            }
-        }
-        out.rd_hi_int = out.rd_hi;
-        out.rd_lo_int = out.rd_lo;
-        for (int64_t k = 0; k < m; ++k)
-            if (coff[k + 1] == coff[k]) {  // tip
-                const int64_t pq = out.q_of_id[k];
-                out.rd_hi_int[pq] = parent[k] >= 0 ? hi[parent[k]] : 0.0;
-                out.rd_lo_int[pq] = parent[k] >= 0 ? lo[parent[k]] : 0.0;
-            }
     }
     for (int64_t s = (m + 127) / 128; s <= out.mpad / 128; ++s) out.depth_at[s] = depth;
     if (m % 128 == 0) out.depth_at[m / 128] = depth;
