@@ -148,8 +148,9 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * skipping would make (both 0 when skipping was not used), [10] the part of [1] spent on
  * the skipping bitmaps and closed-form sums, [11] kernels launched by the last compute (all
  * of them: embedding, bitmaps, pair launches, closed form, finalize), [12] duration of the
- * sparse tip-row kernel (0 when the tips went through the dense kernel), [13] number of
- * near-duplicate pairs that made the last compute redo the tips densely (normally 0),
+ * sparse-row intersection kernel (0 when every row went through the dense kernel), [13] number of
+ * pairs the fixed-point guard flagged (near-duplicate samples; normally 0) - just those pairs were
+ * recomputed in floating point from the resident embedding,
  * [14] largest number of tips below a node whose row went through the sparse intersection
  * kernel (0: none, 1: tip rows only), [15] entries of those rows, [16] (sample pair, row) matches
  * that kernel accumulated.  n: slots to fill (<= 17). */
@@ -192,7 +193,10 @@ int b2d_beta_diversity_features(int metric, int device,
  *   "sparse_features"   -1 auto, 0 never, 1 whenever legal: intersection kernel for integer
  *                       feature tables (Bray-Curtis / Jaccard)
  *   "walk_decomposed"   0: always the sequential tree walk;  "plain_kernels" 1: cross-check
- *                       kernels without bulk copies. */
+ *                       kernels without bulk copies.
+ *   "isect_kernel"      1 (default): pipelined intersection kernel for the sparse rows
+ *                       (b2d_isect.cuh); 0: the first-generation kernels (cross-check)
+ *   "isect_group"       lanes sharing one row entry in that kernel: 1, 2, 4 (default) or 8 */
 int b2d_set_option(const char* name, int64_t value);
 
 /* On-device micro-benchmarks used by bench.py for the roofline denominators:

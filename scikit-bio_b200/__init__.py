@@ -7,7 +7,7 @@ from ._tree import (SimpleTreeNode, FlatTree, read_newick, read_newick_flat, fla
 from ._dm import DistanceMatrix, SimpleDistanceMatrix  # noqa: F401
 from ._capi import EngineError, available  # noqa: F401
 from ._driver import (alpha_diversity, beta_diversity, block_beta_diversity,  # noqa: F401
-                      partial_beta_diversity, install)
+                      partial_beta_diversity, install, last_call_profile)
 
 from ._stats import permanova  # noqa: F401
 

@@ -13,12 +13,14 @@ else the same ``scipy.spatial.distance.pdist`` call the reference makes).
 Engine-only keyword arguments (not forwarded to any metric):
     devices   : int or list of int, GPUs to shard the pair triangle over (default [0])
     condensed : keep the result in condensed form (skbio >= 0.7 ``DistanceMatrix(...,
-                condensed=True)``); default False like the reference
+                condensed=True)``).  Default: square like the reference up to 16,384 samples,
+                condensed above (the square form of 100,000 samples is 80 GB)
 """
 
 from __future__ import annotations
 
 import threading
+import time
 import warnings
 from functools import partial
 from inspect import signature
@@ -69,16 +71,27 @@ def _devices_arg(devices):
     return devs
 
 
+# condensed results above this many samples stay condensed unless the caller asks otherwise
+# (the reference always expands to n x n, _base.py:1292-1299: +80 GB at 100,000 samples)
+_AUTO_CONDENSED_ABOVE = 16384
+
+_profile = {}
+
+
+def last_call_profile():
+    """Host-side time split (seconds) of the last engine call on this thread's process:
+    validate / flatten / csr / lookup / engine (create + compute + fetch) / result object."""
+    return dict(_profile)
+
+
 def _run_sharded(make_problem, metric_key, n, devices):
-    """One problem (shard) per device, each driven by its own host thread; every shard
-    writes its own disjoint slices of one page-locked condensed vector."""
+    """One problem (shard) per device, each driven by its own host thread; every shard writes
+    its own disjoint slices of ONE condensed vector (no gather step, no extra copy)."""
     if _capi.load().b2d_device_count() <= 0:
         raise _capi.EngineError(
             "no CUDA device visible: the B200 engine has no CPU fallback for "
             f"'{metric_key}'.")
-    total = n * (n - 1) // 2
-    buf = _capi.PinnedBuffer(total)
-    out = buf.array
+    out = np.empty(n * (n - 1) // 2, dtype=np.float64)
     errors = []
 
     def work(shard, dev):
@@ -98,11 +111,8 @@ def _run_sharded(make_problem, metric_key, n, devices):
         for t in threads:
             t.join()
     if errors:
-        buf.free()
         raise errors[0]
-    result = np.array(out, copy=True)  # detach from pinned memory owned by the library
-    buf.free()
-    return result
+    return out
 
 
 def _unifrac_engine(metric_key, counts, taxa, tree, validate, devices):
@@ -111,26 +121,26 @@ def _unifrac_engine(metric_key, counts, taxa, tree, validate, devices):
     observed taxa mapping to one node (only reachable with validate=False) follow the
     reference's assignment semantics: the last column wins (_phylogenetic.pyx:208-218)."""
     make = _prepare_unifrac_problem(metric_key, counts, taxa, tree, validate)
-    return _run_sharded(make, metric_key, counts.shape[0], devices)
+    t0 = time.perf_counter()
+    vec = _run_sharded(make, metric_key, counts.shape[0], devices)
+    _profile["engine_s"] = time.perf_counter() - t0
+    return vec
 
 
-def _dedupe_last_wins(indptr, node_ids, vals):
+def _dedupe_last_wins(indptr, cols, node_ids, vals):
+    """Several observed columns mapped to one node: the reference assigns
+    ``count_array[node, :] = counts[:, col]`` column by column in ascending order
+    (_phylogenetic.pyx:208-218), zeros included, so the LAST observed column of a node decides
+    every sample's count.  Keep only the CSR entries of those winning columns."""
     n = len(indptr) - 1
+    winner = np.full(int(node_ids.max()) + 1 if len(node_ids) else 1, -1, dtype=np.int64)
+    np.maximum.at(winner, node_ids, cols.astype(np.int64))
+    keep = winner[node_ids] == cols
+    rows = np.repeat(np.arange(n), np.diff(indptr))[keep]
     new_ptr = np.zeros(n + 1, dtype=np.int64)
-    ids_out, vals_out = [], []
-    for s in range(n):
-        a, b = indptr[s], indptr[s + 1]
-        seen = {}
-        for e in range(a, b):
-            seen[int(node_ids[e])] = e
-        es = sorted(seen.values())
-        ids_out.append(node_ids[es])
-        if vals is not None:
-            vals_out.append(vals[es])
-        new_ptr[s + 1] = new_ptr[s] + len(es)
-    ids = np.concatenate(ids_out) if ids_out else node_ids[:0]
-    v = None if vals is None else (np.concatenate(vals_out) if vals_out else vals[:0])
-    return new_ptr, ids.astype(np.int32), v
+    np.cumsum(np.bincount(rows, minlength=n), out=new_ptr[1:])
+    v = None if vals is None else np.ascontiguousarray(vals[keep])
+    return new_ptr, np.ascontiguousarray(node_ids[keep], dtype=np.int32), v
 
 
 def _features_engine(metric_key, counts, devices):
@@ -152,8 +162,9 @@ def beta_diversity(metric, counts, ids=None, validate=True, pairwise_func=None, 
     (/root/reference/skbio/diversity/_driver.py:231-355).
     """
     devices = _devices_arg(kwargs.pop("devices", None))
-    condensed = bool(kwargs.pop("condensed", False))
+    condensed = kwargs.pop("condensed", None)
     taxa = kwargs.pop("taxa", None)
+    t_start = time.perf_counter()
     counts, ids, taxa = ingest_table(counts, ids, taxa)
     if 0 in counts.shape:
         # _driver.py:295-300
@@ -187,22 +198,37 @@ def beta_diversity(metric, counts, ids=None, validate=True, pairwise_func=None, 
                 f"pdist metric '{metric}' got an unexpected keyword argument "
                 f"'{next(iter(kwargs))}'")
         vec = _features_engine(metric, counts, devices)
-    return make_distance_matrix(vec, ids, condensed=condensed, n=n)
+    if condensed is None:
+        condensed = n > _AUTO_CONDENSED_ABOVE
+    t_dm = time.perf_counter()
+    dm = make_distance_matrix(vec, ids, condensed=bool(condensed), n=n)
+    _profile["result_object_s"] = time.perf_counter() - t_dm
+    _profile["total_s"] = time.perf_counter() - t_start
+    return dm
 
 
 def _prepare_unifrac_problem(key, counts, taxa, tree, validate):
     """Host half of the UniFrac path: validate, flatten, CSR, name lookup -> factory of shards."""
+    t0 = time.perf_counter()
     if validate:
         validate_taxa_and_tree(taxa, tree)
+    t1 = time.perf_counter()
     parent, length, names = flatten_tree(tree)
+    t2 = time.perf_counter()
     mode = "presence" if key == "unweighted_unifrac" else "int64"
     indptr, cols, vals = to_csr(counts, mode)
+    t3 = time.perf_counter()
     n = counts.shape[0]
-    observed_cols = np.unique(cols)
+    observed = np.zeros(counts.shape[1], dtype=bool)
+    observed[cols] = True
+    observed_cols = np.flatnonzero(observed)
     node_of_col = map_taxa_to_nodes(taxa, observed_cols, names)
     node_ids = node_of_col[cols]
     if len(np.unique(node_of_col[observed_cols])) != len(observed_cols):
-        indptr, node_ids, vals = _dedupe_last_wins(indptr, node_ids, vals)
+        indptr, node_ids, vals = _dedupe_last_wins(indptr, cols, node_ids, vals)
+    t4 = time.perf_counter()
+    _profile.clear()
+    _profile.update(validate_s=t1 - t0, flatten_s=t2 - t1, csr_s=t3 - t2, lookup_s=t4 - t3)
 
     def make(dev, shard=0, nshards=1):
         return _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, device=dev,

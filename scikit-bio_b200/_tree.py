@@ -340,18 +340,13 @@ def map_taxa_to_nodes(taxa, observed_cols, names):
     ``KeyError`` exactly like the reference's ``node_lookup[n]`` does (only reachable with
     ``validate=False``).
     """
-    taxa = np.asarray(taxa, dtype=object) if not isinstance(taxa, np.ndarray) else taxa
     out = np.full(len(taxa), -1, dtype=np.int32)
-    observed = {}
-    for c in observed_cols:
-        observed[taxa[c]] = -1
-    for k in range(len(names)):
-        nm = names[k]
-        if nm in observed:
-            observed[nm] = k
-    for c in observed_cols:
-        k = observed[taxa[c]]
-        if k < 0:
-            raise KeyError(taxa[c])
-        out[c] = k
+    if len(observed_cols) == 0:
+        return out
+    # one dict over all node names, built in id order: a later node overwrites an earlier one
+    lookup = dict(zip(names.tolist() if isinstance(names, np.ndarray) else list(names), range(len(names))))
+    lookup.pop(None, None)
+    taxa_list = taxa.tolist() if isinstance(taxa, np.ndarray) else list(taxa)
+    cols = observed_cols.tolist() if isinstance(observed_cols, np.ndarray) else list(observed_cols)
+    out[cols] = [lookup[taxa_list[c]] for c in cols]   # KeyError(taxon) like node_lookup[n]
     return out

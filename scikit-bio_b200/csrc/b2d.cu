@@ -21,6 +21,7 @@
 #include "b2d_pair.cuh"
 #include "b2d_skip.cuh"
 #include "b2d_tips.cuh"
+#include "b2d_isect.cuh"
 #include "b2d_sparse.cuh"
 #include "b2d_permanova.cuh"
 #include "b2d_tree.h"
@@ -39,6 +40,8 @@ static int g_tips_sparse = 1;                  // tip rows of the weighted kerne
 static int g_cache_embedding = 1;              // keep the embedding buffer of a destroyed problem
 static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
+static int g_isect_kernel = 1;                 // 1: pipelined intersection kernel (b2d_isect.cuh); 0: first generation
+static int g_isect_group = 4;                  // lanes sharing one row entry in that kernel (1, 2, 4 or 8)
 
 static bool plain_kernels() {
     if (g_plain_kernels < 0) {
@@ -108,6 +111,38 @@ __global__ void k_bench_atoms(int* out, int iters) {
     }
     __syncthreads();
     if (threadIdx.x == 0) out[blockIdx.x] = s_acc[0];
+}
+// Shared-memory atomic rates under the access patterns of the intersection kernels, on a
+// 64 x 128 cell tile (32 KB per half, so that two 1024-thread CTAs fit one SM):
+//   SPREAD  1: lane l always hits bank l (row pseudo-random): conflict-free by construction
+//           0: pseudo-random cells (bank conflicts as they fall)
+//   PAIR    1: the 64-bit add of k_pair_tips - low half with return, carry into the high half
+//           0: one fire-and-forget 32-bit add
+// Counts one unit per 32-bit atomic issued.
+template <int SPREAD, int PAIR>
+__global__ void __launch_bounds__(1024)
+k_bench_atoms2(int* out, int iters) {
+    extern __shared__ int s_acc[];   // [2][64 * 128]
+    uint32_t* lo = reinterpret_cast<uint32_t*>(s_acc);
+    uint32_t* hi = lo + 64 * 128;
+    for (int i = threadIdx.x; i < 2 * 64 * 128; i += blockDim.x) s_acc[i] = 0;
+    __syncthreads();
+    unsigned x = (threadIdx.x + 1 + blockIdx.x * 977u) * 2654435761u;
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        const unsigned cell = SPREAD ? (((x >> 19) & 0x1fe0u) | lane) : (x >> 19);
+        if (PAIR) {
+            const uint32_t add = x | 0x80000000u;
+            const uint32_t old = atomicAdd(&lo[cell], add);
+            atomicAdd(&hi[cell], 3u + (old + add < old ? 1u : 0u));
+        } else {
+            atomicAdd(&lo[cell], 1u);
+        }
+        x = x * 1664525u + 1013904223u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = s_acc[0] + s_acc[64 * 128];
 }
 __global__ void k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,6 +397,8 @@ struct b2d_problem {
     double* d_rows_upart = nullptr;         // [nch * 4][npad]
     int64_t tip_nch = 0;
     double tips_flagged = 0, t_tips = 0, tip_matches = 0;
+    unsigned* d_tip_cnt = nullptr;          // [npad] sparse-row entries per sample (guard: quantisation term)
+    FlaggedPair* d_flag_list = nullptr;     // [FLAG_CAP] pairs the guard flagged (recomputed in floating point)
     // sparse feature-table path
     SpEntry* d_sp_entries = nullptr;
     int64_t* d_sp_ptr = nullptr;
@@ -397,6 +434,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_rows_qcount); b2d_free(p->d_rows_upart);
     b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend); b2d_free(p->d_hc_pos);
     b2d_free(p->d_ukeys); b2d_free(p->d_lenfx); b2d_free(p->d_bitsd); b2d_free(p->d_ulend);
+    b2d_free(p->d_tip_cnt); b2d_free(p->d_flag_list);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -537,6 +575,22 @@ static int check_common(b2d_problem** out, int device, int64_t n, int64_t m,
     return B2D_OK;
 }
 
+// the pipelined intersection kernel over all owned tiles (weighted: TipEntry[], unweighted: keys + lenfx)
+template <bool W>
+static int launch_isect(b2d_problem* p, cudaStream_t st, const void* entries, const long long* lenfx,
+                        const PairArgs& a) {
+    void (*kern)(const void*, const int64_t*, const unsigned short*, const long long*, int64_t, const long long*,
+                 const double*, unsigned long long*, PairArgs) =
+        g_isect_group == 1 ? k_pair_isect<W, 1> : g_isect_group == 2 ? k_pair_isect<W, 2>
+        : g_isect_group == 8 ? k_pair_isect<W, 8> : k_pair_isect<W, 4>;
+    B2D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)is_smem<W>()));
+    kern<<<(unsigned)p->ntiles, IS_THREADS, is_smem<W>(), st>>>(entries, p->d_tip_ptr, p->d_tip_runs, lenfx,
+                                                               p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
+                                                               p->d_tip_word + 2, a);
+    B2D_CUDA(cudaGetLastError());
+    return B2D_OK;
+}
+
 extern "C" {
 
 int b2d_api_version(void) { return B2D_API_VERSION; }
@@ -588,6 +642,10 @@ int b2d_set_option(const char* name, int64_t value) {
         if (!value) pool_clear();
     } else if (s == "weighted_skip") {
         g_weighted_skip = value ? 1 : 0;
+    } else if (s == "isect_kernel") {
+        g_isect_kernel = value ? 1 : 0;
+    } else if (s == "isect_group") {
+        g_isect_group = (value == 1 || value == 2 || value == 8) ? (int)value : 4;
     } else {
         return fail(B2D_ERR_INVALID_ARGUMENT, "unknown option " + s);
     }
@@ -800,8 +858,11 @@ static int tips_buffers(b2d_problem* p) {
         B2D_CUDA(b2d_malloc(&p->d_tip_counts, (nbuckets + 1) * sizeof(unsigned)));
         B2D_CUDA(b2d_malloc(&p->d_tip_ptr, (nbuckets + 1) * sizeof(int64_t)));
         B2D_CUDA(b2d_malloc(&p->d_tip_runs, (size_t)nbuckets * (TP_CHUNK + 8) * sizeof(unsigned short)));
+        B2D_CUDA(b2d_malloc(&p->d_tip_cnt, p->npad * sizeof(unsigned)));
+        B2D_CUDA(b2d_malloc(&p->d_flag_list, FLAG_CAP * sizeof(FlaggedPair)));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
     }
+    B2D_CUDA(cudaMemsetAsync(p->d_tip_cnt, 0, p->npad * sizeof(unsigned), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_u, 0, p->npad * sizeof(double), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_ufx, 0, p->npad * sizeof(long long), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 4 * sizeof(unsigned long long), p->stream));
@@ -842,7 +903,8 @@ static int tips_build(b2d_problem* p) {
     B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
     k_tip_scatter<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, vals, p->d_total, p->d_flags,
                                                        p->d_len, p->d_tip_scale, p->n, nch, p->d_tip_ptr,
-                                                       p->d_tip_counts, p->d_tip_entries, p->d_tip_ufx);
+                                                       p->d_tip_counts, p->d_tip_entries, p->d_tip_ufx,
+                                                       p->d_tip_cnt);
     B2D_CUDA(cudaFuncSetAttribute(k_tip_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SORT_SMEM));
     k_tip_sort<<<(unsigned)nbuckets, 256, TP_SORT_SMEM, p->stream>>>(p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs);
     int status = 0;
@@ -953,7 +1015,7 @@ static int rows_build(b2d_problem* p, int64_t QR) {
         k_rows_scatter<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
             (const double*)p->d_emb, p->d_len, p->d_rows_sparse, p->d_tip_scale, rows, QR, nch,
             p->d_rows_qcount, p->d_tip_ptr, p->d_tip_entries, p->d_tip_runs,
-            (unsigned long long*)p->d_tip_ufx);
+            (unsigned long long*)p->d_tip_ufx, p->d_tip_cnt);
         // the rows left to the dense pair kernel, packed
         const size_t need = (size_t)p->nb * p->n_dense_pad * TILE * sizeof(double);
         if (p->embd_bytes < need) {
@@ -1015,7 +1077,7 @@ static int urows_build(b2d_problem* p) {
             b2d_free(p->d_ukeys);
             p->d_ukeys = nullptr;
             p->ukeys_cap = 0;
-            B2D_CUDA(b2d_malloc(&p->d_ukeys, std::max<int64_t>(total, 1) * sizeof(uint32_t)));
+            B2D_CUDA(b2d_malloc(&p->d_ukeys, (std::max<int64_t>(total, 1) + 8) * sizeof(uint32_t)));  // + bulk-copy slack
             p->ukeys_cap = total;
         }
         p->rows_entries = (double)total;
@@ -1036,7 +1098,7 @@ static int urows_build(b2d_problem* p) {
                                                                                     p->mpad, p->d_lenfx);
         k_ubits_scatter<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
             (const uint32_t*)p->d_emb, p->d_lenfx, p->d_rows_sparse, p->mpad, p->NS, nch, p->d_rows_qcount,
-            p->d_tip_ptr, p->d_ukeys, p->d_tip_runs, (unsigned long long*)p->d_tip_ufx);
+            p->d_tip_ptr, p->d_ukeys, p->d_tip_runs, (unsigned long long*)p->d_tip_ufx, p->d_tip_cnt);
         k_pack_bits<<<dim3((unsigned)NSd, (unsigned)p->nb), 128, 0, p->stream>>>(
             (const uint32_t*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->NS, NSd, p->d_bitsd, p->d_ulend);
         B2D_CUDA(cudaGetLastError());
@@ -1347,11 +1409,15 @@ static int compute_dense(b2d_problem* p, int metric) {
                 a.epilogue = epilogue;
                 cudaStream_t st;
                 if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
-                B2D_CUDA(cudaFuncSetAttribute(k_pair_tips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
                 B2D_CUDA(cudaEventRecord(p->ev[7], st));
-                k_pair_tips<<<(unsigned)p->ntiles, TP_THREADS, TP_SMEM, st>>>(
-                    p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
-                    p->d_tip_word + 2, a);
+                if (g_isect_kernel) {
+                    if ((rc = launch_isect<true>(p, st, p->d_tip_entries, nullptr, a))) return rc;
+                } else {
+                    B2D_CUDA(cudaFuncSetAttribute(k_pair_tips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
+                    k_pair_tips<<<(unsigned)p->ntiles, TP_THREADS, TP_SMEM, st>>>(
+                        p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
+                        p->d_tip_word + 2, a);
+                }
                 B2D_CUDA(cudaEventRecord(p->ev[8], st));
                 tips_timed = true;
                 p->n_kernels += 1;
@@ -1377,7 +1443,15 @@ static int compute_dense(b2d_problem* p, int metric) {
                         p->n_kernels += 1;
                         k_tip_guard<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                             p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, p->d_owned,
-                            p->d_row_base, p->n, p->d_tip_u, p->d_tip_word + 1);
+                            p->d_row_base, p->n, p->d_tip_u, p->d_tip_cnt, p->d_tip_scale, p->d_tip_word + 1,
+                            p->rows_general ? p->d_flag_list : nullptr);
+                        if (p->rows_general) {
+                            // whole embedding resident (proportions): the flagged pairs again in fp64
+                            p->n_kernels += 1;
+                            k_fix_pairs_weighted<<<296, 256, 0, p->stream>>>(
+                                (const double*)p->d_emb, p->d_len, QR, p->mpad, p->d_flag_list, p->d_tip_word + 1,
+                                p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr);
+                        }
                     }
                 }
                 if ((rc = finalize(p, epilogue))) return rc;
@@ -1409,9 +1483,11 @@ static int compute_dense(b2d_problem* p, int metric) {
         B2D_CUDA(cudaMemcpy(fm, p->d_tip_word + 1, sizeof(fm), cudaMemcpyDeviceToHost));
         const unsigned long long flagged = fm[0];
         p->tip_matches = (double)fm[1];
-        if (flagged) {  // near-duplicate samples: redo with the tips in the dense kernel
+        p->tips_flagged = (double)flagged;
+        // several node passes (no resident embedding to recompute pairs from) or more flagged pairs
+        // than the list holds: redo the whole compute with every row in the dense kernel
+        if (flagged && (!p->rows_general || flagged > (unsigned long long)FLAG_CAP)) {
             p->tips_mode = -1;
-            p->tips_flagged = (double)flagged;
             return compute_dense(p, metric);
         }
     }
@@ -1480,11 +1556,15 @@ static int compute_bits(b2d_problem* p, int metric) {
             a.epilogue = EPI_UNWEIGHTED;
             cudaStream_t st;
             if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
-            B2D_CUDA(cudaFuncSetAttribute(k_pair_utips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UT_SMEM));
             B2D_CUDA(cudaEventRecord(p->ev[7], st));
-            k_pair_utips<<<(unsigned)p->ntiles, TP_THREADS, UT_SMEM, st>>>(
-                p->d_ukeys, p->d_tip_ptr, p->d_tip_runs, p->d_lenfx, p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
-                p->d_tip_word + 2, a);
+            if (g_isect_kernel) {
+                if ((rc = launch_isect<false>(p, st, p->d_ukeys, p->d_lenfx, a))) return rc;
+            } else {
+                B2D_CUDA(cudaFuncSetAttribute(k_pair_utips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UT_SMEM));
+                k_pair_utips<<<(unsigned)p->ntiles, TP_THREADS, UT_SMEM, st>>>(
+                    p->d_ukeys, p->d_tip_ptr, p->d_tip_runs, p->d_lenfx, p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
+                    p->d_tip_word + 2, a);
+            }
             B2D_CUDA(cudaEventRecord(p->ev[8], st));
             utips_timed = true;
             p->n_kernels += 1;
@@ -1526,7 +1606,11 @@ static int compute_bits(b2d_problem* p, int metric) {
             p->n_kernels += 1;
             k_tip_guard<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                 p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, p->d_owned, p->d_row_base, p->n,
-                p->d_tip_u, p->d_tip_word + 1);
+                p->d_tip_u, p->d_tip_cnt, p->d_tip_scale, p->d_tip_word + 1, p->d_flag_list);
+            p->n_kernels += 1;
+            k_fix_pairs_unweighted<<<296, 256, 0, p->stream>>>(
+                (const uint4*)p->d_emb, p->d_len, p->NS, p->d_flag_list, p->d_tip_word + 1, p->d_out,
+                p->chunk_counter >= 2 ? p->d_out2 : nullptr);
         }
         if ((rc = finalize(p, metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED))) return rc;
     }
@@ -1537,9 +1621,9 @@ static int compute_bits(b2d_problem* p, int metric) {
         unsigned long long fm[2] = {0, 0};
         B2D_CUDA(cudaMemcpy(fm, p->d_tip_word + 1, sizeof(fm), cudaMemcpyDeviceToHost));
         p->tip_matches = (double)fm[1];
-        if (fm[0]) {  // near-duplicate samples: redo with every row in the look-up-table kernel
+        p->tips_flagged = (double)fm[0];
+        if (fm[0] > (unsigned long long)FLAG_CAP) {  // more than the list holds: every row in the LUT kernel
             p->tips_mode = -1;
-            p->tips_flagged = (double)fm[0];
             return compute_bits(p, metric);
         }
         if (utips_timed) {
@@ -2170,6 +2254,33 @@ int b2d_microbench(int device, int kind, double* result) {
         }
         b2d_free(d);
         *result = (double)blocks * threads * (double)iters / (best * 1e-3);
+    } else if (kind >= 4 && kind <= 11) {
+        // 4/5: conflict-free single adds at 32 / 64 warps per SM; 6/9: random cells, single;
+        // 7/10: random cells, 64-bit pair with carry; 8/11: conflict-free pair
+        static const int spread_of[8] = {1, 1, 0, 0, 1, 0, 0, 1};
+        static const int pair_of[8] = {0, 0, 0, 1, 1, 0, 1, 1};
+        static const int ctas_of[8] = {1, 2, 1, 1, 1, 2, 2, 2};
+        const int spread = spread_of[kind - 4], pair = pair_of[kind - 4], per_sm = ctas_of[kind - 4];
+        cudaDeviceProp prop;
+        B2D_CUDA(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount * per_sm, threads = 1024, iters = 1 << 12;
+        const int smem = 2 * 64 * 128 * sizeof(int);
+        void (*kern)(int*, int) = spread ? (pair ? k_bench_atoms2<1, 1> : k_bench_atoms2<1, 0>)
+                                         : (pair ? k_bench_atoms2<0, 1> : k_bench_atoms2<0, 0>);
+        B2D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int* d = nullptr;
+        B2D_CUDA(b2d_malloc(&d, (size_t)blocks * sizeof(int)));
+        for (int rep = 0; rep < 6; ++rep) {
+            B2D_CUDA(cudaEventRecord(e0));
+            kern<<<blocks, threads, smem>>>(d, iters);
+            B2D_CUDA(cudaEventRecord(e1));
+            B2D_CUDA(cudaEventSynchronize(e1));
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        b2d_free(d);
+        *result = (double)blocks * threads * (double)iters * (pair ? 2.0 : 1.0) / (best * 1e-3);
     } else {
         return fail(B2D_ERR_INVALID_ARGUMENT, "unknown microbench kind");
     }

@@ -1,0 +1,262 @@
+// Intersection tile kernel for the sparse node rows (weighted and unweighted UniFrac), second
+// generation: a warp-specialised producer / consumer pipeline instead of barriers around a
+// single staging buffer (k_pair_tips / k_pair_utips in b2d_tips.cuh, kept as cross-checks).
+//
+//   T(i,j) = U_i + U_j - 2 * sum_{q in both} min(w_qi, w_qj)       (weighted,  b2d_tips.cuh)
+//   T(i,j) = U_i + U_j - 2 * sum_{q in both} lenfx_q                (unweighted)
+//
+// exact in 61-bit fixed point.  One CTA per 128 x 128 tile of sample pairs:
+//   * warp 31 is the PRODUCER.  Per (tile, position chunk) it cuts the column bucket into
+//     batches at position boundaries (a whole bucket when it fits), and for every batch issues
+//     1-D bulk copies (cp.async.bulk, SASS UBLKCP) of the column entries, the slice of the
+//     column run table and - unweighted - the fixed-point lengths into one of two stages, with
+//     a small header (row-entry range, position range).  full / empty mbarriers per stage; the
+//     next batch lands while the current one is consumed.
+//   * warps 0..30 are CONSUMERS.  Row entries come straight from global memory (coalesced,
+//     L2-resident); G = 4 lanes share one row entry and stride over the column run of its
+//     position, so a warp keeps eight row entries in flight and a run of k column entries costs
+//     ceil(k / 4) steps instead of k (the one-thread-per-row-entry walk left 43 % of the lanes
+//     idle: run lengths differ from lane to lane).  Every match adds into a 128 x 128 tile of
+//     64-bit sums kept as two 32-bit halves (shared memory has native 32-bit atomic adds only;
+//     the add that wraps the low half carries into the high one), cells XOR-swizzled by the row.
+//   * no __syncthreads between the prologue (zeroing the tile) and the epilogue (emit).
+#pragma once
+
+#include "b2d_common.cuh"
+#include "b2d_pair.cuh"
+#include "b2d_tips.cuh"
+
+namespace b2d {
+
+constexpr int IS_THREADS = 1024;
+constexpr int IS_CWARPS = 31;                       // consumer warps; warp 31 produces
+constexpr int IS_STAGES = 2;
+constexpr int IS_ENT_BYTES = 40960;                 // weighted: column entries per stage
+constexpr int IS_CAP_W = IS_ENT_BYTES / 16;         // 2560 entries of 16 B
+constexpr int IS_ENT_BYTES_U = 24576;               // unweighted: column keys per stage
+constexpr int IS_CAP_U2 = IS_ENT_BYTES_U / 4 - 8;   // 6136 keys of 4 B (+ alignment slack)
+constexpr int IS_RUN_BYTES = (TP_CHUNK + 8) * 2 + 16;   // 4128: run starts of a whole chunk
+constexpr int IS_LF_BYTES = TP_CHUNK * 8;               // 16384: fixed-point lengths (unweighted only)
+struct IsHeader {
+    long long r_lo, r_hi;   // global row-entry range of the batch
+    int coff;               // column entry e (relative to its bucket) lives in slot e + coff
+    int f0;                 // first position of the batch (multiple of 8)
+    int done;               // 1: no more work for this tile
+    int pad[9];
+};
+static_assert(sizeof(IsHeader) == 64, "header is 64 bytes");
+template <bool W>
+constexpr size_t is_smem() {
+    return (size_t)TILE * TILE * 8 + (size_t)IS_STAGES * ((W ? IS_ENT_BYTES : IS_ENT_BYTES_U) + IS_RUN_BYTES +
+                                                           (W ? 0 : IS_LF_BYTES) + 64) + 4 * sizeof(uint64_t);
+}
+static_assert(is_smem<true>() <= 232448 && is_smem<false>() <= 232448, "shared memory per CTA");
+
+// W = true : entries = TipEntry[], lenfx unused.   W = false: entries = uint32 keys[], lenfx table.
+template <bool W, int G>
+__global__ void __launch_bounds__(IS_THREADS, 1)
+k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ bucket_ptr,
+             const unsigned short* __restrict__ runs, const long long* __restrict__ lenfx, int64_t nch,
+             const long long* __restrict__ Ufx, const double* __restrict__ scale,
+             unsigned long long* __restrict__ n_matches, PairArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* acc_lo = reinterpret_cast<uint32_t*>(smem_raw);   // [128][128]
+    uint32_t* acc_hi = acc_lo + TILE * TILE;
+    unsigned char* stage0 = smem_raw + (size_t)TILE * TILE * 8;
+    constexpr int ENT = W ? IS_ENT_BYTES : IS_ENT_BYTES_U;
+    constexpr int CAP = W ? IS_CAP_W : IS_CAP_U2;
+    constexpr int STAGE = ENT + IS_RUN_BYTES + (W ? 0 : IS_LF_BYTES) + 64;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)IS_STAGES * STAGE);
+    uint64_t* empty = full + IS_STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
+    for (int x = tid; x < 2 * TILE * TILE; x += IS_THREADS) acc_lo[x] = 0u;
+    if (tid == 0) {
+        for (int s = 0; s < IS_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], IS_CWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const TipEntry* ent_w = reinterpret_cast<const TipEntry*>(entries_v);
+    const uint32_t* ent_u = reinterpret_cast<const uint32_t*>(entries_v);
+    unsigned nm = 0;  // matches this thread accumulated
+
+    if (warp == IS_CWARPS) {
+        // ------------------------------- producer -------------------------------
+        int s = 0;
+        uint32_t ph = 0;
+        int64_t it = 0;
+        for (int64_t ch = 0; ch <= nch; ++ch) {
+            const bool last = ch == nch;
+            int64_t r0 = 0, r1 = 0, c0 = 0, c1 = 0;
+            const unsigned short* crun = nullptr;
+            const unsigned short* rrun = nullptr;
+            if (!last) {
+                const int64_t rbk = (int64_t)bi * nch + ch, cbk = (int64_t)bj * nch + ch;
+                r0 = bucket_ptr[rbk];
+                r1 = bucket_ptr[rbk + 1];
+                c0 = bucket_ptr[cbk];
+                c1 = bucket_ptr[cbk + 1];
+                if (r1 == r0 || c1 == c0) continue;
+                crun = runs + (size_t)cbk * (TP_CHUNK + 8);
+                rrun = runs + (size_t)rbk * (TP_CHUNK + 8);
+            }
+            int f0 = 0, ce0 = 0, re0 = 0;
+            const int cn = (int)(c1 - c0), rn = (int)(r1 - r0);
+            while (last || f0 < TP_CHUNK) {
+                int f1 = TP_CHUNK, ce1 = cn, re1 = rn;
+                if (!last && cn - ce0 > CAP) {
+                    // largest f1 in (f0, TP_CHUNK], a multiple of 8, with crun[f1] - ce0 <= CAP:
+                    // 64-position strides first, then 8-position strides (run starts are monotone)
+                    int base = f0;
+                    {
+                        const int cand = base + 64 * (lane + 1);
+                        const bool ok = cand <= TP_CHUNK && (int)crun[cand] - ce0 <= CAP;
+                        base += 64 * __popc(__ballot_sync(0xffffffffu, ok));
+                    }
+                    {
+                        const int cand = base + 8 * (lane + 1);
+                        const bool ok = lane < 7 && cand <= TP_CHUNK && (int)crun[cand] - ce0 <= CAP;
+                        base += 8 * __popc(__ballot_sync(0xffffffffu, ok));
+                    }
+                    f1 = base;   // > f0: eight positions hold at most 1024 entries <= CAP
+                    ce1 = (int)crun[f1];
+                    re1 = (int)rrun[f1];
+                }
+                if (last || (ce1 > ce0 && re1 > re0)) {
+                    if (it >= IS_STAGES) mbar_wait(&empty[s], ph ^ 1u);
+                    if (lane == 0) {
+                        unsigned char* st = stage0 + (size_t)s * STAGE;
+                        IsHeader* h = reinterpret_cast<IsHeader*>(st + ENT + IS_RUN_BYTES + (W ? 0 : IS_LF_BYTES));
+                        h->done = last ? 1 : 0;
+                        if (last) {
+                            mbar_arrive(&full[s]);
+                        } else {
+                            // global index of smem slot 0 (keys: aligned down to 16 bytes)
+                            const int64_t g0 = W ? (c0 + ce0) : ((c0 + ce0) & ~(int64_t)3);
+                            const int64_t g1 = W ? (c0 + ce1) : ((c0 + ce1 + 3) & ~(int64_t)3);
+                            const uint32_t ebytes = (uint32_t)(g1 - g0) * (W ? 16u : 4u);
+                            const uint32_t rbytes = (uint32_t)(f1 - f0 + 8) * 2u;
+                            const uint32_t lbytes = W ? 0u : (uint32_t)(f1 - f0) * 8u;
+                            h->r_lo = r0 + re0;
+                            h->r_hi = r0 + re1;
+                            h->coff = (int)(c0 - g0);
+                            h->f0 = f0;
+                            mbar_arrive_expect_tx(&full[s], ebytes + rbytes + lbytes);
+                            if (W) bulk_g2s(st, ent_w + g0, ebytes, &full[s]);
+                            else bulk_g2s(st, ent_u + g0, ebytes, &full[s]);
+                            bulk_g2s(st + ENT, crun + f0, rbytes, &full[s]);
+                            if (!W) bulk_g2s(st + ENT + IS_RUN_BYTES, lenfx + ch * TP_CHUNK + f0, lbytes, &full[s]);
+                        }
+                    }
+                    __syncwarp();
+                    ++it;
+                    if (++s == IS_STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                if (last) break;
+                f0 = f1;
+                ce0 = ce1;
+                re0 = re1;
+            }
+        }
+    } else {
+        // ------------------------------- consumers -------------------------------
+        constexpr int SLOTS = 32 / G;
+        const int slot = lane / G, g = lane % G;
+        int s = 0;
+        uint32_t ph = 0;
+        for (;;) {
+            mbar_wait(&full[s], ph);
+            const unsigned char* st = stage0 + (size_t)s * STAGE;
+            const IsHeader* h = reinterpret_cast<const IsHeader*>(st + ENT + IS_RUN_BYTES + (W ? 0 : IS_LF_BYTES));
+            if (h->done) break;
+            const unsigned short* fstart = reinterpret_cast<const unsigned short*>(st + ENT);
+            const int coff = h->coff, f0 = h->f0;
+            const int64_t r_lo = h->r_lo, r_hi = h->r_hi;
+            if (W) {
+                const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
+                int64_t x = r_lo + warp * SLOTS + slot;
+                TipEntry re;
+                if (x < r_hi) re = ent_w[x];
+                while (x < r_hi) {
+                    const TipEntry cur = re;
+                    const int64_t xn = x + IS_CWARPS * SLOTS;
+                    if (xn < r_hi) re = ent_w[xn];   // next row entry in flight during the walk
+                    const uint32_t f = (cur.key >> 7) - (uint32_t)f0, r = cur.key & 127u;
+                    const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                    const uint32_t rbase = r * TILE, rx = r & 31u;
+                    if (g == 0) nm += (unsigned)(e1 - e0);
+#pragma unroll 2
+                    for (int e = e0 + g; e < e1; e += G) {
+                        const TipEntry ce = centry[e];
+                        // min of two non-negative 61-bit integers: their bit patterns order like doubles
+                        const unsigned long long add = (unsigned long long)__double_as_longlong(
+                            fmin(__longlong_as_double(cur.val), __longlong_as_double(ce.val)));
+                        const uint32_t cell = rbase + ((ce.key & 127u) ^ rx);
+                        const uint32_t alo = (uint32_t)add;
+                        const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                        atomicAdd(&acc_hi[cell], (uint32_t)(add >> 32) + (old + alo < old ? 1u : 0u));
+                    }
+                    x = xn;
+                }
+            } else {
+                const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
+                const long long* lf = reinterpret_cast<const long long*>(st + ENT + IS_RUN_BYTES);
+                int64_t x = r_lo + warp * SLOTS + slot;
+                uint32_t rk = 0;
+                if (x < r_hi) rk = ent_u[x];
+                while (x < r_hi) {
+                    const uint32_t cur = rk;
+                    const int64_t xn = x + IS_CWARPS * SLOTS;
+                    if (xn < r_hi) rk = ent_u[xn];
+                    const uint32_t f = (cur >> 7) - (uint32_t)f0, r = cur & 127u;
+                    const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                    const unsigned long long add = (unsigned long long)lf[f];
+                    const uint32_t alo = (uint32_t)add, ahi = (uint32_t)(add >> 32);
+                    const uint32_t rbase = r * TILE, rx = r & 31u;
+                    if (g == 0) nm += (unsigned)(e1 - e0);
+#pragma unroll 2
+                    for (int e = e0 + g; e < e1; e += G) {
+                        const uint32_t cell = rbase + ((ckey[e] & 127u) ^ rx);
+                        const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                        atomicAdd(&acc_hi[cell], ahi + (old + alo < old ? 1u : 0u));
+                    }
+                    x = xn;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == IS_STAGES) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+    if (n_matches) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, o);
+        if (lane == 0 && nm) atomicAdd(n_matches, (unsigned long long)nm);
+    }
+    const double inv = scale[1];
+    const int64_t base = a.row_base[bi];
+    const int64_t i0 = (int64_t)bi * TILE;
+    for (int x = tid; x < TILE * TILE; x += IS_THREADS) {
+        const int rr = x / TILE, c = x % TILE;
+        const int64_t i = i0 + rr, j = (int64_t)bj * TILE + c;
+        if (i >= j || j >= a.n) continue;
+        const int xs = rr * TILE + (c ^ (rr & 31));
+        const long long m = (long long)(((unsigned long long)acc_hi[xs] << 32) | acc_lo[xs]);
+        const long long t = Ufx[i] + Ufx[j] - 2 * m;
+        emit(a, base, i0, i, j, (double)t * inv);
+    }
+}
+
+}  // namespace b2d

@@ -142,7 +142,8 @@ __global__ void k_tip_scatter(const int64_t* __restrict__ indptr, const int32_t*
                               const uint8_t* __restrict__ flags, const double* __restrict__ len,
                               const double* __restrict__ scale, int64_t n, int64_t nch,
                               const int64_t* __restrict__ bucket_ptr, unsigned* __restrict__ cursor,
-                              TipEntry* __restrict__ entries, long long* __restrict__ Ufx) {
+                              TipEntry* __restrict__ entries, long long* __restrict__ Ufx,
+                              unsigned* __restrict__ nent) {
     const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= n) return;
@@ -151,11 +152,13 @@ __global__ void k_tip_scatter(const int64_t* __restrict__ indptr, const int32_t*
     const long long tot = total[s];
     const double sc = scale[0];
     long long u = 0;
+    unsigned cnt = 0;
     for (int64_t e = indptr[s] + lane; e < indptr[s + 1]; e += 32) {
         const int32_t q = qidx[e];
         if (flags[q] & NF_HAS_CHILDREN) continue;
         const long long w = __double2ll_rn(tip_weight(values, tot, len, q, e) * sc);
         u += w;
+        ++cnt;
         const int64_t b = blk * nch + q / TP_CHUNK;
         const unsigned pos = atomicAdd(&cursor[b], 1u);
         TipEntry en;
@@ -165,8 +168,14 @@ __global__ void k_tip_scatter(const int64_t* __restrict__ indptr, const int32_t*
         entries[bucket_ptr[b] + pos] = en;
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
-    if (lane == 0) Ufx[s] = u;
+    for (int o = 16; o; o >>= 1) {
+        u += __shfl_xor_sync(0xffffffffu, u, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+        Ufx[s] = u;
+        nent[s] = cnt;
+    }
 }
 
 // 6. sort every bucket by position (counting sort in shared memory, one CTA per bucket) and keep
@@ -319,24 +328,128 @@ __global__ void k_mask_tip_rows(uint32_t* __restrict__ nz, const uint32_t* __res
     nz[g * words + w] &= hc[w];
 }
 
-// near-duplicate pairs: 0 < x(i,j) < 2.5e-4 * (U_i + U_j) on the raw sums (before the epilogue)
+// Pairs whose fixed-point result cannot be trusted to 1e-12 relative, on the raw sums (before the
+// epilogue): (a) near-duplicates, 0 < x(i,j) < 2.5e-4 * (U_i + U_j), where the 2^-53 relative
+// rounding of every w (at most 2.3e-16 * (U_i + U_j) in all) could exceed 1e-12 * x; (b) pairs
+// where the quantisation itself could: every entry is rounded to a multiple of q = scale[1], so
+// U_i + U_j - 2 * M is off by at most (K_i + K_j) * q with K the entries of a sample (a sample
+// whose U is far below max U has coarse entries).  Such pairs are appended to `list` (at most
+// `cap`; `flagged` counts all of them) and k_fix_pairs_* recomputes just those pairs from the
+// resident embedding, every row, in floating point - no recomputation of anything else.
+struct FlaggedPair {
+    int32_t i, j;
+    int64_t off;   // position in the shard's compact result
+};
+constexpr int64_t FLAG_CAP = 1 << 20;
+
 __global__ void __launch_bounds__(256)
 k_tip_guard(const double* __restrict__ out, const double* __restrict__ out2,
             const int64_t* __restrict__ owned, const int64_t* __restrict__ row_base, int64_t n,
-            const double* __restrict__ U, unsigned long long* __restrict__ flagged) {
+            const double* __restrict__ U, const unsigned* __restrict__ nent, const double* __restrict__ scale,
+            unsigned long long* __restrict__ flagged, FlaggedPair* __restrict__ list) {
     const int64_t b = owned[blockIdx.x / TILE];
     const int64_t i0 = b * TILE, i = i0 + (blockIdx.x % TILE);
     if (i >= n - 1) return;
     const int64_t off = row_base[b] + (cond_row_start(i, n) - cond_row_start(i0, n));
     const int64_t cnt = n - 1 - i;
-    const double ui = U[i];
-    unsigned c = 0;
+    const double ui = U[i], q = scale[1], ki = (double)nent[i];
     for (int64_t t = threadIdx.x; t < cnt; t += blockDim.x) {
         double x = out[off + t];
         if (out2) x += out2[off + t];
-        if (x != 0.0 && x < 2.5e-4 * (ui + U[i + 1 + t])) ++c;
+        const int64_t j = i + 1 + t;
+        if (x != 0.0 && (x < 2.5e-4 * (ui + U[j]) || (ki + (double)nent[j]) * q > 1e-12 * x)) {
+            const unsigned long long slot = atomicAdd(flagged, 1ull);
+            if (list && slot < (unsigned long long)FLAG_CAP) {
+                FlaggedPair fp;
+                fp.i = (int32_t)i;
+                fp.j = (int32_t)j;
+                fp.off = off + t;
+                list[slot] = fp;
+            }
+        }
     }
-    if (c) atomicAdd(flagged, (unsigned long long)c);
+}
+
+// deterministic block sum (fixed tree), result valid in thread 0
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (tid < o) sh[tid] += sh[tid + o];
+        __syncthreads();
+    }
+    return sh[0];
+}
+
+// flagged pairs again, straight from the resident fp64 proportions: x = sum over ALL node rows of
+// len_q * |p_qi - p_qj| (the reference's own per-term arithmetic, no subtraction of large sums).
+// Fixed grid; a CTA takes pairs blockIdx.x, blockIdx.x + gridDim.x, ...; nothing to do -> exits.
+__global__ void __launch_bounds__(256)
+k_fix_pairs_weighted(const double* __restrict__ emb, const double* __restrict__ len, int64_t QR, int64_t rows,
+                     const FlaggedPair* __restrict__ list, const unsigned long long* __restrict__ flagged,
+                     double* __restrict__ out, double* __restrict__ out2) {
+    __shared__ double sh[256];
+    const unsigned long long total = *flagged;
+    const int64_t cnt = total < (unsigned long long)FLAG_CAP ? (int64_t)total : FLAG_CAP;
+    for (int64_t k = blockIdx.x; k < cnt; k += gridDim.x) {
+        const FlaggedPair fp = list[k];
+        const double* pa = emb + ((int64_t)(fp.i / TILE) * QR) * TILE + fp.i % TILE;
+        const double* pb = emb + ((int64_t)(fp.j / TILE) * QR) * TILE + fp.j % TILE;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int64_t q = threadIdx.x;
+        for (; q + 768 < rows; q += 1024) {
+            s0 = fma(fabs(pa[q * TILE] - pb[q * TILE]), len[q], s0);
+            s1 = fma(fabs(pa[(q + 256) * TILE] - pb[(q + 256) * TILE]), len[q + 256], s1);
+            s2 = fma(fabs(pa[(q + 512) * TILE] - pb[(q + 512) * TILE]), len[q + 512], s2);
+            s3 = fma(fabs(pa[(q + 768) * TILE] - pb[(q + 768) * TILE]), len[q + 768], s3);
+        }
+        for (; q < rows; q += 256) s0 = fma(fabs(pa[q * TILE] - pb[q * TILE]), len[q], s0);
+        const double s = block_sum_256((s0 + s1) + (s2 + s3), sh);
+        if (threadIdx.x == 0) {
+            out[fp.off] = s;
+            if (out2) out2[fp.off] = 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+// the same on the presence bits: x = sum over all node rows of len_q * [u_qi xor u_qj]
+__global__ void __launch_bounds__(256)
+k_fix_pairs_unweighted(const uint4* __restrict__ bits, const double* __restrict__ len, int64_t NS,
+                       const FlaggedPair* __restrict__ list, const unsigned long long* __restrict__ flagged,
+                       double* __restrict__ out, double* __restrict__ out2) {
+    __shared__ double sh[256];
+    const unsigned long long total = *flagged;
+    const int64_t cnt = total < (unsigned long long)FLAG_CAP ? (int64_t)total : FLAG_CAP;
+    for (int64_t k = blockIdx.x; k < cnt; k += gridDim.x) {
+        const FlaggedPair fp = list[k];
+        const uint4* ra = bits + ((int64_t)(fp.i / TILE) * NS) * TILE + fp.i % TILE;
+        const uint4* rb = bits + ((int64_t)(fp.j / TILE) * NS) * TILE + fp.j % TILE;
+        double s = 0.0;
+        for (int64_t st = threadIdx.x; st < NS; st += 256) {
+            const uint4 u = ra[st * TILE], v = rb[st * TILE];
+            const uint32_t x[4] = {u.x ^ v.x, u.y ^ v.y, u.z ^ v.z, u.w ^ v.w};
+            const double* l = len + st * NODE_STRIPE;
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                uint32_t m = x[w];
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    t += l[w * 32 + bit];
+                }
+            }
+            s += t;
+        }
+        s = block_sum_256(s, sh);
+        if (threadIdx.x == 0) {
+            out[fp.off] = s;
+            if (out2) out2[fp.off] = 0.0;
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -400,7 +513,7 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
                const double* __restrict__ scale, int64_t rows, int64_t QR, int64_t nch,
                const unsigned* __restrict__ qcount, const int64_t* __restrict__ bucket_ptr,
                TipEntry* __restrict__ entries, unsigned short* __restrict__ runs,
-               unsigned long long* __restrict__ Ufx) {
+               unsigned long long* __restrict__ Ufx, unsigned* __restrict__ nent) {
     const int64_t b = blockIdx.y, ch = blockIdx.x;  // chunks (up to 2^19) in x, sample blocks in y
     const int64_t bucket = b * nch + ch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -413,6 +526,7 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
     unsigned short* rs = runs + (size_t)bucket * (TP_CHUNK + 8);
     const double sc = scale[0];
     long long ufx[4] = {0, 0, 0, 0};
+    unsigned kcnt[4] = {0u, 0u, 0u, 0u};
     for (int64_t q = qa; q < qa + TP_QROWS; ++q) {
         if (lane == 0) rs[q - ch * TP_CHUNK] = (unsigned short)run;
         if (q >= qb || !((sparse[q >> 5] >> (q & 31)) & 1u)) continue;  // warp-uniform
@@ -424,6 +538,7 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
             if (v != 0.0) {
                 const long long wv = __double2ll_rn(l * v * sc);
                 ufx[k] += wv;
+                ++kcnt[k];
                 TipEntry en;
                 en.key = ((uint32_t)(q - ch * TP_CHUNK) << 7) | (uint32_t)(32 * k + lane);
                 en.pad = 0;
@@ -436,7 +551,10 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
     if (warp == 3 && lane == 0) rs[TP_CHUNK] = (unsigned short)run;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (ufx[k]) atomicAdd(&Ufx[b * TILE + 32 * k + lane], (unsigned long long)ufx[k]);
+        if (kcnt[k]) {
+            atomicAdd(&Ufx[b * TILE + 32 * k + lane], (unsigned long long)ufx[k]);
+            atomicAdd(&nent[b * TILE + 32 * k + lane], kcnt[k]);
+        }
 }
 
 // The rows that stay with the dense pair kernel, packed: embd[block][r][128] = emb[block][pos[r] - q0][128]
@@ -520,7 +638,7 @@ k_ubits_scatter(const uint32_t* __restrict__ bits, const long long* __restrict__
                 const uint32_t* __restrict__ sparse, int64_t mpad, int64_t NS, int64_t nch,
                 const unsigned* __restrict__ qcount, const int64_t* __restrict__ bucket_ptr,
                 uint32_t* __restrict__ keys, unsigned short* __restrict__ runs,
-                unsigned long long* __restrict__ Ufx) {
+                unsigned long long* __restrict__ Ufx, unsigned* __restrict__ nent) {
     const int64_t b = blockIdx.y, ch = blockIdx.x;
     const int64_t bucket = b * nch + ch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -531,6 +649,7 @@ k_ubits_scatter(const uint32_t* __restrict__ bits, const long long* __restrict__
     uint32_t* out = keys + bucket_ptr[bucket];
     unsigned short* rs = runs + (size_t)bucket * (TP_CHUNK + 8);
     long long ufx[4] = {0, 0, 0, 0};
+    unsigned kcnt[4] = {0u, 0u, 0u, 0u};
     for (int64_t W = q0 / 32; W < (q0 + TP_QROWS) / 32; ++W) {
         const bool in = W < mpad / 32;
         const uint32_t mask = in ? sparse[W] : 0u;
@@ -551,6 +670,7 @@ k_ubits_scatter(const uint32_t* __restrict__ bits, const long long* __restrict__
                 const uint32_t m = __ballot_sync(0xffffffffu, on);
                 if (on) {
                     ufx[k] += lf;
+                    ++kcnt[k];
                     out[run + __popc(m & lt)] = ((uint32_t)(q - ch * TP_CHUNK) << 7) | (uint32_t)(32 * k + lane);
                 }
                 run += __popc(m);
@@ -560,7 +680,10 @@ k_ubits_scatter(const uint32_t* __restrict__ bits, const long long* __restrict__
     if (warp == 3 && lane == 0) rs[TP_CHUNK] = (unsigned short)run;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (ufx[k]) atomicAdd(&Ufx[b * TILE + 32 * k + lane], (unsigned long long)ufx[k]);
+        if (kcnt[k]) {
+            atomicAdd(&Ufx[b * TILE + 32 * k + lane], (unsigned long long)ufx[k]);
+            atomicAdd(&nent[b * TILE + 32 * k + lane], kcnt[k]);
+        }
 }
 
 // the tile kernel: T(i,j) = U_i + U_j - 2 * sum_{q in both} lenfx[q]

@@ -659,7 +659,7 @@ def test_randomised_sweep_weighted_and_dense_braycurtis():
 def test_sparse_tip_rows_agree_with_the_dense_kernel_and_fall_back_when_they_must():
     """Tip rows as a fixed-point sparse intersection (default) vs the dense kernel; the two
     fall-backs: a table too dense for the position buckets, and near-duplicate samples (where
-    U_i + U_j - 2 * intersection would cancel) which make the engine redo the tips densely."""
+    U_i + U_j - 2 * intersection would cancel): those pairs alone are recomputed in floating point."""
     _skbio_b200()
     from oracle import oracle_fast
     from skbio_b200 import _capi, synthetic
@@ -700,7 +700,7 @@ def test_sparse_tip_rows_agree_with_the_dense_kernel_and_fall_back_when_they_mus
     indptr2 = np.concatenate([[0], np.cumsum([len(r[0]) for r in rows])]).astype(np.int64)
     exp2 = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr2, cols2, vals2, tips), tip_node, parent, length)
     got, t = run(parent, length, indptr2, cols2, vals2, tip_node, n, "weighted_unifrac", 1)
-    assert t["tips_flagged"] > 0 and t["tips_ms"] == 0          # redone with dense tips
+    assert t["tips_flagged"] > 0 and t["tips_ms"] > 0           # only the flagged pairs are redone (fp64)
     assert got[0] == 0.0                                          # pair (0, 1): identical samples
     assert_close_rel(got, exp2["weighted_unifrac"], UNIFRAC_RTOL, "near-duplicates")
 
@@ -852,7 +852,7 @@ def test_unweighted_sparse_rows_agree_with_the_lut_kernel_and_fall_back(cat):
     assert_close_rel(got, exp2["unweighted_unifrac"], UNIFRAC_RTOL, "unweighted with a duplicate sample")
 
     # a near-duplicate (one extra taxon on a 1e-9 branch whose parent the sample already reaches):
-    # the guard makes the engine redo the computation with every row in the LUT kernel
+    # the guard has the engine recompute that pair from the presence bits, every row
     in0 = np.zeros(tips, dtype=bool)
     in0[rows[0]] = True
     par_of_tip = parent[tip_node]
@@ -876,5 +876,84 @@ def test_unweighted_sparse_rows_agree_with_the_lut_kernel_and_fall_back(cat):
         prob.compute("unweighted_unifrac")
         t = prob.timings()
         got = prob.fetch(np.empty(total))
-    assert t["tips_flagged"] > 0 and t["tips_ms"] == 0
+    assert t["tips_flagged"] > 0 and t["tips_ms"] > 0   # the flagged pairs alone are recomputed
     assert_close_rel(got, exp3["unweighted_unifrac"], UNIFRAC_RTOL, "unweighted near-duplicates")
+
+
+@pytest.mark.parametrize("key", ["weighted_unifrac_normalized", "unweighted_unifrac"])
+def test_pipelined_intersection_kernel_matches_the_first_generation_bit_for_bit(key):
+    """b2d_isect.cuh (producer warp + bulk-copy ring, G lanes per row entry) against k_pair_tips /
+    k_pair_utips: the sparse-row sums are integers, so every variant must give identical bits -
+    single-batch buckets (sparse table) and buckets cut into several batches (denser table,
+    several sample blocks), shards included."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    for n, tips, lam, seed in ((300, 3000, 0.02, 81), (520, 2600, 0.06, 82)):
+        parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, lam, seed)
+        exp = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr, cols, vals, tips), tip_node, parent, length)
+        total = n * (n - 1) // 2
+        res = {}
+        try:
+            for kern, grp in ((0, 4), (1, 1), (1, 2), (1, 4), (1, 8)):
+                _capi.set_option("isect_kernel", kern)
+                _capi.set_option("isect_group", grp)
+                for shards in (1, 3):
+                    out = np.full(total, -1.0)
+                    for sh in range(shards):
+                        with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n, shard=sh,
+                                                n_shards=shards) as prob:
+                            prob.compute(key)
+                            t = prob.timings()
+                            assert t["tips_ms"] > 0 and t["sparse_row_matches"] > 0
+                            prob.fetch(out)
+                    res[(kern, grp, shards)] = out
+        finally:
+            _capi.set_option("isect_kernel", 1)
+            _capi.set_option("isect_group", 4)
+        base = res[(0, 4, 1)]
+        assert_close_rel(base, exp[key], UNIFRAC_RTOL, key + " first-generation kernel vs oracle")
+        for k, v in res.items():
+            assert np.array_equal(v, base), (key, n, k)
+
+
+def test_flagged_pairs_are_recomputed_alone():
+    """Three near-duplicate pairs among 1 500 samples: the guard flags exactly those, the intersection
+    kernel still runs (no dense redo of the step), the result is within 1e-12 of the oracle, exact
+    copies stay at exactly 0, and the step takes about as long as without them."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 1500, 6000
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.02, 91)
+    rows = [(cols[indptr[s]:indptr[s + 1]].copy(), vals[indptr[s]:indptr[s + 1]].copy() * 1000000) for s in range(n)]
+
+    def timed(rows_):
+        c = np.concatenate([r[0] for r in rows_])
+        v = np.concatenate([r[1] for r in rows_])
+        ip = np.concatenate([[0], np.cumsum([len(r[0]) for r in rows_])]).astype(np.int64)
+        with _capi.Problem.tree(parent, length, ip, tip_node[c], v, n) as prob:
+            ms = []
+            for _ in range(4):
+                prob.compute("weighted_unifrac")
+                ms.append(prob.timings()["compute_ms"])
+            return prob.fetch(np.empty(n * (n - 1) // 2)), prob.timings(), min(ms[1:]), (ip, c, v)
+
+    base, t0, ms0, _ = timed(rows)
+    assert t0["tips_flagged"] == 0 and t0["tips_ms"] > 0
+    dup = [list(r) for r in rows]
+    for a, b in ((7, 700), (130, 131), (900, 1499)):   # three tiles, b := a with one count off by 1e-6
+        c, v = rows[a][0].copy(), rows[a][1].copy()
+        v[len(v) // 2] += 1
+        dup[b] = [c, v]
+    dup[3] = [rows[2][0].copy(), rows[2][1].copy()]   # an exact copy as well
+    got, t1, ms1, (ip, c, v) = timed([tuple(r) for r in dup])
+    assert t1["tips_flagged"] == 3 and t1["tips_ms"] > 0
+    dense = synthetic.csr_to_dense(ip, c, v, tips)
+    exp = oracle_fast.weighted(oracle_fast.counts_by_node(dense, tip_node, parent),
+                               np.ascontiguousarray(length, dtype=np.float64), parent, False)
+    assert_close_rel(got, exp, UNIFRAC_RTOL, "three flagged pairs")
+    assert got[2 * n - (2 + 2) * (2 + 1) // 2 + 3] == 0.0   # pair (2, 3): exact copies
+    assert ms1 <= 1.25 * ms0 + 0.5, (ms0, ms1)
