@@ -186,10 +186,12 @@ int b2d_beta_diversity_features(int metric, int device,
  *   "sparse_rows_max_tips"  0 (default): when the whole embedding is resident, rows of nodes with
  *                       up to about 0.3 / (table density) tips below them (0.16 / density for
  *                       unweighted UniFrac) join the tips in the intersection kernel; k > 0: up to k tips (1 = tip rows only)
- *   "cache_embedding"   1 (default): device buffers (the embedding above all) are parked per
- *                       device when a problem is destroyed and reused by the
- *                       next one (cudaMalloc / cudaFree of tens of GB cost 0.1 - 0.7 s); they
- *                       are released when an allocation fails; 0: release now, stop parking
+ *   "cache_embedding"   1 (default): device buffers are parked per device when a problem is
+ *                       destroyed and reused by the next one (cudaMalloc / cudaFree of large blocks
+ *                       cost 0.1 - 0.7 s), up to "cache_limit_bytes" per device; they are released
+ *                       when an allocation fails; 0: release now, stop parking
+ *   "cache_limit_bytes" most bytes parked per device (default 4 GiB; what does not fit goes back
+ *                       to the driver when it is freed); "release_cache": release everything now
  *   "sparse_features"   -1 auto, 0 never, 1 whenever legal: intersection kernel for integer
  *                       feature tables (Bray-Curtis / Jaccard)
  *   "walk_decomposed"   0: always the sequential tree walk;  "plain_kernels" 1: cross-check
@@ -216,6 +218,23 @@ int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_g
                      const int32_t* groupings, int32_t n_groups, const double* inv_group_size,
                      double* s_w_out);
 
+/* Rows [r0, r1) of the square (redundant) distance matrix, out[(i - r0) * n + j], gathered on the
+ * device from the condensed result of a problem that owns the whole triangle (n_shards == 1, no tile
+ * selection).  This is what a streaming lsmat / binary_dm writer consumes row block by row block
+ * (/root/reference/skbio/io/format/lsmat.py:266-279, binary_dm.py:157-184) without ever holding the
+ * n x n matrix. */
+int b2d_problem_fetch_square_rows(b2d_problem* p, int64_t r0, int64_t r1, double* out);
+
+/* Gower centering of the distance matrix, the first step of pcoa: E = -d^2/2, its row means and
+ * global mean, F = E - mean_row - mean_col + mean (replaces e_matrix_means_cy + f_matrix_inplace_cy,
+ * /root/reference/skbio/stats/ordination/_cutils.pyx:19-123).  row_means[n], *global_mean and
+ * f_matrix[n*n] are host outputs; each may be NULL.  b2d_problem_center works on the device-resident
+ * result of a problem that owns the whole triangle (the 8*P bytes never travel to the host);
+ * b2d_center_condensed takes a condensed host vector. */
+int b2d_problem_center(b2d_problem* p, double* row_means, double* global_mean, double* f_matrix);
+int b2d_center_condensed(int device, int64_t n, const double* condensed, double* row_means,
+                         double* global_mean, double* f_matrix);
+
 /* Host only: Newick text -> flat tree in the reference's node id order, without node objects
  * (stands in for TreeNode.read + TreeNode.to_array, /root/reference/skbio/io/format/newick.py:270-336,
  * /root/reference/skbio/tree/_tree.py:6235-6329).  length[k] is NaN where the text gave none;
@@ -234,6 +253,16 @@ void b2d_flat_tree_free(b2d_flat_tree* t);
  * layout b2d_problem_fetch_compact returns. */
 int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe_offsets,
                      int64_t* n_stripes_out, int64_t* total_out);
+
+/* Test hook (needs the GPU): the per-node sample embedding the device builds - CSR scatter + tree
+ * propagation, the engine's replacement of _nodes_by_counts / _traverse_reduce
+ * (/root/reference/skbio/diversity/_phylogenetic.pyx:73-222) - copied back as
+ * out[n_samples][n_nodes] int64 in REFERENCE node id order, i.e. the matrix
+ * vectorize_counts_and_tree returns (/root/reference/skbio/diversity/_util.py:123-170; pinned by
+ * /root/reference/skbio/diversity/tests/test_util.py:27-34).  variant 0: subtree counts, sequential
+ * walk in node passes (honours "emb_budget_bytes"); 1: subtree counts, subtree-decomposed walk;
+ * 2: presence bits as 0 / 1. */
+int b2d_debug_fetch_embedding(b2d_problem* p, int variant, int64_t* out);
 
 /* Test hook (host only, no GPU needed): the engine's node order for a flat tree.  Arrays
  * sized n_nodes (q_of_id) or n_nodes rounded up to a multiple of 128 (the others); any may

@@ -105,6 +105,14 @@ def _declare(lib):
     lib.b2d_flat_tree_free.argtypes = [ctypes.c_void_p]
     lib.b2d_shard_layout.restype = ctypes.c_int
     lib.b2d_shard_layout.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _i64p, _i64p, _i64p]
+    lib.b2d_problem_fetch_square_rows.restype = ctypes.c_int
+    lib.b2d_problem_fetch_square_rows.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _f64p]
+    lib.b2d_problem_center.restype = ctypes.c_int
+    lib.b2d_problem_center.argtypes = [ctypes.c_void_p, _f64p, _f64p, _f64p]
+    lib.b2d_center_condensed.restype = ctypes.c_int
+    lib.b2d_center_condensed.argtypes = [ctypes.c_int, ctypes.c_int64, _f64p, _f64p, _f64p, _f64p]
+    lib.b2d_debug_fetch_embedding.restype = ctypes.c_int
+    lib.b2d_debug_fetch_embedding.argtypes = [ctypes.c_void_p, ctypes.c_int, _i64p]
     lib.b2d_debug_tree_order.restype = ctypes.c_int
     lib.b2d_debug_tree_order.argtypes = [
         ctypes.c_int64, _i32p, _f64p, _i32p, ctypes.POINTER(ctypes.c_uint8), _f64p, _f64p,
@@ -119,7 +127,8 @@ EXPORTED_SYMBOLS = [
     "b2d_beta_diversity_tree", "b2d_beta_diversity_features", "b2d_set_option",
     "b2d_microbench", "b2d_debug_tree_order", "b2d_shard_layout", "b2d_problem_select_tiles",
     "b2d_newick_parse", "b2d_flat_tree_nodes", "b2d_flat_tree_name_bytes", "b2d_flat_tree_get",
-    "b2d_flat_tree_free", "b2d_permanova_sw", "b2d_problem_phydiv",
+    "b2d_flat_tree_free", "b2d_permanova_sw", "b2d_problem_phydiv", "b2d_debug_fetch_embedding",
+    "b2d_problem_fetch_square_rows", "b2d_problem_center", "b2d_center_condensed",
 ]
 
 
@@ -165,6 +174,22 @@ def set_option(name, value):
     _check(load().b2d_set_option(name.encode(), int(value)))
 
 
+def release_cache():
+    """Give every device buffer the library has parked back to the CUDA driver.
+
+    Freed buffers of a finished problem are parked per device (up to ``cache_limit_bytes``,
+    4 GiB by default) because cudaMalloc / cudaFree of large blocks cost 0.1 - 0.7 s; call this
+    before handing the GPU to another library in the same process."""
+    set_option("release_cache", 1)
+
+
+def set_cache_limit(nbytes):
+    """Upper bound (bytes per device) on parked device memory; 0 parks nothing.  Loops that
+    create and destroy many large problems (benchmarks, block-wise runs) may raise it so that
+    the embedding buffer itself is reused."""
+    set_option("cache_limit_bytes", int(nbytes))
+
+
 def microbench(kind, device=0):
     out = ctypes.c_double(0.0)
     _check(load().b2d_microbench(int(device), int(kind), ctypes.byref(out)))
@@ -182,6 +207,22 @@ def permanova_sw(condensed, groupings, inv_group_size, device=0):
     _check(lib.b2d_permanova_sw(int(device), n, _ptr(condensed, _f64p), k, _ptr(groupings, _i32p),
                                 len(inv), _ptr(inv, _f64p), _ptr(out, _f64p)))
     return out
+
+
+def center_condensed(condensed, device=0, want_matrix=True):
+    """(F [n x n] or None, row means of E [n], global mean of E) for a condensed distance vector."""
+    lib = load()
+    condensed = np.ascontiguousarray(condensed, dtype=np.float64)
+    ln = len(condensed)
+    n = int(round((1.0 + np.sqrt(1.0 + 8.0 * ln)) / 2.0))
+    if n * (n - 1) // 2 != ln:
+        raise ValueError("not a condensed vector: its length is not n(n-1)/2")
+    rm = np.empty(n, dtype=np.float64)
+    gm = ctypes.c_double(0.0)
+    f = np.empty((n, n), dtype=np.float64) if want_matrix else None
+    _check(lib.b2d_center_condensed(int(device), n, _ptr(condensed, _f64p), _ptr(rm, _f64p), ctypes.byref(gm),
+                                    _ptr(f, _f64p)))
+    return f, rm, gm.value
 
 
 def newick_to_flat(text):
@@ -372,6 +413,21 @@ class Problem:
                                              ctypes.byref(cnt)))
         return out, offs[: 2 * cnt.value].reshape(-1, 2)
 
+    def fetch_square_rows(self, r0, r1):
+        """Rows [r0, r1) of the square distance matrix, gathered on the device (single shard)."""
+        out = np.empty((int(r1) - int(r0), self.n), dtype=np.float64)
+        if out.size:
+            _check(load().b2d_problem_fetch_square_rows(self._h, int(r0), int(r1), _ptr(out, _f64p)))
+        return out
+
+    def center(self, want_matrix=True):
+        """Gower centering of the device-resident result: (F or None, row means, global mean)."""
+        rm = np.empty(self.n, dtype=np.float64)
+        gm = ctypes.c_double(0.0)
+        f = np.empty((self.n, self.n), dtype=np.float64) if want_matrix else None
+        _check(load().b2d_problem_center(self._h, _ptr(rm, _f64p), ctypes.byref(gm), _ptr(f, _f64p)))
+        return f, rm, gm.value
+
     def sample_vector(self):
         out = np.empty(self.n, dtype=np.float64)
         if self.n:
@@ -382,6 +438,14 @@ class Problem:
         out = np.empty(self.n, dtype=np.float64)
         if self.n:
             _check(load().b2d_problem_phydiv(self._h, 1 if rooted else 0, float(weight), _ptr(out, _f64p)))
+        return out
+
+    def fetch_embedding(self, variant=0, n_nodes=None):
+        """Test hook: the device-built embedding as (n_samples x n_nodes) int64 in reference id
+        order (variant 0 / 1: subtree counts, sequential / decomposed walk; 2: presence)."""
+        out = np.zeros((self.n, int(n_nodes)), dtype=np.int64)
+        if out.size:
+            _check(load().b2d_debug_fetch_embedding(self._h, int(variant), _ptr(out, _i64p)))
         return out
 
     def timings(self):

@@ -207,8 +207,9 @@ def beta_diversity(metric, counts, ids=None, validate=True, pairwise_func=None, 
     return dm
 
 
-def _prepare_unifrac_problem(key, counts, taxa, tree, validate):
-    """Host half of the UniFrac path: validate, flatten, CSR, name lookup -> factory of shards."""
+def _unifrac_host_arrays(key, counts, taxa, tree, validate):
+    """Host half of the UniFrac path: validate, flatten, CSR, name lookup.  Returns the flat
+    arrays the C ABI takes: ``(parent, length, indptr, node_ids, values, n_samples)``."""
     t0 = time.perf_counter()
     if validate:
         validate_taxa_and_tree(taxa, tree)
@@ -229,6 +230,12 @@ def _prepare_unifrac_problem(key, counts, taxa, tree, validate):
     t4 = time.perf_counter()
     _profile.clear()
     _profile.update(validate_s=t1 - t0, flatten_s=t2 - t1, csr_s=t3 - t2, lookup_s=t4 - t3)
+    return parent, length, indptr, node_ids, vals, n
+
+
+def _prepare_unifrac_problem(key, counts, taxa, tree, validate):
+    """Host arrays -> factory of shards (one problem per device)."""
+    parent, length, indptr, node_ids, vals, n = _unifrac_host_arrays(key, counts, taxa, tree, validate)
 
     def make(dev, shard=0, nshards=1):
         return _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, device=dev,

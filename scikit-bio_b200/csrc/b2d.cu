@@ -11,10 +11,14 @@
 #include <string.h>
 
 #include <map>
+#include <new>
+#include <stdexcept>
 #include <mutex>
 #include <unordered_map>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "b2d_common.cuh"
 #include "b2d_embed.cuh"
@@ -24,6 +28,7 @@
 #include "b2d_isect.cuh"
 #include "b2d_sparse.cuh"
 #include "b2d_permanova.cuh"
+#include "b2d_post.cuh"
 #include "b2d_tree.h"
 #include "b2d_newick.h"
 
@@ -37,7 +42,8 @@ static int g_walk_decomposed = 1;              // 0 = always the sequential weig
 constexpr int SKIP_GW = 8;                     // group words per zero-path table (256 groups)
 static int g_sparse_rows_max_tips = 0;         // 0 = from the table's density; 1 = tips only
 static int g_tips_sparse = 1;                  // tip rows of the weighted kernel as a sparse intersection
-static int g_cache_embedding = 1;              // keep the embedding buffer of a destroyed problem
+static int g_cache_embedding = 1;              // park freed device buffers for the next problem
+static int64_t g_cache_limit_bytes = (int64_t)4 << 30;  // ... but at most this much per device
 static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 static int g_isect_kernel = 1;                 // 1: pipelined intersection kernel (b2d_isect.cuh); 0: first generation
@@ -154,6 +160,27 @@ __global__ void k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ 
 
 using namespace b2d;
 
+// NVTX ranges around the phases of a call (H2D, embedding, sparse rows, pair kernels, D2H) so that
+// nsys / ncu timelines name them; header-only NVTX v3, a no-op without a profiler attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+// No C++ exception may cross the C boundary: std::bad_alloc (host vectors sized by the input) and
+// anything else thrown below become status codes.
+#define B2D_GUARDED(call)                                                        \
+    try {                                                                        \
+        return (call);                                                           \
+    } catch (const std::bad_alloc&) {                                            \
+        return fail(B2D_ERR_OUT_OF_MEMORY, "out of host memory");                \
+    } catch (const std::exception& e) {                                          \
+        return fail(B2D_ERR_STATE, std::string("internal error: ") + e.what()); \
+    } catch (...) {                                                              \
+        return fail(B2D_ERR_STATE, "internal error");                            \
+    }
+
+
 // Device memory is kept across problems.  cudaMalloc / cudaFree of the large buffers (the
 // embedding: up to 85 % of the device; results, zero-path table, tip buckets: 0.3 - 0.4 GB each)
 // cost tens to hundreds of milliseconds per call (and now and then even a small cudaFree stalls for
@@ -167,6 +194,7 @@ struct DevPool {
     std::multimap<size_t, void*> idle;        // parked blocks by size
     void* emb = nullptr;                      // parked embedding buffer
     size_t emb_bytes = 0;
+    size_t parked = 0;                        // bytes parked (idle + emb)
 };
 static std::mutex g_pool_mu;
 static DevPool g_pool[64];
@@ -194,6 +222,7 @@ static void pool_clear() {
             pl.emb = nullptr;
             pl.emb_bytes = 0;
         }
+        pl.parked = 0;
     }
     cudaSetDevice(cur);
 }
@@ -215,6 +244,7 @@ static cudaError_t b2d_malloc(T** ptr, size_t bytes) {
         if (it != pl.idle.end() && it->first <= bytes + bytes / 4) {
             *ptr = (T*)it->second;
             pl.live[it->second] = it->first;
+            pl.parked -= it->first;
             pl.idle.erase(it);
             return cudaSuccess;
         }
@@ -241,8 +271,11 @@ static void b2d_free(void* ptr) {
         if (it != pl.live.end()) {
             const size_t bytes = it->second;
             pl.live.erase(it);
-            if (g_cache_embedding) {
+            // retention is bounded: what does not fit under the limit goes back to the driver now,
+            // so that other libraries in the process (PyTorch, CuPy) see the memory again
+            if (g_cache_embedding && (int64_t)(pl.parked + bytes) <= g_cache_limit_bytes) {
                 pl.idle.insert({bytes, ptr});
+                pl.parked += bytes;
                 return;
             }
         }
@@ -268,6 +301,7 @@ static void* emb_cache_take(int device, size_t need, size_t* got) {
     const size_t bytes = pl.emb_bytes;
     pl.emb = nullptr;
     pl.emb_bytes = 0;
+    pl.parked -= bytes;
     if (bytes >= need) {
         *got = bytes;
         return ptr;
@@ -280,7 +314,9 @@ static void emb_cache_put(int device, void* ptr, size_t bytes) {
     if (!ptr) return;
     std::lock_guard<std::mutex> lk(g_pool_mu);
     DevPool& pl = g_pool[device >= 0 && device < 64 ? device : 0];
-    if (!g_cache_embedding || device < 0 || device >= 64 || (pl.emb && pl.emb_bytes >= bytes)) {
+    const size_t others = pl.parked - pl.emb_bytes;
+    if (!g_cache_embedding || device < 0 || device >= 64 || (pl.emb && pl.emb_bytes >= bytes) ||
+        (int64_t)(others + bytes) > g_cache_limit_bytes) {
         pl.live.erase(ptr);
         cudaFree(ptr);
         return;
@@ -288,9 +324,11 @@ static void emb_cache_put(int device, void* ptr, size_t bytes) {
     if (pl.emb) {
         pl.live.erase(pl.emb);
         cudaFree(pl.emb);
+        pl.parked -= pl.emb_bytes;
     }
     pl.emb = ptr;
     pl.emb_bytes = bytes;
+    pl.parked += bytes;
 }
 
 struct b2d_problem {
@@ -416,6 +454,11 @@ struct b2d_problem {
 static void free_problem(b2d_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    // kernels of a failed compute may still be in flight: the blocks go back to a pool that hands
+    // them to other problems (other streams), so drain both streams first (errors ignored)
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->stream2) cudaStreamSynchronize(p->stream2);
+    cudaGetLastError();
     b2d_free(p->d_indptr); b2d_free(p->d_qidx); b2d_free(p->d_values); b2d_free(p->d_flags);
     b2d_free(p->d_hc); b2d_free(p->d_fold); b2d_free(p->d_len); b2d_free(p->d_tipdist);
     b2d_free(p->d_tiles); b2d_free(p->d_row_base); b2d_free(p->d_out); b2d_free(p->d_total);
@@ -452,6 +495,7 @@ static int upload(T** dst, const T* src, size_t count, cudaStream_t s) {
 static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* ids,
                         const void* values, size_t value_size) {
     cudaEvent_t e0, e1;
+    NvtxRange range("b2d:create (H2D of tree + CSR)");
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
     for (auto& e : p->ev) B2D_CUDA(cudaEventCreate(&e));
@@ -640,6 +684,11 @@ int b2d_set_option(const char* name, int64_t value) {
     } else if (s == "cache_embedding") {
         g_cache_embedding = value ? 1 : 0;
         if (!value) pool_clear();
+    } else if (s == "cache_limit_bytes") {
+        g_cache_limit_bytes = value < 0 ? 0 : value;
+        pool_clear();
+    } else if (s == "release_cache") {
+        pool_clear();
     } else if (s == "weighted_skip") {
         g_weighted_skip = value ? 1 : 0;
     } else if (s == "isect_kernel") {
@@ -652,7 +701,7 @@ int b2d_set_option(const char* name, int64_t value) {
     return B2D_OK;
 }
 
-int b2d_problem_create_tree(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes,
+static int b2d_problem_create_tree_impl(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes,
                             const int32_t* parent, const double* length, const int64_t* indptr,
                             const int32_t* node_ids, const int64_t* values, int shard,
                             int n_shards) {
@@ -693,7 +742,7 @@ int b2d_problem_create_tree(b2d_problem** out, int device, int64_t n_samples, in
     return B2D_OK;
 }
 
-int b2d_problem_create_features(b2d_problem** out, int device, int64_t n_samples,
+static int b2d_problem_create_features_impl(b2d_problem** out, int device, int64_t n_samples,
                                 int64_t n_features, const int64_t* indptr,
                                 const int32_t* feature_ids, const double* values, int shard,
                                 int n_shards) {
@@ -1314,6 +1363,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
         int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
         B2D_CUDA(cudaEventRecord(ea, p->stream));
+        nvtxRangePushA("b2d:embed (scatter + propagate)");
         B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, (size_t)QR * row_bytes, p->stream));
         if (p->n) {
             if (tree) {
@@ -1357,8 +1407,10 @@ static int compute_dense(b2d_problem* p, int metric) {
                     (unsigned long long*)p->d_emb, 1);
             }
         }
+        nvtxRangePop();
         B2D_CUDA(cudaEventRecord(eb, p->stream));
         if (p->ntiles) {
+            NvtxRange pair_range("b2d:pair (sparse rows + tile kernels + closed form)");
             if (skip) {
                 if (p->rows_general) {
                     if ((rc = rows_build(p, QR))) return rc;
@@ -1512,6 +1564,7 @@ static int compute_bits(b2d_problem* p, int metric) {
     if (rc) return rc;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     B2D_CUDA(cudaEventRecord(ea, p->stream));
+    nvtxRangePushA("b2d:embed (scatter + propagate bits)");
     B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, bytes, p->stream));
     if (p->n) {
         p->n_kernels += 1;
@@ -1521,7 +1574,9 @@ static int compute_bits(b2d_problem* p, int metric) {
         k_propagate_bits<<<(unsigned)p->nb, TILE, 0, p->stream>>>(
             (uint4*)p->d_emb, p->d_hc, p->d_fold, p->d_len, p->NS, p->d_svec);
     }
+    nvtxRangePop();
     B2D_CUDA(cudaEventRecord(eb, p->stream));
+    NvtxRange pair_range("b2d:pair (sparse rows + tile kernels)");
     p->n_launch = 0;
     p->skip_executed = p->skip_dense = p->t_skip_prep = 0;
     B2D_CUDA(cudaFuncSetAttribute(k_pair_unweighted_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1767,9 +1822,10 @@ static bool want_sparse(b2d_problem* p) {
     return true;
 }
 
-int b2d_problem_compute(b2d_problem* p, int metric) {
+static int b2d_problem_compute_impl(b2d_problem* p, int metric) {
     if (!p) return fail(B2D_ERR_INVALID_ARGUMENT, "problem is NULL");
     B2D_CUDA(cudaSetDevice(p->device));
+    NvtxRange range("b2d:compute");
     if (p->custom_tiles && p->out_len)
         B2D_CUDA(cudaMemsetAsync(p->d_out, 0, p->out_len * sizeof(double), p->stream));
     p->n_kernels = 0;
@@ -1825,7 +1881,7 @@ int b2d_problem_compute(b2d_problem* p, int metric) {
     return B2D_OK;
 }
 
-int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_tiles) {
+static int b2d_problem_select_tiles_impl(b2d_problem* p, const int32_t* tiles, int64_t n_tiles) {
     if (!p || (!tiles && n_tiles)) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
     B2D_CUDA(cudaSetDevice(p->device));
     std::vector<uint8_t> want(p->nb, 0);
@@ -1876,7 +1932,7 @@ int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_til
     return B2D_OK;
 }
 
-int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n) {
+static int b2d_problem_phydiv_impl(b2d_problem* p, int rooted, double weight, double* out_n) {
     if (!p || !out_n) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
     if (p->kind != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "phydiv needs a tree problem");
     if (!(weight >= 0.0 && weight <= 1.0)) return fail(B2D_ERR_INVALID_ARGUMENT, "weight must be in [0, 1]");
@@ -1932,6 +1988,88 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
     return B2D_OK;
 }
 
+// Test hook: the per-node sample embedding the device builds (K1: CSR scatter + tree propagation),
+// back on the host as out[n_samples][n_nodes] int64 in REFERENCE id order - the matrix
+// vectorize_counts_and_tree returns (count_array.T, /root/reference/skbio/diversity/_util.py:123-170).
+// variant 0: int64 subtree counts, sequential walk in node passes (honours emb_budget_bytes);
+// variant 1: the same with the subtree-decomposed walk (whole tree resident, as compute uses it);
+// variant 2: presence bits (scatter_bits + propagate_bits), returned as 0 / 1.
+static int b2d_debug_fetch_embedding_impl(b2d_problem* p, int variant, int64_t* out) {
+    if (!p || !out) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (p->kind != 0) return fail(B2D_ERR_INVALID_ARGUMENT, "fetch_embedding needs a tree problem");
+    if (variant < 0 || variant > 2) return fail(B2D_ERR_INVALID_ARGUMENT, "variant must be 0, 1 or 2");
+    if (variant != 2 && !p->has_values) return fail(B2D_ERR_INVALID_ARGUMENT, "count variants need count values");
+    B2D_CUDA(cudaSetDevice(p->device));
+    if (p->n == 0) return B2D_OK;
+    const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
+    const std::vector<int32_t>& qof = p->order.q_of_id;
+    p->computed = false;
+    if (variant == 2) {
+        const size_t bytes = (size_t)p->nb * p->NS * TILE * sizeof(uint4);
+        int rc = ensure_emb(p, std::max<size_t>(bytes, 16));
+        if (rc) return rc;
+        B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, bytes, p->stream));
+        k_scatter_bits<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->n, p->NS, (uint32_t*)p->d_emb);
+        k_propagate_bits<<<(unsigned)p->nb, TILE, 0, p->stream>>>((uint4*)p->d_emb, p->d_hc, p->d_fold, p->d_len,
+                                                                 p->NS, p->d_svec);
+        std::vector<uint32_t> h(bytes / sizeof(uint32_t));
+        B2D_CUDA(cudaMemcpyAsync(h.data(), p->d_emb, bytes, cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        B2D_CUDA(cudaGetLastError());
+        for (int64_t s = 0; s < p->n; ++s)
+            for (int64_t id = 0; id < p->m; ++id) {
+                const int64_t q = qof[id];
+                const uint32_t w = h[(((s / TILE) * p->NS + q / 128) * TILE + s % TILE) * 4 + (q % 128) / 32];
+                out[s * p->m + id] = (w >> (q % 32)) & 1u;
+            }
+        return B2D_OK;
+    }
+    size_t free_b = 0, total_b = 0;
+    B2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t row_bytes = (size_t)p->nb * TILE * sizeof(double);
+    const size_t budget = g_emb_budget_bytes ? (size_t)g_emb_budget_bytes
+                                             : (size_t)((double)(free_b + p->emb_bytes + emb_cache_bytes(p->device)) * 0.5);
+    int64_t QR = (int64_t)(budget / std::max<size_t>(row_bytes, 1)) / NODE_STRIPE * NODE_STRIPE;
+    if (QR < NODE_STRIPE) return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for one node stripe");
+    QR = std::min<int64_t>(QR, p->mpad);
+    int rc = ensure_emb(p, (size_t)QR * row_bytes);
+    if (rc) return rc;
+    if (!p->d_state) B2D_CUDA(b2d_malloc(&p->d_state, (size_t)MAX_STACK * p->npad * sizeof(long long)));
+    const bool decomposed = variant == 1 && p->order.decomposed && QR == p->mpad;
+    std::vector<long long> h((size_t)QR * p->nb * TILE);
+    std::vector<int32_t> id_of_q(p->mpad, -1);
+    for (int64_t id = 0; id < p->m; ++id) id_of_q[qof[id]] = (int32_t)id;
+    for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
+        const int64_t q1 = std::min<int64_t>(p->mpad, q0 + QR);
+        B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, (size_t)QR * row_bytes, p->stream));
+        k_scatter_dense<int64_t><<<sblocks, wpb * 32, 0, p->stream>>>(
+            p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->n, q0, q1, QR, (unsigned long long*)p->d_emb, 0);
+        if (decomposed) {
+            const int64_t nspans = (int64_t)p->order.spans.size() / 2;
+            if (nspans)
+                k_propagate_weighted_spans<<<dim3((unsigned)(p->npad / 128), (unsigned)nspans), 128, 0, p->stream>>>(
+                    (unsigned long long*)p->d_emb, p->d_flags1, p->d_spans, p->npad, QR);
+            k_propagate_weighted_top<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
+                (unsigned long long*)p->d_emb, p->d_top_pos, p->d_top_flags, (int64_t)p->order.top_pos.size(),
+                p->npad, QR);
+        } else {
+            k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
+                (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR, p->d_state,
+                p->order.depth_at[q0 / NODE_STRIPE]);
+        }
+        B2D_CUDA(cudaMemcpyAsync(h.data(), p->d_emb, (size_t)QR * row_bytes, cudaMemcpyDeviceToHost, p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        B2D_CUDA(cudaGetLastError());
+        for (int64_t q = q0; q < q1; ++q) {
+            const int32_t id = id_of_q[q];
+            if (id < 0) continue;
+            for (int64_t s = 0; s < p->n; ++s)
+                out[s * p->m + id] = h[((s / TILE) * QR + (q - q0)) * TILE + s % TILE];
+        }
+    }
+    return B2D_OK;
+}
+
 int64_t b2d_problem_result_len(const b2d_problem* p) { return p ? p->out_len : 0; }
 
 static void stripe_range(const b2d_problem* p, int64_t b, int64_t* first, int64_t* count) {
@@ -1942,10 +2080,11 @@ static void stripe_range(const b2d_problem* p, int64_t b, int64_t* first, int64_
     *count = cnt;
 }
 
-int b2d_problem_fetch(b2d_problem* p, double* out) {
+static int b2d_problem_fetch_impl(b2d_problem* p, double* out) {
     if (!p || !out) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!p->computed) return fail(B2D_ERR_STATE, "fetch before compute");
     B2D_CUDA(cudaSetDevice(p->device));
+    NvtxRange range("b2d:fetch (D2H)");
     B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
     for (int64_t b : p->owned) {
         int64_t first, cnt;
@@ -1961,11 +2100,12 @@ int b2d_problem_fetch(b2d_problem* p, double* out) {
     return B2D_OK;
 }
 
-int b2d_problem_fetch_compact(b2d_problem* p, double* out, int64_t* stripe_offsets,
+static int b2d_problem_fetch_compact_impl(b2d_problem* p, double* out, int64_t* stripe_offsets,
                               int64_t* n_stripes_out) {
     if (!p || (!out && p->out_len)) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!p->computed) return fail(B2D_ERR_STATE, "fetch before compute");
     B2D_CUDA(cudaSetDevice(p->device));
+    NvtxRange range("b2d:fetch_compact (D2H)");
     B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
     if (p->out_len)
         B2D_CUDA(cudaMemcpyAsync(out, p->d_out, p->out_len * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1986,7 +2126,7 @@ int b2d_problem_fetch_compact(b2d_problem* p, double* out, int64_t* stripe_offse
     return B2D_OK;
 }
 
-int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
+static int b2d_problem_sample_vector_impl(b2d_problem* p, double* out_n) {
     if (!p || !out_n) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!p->computed) return fail(B2D_ERR_STATE, "sample_vector before compute");
     B2D_CUDA(cudaSetDevice(p->device));
@@ -2041,7 +2181,7 @@ int b2d_beta_diversity_features(int metric, int device, int64_t n_samples, int64
     return rc;
 }
 
-int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe_offsets,
+static int b2d_shard_layout_impl(int64_t n_samples, int shard, int n_shards, int64_t* stripe_offsets,
                      int64_t* n_stripes_out, int64_t* total_out) {
     if (n_samples < 0 || n_shards < 1 || shard < 0 || shard >= n_shards)
         return fail(B2D_ERR_INVALID_ARGUMENT, "need n_samples >= 0 and 0 <= shard < n_shards");
@@ -2065,7 +2205,7 @@ int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe
     return B2D_OK;
 }
 
-int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_groupings,
+static int b2d_permanova_sw_impl(int device, int64_t n, const double* condensed, int64_t n_groupings,
                      const int32_t* groupings, int32_t n_groups, const double* inv_group_size,
                      double* s_w_out) {
     if (!condensed || !groupings || !inv_group_size || !s_w_out)
@@ -2102,11 +2242,107 @@ int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_g
     return B2D_OK;
 }
 
+// rows [r0, r1) of the square matrix / of the Gower-centred matrix from a condensed vector on the
+// device, staged through `d_stage` (rows_per_batch x n doubles) to the host
+static int square_or_centered_rows(const double* d_cond, int64_t n, int64_t r0, int64_t r1, const double* d_rm,
+                                   const double* d_gm, double* host_out, cudaStream_t st) {
+    if (r1 <= r0) return B2D_OK;
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(r1 - r0, ((int64_t)256 << 20) / (8 * std::max<int64_t>(n, 1))));
+    double* d_stage = nullptr;
+    B2D_CUDA(b2d_malloc(&d_stage, (size_t)per * n * sizeof(double)));
+    for (int64_t a = r0; a < r1; a += per) {
+        const int64_t b = std::min(r1, a + per);
+        if (d_rm)
+            k_center_fill<<<(unsigned)(b - a), 256, 0, st>>>(d_cond, n, a, d_rm, d_gm, d_stage);
+        else
+            k_square_rows<<<(unsigned)(b - a), 256, 0, st>>>(d_cond, n, a, d_stage);
+        B2D_CUDA(cudaMemcpyAsync(host_out + (a - r0) * n, d_stage, (size_t)(b - a) * n * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+        B2D_CUDA(cudaStreamSynchronize(st));
+    }
+    B2D_CUDA(cudaGetLastError());
+    b2d_free(d_stage);
+    return B2D_OK;
+}
+
+static int center_on_device(const double* d_cond, int64_t n, double* row_means, double* global_mean,
+                            double* f_out, cudaStream_t st) {
+    double *d_rs = nullptr, *d_rm = nullptr, *d_gm = nullptr;
+    B2D_CUDA(b2d_malloc(&d_rs, n * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&d_rm, n * sizeof(double)));
+    B2D_CUDA(b2d_malloc(&d_gm, sizeof(double)));
+    k_center_rowsums<<<(unsigned)n, 256, 0, st>>>(d_cond, n, d_rs, d_rm);
+    k_center_global<<<1, 256, 0, st>>>(d_rs, n, d_gm);
+    if (row_means) B2D_CUDA(cudaMemcpyAsync(row_means, d_rm, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (global_mean) B2D_CUDA(cudaMemcpyAsync(global_mean, d_gm, sizeof(double), cudaMemcpyDeviceToHost, st));
+    B2D_CUDA(cudaStreamSynchronize(st));
+    B2D_CUDA(cudaGetLastError());
+    int rc = B2D_OK;
+    if (f_out) rc = square_or_centered_rows(d_cond, n, 0, n, d_rm, d_gm, f_out, st);
+    b2d_free(d_rs);
+    b2d_free(d_rm);
+    b2d_free(d_gm);
+    return rc;
+}
+
+// a problem whose compact result IS the condensed vector: every stripe owned, nothing deselected
+static int whole_result(const b2d_problem* p) {
+    if (!p->computed) return fail(B2D_ERR_STATE, "no computed result on the device");
+    if (p->n_shards != 1 || p->custom_tiles || p->out_len != p->n * (p->n - 1) / 2)
+        return fail(B2D_ERR_STATE, "needs a problem that owns the whole triangle (one shard, no tile selection)");
+    return B2D_OK;
+}
+
+int b2d_problem_fetch_square_rows(b2d_problem* p, int64_t r0, int64_t r1, double* out) {
+    if (!p || !out) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    int rc = whole_result(p);
+    if (rc) return rc;
+    if (r0 < 0 || r1 < r0 || r1 > p->n) return fail(B2D_ERR_INVALID_ARGUMENT, "need 0 <= r0 <= r1 <= n_samples");
+    B2D_CUDA(cudaSetDevice(p->device));
+    NvtxRange range("b2d:fetch_square_rows");
+    B2D_GUARDED(square_or_centered_rows(p->d_out, p->n, r0, r1, nullptr, nullptr, out, p->stream));
+}
+
+int b2d_problem_center(b2d_problem* p, double* row_means, double* global_mean, double* f_matrix) {
+    if (!p) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    int rc = whole_result(p);
+    if (rc) return rc;
+    if (p->n < 1) return B2D_OK;
+    B2D_CUDA(cudaSetDevice(p->device));
+    NvtxRange range("b2d:center");
+    B2D_GUARDED(center_on_device(p->d_out, p->n, row_means, global_mean, f_matrix, p->stream));
+}
+
+int b2d_center_condensed(int device, int64_t n, const double* condensed, double* row_means,
+                         double* global_mean, double* f_matrix) {
+    if (n < 1 || (!condensed && n > 1)) return fail(B2D_ERR_INVALID_ARGUMENT, "need n >= 1 and a condensed vector");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2D_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(B2D_ERR_INVALID_ARGUMENT, "device index out of range");
+    B2D_CUDA(cudaSetDevice(device));
+    NvtxRange range("b2d:center");
+    const int64_t P = n * (n - 1) / 2;
+    double* d_cond = nullptr;
+    B2D_CUDA(b2d_malloc(&d_cond, std::max<int64_t>(P, 1) * sizeof(double)));
+    if (P) B2D_CUDA(cudaMemcpy(d_cond, condensed, P * sizeof(double), cudaMemcpyHostToDevice));
+    int rc;
+    try {
+        rc = center_on_device(d_cond, n, row_means, global_mean, f_matrix, 0);
+    } catch (const std::exception&) {
+        rc = fail(B2D_ERR_STATE, "internal error");
+    }
+    b2d_free(d_cond);
+    return rc;
+}
+
 struct b2d_flat_tree {
     FlatTree t;
 };
 
-int b2d_newick_parse(const char* text, int64_t len, b2d_flat_tree** out) {
+static int b2d_newick_parse_impl(const char* text, int64_t len, b2d_flat_tree** out) {
     if (!text || !out || len < 0) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
     b2d_flat_tree* h = new b2d_flat_tree();
     std::string err = parse_newick(text, len, h->t);
@@ -2136,7 +2372,7 @@ int b2d_flat_tree_get(const b2d_flat_tree* t, int32_t* parent, double* length, i
 
 void b2d_flat_tree_free(b2d_flat_tree* t) { delete t; }
 
-int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* length,
+static int b2d_debug_tree_order_impl(int64_t n_nodes, const int32_t* parent, const double* length,
                          int32_t* q_of_id, uint8_t* flags_mpad, double* len_q_mpad,
                          double* tipdist_q_mpad, int32_t* max_depth) {
     if (!parent || !length) return fail(B2D_ERR_INVALID_ARGUMENT, "parent/length is NULL");
@@ -2151,7 +2387,7 @@ int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* l
     return B2D_OK;
 }
 
-int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* length,
+static int b2d_debug_tree_paths_impl(int64_t n_nodes, const int32_t* parent, const double* length,
                          int32_t* parent_q_mpad, int32_t* size_q_mpad, double* rd_hi_mpad,
                          double* rd_lo_mpad, int32_t* tips_q_mpad, double* rd_hi_int_mpad,
                          double* rd_lo_int_mpad) {
@@ -2169,7 +2405,7 @@ int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* l
     return B2D_OK;
 }
 
-int b2d_microbench(int device, int kind, double* result) {
+static int b2d_microbench_impl(int device, int kind, double* result) {
     if (!result) return fail(B2D_ERR_INVALID_ARGUMENT, "result is NULL");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -2287,6 +2523,67 @@ int b2d_microbench(int device, int kind, double* result) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return B2D_OK;
+}
+
+
+int b2d_problem_create_tree(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes, const int32_t* parent, const double* length, const int64_t* indptr, const int32_t* node_ids, const int64_t* values, int shard, int n_shards) {
+    B2D_GUARDED(b2d_problem_create_tree_impl(out, device, n_samples, n_nodes, parent, length, indptr, node_ids, values, shard, n_shards));
+}
+
+int b2d_problem_create_features(b2d_problem** out, int device, int64_t n_samples, int64_t n_features, const int64_t* indptr, const int32_t* feature_ids, const double* values, int shard, int n_shards) {
+    B2D_GUARDED(b2d_problem_create_features_impl(out, device, n_samples, n_features, indptr, feature_ids, values, shard, n_shards));
+}
+
+int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_tiles) {
+    B2D_GUARDED(b2d_problem_select_tiles_impl(p, tiles, n_tiles));
+}
+
+int b2d_problem_compute(b2d_problem* p, int metric) {
+    B2D_GUARDED(b2d_problem_compute_impl(p, metric));
+}
+
+int b2d_problem_fetch(b2d_problem* p, double* out) {
+    B2D_GUARDED(b2d_problem_fetch_impl(p, out));
+}
+
+int b2d_problem_fetch_compact(b2d_problem* p, double* out, int64_t* stripe_offsets, int64_t* n_stripes_out) {
+    B2D_GUARDED(b2d_problem_fetch_compact_impl(p, out, stripe_offsets, n_stripes_out));
+}
+
+int b2d_problem_sample_vector(b2d_problem* p, double* out_n) {
+    B2D_GUARDED(b2d_problem_sample_vector_impl(p, out_n));
+}
+
+int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n) {
+    B2D_GUARDED(b2d_problem_phydiv_impl(p, rooted, weight, out_n));
+}
+
+int b2d_debug_fetch_embedding(b2d_problem* p, int variant, int64_t* out) {
+    B2D_GUARDED(b2d_debug_fetch_embedding_impl(p, variant, out));
+}
+
+int b2d_permanova_sw(int device, int64_t n, const double* condensed, int64_t n_groupings, const int32_t* groupings, int32_t n_groups, const double* inv_group_size, double* s_w_out) {
+    B2D_GUARDED(b2d_permanova_sw_impl(device, n, condensed, n_groupings, groupings, n_groups, inv_group_size, s_w_out));
+}
+
+int b2d_newick_parse(const char* text, int64_t len, b2d_flat_tree** out) {
+    B2D_GUARDED(b2d_newick_parse_impl(text, len, out));
+}
+
+int b2d_debug_tree_order(int64_t n_nodes, const int32_t* parent, const double* length, int32_t* q_of_id, uint8_t* flags_mpad, double* len_q_mpad, double* tipdist_q_mpad, int32_t* max_depth) {
+    B2D_GUARDED(b2d_debug_tree_order_impl(n_nodes, parent, length, q_of_id, flags_mpad, len_q_mpad, tipdist_q_mpad, max_depth));
+}
+
+int b2d_debug_tree_paths(int64_t n_nodes, const int32_t* parent, const double* length, int32_t* parent_q_mpad, int32_t* size_q_mpad, double* rd_hi_mpad, double* rd_lo_mpad, int32_t* tips_q_mpad, double* rd_hi_int_mpad, double* rd_lo_int_mpad) {
+    B2D_GUARDED(b2d_debug_tree_paths_impl(n_nodes, parent, length, parent_q_mpad, size_q_mpad, rd_hi_mpad, rd_lo_mpad, tips_q_mpad, rd_hi_int_mpad, rd_lo_int_mpad));
+}
+
+int b2d_shard_layout(int64_t n_samples, int shard, int n_shards, int64_t* stripe_offsets, int64_t* n_stripes_out, int64_t* total_out) {
+    B2D_GUARDED(b2d_shard_layout_impl(n_samples, shard, n_shards, stripe_offsets, n_stripes_out, total_out));
+}
+
+int b2d_microbench(int device, int kind, double* result) {
+    B2D_GUARDED(b2d_microbench_impl(device, kind, result));
 }
 
 }  // extern "C"

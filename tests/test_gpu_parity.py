@@ -957,3 +957,154 @@ def test_flagged_pairs_are_recomputed_alone():
     assert_close_rel(got, exp, UNIFRAC_RTOL, "three flagged pairs")
     assert got[2 * n - (2 + 2) * (2 + 1) // 2 + 3] == 0.0   # pair (2, 3): exact copies
     assert ms1 <= 1.25 * ms0 + 0.5, (ms0, ms1)
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_device_embedding_equals_vectorize_counts_and_tree(case):
+    """K1 pinned directly (mirrors /root/reference/skbio/diversity/tests/test_util.py:27-34): the
+    node-count matrix the device builds (CSR scatter + tree propagation) is, in reference id order,
+    exactly what vectorize_counts_and_tree returned for the same inputs - with the sequential walk,
+    with the subtree-decomposed walk, with the walk cut into node passes, and as presence bits."""
+    sb = _skbio_b200()
+    from oracle import oracle_np
+    from skbio_b200 import _capi, _driver
+
+    counts, parent, length, names = case_arrays(case)
+    exp = np.array(case["counts_by_node"], dtype=np.int64)
+    tree = sb.read_newick_flat(case["newick"])
+    p, l, ip, ids, vals, n = _driver._unifrac_host_arrays("weighted_unifrac", counts, case["taxa"], tree, False)
+    m = len(p)
+    assert exp.shape == (n, m)
+    with _capi.Problem.tree(p, l, ip, ids, vals, n) as prob:
+        assert np.array_equal(prob.fetch_embedding(0, m), exp)
+        assert np.array_equal(prob.fetch_embedding(1, m), exp)
+        try:
+            _capi.set_option("emb_budget_bytes", 128 * 8 * 128)   # one 128-node stripe per pass
+            assert np.array_equal(prob.fetch_embedding(0, m), exp)
+        finally:
+            _capi.set_option("emb_budget_bytes", 0)
+    # presence: the reference vectorises (counts > 0) for unweighted UniFrac (_driver.py:303-304)
+    p, l, ip, ids, vals, n = _driver._unifrac_host_arrays("unweighted_unifrac", counts, case["taxa"], tree, False)
+    with _capi.Problem.tree(p, l, ip, ids, None, n) as prob:
+        bits = prob.fetch_embedding(2, m)
+    pres = oracle_np.nodes_by_counts(np.atleast_2d(counts) > 0, case["taxa"], names,
+                                     oracle_np.child_index_from_parent(parent))
+    assert np.array_equal(bits, (np.asarray(pres).T > 0).astype(np.int64))
+
+
+@pytest.mark.parametrize("cat", [False, True])
+def test_device_embedding_random_trees_and_passes(cat):
+    """The same on seeded random inputs (random-join and caterpillar trees, 300 samples over three
+    sample blocks), whole tree resident and in several node passes, against the C oracle."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 300, 1500
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.03, 17, caterpillar=cat)
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    exp = oracle_fast.counts_by_node(dense, tip_node, parent)
+    m = len(parent)
+    with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+        assert np.array_equal(prob.fetch_embedding(0, m), exp)
+        assert np.array_equal(prob.fetch_embedding(1, m), exp)
+        try:
+            _capi.set_option("emb_budget_bytes", 384 * 8 * 256)   # 256 node rows per pass
+            assert np.array_equal(prob.fetch_embedding(0, m), exp)
+        finally:
+            _capi.set_option("emb_budget_bytes", 0)
+        assert np.array_equal(prob.fetch_embedding(2, m), (exp > 0).astype(np.int64))
+
+
+def test_devices_argument_runs_one_shard_per_host_thread():
+    """beta_diversity(..., devices=[0, 0]): two shards, two host threads, (here) one device, each
+    writing its own stripes of one condensed vector - identical to the single-shard call
+    (tiles == full, /root/reference/skbio/diversity/_block.py:263-356)."""
+    sb = _skbio_b200()
+    from skbio_b200 import synthetic
+
+    n, tips = 700, 1200
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.04, 23)
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    tree = sb.FlatTree(parent, length, names)
+    taxa = [f"T{i}" for i in range(tips)]
+    for metric, kw in (("weighted_unifrac", {"normalized": True}), ("unweighted_unifrac", {}),
+                       ("braycurtis", {}), ("jaccard", {})):
+        if "unifrac" in metric:
+            kw = dict(kw, tree=tree, taxa=taxa)
+        one = sb.beta_diversity(metric, dense, **kw).condensed_form()
+        for devs in ([0, 0], [0, 0, 0]):
+            many = sb.beta_diversity(metric, dense, devices=devs, **kw).condensed_form()
+            assert np.array_equal(one, many, equal_nan=True), (metric, devs)
+
+
+def test_pcoa_centering_and_square_rows_on_the_resident_result():
+    """Gower centering (pcoa's first step, /root/reference/skbio/stats/ordination/_cutils.pyx:19-123)
+    and square-row gathering on the device-resident condensed result, against NumPy on the fetched
+    vector (and against scikit-bio's own center_distance_matrix where the reference build is here)."""
+    sb = _skbio_b200()
+    from skbio_b200 import _capi
+    from skbio_b200._dm import squareform
+
+    n, tips = 333, 900
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.05, 33)
+    with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+        prob.compute("weighted_unifrac_normalized")
+        vec = prob.fetch(np.empty(n * (n - 1) // 2))
+        f, rm, gm = prob.center()
+        rows = prob.fetch_square_rows(100, 229)
+        text = __import__("io").StringIO()
+        sb.write_lsmat(prob, text, ids=[f"s{i}" for i in range(n)], block_rows=100)
+    sq = squareform(vec, n)
+    assert np.array_equal(rows, sq[100:229])
+    e = -0.5 * sq * sq
+    erm = e.mean(axis=1)
+    ef = e + ((e.mean() - erm)[:, None] - erm[None, :])
+    assert np.allclose(rm, erm, rtol=1e-13, atol=0)
+    assert abs(gm - e.mean()) <= 1e-13 * abs(e.mean())
+    assert np.allclose(f, ef, rtol=0, atol=1e-13 * np.abs(ef).max())
+    f2 = sb.center_distance_matrix(vec)
+    assert np.array_equal(f2, f)
+    lines = text.getvalue().split("\n")
+    assert lines[0].split("\t")[1:] == [f"s{i}" for i in range(n)]
+    assert lines[5].split("\t")[0] == "s4" and [float(x) for x in lines[5].split("\t")[1:]] == list(sq[4])
+    from oracle import ref_skbio
+
+    if ref_skbio.available():
+        ref_skbio.load()
+        from skbio.stats.ordination._principal_coordinate_analysis import center_distance_matrix
+
+        assert np.allclose(f, center_distance_matrix(sq), rtol=0, atol=1e-13 * np.abs(ef).max())
+    # a sharded problem has no whole result on one device
+    with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n, shard=0, n_shards=2) as prob:
+        prob.compute("weighted_unifrac")
+        with pytest.raises(_capi.EngineError, match="whole triangle"):
+            prob.center()
+
+
+def test_sparse_table_50k_by_50k_through_the_public_api():
+    """BASELINE config 3 at full size through beta_diversity() with a scipy.sparse table (stays
+    sparse all the way to the device): Bray-Curtis and Jaccard, bit-exact on the pairs among 96
+    samples spread over the table (SciPy on the densified rows), condensed result by default."""
+    sb = _skbio_b200()
+    import scipy.sparse as sp
+    from scipy.spatial.distance import pdist
+
+    from skbio_b200 import synthetic
+
+    n = f = 50000
+    indptr, cols, vals = synthetic.poisson_csr(n, f, 0.01, seed=0)
+    table = sp.csr_matrix((vals, cols, indptr), shape=(n, f))
+    pick = np.unique(np.concatenate([np.arange(0, 40), np.arange(24990, 25020), np.arange(n - 26, n)]))
+    dense = np.asarray(table[pick].todense())
+    for metric in ("braycurtis", "jaccard"):
+        dm = sb.beta_diversity(metric, table)
+        vec = dm.condensed_form()
+        assert vec.shape == (n * (n - 1) // 2,)
+        i, j = np.triu_indices(len(pick), k=1)
+        gi, gj = pick[i], pick[j]
+        got = vec[gi * n - ((gi + 2) * (gi + 1)) // 2 + gj]
+        with np.errstate(all="ignore"):
+            exp = pdist(dense > 0, "jaccard") if metric == "jaccard" else pdist(dense.astype(np.float64), "braycurtis")
+        assert np.array_equal(got, exp, equal_nan=True), metric
+        del dm, vec
