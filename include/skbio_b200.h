@@ -95,6 +95,30 @@ int b2d_problem_create_tree(b2d_problem** out, int device,
                             const int64_t* values,
                             int shard, int n_shards);
 
+/* The same with the CSR indices given as TABLE COLUMNS plus a column -> node id table
+ * (node_of_col[n_cols], -1 for a column whose taxon is not in the tree; such a column must not be
+ * observed): the composition column -> node -> engine position happens on the device, so the host
+ * never rewrites the nnz-long index array (20 M entries at config 2). */
+int b2d_problem_create_tree_columns(b2d_problem** out, int device,
+                                    int64_t n_samples, int64_t n_nodes,
+                                    const int32_t* parent, const double* length,
+                                    const int64_t* indptr, const int32_t* col_ids,
+                                    const int64_t* values, const int32_t* node_of_col,
+                                    int64_t n_cols, int shard, int n_shards);
+
+/* Host only: taxon name -> node id with the reference's lookup semantics (every node name scanned in
+ * id order, a later node with the same name wins, /root/reference/skbio/diversity/_phylogenetic.pyx:195-199);
+ * names and queries are byte blobs with offsets [count + 1] (every query entry is followed by
+ * query_sep separator bytes that are not part of the name); out[k] = node id or -1.
+ * b2d_names_validate: the name checks of _validate_taxa_and_tree (/root/reference/skbio/tree/_utils.py:83-90):
+ * *dup_tips = a tip name occurs twice, *n_missing = distinct query names that are not tip names. */
+int b2d_names_lookup(const char* name_buf, const int64_t* name_off, const uint8_t* has_name, int64_t n_names,
+                     const char* query_buf, const int64_t* query_off, int64_t n_queries, int query_sep,
+                     int32_t* out);
+int b2d_names_validate(const char* name_buf, const int64_t* name_off, const uint8_t* has_name,
+                       const int32_t* parent, int64_t n_names, const char* query_buf, const int64_t* query_off,
+                       int64_t n_queries, int query_sep, int* dup_tips, int64_t* n_missing);
+
 /*
  * Feature-table problem (Bray-Curtis, Jaccard): CSR sample x feature, values fp64 (SciPy
  * promotes the table to double, scipy/spatial/distance.py pdist); values may be NULL for

@@ -55,6 +55,17 @@ def _declare(lib):
     lib.b2d_problem_create_tree.argtypes = [
         ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
         _i32p, _f64p, _i64p, _i32p, _i64p, ctypes.c_int, ctypes.c_int]
+    lib.b2d_problem_create_tree_columns.restype = ctypes.c_int
+    lib.b2d_problem_create_tree_columns.argtypes = [
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+        _i32p, _f64p, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    lib.b2d_names_lookup.restype = ctypes.c_int
+    lib.b2d_names_lookup.argtypes = [ctypes.c_char_p, _i64p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int64,
+                                     ctypes.c_char_p, _i64p, ctypes.c_int64, ctypes.c_int, _i32p]
+    lib.b2d_names_validate.restype = ctypes.c_int
+    lib.b2d_names_validate.argtypes = [ctypes.c_char_p, _i64p, ctypes.POINTER(ctypes.c_uint8), _i32p,
+                                       ctypes.c_int64, ctypes.c_char_p, _i64p, ctypes.c_int64, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_int), _i64p]
     lib.b2d_problem_create_features.restype = ctypes.c_int
     lib.b2d_problem_create_features.argtypes = [
         ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
@@ -129,6 +140,7 @@ EXPORTED_SYMBOLS = [
     "b2d_newick_parse", "b2d_flat_tree_nodes", "b2d_flat_tree_name_bytes", "b2d_flat_tree_get",
     "b2d_flat_tree_free", "b2d_permanova_sw", "b2d_problem_phydiv", "b2d_debug_fetch_embedding",
     "b2d_problem_fetch_square_rows", "b2d_problem_center", "b2d_center_condensed",
+    "b2d_problem_create_tree_columns", "b2d_names_lookup", "b2d_names_validate",
 ]
 
 
@@ -225,9 +237,69 @@ def center_condensed(condensed, device=0, want_matrix=True):
     return f, rm, gm.value
 
 
+class NameBlob:
+    """Node names as one UTF-8 byte buffer with offsets (no per-node Python strings)."""
+
+    __slots__ = ("buf", "off", "has")
+
+    def __init__(self, buf, off, has):
+        self.buf = buf                                   # bytes
+        self.off = np.ascontiguousarray(off, dtype=np.int64)   # [m + 1]
+        self.has = np.ascontiguousarray(has, dtype=np.uint8)   # [m]
+
+    def decode(self):
+        m = len(self.has)
+        text = self.buf.decode("utf-8")
+        offl = self.off.tolist()
+        if len(text) != len(self.buf):   # multi-byte characters: slice the bytes
+            names = [self.buf[offl[k]:offl[k + 1]].decode("utf-8") for k in range(m)]
+        else:
+            names = [text[offl[k]:offl[k + 1]] for k in range(m)]
+        out = np.empty(m, dtype=object)
+        out[:] = names
+        out[self.has == 0] = None
+        return out
+
+
+def query_blob(names):
+    """(bytes, offsets int64[k + 1]) of a list of strings."""
+    names = [x if isinstance(x, str) else str(x) for x in names]
+    joined = "\0".join(names)
+    buf = joined.encode("utf-8")
+    off = np.zeros(len(names) + 1, dtype=np.int64)
+    if len(buf) == len(joined):     # ASCII: byte lengths are the string lengths
+        np.cumsum(np.fromiter(map(len, names), dtype=np.int64, count=len(names)) + 1, out=off[1:])
+    else:
+        np.cumsum([len(x.encode("utf-8")) + 1 for x in names], out=off[1:])
+    # the separators are part of the buffer but of no entry: entry k is buf[off[k] : off[k + 1] - 1]
+    return buf + b"\0", off
+
+
+def names_lookup(blob, queries, qblob=None):
+    """Node id (last node carrying the name wins) or -1 for every query string - host only."""
+    qb, qo = qblob if qblob is not None else query_blob(queries)
+    out = np.empty(len(queries), dtype=np.int32)
+    _check(load().b2d_names_lookup(blob.buf, _ptr(blob.off, _i64p),
+                                   blob.has.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), len(blob.has),
+                                   qb, _ptr(qo, _i64p), len(queries), 1, _ptr(out, _i32p)))
+    return out
+
+
+def names_validate(blob, parent, queries, qblob=None):
+    """(a tip name occurs twice, number of distinct queries that are not tip names) - host only."""
+    qb, qo = qblob if qblob is not None else query_blob(queries)
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    dup, missing = ctypes.c_int(0), ctypes.c_int64(0)
+    _check(load().b2d_names_validate(blob.buf, _ptr(blob.off, _i64p),
+                                     blob.has.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                     _ptr(parent, _i32p), len(blob.has), qb, _ptr(qo, _i64p), len(queries), 1,
+                                     ctypes.byref(dup), ctypes.byref(missing)))
+    return bool(dup.value), int(missing.value)
+
+
 def newick_to_flat(text):
-    """(parent int32[m], length float64[m] with NaN for 'no length', names object[m]) straight
-    from Newick text, in the reference's node id order - no node objects (host only)."""
+    """(parent int32[m], length float64[m] with NaN for 'no length', NameBlob) straight from
+    Newick text, in the reference's node id order - no node objects (host only)."""
     lib = load()
     raw = text.encode("utf-8") if isinstance(text, str) else bytes(text)
     h = ctypes.c_void_p()
@@ -244,13 +316,7 @@ def newick_to_flat(text):
                                      has.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), buf))
     finally:
         lib.b2d_flat_tree_free(h)
-    blob = buf.raw[:nb]
-    names = np.empty(m, dtype=object)
-    hasl = has.tolist()
-    offl = off.tolist()
-    for k in range(m):
-        names[k] = blob[offl[k]:offl[k + 1]].decode("utf-8") if hasl[k] else None
-    return parent, length, names
+    return parent, length, NameBlob(buf.raw[:nb], off, has)
 
 
 def shard_layout(n_samples, shard, n_shards):
@@ -351,7 +417,9 @@ class Problem:
 
     @classmethod
     def tree(cls, parent, length, indptr, node_ids, values, n_samples, device=0, shard=0,
-             n_shards=1):
+             n_shards=1, node_of_col=None):
+        """`node_ids` are node ids, or - with `node_of_col` - table columns that the device maps
+        through that table (column -> node id)."""
         lib = load()
         parent = np.ascontiguousarray(parent, dtype=np.int32)
         length = np.ascontiguousarray(length, dtype=np.float64)
@@ -360,10 +428,18 @@ class Problem:
         if values is not None:
             values = np.ascontiguousarray(values, dtype=np.int64)
         h = ctypes.c_void_p()
-        _check(lib.b2d_problem_create_tree(
-            ctypes.byref(h), int(device), int(n_samples), int(len(parent)),
-            _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(indptr, _i64p),
-            _ptr(node_ids, _i32p), _ptr(values, _i64p), int(shard), int(n_shards)))
+        if node_of_col is not None:
+            node_of_col = np.ascontiguousarray(node_of_col, dtype=np.int32)
+            _check(lib.b2d_problem_create_tree_columns(
+                ctypes.byref(h), int(device), int(n_samples), int(len(parent)),
+                _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(indptr, _i64p),
+                _ptr(node_ids, _i32p), _ptr(values, _i64p), _ptr(node_of_col, _i32p), len(node_of_col),
+                int(shard), int(n_shards)))
+        else:
+            _check(lib.b2d_problem_create_tree(
+                ctypes.byref(h), int(device), int(n_samples), int(len(parent)),
+                _ptr(parent, _i32p), _ptr(length, _f64p), _ptr(indptr, _i64p),
+                _ptr(node_ids, _i32p), _ptr(values, _i64p), int(shard), int(n_shards)))
         return cls(h, int(n_samples))
 
     @classmethod

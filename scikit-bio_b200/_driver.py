@@ -30,7 +30,8 @@ import numpy as np
 from . import _capi
 from ._dm import make_distance_matrix
 from ._table import ingest_table, to_csr, validate_counts_matrix, _is_sparse
-from ._tree import FlatTree, flatten_tree, map_taxa_to_nodes, validate_taxa_and_tree
+from ._tree import (FlatTree, flatten_for_engine, flatten_tree, map_all_taxa, map_taxa_to_nodes,
+                    validate_taxa_and_tree)
 
 # /root/reference/skbio/diversity/_driver.py:43-52
 _qualitative_metrics = {
@@ -210,36 +211,58 @@ def beta_diversity(metric, counts, ids=None, validate=True, pairwise_func=None, 
 def _unifrac_host_arrays(key, counts, taxa, tree, validate):
     """Host half of the UniFrac path: validate, flatten, CSR, name lookup.  Returns the flat
     arrays the C ABI takes: ``(parent, length, indptr, node_ids, values, n_samples)``."""
+    h = _unifrac_host(key, counts, taxa, tree, validate)
+    ids = h["ids"] if h["node_of_col"] is None else h["node_of_col"][h["ids"]]
+    return h["parent"], h["length"], h["indptr"], ids, h["vals"], h["n"]
+
+
+def _unifrac_host(key, counts, taxa, tree, validate):
+    """validate -> flatten -> CSR -> taxon lookup.  The nnz-long index array is never rewritten on
+    the host: in the normal case the CSR keeps its table COLUMNS and the device applies the column
+    -> node table (``node_of_col``); only when several observed columns share a node (reachable
+    with validate=False) is the table applied here, followed by the reference's last-column-wins
+    rule."""
     t0 = time.perf_counter()
+    # the taxon names as one byte buffer, built once for the native name checks and the lookup
+    qblob = _capi.query_blob(taxa) if isinstance(tree, FlatTree) and tree._names is None else None
     if validate:
-        validate_taxa_and_tree(taxa, tree)
+        validate_taxa_and_tree(taxa, tree, _qblob=qblob)
     t1 = time.perf_counter()
-    parent, length, names = flatten_tree(tree)
+    parent, length, names = flatten_for_engine(tree)
     t2 = time.perf_counter()
     mode = "presence" if key == "unweighted_unifrac" else "int64"
     indptr, cols, vals = to_csr(counts, mode)
     t3 = time.perf_counter()
     n = counts.shape[0]
-    observed = np.zeros(counts.shape[1], dtype=bool)
-    observed[cols] = True
-    observed_cols = np.flatnonzero(observed)
-    node_of_col = map_taxa_to_nodes(taxa, observed_cols, names)
-    node_ids = node_of_col[cols]
-    if len(np.unique(node_of_col[observed_cols])) != len(observed_cols):
-        indptr, node_ids, vals = _dedupe_last_wins(indptr, cols, node_ids, vals)
+    node_of_col = map_all_taxa(taxa, names, qblob)
+    mapped = node_of_col[node_of_col >= 0]
+    out = dict(parent=parent, length=length, indptr=indptr, ids=cols, vals=vals, n=n,
+               node_of_col=node_of_col)
+    shared = len(mapped) and int(np.bincount(mapped, minlength=len(parent)).max()) > 1
+    if shared or len(mapped) != len(node_of_col):
+        # rare: duplicate nodes among the taxa, or taxa without a node - decide on the OBSERVED columns
+        observed = np.zeros(counts.shape[1], dtype=bool)
+        observed[cols] = True
+        observed_cols = np.flatnonzero(observed)
+        node_of_obs = map_taxa_to_nodes(taxa, observed_cols, names)   # KeyError for a missing one
+        if len(np.unique(node_of_obs[observed_cols])) != len(observed_cols):
+            indptr, ids, vals = _dedupe_last_wins(indptr, cols, node_of_obs[cols], vals)
+            out.update(indptr=indptr, ids=ids, vals=vals, node_of_col=None)
+        else:
+            out.update(node_of_col=node_of_obs)
     t4 = time.perf_counter()
     _profile.clear()
     _profile.update(validate_s=t1 - t0, flatten_s=t2 - t1, csr_s=t3 - t2, lookup_s=t4 - t3)
-    return parent, length, indptr, node_ids, vals, n
+    return out
 
 
 def _prepare_unifrac_problem(key, counts, taxa, tree, validate):
     """Host arrays -> factory of shards (one problem per device)."""
-    parent, length, indptr, node_ids, vals, n = _unifrac_host_arrays(key, counts, taxa, tree, validate)
+    h = _unifrac_host(key, counts, taxa, tree, validate)
 
     def make(dev, shard=0, nshards=1):
-        return _capi.Problem.tree(parent, length, indptr, node_ids, vals, n, device=dev,
-                                  shard=shard, n_shards=nshards)
+        return _capi.Problem.tree(h["parent"], h["length"], h["indptr"], h["ids"], h["vals"], h["n"],
+                                  device=dev, shard=shard, n_shards=nshards, node_of_col=h["node_of_col"])
 
     return make
 

@@ -109,19 +109,20 @@ def to_csr(counts, mode):
     """
     if _is_sparse(counts):
         csr = counts.tocsr()
-        csr.sort_indices()
         data = csr.data
+        # the common case - every stored entry counts - passes the caller's arrays on untouched
         if mode == "presence":
-            keep = data > 0.0
+            nkeep = int(np.count_nonzero(data > 0.0))
         elif mode == "int64":
-            data = data.astype(np.int64)
-            keep = data != 0
+            data = data.astype(np.int64, copy=False)
+            nkeep = int(np.count_nonzero(data))
         else:
-            data = data.astype(np.float64)
-            keep = data != 0
+            data = data.astype(np.float64, copy=False)
+            nkeep = int(np.count_nonzero(data))
         indptr = csr.indptr.astype(np.int64)
         cols = csr.indices
-        if not keep.all():
+        if nkeep != len(data):
+            keep = (csr.data > 0.0) if mode == "presence" else (data != 0)
             rows = np.repeat(np.arange(csr.shape[0]), np.diff(indptr))[keep]
             cols = cols[keep]
             data = data[keep]

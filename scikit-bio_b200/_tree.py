@@ -201,17 +201,28 @@ class FlatTree:
 
     Accepted wherever ``beta_diversity`` takes ``tree=``; skips node objects altogether.
     ``length`` holds NaN where the source gave no branch length (``None`` on a TreeNode).
-    Build one with ``read_newick_flat`` (native parser) or from your own arrays.
+    Build one with ``read_newick_flat`` (native parser: the names then stay one byte buffer,
+    ``name_blob``, and ``names`` is only decoded if somebody asks) or from your own arrays.
     """
 
-    __slots__ = ("parent", "length", "names")
+    __slots__ = ("parent", "length", "_names", "name_blob")
 
-    def __init__(self, parent, length, names):
+    def __init__(self, parent, length, names=None, name_blob=None):
         self.parent = np.ascontiguousarray(parent, dtype=np.int32)
         self.length = np.ascontiguousarray(length, dtype=np.float64)
-        self.names = np.asarray(names, dtype=object)
-        if not (len(self.parent) == len(self.length) == len(self.names)):
+        self.name_blob = name_blob
+        self._names = None if names is None else np.asarray(names, dtype=object)
+        if names is None and name_blob is None:
+            raise ValueError("FlatTree needs names (or a name_blob)")
+        m = len(self._names) if self._names is not None else len(name_blob.has)
+        if not (len(self.parent) == len(self.length) == m):
             raise ValueError("parent, length and names must have the same length")
+
+    @property
+    def names(self):
+        if self._names is None:
+            self._names = self.name_blob.decode()
+        return self._names
 
     def __len__(self):
         return len(self.parent)
@@ -223,14 +234,14 @@ class FlatTree:
 
 
 def read_newick_flat(text):
-    """Newick text (or an open file / path-like ending in a Newick file) -> ``FlatTree``,
-    parsed natively (libskbb200) straight into reference id order."""
+    """Newick text (or an open file) -> ``FlatTree``, parsed natively (libskbb200) straight into
+    reference id order."""
     from . import _capi
 
     if hasattr(text, "read"):
         text = text.read()
-    parent, length, names = _capi.newick_to_flat(text)
-    return FlatTree(parent, length, names)
+    parent, length, blob = _capi.newick_to_flat(text)
+    return FlatTree(parent, length, name_blob=blob)
 
 
 def _root_of(tree):
@@ -241,6 +252,16 @@ def _root_of(tree):
     while getattr(node, "parent", None) is not None:
         node = node.parent
     return node
+
+
+def flatten_for_engine(tree):
+    """``flatten_tree`` for the engine's host path: the names of a natively parsed ``FlatTree`` stay
+    a ``NameBlob`` (no per-node Python strings are ever made)."""
+    if isinstance(tree, FlatTree) and tree._names is None:
+        length = tree.length.copy()
+        length[np.isnan(length)] = 0.0
+        return tree.parent, length, tree.name_blob
+    return flatten_tree(tree)
 
 
 def flatten_tree(tree, assign_ids=True):
@@ -291,7 +312,7 @@ def flatten_tree(tree, assign_ids=True):
     return parent, length, names
 
 
-def validate_taxa_and_tree(taxa, tree, rooted=True):
+def validate_taxa_and_tree(taxa, tree, rooted=True, _qblob=None):
     """Same checks, order, exception types and messages as the reference's
     ``_validate_taxa_and_tree(taxa, tree, rooted=True, lengths=True)``
     (/root/reference/skbio/tree/_utils.py:29-90)."""
@@ -304,14 +325,20 @@ def validate_taxa_and_tree(taxa, tree, rooted=True):
             raise ValueError("The tree must be rooted.")
         if np.isnan(tree.length[: m - 1]).any():
             raise ValueError("All non-root nodes in the tree must have a branch length.")
-        tip_names = list(tree.names[:m][tree.tip_mask()]) if m > 1 else []
-        tip_name_set = set(tip_names)
-        if len(tip_names) != len(tip_name_set):
+        if tree._names is None:   # names still one byte buffer: the name checks run natively
+            from . import _capi
+
+            dup, n_missing = _capi.names_validate(tree.name_blob, tree.parent, list(taxa), _qblob)
+        else:
+            tip_names = list(tree.names[:m][tree.tip_mask()]) if m > 1 else []
+            tip_name_set = set(tip_names)
+            dup = len(tip_names) != len(tip_name_set)
+            n_missing = len(taxon_set - tip_name_set)
+        if dup:
             raise DuplicateNodeError("All tip names in the tree must be unique.")
-        missing = taxon_set - tip_name_set
-        if missing:
+        if n_missing:
             raise MissingNodeError(
-                f"{len(missing)} taxa are not present as tip names in the tree.")
+                f"{n_missing} taxa are not present as tip names in the tree.")
         return
     if rooted and len(_root_of(tree).children) > 2:
         raise ValueError("The tree must be rooted.")
@@ -331,22 +358,31 @@ def validate_taxa_and_tree(taxa, tree, rooted=True):
         )
 
 
-def map_taxa_to_nodes(taxa, observed_cols, names):
-    """Node id for every *observed* taxon column; ``-1`` for unobserved columns.
+def map_all_taxa(taxa, names, _qblob=None):
+    """Node id of every taxon, ``-1`` where no node carries the name.
 
-    Mirrors the lookup in ``_nodes_by_counts`` (_phylogenetic.pyx:190-206): all node names
-    are scanned in id order, tips and internal nodes alike, and a later node with the same
-    name overwrites an earlier one.  An observed taxon that matches no node raises
-    ``KeyError`` exactly like the reference's ``node_lookup[n]`` does (only reachable with
-    ``validate=False``).
-    """
-    out = np.full(len(taxa), -1, dtype=np.int32)
-    if len(observed_cols) == 0:
-        return out
-    # one dict over all node names, built in id order: a later node overwrites an earlier one
+    Mirrors the lookup in ``_nodes_by_counts`` (_phylogenetic.pyx:190-206): all node names are
+    scanned in id order, tips and internal nodes alike, and a later node with the same name
+    overwrites an earlier one.  `names` is an object array or a ``NameBlob`` (native lookup)."""
+    from . import _capi
+
+    taxa_list = taxa.tolist() if isinstance(taxa, np.ndarray) else list(taxa)
+    if isinstance(names, _capi.NameBlob):
+        return _capi.names_lookup(names, taxa_list, _qblob)
     lookup = dict(zip(names.tolist() if isinstance(names, np.ndarray) else list(names), range(len(names))))
     lookup.pop(None, None)
-    taxa_list = taxa.tolist() if isinstance(taxa, np.ndarray) else list(taxa)
-    cols = observed_cols.tolist() if isinstance(observed_cols, np.ndarray) else list(observed_cols)
-    out[cols] = [lookup[taxa_list[c]] for c in cols]   # KeyError(taxon) like node_lookup[n]
+    return np.fromiter((lookup.get(t, -1) for t in taxa_list), dtype=np.int32, count=len(taxa_list))
+
+
+def map_taxa_to_nodes(taxa, observed_cols, names):
+    """Node id for every *observed* taxon column; ``-1`` for unobserved columns.  An observed
+    taxon that matches no node raises ``KeyError`` exactly like the reference's
+    ``node_lookup[n]`` does (only reachable with ``validate=False``)."""
+    node_of_col = map_all_taxa(taxa, names)
+    out = np.full(len(node_of_col), -1, dtype=np.int32)
+    observed_cols = np.asarray(observed_cols, dtype=np.int64)
+    out[observed_cols] = node_of_col[observed_cols]
+    bad = observed_cols[out[observed_cols] < 0]
+    if len(bad):
+        raise KeyError(taxa[int(bad[0])])
     return out

@@ -57,11 +57,24 @@ static bool plain_kernels() {
     return g_plain_kernels == 1;
 }
 
-__global__ void k_map_ids(const int32_t* ids, const int32_t* __restrict__ q_of_id,
-                          int32_t* qidx, int64_t nnz, int64_t m, int* err) {
+__global__ void k_map_ids(const int32_t* ids, const int32_t* __restrict__ node_of_col, int64_t n_cols,
+                          const int32_t* __restrict__ q_of_id, int32_t* qidx, int64_t nnz, int64_t m, int* err) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     int32_t id = ids[e];
+    if (node_of_col) {  // ids are table columns: column -> node id first
+        if (id < 0 || id >= n_cols) {
+            *err = 1;
+            qidx[e] = 0;
+            return;
+        }
+        id = node_of_col[id];
+        if (id < 0) {   // an observed column whose taxon is not in the tree
+            atomicMax(err, 2);
+            qidx[e] = 0;
+            return;
+        }
+    }
     if (id < 0 || id >= m) {
         *err = 1;
         qidx[e] = 0;
@@ -493,7 +506,8 @@ static int upload(T** dst, const T* src, size_t count, cudaStream_t s) {
 }
 
 static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* ids,
-                        const void* values, size_t value_size) {
+                        const void* values, size_t value_size, const int32_t* node_of_col = nullptr,
+                        int64_t n_cols = 0) {
     cudaEvent_t e0, e1;
     NvtxRange range("b2d:create (H2D of tree + CSR)");
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
@@ -527,22 +541,26 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     // node id -> engine position, on the device
     {
         int32_t* d_qof = nullptr;
+        int32_t* d_noc = nullptr;
         int* d_err = nullptr;
         if (p->kind == 0) {
             if ((rc = upload(&d_qof, o.q_of_id.data(), o.q_of_id.size(), p->stream))) return rc;
         }
+        if (node_of_col && (rc = upload(&d_noc, node_of_col, (size_t)n_cols, p->stream))) return rc;
         B2D_CUDA(b2d_malloc(&d_err, sizeof(int)));
         B2D_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), p->stream));
         if (p->nnz) {
             int64_t blocks = (p->nnz + 255) / 256;
-            k_map_ids<<<(unsigned)blocks, 256, 0, p->stream>>>(p->d_qidx, d_qof, p->d_qidx, p->nnz,
-                                                               p->m, d_err);
+            k_map_ids<<<(unsigned)blocks, 256, 0, p->stream>>>(p->d_qidx, d_noc, n_cols, d_qof, p->d_qidx,
+                                                               p->nnz, p->m, d_err);
         }
         int herr = 0;
         B2D_CUDA(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
         b2d_free(d_qof);
+        b2d_free(d_noc);
         b2d_free(d_err);
+        if (herr == 2) return fail(B2D_ERR_INVALID_ARGUMENT, "an observed column maps to no node (node_of_col < 0)");
         if (herr) return fail(B2D_ERR_INVALID_ARGUMENT, "node/feature id out of range in CSR indices");
     }
     // shard geometry: owned row stripes, tiles, compact output offsets
@@ -701,10 +719,10 @@ int b2d_set_option(const char* name, int64_t value) {
     return B2D_OK;
 }
 
-static int b2d_problem_create_tree_impl(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes,
+static int create_tree_common(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes,
                             const int32_t* parent, const double* length, const int64_t* indptr,
                             const int32_t* node_ids, const int64_t* values, int shard,
-                            int n_shards) {
+                            int n_shards, const int32_t* node_of_col, int64_t n_cols) {
     int rc = check_common(out, device, n_samples, n_nodes, indptr, node_ids, shard, n_shards);
     if (rc) return rc;
     if (!parent || !length) return fail(B2D_ERR_INVALID_ARGUMENT, "parent/length is NULL");
@@ -733,13 +751,50 @@ static int b2d_problem_create_tree_impl(b2d_problem** out, int device, int64_t n
             p->tips_mode = -1;
             break;
         }
-    rc = setup_common(p, indptr, node_ids, values, sizeof(int64_t));
+    rc = setup_common(p, indptr, node_ids, values, sizeof(int64_t), node_of_col, n_cols);
     if (rc) {
         free_problem(p);
         return rc;
     }
     *out = p;
     return B2D_OK;
+}
+
+static int b2d_problem_create_tree_impl(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes,
+                            const int32_t* parent, const double* length, const int64_t* indptr,
+                            const int32_t* node_ids, const int64_t* values, int shard,
+                            int n_shards) {
+    return create_tree_common(out, device, n_samples, n_nodes, parent, length, indptr, node_ids, values, shard,
+                              n_shards, nullptr, 0);
+}
+
+int b2d_problem_create_tree_columns(b2d_problem** out, int device, int64_t n_samples, int64_t n_nodes,
+                                    const int32_t* parent, const double* length, const int64_t* indptr,
+                                    const int32_t* col_ids, const int64_t* values, const int32_t* node_of_col,
+                                    int64_t n_cols, int shard, int n_shards) {
+    if (!node_of_col || n_cols < 0) return fail(B2D_ERR_INVALID_ARGUMENT, "node_of_col is NULL");
+    B2D_GUARDED(create_tree_common(out, device, n_samples, n_nodes, parent, length, indptr, col_ids, values, shard,
+                                   n_shards, node_of_col, n_cols));
+}
+
+int b2d_names_lookup(const char* name_buf, const int64_t* name_off, const uint8_t* has_name, int64_t n_names,
+                     const char* query_buf, const int64_t* query_off, int64_t n_queries, int query_sep,
+                     int32_t* out) {
+    if (!name_off || !has_name || !query_off || (!out && n_queries))
+        return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (query_sep < 0) return fail(B2D_ERR_INVALID_ARGUMENT, "query_sep must be >= 0");
+    B2D_GUARDED((lookup_names(name_buf, name_off, has_name, n_names, query_buf, query_off, n_queries, query_sep, out),
+                 B2D_OK));
+}
+
+int b2d_names_validate(const char* name_buf, const int64_t* name_off, const uint8_t* has_name,
+                       const int32_t* parent, int64_t n_names, const char* query_buf, const int64_t* query_off,
+                       int64_t n_queries, int query_sep, int* dup_tips, int64_t* n_missing) {
+    if (!name_off || !has_name || !parent || !query_off || !dup_tips || !n_missing)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (query_sep < 0) return fail(B2D_ERR_INVALID_ARGUMENT, "query_sep must be >= 0");
+    B2D_GUARDED((validate_names(name_buf, name_off, has_name, parent, n_names, query_buf, query_off, n_queries,
+                                query_sep, dup_tips, n_missing), B2D_OK));
 }
 
 static int b2d_problem_create_features_impl(b2d_problem** out, int device, int64_t n_samples,

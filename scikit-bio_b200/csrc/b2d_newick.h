@@ -10,8 +10,11 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <charconv>
 #include <cmath>
 #include <string>
+#include <string_view>
+#include <unordered_map>
 #include <vector>
 
 namespace b2d {
@@ -34,6 +37,8 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
     };
     std::vector<Node> nodes;
     std::string names;
+    nodes.reserve((size_t)(n / 12 + 16));
+    names.reserve((size_t)(n / 4 + 16));
     auto new_node = [&](int32_t parent) {
         Node nd{parent, -1, -1, -1, std::nan(""), 0, 0, false};
         nodes.push_back(nd);
@@ -134,10 +139,19 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
             std::string tok;
             bool quoted;
             if (!read_token(tok, quoted)) return "could not parse Newick: malformed length";
-            char* endp = nullptr;
-            double v = strtod(tok.c_str(), &endp);
-            if (tok.empty() || endp == tok.c_str() || *endp != '\0')
-                return "Could not read length as numeric type: " + tok + ".";
+            // plain decimal / exponent forms go through from_chars (several times faster than
+            // strtod, correctly rounded as well); anything it does not take whole (a leading '+',
+            // "inf", hex) gets strtod's verdict
+            double v = 0.0;
+            const char* tb = tok.data();
+            const char* te = tb + tok.size();
+            const auto fc = std::from_chars(tb, te, v);
+            if (tok.empty() || fc.ec != std::errc() || fc.ptr != te) {
+                char* endp = nullptr;
+                v = strtod(tok.c_str(), &endp);
+                if (tok.empty() || endp == tok.c_str() || *endp != '\0')
+                    return "Could not read length as numeric type: " + tok + ".";
+            }
             nodes[cur].length = v;
         } else {
             std::string tok;
@@ -195,6 +209,56 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
     }
     out.name_off[m] = (int64_t)out.name_buf.size();
     return "";
+}
+
+// Name -> node id for a list of query names, with the reference's lookup semantics
+// (/root/reference/skbio/diversity/_phylogenetic.pyx:195-199): every node name is scanned in id order,
+// tips and internal nodes alike, and a later node with the same name overwrites an earlier one.
+// out[k] = node id or -1.  Names and queries are byte blobs with offsets; query entries may be
+// followed by `query_sep` separator bytes that are not part of the name.
+inline void lookup_names(const char* name_buf, const int64_t* name_off, const uint8_t* has_name, int64_t m,
+                         const char* query_buf, const int64_t* query_off, int64_t k, int query_sep, int32_t* out) {
+    std::unordered_map<std::string_view, int32_t> map;
+    map.reserve((size_t)m * 2);
+    for (int64_t v = 0; v < m; ++v)
+        if (has_name[v])
+            map[std::string_view(name_buf + name_off[v], (size_t)(name_off[v + 1] - name_off[v]))] = (int32_t)v;
+    for (int64_t q = 0; q < k; ++q) {
+        const auto it = map.find(std::string_view(query_buf + query_off[q], (size_t)(query_off[q + 1] - query_off[q] - query_sep)));
+        out[q] = it == map.end() ? -1 : it->second;
+    }
+}
+
+// The name checks of _validate_taxa_and_tree (/root/reference/skbio/tree/_utils.py:83-90) on flat
+// arrays: *dup_tips = some tip name occurs on two tips; *n_missing = distinct query names that are
+// not tip names.  (An unnamed tip counts as the name None, as in the reference's list of tip names.)
+inline void validate_names(const char* name_buf, const int64_t* name_off, const uint8_t* has_name,
+                           const int32_t* parent, int64_t m, const char* query_buf, const int64_t* query_off,
+                           int64_t k, int query_sep, int* dup_tips, int64_t* n_missing) {
+    std::vector<uint8_t> has_child((size_t)m, 0);
+    for (int64_t v = 0; v < m; ++v)
+        if (parent[v] >= 0) has_child[parent[v]] = 1;
+    std::unordered_map<std::string_view, int32_t> tips;
+    tips.reserve((size_t)m);
+    int dup = 0;
+    int64_t unnamed = 0;
+    for (int64_t v = 0; v < m; ++v) {
+        if (has_child[v] || parent[v] < 0) continue;   // postorder(include_self=False): never the root
+        if (!has_name[v]) {
+            if (++unnamed > 1) dup = 1;
+            continue;
+        }
+        const auto r = tips.emplace(std::string_view(name_buf + name_off[v], (size_t)(name_off[v + 1] - name_off[v])), 0);
+        if (!r.second) dup = 1;
+    }
+    int64_t missing = 0;
+    std::unordered_map<std::string_view, int32_t> seen;
+    for (int64_t q = 0; q < k; ++q) {
+        const std::string_view sv(query_buf + query_off[q], (size_t)(query_off[q + 1] - query_off[q] - query_sep));
+        if (tips.find(sv) == tips.end() && seen.emplace(sv, 0).second) ++missing;
+    }
+    *dup_tips = dup;
+    *n_missing = missing;
 }
 
 }  // namespace b2d
