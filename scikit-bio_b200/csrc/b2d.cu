@@ -452,6 +452,7 @@ struct b2d_problem {
     FlaggedPair* d_flag_list = nullptr;     // [FLAG_CAP] pairs the guard flagged (recomputed in floating point)
     // sparse feature-table path
     SpEntry* d_sp_entries = nullptr;
+    unsigned short* d_sp_runs = nullptr;    // [nbuckets][SP_CHUNK + 8] run start of every feature
     int64_t* d_sp_ptr = nullptr;
     int64_t sp_nch = 0;
     int sp_ready = 0;           // 0 not built, 1 built, -1 not eligible
@@ -478,7 +479,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_svec); emb_cache_put(p->device, p->d_emb, p->emb_bytes); b2d_free(p->d_state);
     b2d_free(p->d_out2); b2d_free(p->d_owned);
     b2d_free(p->d_flags1); b2d_free(p->d_spans); b2d_free(p->d_top_pos); b2d_free(p->d_top_flags);
-    b2d_free(p->d_sp_entries); b2d_free(p->d_sp_ptr);
+    b2d_free(p->d_sp_entries); b2d_free(p->d_sp_ptr); b2d_free(p->d_sp_runs);
     b2d_free(p->d_nz); b2d_free(p->d_skipsum); b2d_free(p->d_exec);
     for (int k = 0; k < 2; ++k) b2d_free(p->d_sblist[k]);
     b2d_free(p->d_zt); b2d_free(p->d_gperm); b2d_free(p->d_zpath);
@@ -637,18 +638,19 @@ static int check_common(b2d_problem** out, int device, int64_t n, int64_t m,
     return B2D_OK;
 }
 
-// the pipelined intersection kernel over all owned tiles (weighted: TipEntry[], unweighted: keys + lenfx)
-template <bool W>
-static int launch_isect(b2d_problem* p, cudaStream_t st, const void* entries, const long long* lenfx,
-                        const PairArgs& a) {
+// the pipelined intersection kernel over all owned tiles (weighted: TipEntry[], unweighted: keys + lenfx,
+// feature tables: SpEntry[])
+template <int MODE, int CHUNK>
+static int launch_isect(b2d_problem* p, cudaStream_t st, const void* entries, const int64_t* bucket_ptr,
+                        const unsigned short* runs, const long long* lenfx, int64_t nch, const PairArgs& a) {
     void (*kern)(const void*, const int64_t*, const unsigned short*, const long long*, int64_t, const long long*,
                  const double*, unsigned long long*, PairArgs) =
-        g_isect_group == 1 ? k_pair_isect<W, 1> : g_isect_group == 2 ? k_pair_isect<W, 2>
-        : g_isect_group == 8 ? k_pair_isect<W, 8> : k_pair_isect<W, 4>;
-    B2D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)is_smem<W>()));
-    kern<<<(unsigned)p->ntiles, IS_THREADS, is_smem<W>(), st>>>(entries, p->d_tip_ptr, p->d_tip_runs, lenfx,
-                                                               p->tip_nch, p->d_tip_ufx, p->d_tip_scale,
-                                                               p->d_tip_word + 2, a);
+        g_isect_group == 1 ? k_pair_isect<MODE, 1, CHUNK> : g_isect_group == 2 ? k_pair_isect<MODE, 2, CHUNK>
+        : g_isect_group == 8 ? k_pair_isect<MODE, 8, CHUNK> : k_pair_isect<MODE, 4, CHUNK>;
+    constexpr size_t smem = IsGeom<MODE, CHUNK>::smem;
+    B2D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)p->ntiles, IS_THREADS, smem, st>>>(entries, bucket_ptr, runs, lenfx, nch, p->d_tip_ufx,
+                                                       p->d_tip_scale, p->d_tip_word ? p->d_tip_word + 2 : nullptr, a);
     B2D_CUDA(cudaGetLastError());
     return B2D_OK;
 }
@@ -1518,7 +1520,9 @@ static int compute_dense(b2d_problem* p, int metric) {
                 if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
                 B2D_CUDA(cudaEventRecord(p->ev[7], st));
                 if (g_isect_kernel) {
-                    if ((rc = launch_isect<true>(p, st, p->d_tip_entries, nullptr, a))) return rc;
+                    if ((rc = launch_isect<IS_WEIGHTED, TP_CHUNK>(p, st, p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, nullptr,
+                                                                  p->tip_nch, a)))
+                        return rc;
                 } else {
                     B2D_CUDA(cudaFuncSetAttribute(k_pair_tips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
                     k_pair_tips<<<(unsigned)p->ntiles, TP_THREADS, TP_SMEM, st>>>(
@@ -1668,7 +1672,9 @@ static int compute_bits(b2d_problem* p, int metric) {
             if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
             B2D_CUDA(cudaEventRecord(p->ev[7], st));
             if (g_isect_kernel) {
-                if ((rc = launch_isect<false>(p, st, p->d_ukeys, p->d_lenfx, a))) return rc;
+                if ((rc = launch_isect<IS_UNWEIGHTED, TP_CHUNK>(p, st, p->d_ukeys, p->d_tip_ptr, p->d_tip_runs, p->d_lenfx,
+                                                                p->tip_nch, a)))
+                    return rc;
             } else {
                 B2D_CUDA(cudaFuncSetAttribute(k_pair_utips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UT_SMEM));
                 k_pair_utips<<<(unsigned)p->ntiles, TP_THREADS, UT_SMEM, st>>>(
@@ -1801,7 +1807,8 @@ static int build_sparse(b2d_problem* p) {
     }
     B2D_CUDA(b2d_malloc(&p->d_sp_ptr, (nbuckets + 1) * sizeof(int64_t)));
     B2D_CUDA(cudaMemcpyAsync(p->d_sp_ptr, ptr.data(), (nbuckets + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
-    B2D_CUDA(b2d_malloc(&p->d_sp_entries, std::max<int64_t>(p->nnz, 1) * sizeof(SpEntry)));
+    B2D_CUDA(b2d_malloc(&p->d_sp_entries, (std::max<int64_t>(p->nnz, 1) + 4) * sizeof(SpEntry)));  // + bulk-copy slack
+    B2D_CUDA(b2d_malloc(&p->d_sp_runs, (size_t)nbuckets * (SP_CHUNK + 8) * sizeof(unsigned short)));
     B2D_CUDA(cudaMemsetAsync(d_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
     p->n_kernels += 1;
     if (p->has_values)
@@ -1812,7 +1819,7 @@ static int build_sparse(b2d_problem* p) {
                                                                   p->n, nch, p->d_sp_ptr, d_counts, p->d_sp_entries);
     B2D_CUDA(cudaFuncSetAttribute(k_sp_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SORT_SMEM));
     p->n_kernels += 1;
-    k_sp_sort<<<(unsigned)nbuckets, 256, SP_SORT_SMEM, p->stream>>>(p->d_sp_entries, p->d_sp_ptr);
+    k_sp_sort<<<(unsigned)nbuckets, 256, SP_SORT_SMEM, p->stream>>>(p->d_sp_entries, p->d_sp_ptr, p->d_sp_runs);
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     B2D_CUDA(cudaGetLastError());
     b2d_free(d_counts);
@@ -1853,8 +1860,18 @@ static int compute_sparse(b2d_problem* p, int metric) {
         cudaStream_t st;
         int rc = chunk_target(p, &st, &a.out, &a.first);
         if (rc) return rc;
-        k_pair_sparse<<<(unsigned)p->ntiles, SP_THREADS, SP_SMEM2, st>>>(
-            p->d_sp_entries, p->d_sp_ptr, p->sp_nch, metric == B2D_JACCARD ? 1 : 0, a);
+        if (g_isect_kernel) {
+            if (metric == B2D_JACCARD)
+                rc = launch_isect<IS_FEAT_COUNT, SP_CHUNK>(p, st, p->d_sp_entries, p->d_sp_ptr, p->d_sp_runs, nullptr,
+                                                           p->sp_nch, a);
+            else
+                rc = launch_isect<IS_FEAT_MIN, SP_CHUNK>(p, st, p->d_sp_entries, p->d_sp_ptr, p->d_sp_runs, nullptr,
+                                                         p->sp_nch, a);
+            if (rc) return rc;
+        } else {
+            k_pair_sparse<<<(unsigned)p->ntiles, SP_THREADS, SP_SMEM2, st>>>(
+                p->d_sp_entries, p->d_sp_ptr, p->sp_nch, metric == B2D_JACCARD ? 1 : 0, a);
+        }
         p->n_launch = 1;
         if ((rc = finalize(p, metric == B2D_JACCARD ? EPI_JACCARD_INTERSECT : EPI_BRAYCURTIS_INTERSECT))) return rc;
     }

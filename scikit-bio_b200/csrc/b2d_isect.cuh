@@ -4,8 +4,10 @@
 //
 //   T(i,j) = U_i + U_j - 2 * sum_{q in both} min(w_qi, w_qj)       (weighted,  b2d_tips.cuh)
 //   T(i,j) = U_i + U_j - 2 * sum_{q in both} lenfx_q                (unweighted)
+//   I(i,j) = sum_{f in both} min(a_f, b_f)  or  |a and b|           (integer feature tables:
+//                                                                    Bray-Curtis / Jaccard, b2d_sparse.cuh)
 //
-// exact in 61-bit fixed point.  One CTA per 128 x 128 tile of sample pairs:
+// exact in 61-bit fixed point (32-bit integers for the feature tables).  One CTA per 128 x 128 tile of sample pairs:
 //   * warp 31 is the PRODUCER.  Per (tile, position chunk) it cuts the column bucket into
 //     batches at position boundaries (a whole bucket when it fits), and for every batch issues
 //     1-D bulk copies (cp.async.bulk, SASS UBLKCP) of the column entries, the slice of the
@@ -24,19 +26,22 @@
 
 #include "b2d_common.cuh"
 #include "b2d_pair.cuh"
+#include "b2d_sparse.cuh"
 #include "b2d_tips.cuh"
 
 namespace b2d {
 
+// what a match adds, and what the entries are
+enum IsMode : int {
+    IS_WEIGHTED = 0,    // TipEntry {key, fixed-point w}: += min(w, w'), 64-bit sums
+    IS_UNWEIGHTED = 1,  // bare uint32 keys + fixed-point length table: += lenfx[position], 64-bit sums
+    IS_FEAT_MIN = 2,    // SpEntry {key, int32 count}: += min(v, v'), 32-bit sums (Bray-Curtis, b2d_sparse.cuh)
+    IS_FEAT_COUNT = 3   // SpEntry, value ignored: += 1 (Jaccard)
+};
+
 constexpr int IS_THREADS = 1024;
 constexpr int IS_CWARPS = 31;                       // consumer warps; warp 31 produces
 constexpr int IS_STAGES = 2;
-constexpr int IS_ENT_BYTES = 40960;                 // weighted: column entries per stage
-constexpr int IS_CAP_W = IS_ENT_BYTES / 16;         // 2560 entries of 16 B
-constexpr int IS_ENT_BYTES_U = 24576;               // unweighted: column keys per stage
-constexpr int IS_CAP_U2 = IS_ENT_BYTES_U / 4 - 8;   // 6136 keys of 4 B (+ alignment slack)
-constexpr int IS_RUN_BYTES = (TP_CHUNK + 8) * 2 + 16;   // 4128: run starts of a whole chunk
-constexpr int IS_LF_BYTES = TP_CHUNK * 8;               // 16384: fixed-point lengths (unweighted only)
 struct IsHeader {
     long long r_lo, r_hi;   // global row-entry range of the batch
     int coff;               // column entry e (relative to its bucket) lives in slot e + coff
@@ -45,33 +50,45 @@ struct IsHeader {
     int pad[9];
 };
 static_assert(sizeof(IsHeader) == 64, "header is 64 bytes");
-template <bool W>
-constexpr size_t is_smem() {
-    return (size_t)TILE * TILE * 8 + (size_t)IS_STAGES * ((W ? IS_ENT_BYTES : IS_ENT_BYTES_U) + IS_RUN_BYTES +
-                                                           (W ? 0 : IS_LF_BYTES) + 64) + 4 * sizeof(uint64_t);
-}
-static_assert(is_smem<true>() <= 232448 && is_smem<false>() <= 232448, "shared memory per CTA");
 
-// W = true : entries = TipEntry[], lenfx unused.   W = false: entries = uint32 keys[], lenfx table.
-template <bool W, int G>
+template <int MODE, int CHUNK>
+struct IsGeom {
+    static constexpr bool wide = MODE == IS_WEIGHTED || MODE == IS_UNWEIGHTED;        // 64-bit sums
+    static constexpr int esize = MODE == IS_WEIGHTED ? 16 : MODE == IS_UNWEIGHTED ? 4 : 8;
+    static constexpr int ent_bytes = MODE == IS_UNWEIGHTED ? 24576 : 40960;           // column entries per stage
+    static constexpr int align_entries = 16 / esize;                                  // bulk copies: 16-byte units
+    static constexpr int cap = ent_bytes / esize - 2 * align_entries;                 // entries per batch
+    static constexpr int run_bytes = (CHUNK + 8) * 2 + 16;                            // run starts of a whole chunk
+    static constexpr int lf_bytes = MODE == IS_UNWEIGHTED ? CHUNK * 8 : 0;            // fixed-point lengths
+    static constexpr int stage_bytes = ent_bytes + run_bytes + lf_bytes + 64;
+    static constexpr size_t acc_bytes = (size_t)TILE * TILE * (wide ? 8 : 4);
+    static constexpr size_t smem = acc_bytes + (size_t)IS_STAGES * stage_bytes + 4 * sizeof(uint64_t);
+    static_assert(cap >= 8 * TILE, "eight positions of a block must fit one batch");
+    static_assert(stage_bytes % 16 == 0 && smem <= 232448, "shared memory per CTA");
+};
+
+// entries_v: TipEntry[] (weighted), uint32 keys[] (unweighted) or SpEntry[] (feature tables);
+// runs: [nbuckets][CHUNK + 8] run starts per position / feature of every bucket.
+template <int MODE, int G, int CHUNK>
 __global__ void __launch_bounds__(IS_THREADS, 1)
 k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ bucket_ptr,
              const unsigned short* __restrict__ runs, const long long* __restrict__ lenfx, int64_t nch,
              const long long* __restrict__ Ufx, const double* __restrict__ scale,
              unsigned long long* __restrict__ n_matches, PairArgs a) {
+    using Geo = IsGeom<MODE, CHUNK>;
+    constexpr bool WIDE = Geo::wide;
+    constexpr int ENT = Geo::ent_bytes, CAP = Geo::cap, STAGE = Geo::stage_bytes;
+    constexpr int HDR = ENT + Geo::run_bytes + Geo::lf_bytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* acc_lo = reinterpret_cast<uint32_t*>(smem_raw);   // [128][128]
-    uint32_t* acc_hi = acc_lo + TILE * TILE;
-    unsigned char* stage0 = smem_raw + (size_t)TILE * TILE * 8;
-    constexpr int ENT = W ? IS_ENT_BYTES : IS_ENT_BYTES_U;
-    constexpr int CAP = W ? IS_CAP_W : IS_CAP_U2;
-    constexpr int STAGE = ENT + IS_RUN_BYTES + (W ? 0 : IS_LF_BYTES) + 64;
+    uint32_t* acc_hi = acc_lo + TILE * TILE;                    // [128][128], 64-bit modes only
+    unsigned char* stage0 = smem_raw + Geo::acc_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)IS_STAGES * STAGE);
     uint64_t* empty = full + IS_STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
-    for (int x = tid; x < 2 * TILE * TILE; x += IS_THREADS) acc_lo[x] = 0u;
+    for (int x = tid; x < (WIDE ? 2 : 1) * TILE * TILE; x += IS_THREADS) acc_lo[x] = 0u;
     if (tid == 0) {
         for (int s = 0; s < IS_STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -81,8 +98,7 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
     }
     __syncthreads();
 
-    const TipEntry* ent_w = reinterpret_cast<const TipEntry*>(entries_v);
-    const uint32_t* ent_u = reinterpret_cast<const uint32_t*>(entries_v);
+    const unsigned char* ent_b = reinterpret_cast<const unsigned char*>(entries_v);
     unsigned nm = 0;  // matches this thread accumulated
 
     if (warp == IS_CWARPS) {
@@ -102,25 +118,26 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                 c0 = bucket_ptr[cbk];
                 c1 = bucket_ptr[cbk + 1];
                 if (r1 == r0 || c1 == c0) continue;
-                crun = runs + (size_t)cbk * (TP_CHUNK + 8);
-                rrun = runs + (size_t)rbk * (TP_CHUNK + 8);
+                crun = runs + (size_t)cbk * (CHUNK + 8);
+                rrun = runs + (size_t)rbk * (CHUNK + 8);
             }
             int f0 = 0, ce0 = 0, re0 = 0;
             const int cn = (int)(c1 - c0), rn = (int)(r1 - r0);
-            while (last || f0 < TP_CHUNK) {
-                int f1 = TP_CHUNK, ce1 = cn, re1 = rn;
+            while (last || f0 < CHUNK) {
+                int f1 = CHUNK, ce1 = cn, re1 = rn;
                 if (!last && cn - ce0 > CAP) {
-                    // largest f1 in (f0, TP_CHUNK], a multiple of 8, with crun[f1] - ce0 <= CAP:
-                    // 64-position strides first, then 8-position strides (run starts are monotone)
+                    // largest f1 in (f0, CHUNK], a multiple of 8, with crun[f1] - ce0 <= CAP: CHUNK / 32
+                    // position strides first, then 8-position strides (run starts are monotone)
+                    constexpr int S1 = CHUNK / 32;
                     int base = f0;
                     {
-                        const int cand = base + 64 * (lane + 1);
-                        const bool ok = cand <= TP_CHUNK && (int)crun[cand] - ce0 <= CAP;
-                        base += 64 * __popc(__ballot_sync(0xffffffffu, ok));
+                        const int cand = base + S1 * (lane + 1);
+                        const bool ok = cand <= CHUNK && (int)crun[cand] - ce0 <= CAP;
+                        base += S1 * __popc(__ballot_sync(0xffffffffu, ok));
                     }
                     {
                         const int cand = base + 8 * (lane + 1);
-                        const bool ok = lane < 7 && cand <= TP_CHUNK && (int)crun[cand] - ce0 <= CAP;
+                        const bool ok = lane < S1 / 8 - 1 && cand <= CHUNK && (int)crun[cand] - ce0 <= CAP;
                         base += 8 * __popc(__ballot_sync(0xffffffffu, ok));
                     }
                     f1 = base;   // > f0: eight positions hold at most 1024 entries <= CAP
@@ -131,26 +148,27 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                     if (it >= IS_STAGES) mbar_wait(&empty[s], ph ^ 1u);
                     if (lane == 0) {
                         unsigned char* st = stage0 + (size_t)s * STAGE;
-                        IsHeader* h = reinterpret_cast<IsHeader*>(st + ENT + IS_RUN_BYTES + (W ? 0 : IS_LF_BYTES));
+                        IsHeader* h = reinterpret_cast<IsHeader*>(st + HDR);
                         h->done = last ? 1 : 0;
                         if (last) {
                             mbar_arrive(&full[s]);
                         } else {
-                            // global index of smem slot 0 (keys: aligned down to 16 bytes)
-                            const int64_t g0 = W ? (c0 + ce0) : ((c0 + ce0) & ~(int64_t)3);
-                            const int64_t g1 = W ? (c0 + ce1) : ((c0 + ce1 + 3) & ~(int64_t)3);
-                            const uint32_t ebytes = (uint32_t)(g1 - g0) * (W ? 16u : 4u);
+                            // global index of smem slot 0, aligned down to a 16-byte unit
+                            constexpr int64_t AL = Geo::align_entries;
+                            const int64_t g0 = (c0 + ce0) / AL * AL;
+                            const int64_t g1 = (c0 + ce1 + AL - 1) / AL * AL;
+                            const uint32_t ebytes = (uint32_t)(g1 - g0) * (uint32_t)Geo::esize;
                             const uint32_t rbytes = (uint32_t)(f1 - f0 + 8) * 2u;
-                            const uint32_t lbytes = W ? 0u : (uint32_t)(f1 - f0) * 8u;
+                            const uint32_t lbytes = MODE == IS_UNWEIGHTED ? (uint32_t)(f1 - f0) * 8u : 0u;
                             h->r_lo = r0 + re0;
                             h->r_hi = r0 + re1;
                             h->coff = (int)(c0 - g0);
                             h->f0 = f0;
                             mbar_arrive_expect_tx(&full[s], ebytes + rbytes + lbytes);
-                            if (W) bulk_g2s(st, ent_w + g0, ebytes, &full[s]);
-                            else bulk_g2s(st, ent_u + g0, ebytes, &full[s]);
+                            bulk_g2s(st, ent_b + g0 * Geo::esize, ebytes, &full[s]);
                             bulk_g2s(st + ENT, crun + f0, rbytes, &full[s]);
-                            if (!W) bulk_g2s(st + ENT + IS_RUN_BYTES, lenfx + ch * TP_CHUNK + f0, lbytes, &full[s]);
+                            if (MODE == IS_UNWEIGHTED)
+                                bulk_g2s(st + ENT + Geo::run_bytes, lenfx + ch * CHUNK + f0, lbytes, &full[s]);
                         }
                     }
                     __syncwarp();
@@ -175,14 +193,15 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
         for (;;) {
             mbar_wait(&full[s], ph);
             const unsigned char* st = stage0 + (size_t)s * STAGE;
-            const IsHeader* h = reinterpret_cast<const IsHeader*>(st + ENT + IS_RUN_BYTES + (W ? 0 : IS_LF_BYTES));
+            const IsHeader* h = reinterpret_cast<const IsHeader*>(st + HDR);
             if (h->done) break;
             const unsigned short* fstart = reinterpret_cast<const unsigned short*>(st + ENT);
             const int coff = h->coff, f0 = h->f0;
             const int64_t r_lo = h->r_lo, r_hi = h->r_hi;
-            if (W) {
+            int64_t x = r_lo + warp * SLOTS + slot;
+            if (MODE == IS_WEIGHTED) {
+                const TipEntry* ent_w = reinterpret_cast<const TipEntry*>(entries_v);
                 const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
-                int64_t x = r_lo + warp * SLOTS + slot;
                 TipEntry re;
                 if (x < r_hi) re = ent_w[x];
                 while (x < r_hi) {
@@ -206,10 +225,10 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                     }
                     x = xn;
                 }
-            } else {
+            } else if (MODE == IS_UNWEIGHTED) {
+                const uint32_t* ent_u = reinterpret_cast<const uint32_t*>(entries_v);
                 const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
-                const long long* lf = reinterpret_cast<const long long*>(st + ENT + IS_RUN_BYTES);
-                int64_t x = r_lo + warp * SLOTS + slot;
+                const long long* lf = reinterpret_cast<const long long*>(st + ENT + Geo::run_bytes);
                 uint32_t rk = 0;
                 if (x < r_hi) rk = ent_u[x];
                 while (x < r_hi) {
@@ -230,6 +249,26 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                     }
                     x = xn;
                 }
+            } else {
+                const SpEntry* ent_f = reinterpret_cast<const SpEntry*>(entries_v);
+                const SpEntry* centry = reinterpret_cast<const SpEntry*>(st);
+                SpEntry re;
+                if (x < r_hi) re = ent_f[x];
+                while (x < r_hi) {
+                    const SpEntry cur = re;
+                    const int64_t xn = x + IS_CWARPS * SLOTS;
+                    if (xn < r_hi) re = ent_f[xn];
+                    const uint32_t f = (cur.key >> 7) - (uint32_t)f0, r = cur.key & 127u;
+                    const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                    const uint32_t rbase = r * TILE, rx = r & 31u;
+                    if (g == 0) nm += (unsigned)(e1 - e0);
+                    for (int e = e0 + g; e < e1; e += G) {
+                        const SpEntry ce = centry[e];
+                        const uint32_t add = MODE == IS_FEAT_COUNT ? 1u : (uint32_t)(cur.val < ce.val ? cur.val : ce.val);
+                        atomicAdd(&acc_lo[rbase + ((ce.key & 127u) ^ rx)], add);
+                    }
+                    x = xn;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -245,17 +284,24 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
         for (int o = 16; o; o >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, o);
         if (lane == 0 && nm) atomicAdd(n_matches, (unsigned long long)nm);
     }
-    const double inv = scale[1];
     const int64_t base = a.row_base[bi];
     const int64_t i0 = (int64_t)bi * TILE;
-    for (int x = tid; x < TILE * TILE; x += IS_THREADS) {
-        const int rr = x / TILE, c = x % TILE;
-        const int64_t i = i0 + rr, j = (int64_t)bj * TILE + c;
-        if (i >= j || j >= a.n) continue;
-        const int xs = rr * TILE + (c ^ (rr & 31));
-        const long long m = (long long)(((unsigned long long)acc_hi[xs] << 32) | acc_lo[xs]);
-        const long long t = Ufx[i] + Ufx[j] - 2 * m;
-        emit(a, base, i0, i, j, (double)t * inv);
+    if (WIDE) {
+        const double inv = scale[1];
+        for (int x = tid; x < TILE * TILE; x += IS_THREADS) {
+            const int rr = x / TILE, c = x % TILE;
+            const int64_t i = i0 + rr, j = (int64_t)bj * TILE + c;
+            if (i >= j || j >= a.n) continue;
+            const int xs = rr * TILE + (c ^ (rr & 31));
+            const long long m = (long long)(((unsigned long long)acc_hi[xs] << 32) | acc_lo[xs]);
+            const long long t = Ufx[i] + Ufx[j] - 2 * m;
+            emit(a, base, i0, i, j, (double)t * inv);
+        }
+    } else {
+        for (int x = tid; x < TILE * TILE; x += IS_THREADS) {
+            const int rr = x / TILE, c = x % TILE;
+            emit(a, base, i0, i0 + rr, (int64_t)bj * TILE + c, (double)acc_lo[rr * TILE + (c ^ (rr & 31))]);
+        }
     }
 }
 

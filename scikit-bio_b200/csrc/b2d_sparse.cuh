@@ -69,14 +69,16 @@ __global__ void k_sp_scatter(const int64_t* __restrict__ indptr, const int32_t* 
 
 // 3. sort every bucket by feature (counting sort in shared memory, one CTA per bucket)
 __global__ void __launch_bounds__(256)
-k_sp_sort(SpEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr) {
+k_sp_sort(SpEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr,
+          unsigned short* __restrict__ runs /*[nbuckets][SP_CHUNK + 8] run start of every feature*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SpEntry* buf = reinterpret_cast<SpEntry*>(smem_raw);
     int* cnt = reinterpret_cast<int*>(buf + SP_SORT_MAX);  // [SP_CHUNK + 1]
     const int64_t b0 = bucket_ptr[blockIdx.x];
     const int nb = (int)(bucket_ptr[blockIdx.x + 1] - b0);
-    if (nb <= 1) return;
+    if (nb == 0) return;   // an empty bucket is never staged: its run table stays unwritten
     const int tid = threadIdx.x;
+    unsigned short* rs = runs + (size_t)blockIdx.x * (SP_CHUNK + 8);
     for (int x = tid; x <= SP_CHUNK; x += 256) cnt[x] = 0;
     for (int x = tid; x < nb; x += 256) buf[x] = entries[b0 + x];
     __syncthreads();
@@ -102,8 +104,10 @@ k_sp_sort(SpEntry* __restrict__ entries, const int64_t* __restrict__ bucket_ptr)
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         cnt[1 + tid * 16 + k] = run;   // start offset of feature tid*16+k (stored at index f+1)
+        rs[tid * 16 + k] = (unsigned short)run;
         run += local[k];
     }
+    if (tid == 255) rs[SP_CHUNK] = (unsigned short)nb;
     __syncthreads();
     for (int x = tid; x < nb; x += 256) {
         const SpEntry e = buf[x];
