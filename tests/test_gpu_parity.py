@@ -1119,7 +1119,7 @@ def test_pipelined_intersection_kernel_on_feature_tables():
 
     from skbio_b200 import _capi, synthetic
 
-    for n, f, lam in ((400, 5000, 0.01), (300, 9000, 0.3)):
+    for n, f, lam in ((400, 5000, 0.01), (300, 9000, 0.03)):
         indptr, cols, vals = synthetic.poisson_csr(n, f, lam, seed=7)
         dense = synthetic.csr_to_dense(indptr, cols, vals, f)
         with np.errstate(all="ignore"):
