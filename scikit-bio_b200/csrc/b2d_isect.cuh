@@ -202,12 +202,16 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
             if (MODE == IS_WEIGHTED) {
                 const TipEntry* ent_w = reinterpret_cast<const TipEntry*>(entries_v);
                 const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
-                TipEntry re;
+                // two row entries in flight ahead of the one being walked (L2 latency >> one walk)
+                constexpr int64_t STEP = IS_CWARPS * SLOTS;
+                TipEntry re, re2;
                 if (x < r_hi) re = ent_w[x];
+                if (x + STEP < r_hi) re2 = ent_w[x + STEP];
                 while (x < r_hi) {
                     const TipEntry cur = re;
-                    const int64_t xn = x + IS_CWARPS * SLOTS;
-                    if (xn < r_hi) re = ent_w[xn];   // next row entry in flight during the walk
+                    const int64_t xn = x + STEP;
+                    re = re2;
+                    if (xn + STEP < r_hi) re2 = ent_w[xn + STEP];
                     const uint32_t f = (cur.key >> 7) - (uint32_t)f0, r = cur.key & 127u;
                     const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
                     const uint32_t rbase = r * TILE, rx = r & 31u;
@@ -229,12 +233,15 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                 const uint32_t* ent_u = reinterpret_cast<const uint32_t*>(entries_v);
                 const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
                 const long long* lf = reinterpret_cast<const long long*>(st + ENT + Geo::run_bytes);
-                uint32_t rk = 0;
+                constexpr int64_t STEP = IS_CWARPS * SLOTS;
+                uint32_t rk = 0, rk2 = 0;
                 if (x < r_hi) rk = ent_u[x];
+                if (x + STEP < r_hi) rk2 = ent_u[x + STEP];
                 while (x < r_hi) {
                     const uint32_t cur = rk;
-                    const int64_t xn = x + IS_CWARPS * SLOTS;
-                    if (xn < r_hi) rk = ent_u[xn];
+                    const int64_t xn = x + STEP;
+                    rk = rk2;
+                    if (xn + STEP < r_hi) rk2 = ent_u[xn + STEP];
                     const uint32_t f = (cur >> 7) - (uint32_t)f0, r = cur & 127u;
                     const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
                     const unsigned long long add = (unsigned long long)lf[f];
@@ -252,12 +259,15 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
             } else {
                 const SpEntry* ent_f = reinterpret_cast<const SpEntry*>(entries_v);
                 const SpEntry* centry = reinterpret_cast<const SpEntry*>(st);
-                SpEntry re;
+                constexpr int64_t STEP = IS_CWARPS * SLOTS;
+                SpEntry re, re2;
                 if (x < r_hi) re = ent_f[x];
+                if (x + STEP < r_hi) re2 = ent_f[x + STEP];
                 while (x < r_hi) {
                     const SpEntry cur = re;
-                    const int64_t xn = x + IS_CWARPS * SLOTS;
-                    if (xn < r_hi) re = ent_f[xn];
+                    const int64_t xn = x + STEP;
+                    re = re2;
+                    if (xn + STEP < r_hi) re2 = ent_f[xn + STEP];
                     const uint32_t f = (cur.key >> 7) - (uint32_t)f0, r = cur.key & 127u;
                     const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
                     const uint32_t rbase = r * TILE, rx = r & 31u;
