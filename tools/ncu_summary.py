@@ -27,17 +27,33 @@ KEYS = [
     "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
 ]
 
-def main(path):
+UNIT_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def main(path, traffic_json=None, workload=None, kernel_alias=None):
+    """Print the summary; with `traffic_json workload [kernel_alias]` also record the capture's DRAM
+    bytes (read + write) of the kernel under profiles/ncu_traffic.json[workload][kernel] (what
+    bench.py reports as roofline.traffic for the default shapes)."""
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")]
-        print(f"== {name.split('(')[0]}")
+        name = r[hdr.index("Kernel Name")].split("(")[0].split("<")[0].split("::")[-1]
+        print(f"== {name}")
         for k in KEYS:
             if k in hdr:
                 i = hdr.index(k)
                 print(f"  {k:85s} {r[i]:>18s} {units[i]}")
+        if traffic_json:
+            import json, os
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(k)
+                tot += float(r[i].replace(",", "")) * UNIT_BYTES[units[i]]
+            tab = json.load(open(traffic_json)) if os.path.exists(traffic_json) else {}
+            tab.setdefault(workload, {})[kernel_alias or name] = tot
+            json.dump(tab, open(traffic_json, "w"), indent=1, sort_keys=True)
+
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(*sys.argv[1:])
