@@ -354,6 +354,8 @@ struct b2d_problem {
     bool has_values = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // odd node chunks run here, into d_out2 (tails overlap)
+    cudaStream_t stream3 = nullptr;   // closed-form sums of zero-block skipping, beside the pair kernels
+    cudaEvent_t ev_cf[2] = {nullptr, nullptr};
     cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_sync[2] = {nullptr, nullptr};
     TreeOrder order;
@@ -472,6 +474,7 @@ static void free_problem(b2d_problem* p) {
     // them to other problems (other streams), so drain both streams first (errors ignored)
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->stream2) cudaStreamSynchronize(p->stream2);
+    if (p->stream3) cudaStreamSynchronize(p->stream3);
     cudaGetLastError();
     b2d_free(p->d_indptr); b2d_free(p->d_qidx); b2d_free(p->d_values); b2d_free(p->d_flags);
     b2d_free(p->d_hc); b2d_free(p->d_fold); b2d_free(p->d_len); b2d_free(p->d_tipdist);
@@ -496,6 +499,8 @@ static void free_problem(b2d_problem* p) {
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->stream2) cudaStreamDestroy(p->stream2);
+    if (p->stream3) cudaStreamDestroy(p->stream3);
+    for (auto& e : p->ev_cf) if (e) cudaEventDestroy(e);
     delete p;
 }
 
@@ -513,6 +518,8 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     NvtxRange range("b2d:create (H2D of tree + CSR)");
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    B2D_CUDA(cudaStreamCreateWithFlags(&p->stream3, cudaStreamNonBlocking));
+    for (auto& e : p->ev_cf) B2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : p->ev) B2D_CUDA(cudaEventCreate(&e));
     for (auto& e : p->ev_sync) B2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     B2D_CUDA(cudaEventCreate(&e0));
@@ -1215,7 +1222,7 @@ static int urows_build(b2d_problem* p) {
 
 // Closed-form sums S[g][s] from the bitmaps of ALL node rows (after the last pass), the tree
 // arrays and the CSR input; groups in chunks of 32 * SKIP_GW (one zero-path table at a time).
-static int skip_closed_form(b2d_problem* p) {
+static int skip_closed_form(b2d_problem* p, cudaStream_t st) {
     const bool tree = p->kind == 0;
     for (int part = 0; part < 2; ++part) {
         // part 0: groups of the owned stripes x every sample; part 1: other groups x owned samples
@@ -1224,21 +1231,21 @@ static int skip_closed_form(b2d_problem* p) {
         if (w1 <= w0 || !p->n_sblist[part]) continue;
         for (int kbeg = w0; kbeg < w1; kbeg += SKIP_GW) {
             const int kcnt = std::min(SKIP_GW, w1 - kbeg);
-            B2D_CUDA(cudaMemsetAsync(p->d_zpath, 0, (size_t)p->mpad * 32 * SKIP_GW * sizeof(double), p->stream));
+            B2D_CUDA(cudaMemsetAsync(p->d_zpath, 0, (size_t)p->mpad * 32 * SKIP_GW * sizeof(double), st));
             const int64_t warps = p->m * kcnt;
             p->n_kernels += 1;
-            k_fill_zero_paths<SKIP_GW><<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
+            k_fill_zero_paths<SKIP_GW><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
                 p->d_zt, p->ngw, kbeg, kcnt, p->d_parent_q, p->d_size_q,
                 p->tips_active ? (p->rows_general ? p->d_rdR_hi : p->d_rd_hi_int) : p->d_rd_hi,
                 p->tips_active ? (p->rows_general ? p->d_rdR_lo : p->d_rd_lo_int) : p->d_rd_lo, p->m, p->d_zpath);
             const unsigned grid = (unsigned)p->n_sblist[part] * 16;
             p->n_kernels += 1;
             if (tree)
-                k_sample_pathsums<SKIP_GW, int64_t><<<grid, 256, 0, p->stream>>>(
+                k_sample_pathsums<SKIP_GW, int64_t><<<grid, 256, 0, st>>>(
                     p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->d_total, p->d_zpath,
                     p->d_gperm, kbeg, kcnt, p->d_sblist[part], p->n, p->npad, p->d_skipsum);
             else
-                k_sample_pathsums<SKIP_GW, double><<<grid, 256, 0, p->stream>>>(
+                k_sample_pathsums<SKIP_GW, double><<<grid, 256, 0, st>>>(
                     p->d_indptr, p->d_qidx, (const double*)p->d_values, nullptr, p->d_zpath,
                     p->d_gperm, kbeg, kcnt, p->d_sblist[part], p->n, p->npad, p->d_skipsum);
         }
@@ -1414,7 +1421,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     p->chunk_counter = 0;
     p->nodes_resident = (double)QR;
     double t_embed = 0, t_pair = 0, t_prep = 0;
-    bool closed_form_timed = false, tips_timed = false;
+    bool closed_form_queued = false, tips_timed = false;
     int64_t pass_nd = 0, pass_nd_pad = 128;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
@@ -1500,6 +1507,16 @@ static int compute_dense(b2d_problem* p, int metric) {
                         p->d_nz, p->d_hc + q0 / 32, ng, QR / 32, nwords);
                 }
                 B2D_CUDA(cudaEventRecord(p->ev[4], p->stream));
+                if (q1 == p->mpad && p->out_len && !p->owned.empty()) {
+                    // every bitmap is known now: the closed-form sums (memory-bound, no shared memory) run on
+                    // their own stream BESIDE the pair kernels, which leave thread and register room on
+                    // every SM (one CTA of at most 1 024 threads, bound by shared memory)
+                    B2D_CUDA(cudaEventRecord(p->ev_cf[0], p->stream));
+                    B2D_CUDA(cudaStreamWaitEvent(p->stream3, p->ev_cf[0], 0));
+                    if ((rc = skip_closed_form(p, p->stream3))) return rc;
+                    B2D_CUDA(cudaEventRecord(p->ev_cf[1], p->stream3));
+                    closed_form_queued = true;
+                }
             }
             if ((rc = fork_streams(p))) return rc;
             if (p->tips_active && q0 == 0) {  // all tip rows at once: sparse intersection
@@ -1543,10 +1560,7 @@ static int compute_dense(b2d_problem* p, int metric) {
             if ((rc = join_streams(p))) return rc;
             if (q1 == p->mpad) {
                 if (skip && p->out_len && !p->owned.empty()) {
-                    B2D_CUDA(cudaEventRecord(p->ev[5], p->stream));
-                    if ((rc = skip_closed_form(p))) return rc;
-                    B2D_CUDA(cudaEventRecord(p->ev[6], p->stream));
-                    closed_form_timed = true;
+                    if (closed_form_queued) B2D_CUDA(cudaStreamWaitEvent(p->stream, p->ev_cf[1], 0));
                     p->n_kernels += 1;
                     k_add_skipsums<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                         p->d_out, p->d_owned, p->d_row_base, p->n, p->npad, p->d_skipsum);
@@ -1577,10 +1591,6 @@ static int compute_dense(b2d_problem* p, int metric) {
         if (skip && p->ntiles) {
             cudaEventElapsedTime(&ms, eb, p->ev[4]);
             t_prep += ms;
-            if (closed_form_timed) {
-                cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]);
-                t_prep += ms;
-            }
             if (tips_timed && q0 == 0) {
                 cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]);
                 p->t_tips = ms;
