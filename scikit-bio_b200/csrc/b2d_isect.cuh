@@ -14,9 +14,10 @@
 //     column run table and - unweighted - the fixed-point lengths into one of two stages, with
 //     a small header (row-entry range, position range).  full / empty mbarriers per stage; the
 //     next batch lands while the current one is consumed.
-//   * warps 0..30 are CONSUMERS.  Row entries come straight from global memory (coalesced,
-//     L2-resident); G = 4 lanes share one row entry and stride over the column run of its
-//     position, so a warp keeps eight row entries in flight and a run of k column entries costs
+//   * warps 0..30 are CONSUMERS.  Row entries come straight from global memory in warp-wide
+//     blocks of 32 (one coalesced load, several blocks in flight ahead: the loop is otherwise
+//     bound by the L2 round trip) and are handed out by shuffles; G = 4 lanes share one row
+//     entry and stride over the column run of its position, so a run of k column entries costs
 //     ceil(k / 4) steps instead of k (the one-thread-per-row-entry walk left 43 % of the lanes
 //     idle: run lengths differ from lane to lane).  Every match adds into a 128 x 128 tile of
 //     64-bit sums kept as two 32-bit halves (shared memory has native 32-bit atomic adds only;
@@ -198,86 +199,92 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
             const unsigned short* fstart = reinterpret_cast<const unsigned short*>(st + ENT);
             const int coff = h->coff, f0 = h->f0;
             const int64_t r_lo = h->r_lo, r_hi = h->r_hi;
-            int64_t x = r_lo + warp * SLOTS + slot;
-            if (MODE == IS_WEIGHTED) {
-                const TipEntry* ent_w = reinterpret_cast<const TipEntry*>(entries_v);
-                const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
-                // two row entries in flight ahead of the one being walked (L2 latency >> one walk)
-                constexpr int64_t STEP = IS_CWARPS * SLOTS;
-                TipEntry re, re2;
-                if (x < r_hi) re = ent_w[x];
-                if (x + STEP < r_hi) re2 = ent_w[x + STEP];
-                while (x < r_hi) {
-                    const TipEntry cur = re;
-                    const int64_t xn = x + STEP;
-                    re = re2;
-                    if (xn + STEP < r_hi) re2 = ent_w[xn + STEP];
-                    const uint32_t f = (cur.key >> 7) - (uint32_t)f0, r = cur.key & 127u;
-                    const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
-                    const uint32_t rbase = r * TILE, rx = r & 31u;
-                    if (g == 0) nm += (unsigned)(e1 - e0);
-#pragma unroll 2
-                    for (int e = e0 + g; e < e1; e += G) {
-                        const TipEntry ce = centry[e];
-                        // min of two non-negative 61-bit integers: their bit patterns order like doubles
-                        const unsigned long long add = (unsigned long long)__double_as_longlong(
-                            fmin(__longlong_as_double(cur.val), __longlong_as_double(ce.val)));
-                        const uint32_t cell = rbase + ((ce.key & 127u) ^ rx);
-                        const uint32_t alo = (uint32_t)add;
-                        const uint32_t old = atomicAdd(&acc_lo[cell], alo);
-                        atomicAdd(&acc_hi[cell], (uint32_t)(add >> 32) + (old + alo < old ? 1u : 0u));
+            // Row entries: the warp takes them in blocks of 32, one coalesced load (lane l holds entry
+            // l of the block), PREF further blocks already in flight in registers - the walk of a
+            // block is far shorter than an L2 round trip, and a kernel that kept only a couple of
+            // entries per warp in flight was bound by exactly that latency (feature tables: one
+            // match per row entry).  The entries of a block are then handed to the SLOTS groups of
+            // G lanes by shuffles, SLOTS at a time.
+            constexpr int PREF = MODE == IS_WEIGHTED ? 2 : 4;
+            constexpr int64_t STEP = (int64_t)IS_CWARPS * 32;
+            uint32_t rkey[PREF + 1], rlo[PREF + 1], rhi[PREF + 1];
+            auto load_block = [&](int64_t xb, uint32_t& k, uint32_t& lo, uint32_t& hi) {
+                const int64_t idx = xb + lane;
+                k = 0xffffffffu;
+                lo = hi = 0u;
+                if (idx < r_hi) {
+                    if (MODE == IS_WEIGHTED) {
+                        const uint4 v = reinterpret_cast<const uint4*>(entries_v)[idx];   // {key, pad, val}
+                        k = v.x;
+                        lo = v.z;
+                        hi = v.w;
+                    } else if (MODE == IS_UNWEIGHTED) {
+                        k = reinterpret_cast<const uint32_t*>(entries_v)[idx];
+                    } else {
+                        const uint2 v = reinterpret_cast<const uint2*>(entries_v)[idx];   // {key, count}
+                        k = v.x;
+                        lo = v.y;
                     }
-                    x = xn;
                 }
-            } else if (MODE == IS_UNWEIGHTED) {
-                const uint32_t* ent_u = reinterpret_cast<const uint32_t*>(entries_v);
-                const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
-                const long long* lf = reinterpret_cast<const long long*>(st + ENT + Geo::run_bytes);
-                constexpr int64_t STEP = IS_CWARPS * SLOTS;
-                uint32_t rk = 0, rk2 = 0;
-                if (x < r_hi) rk = ent_u[x];
-                if (x + STEP < r_hi) rk2 = ent_u[x + STEP];
-                while (x < r_hi) {
-                    const uint32_t cur = rk;
-                    const int64_t xn = x + STEP;
-                    rk = rk2;
-                    if (xn + STEP < r_hi) rk2 = ent_u[xn + STEP];
-                    const uint32_t f = (cur >> 7) - (uint32_t)f0, r = cur & 127u;
-                    const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
-                    const unsigned long long add = (unsigned long long)lf[f];
-                    const uint32_t alo = (uint32_t)add, ahi = (uint32_t)(add >> 32);
-                    const uint32_t rbase = r * TILE, rx = r & 31u;
-                    if (g == 0) nm += (unsigned)(e1 - e0);
-#pragma unroll 2
-                    for (int e = e0 + g; e < e1; e += G) {
-                        const uint32_t cell = rbase + ((ckey[e] & 127u) ^ rx);
-                        const uint32_t old = atomicAdd(&acc_lo[cell], alo);
-                        atomicAdd(&acc_hi[cell], ahi + (old + alo < old ? 1u : 0u));
-                    }
-                    x = xn;
+            };
+            const int64_t xb0 = r_lo + (int64_t)warp * 32;
+#pragma unroll
+            for (int k = 0; k <= PREF; ++k) load_block(xb0 + k * STEP, rkey[k], rlo[k], rhi[k]);
+            for (int64_t xb = xb0; xb < r_hi; xb += STEP) {
+                const uint32_t ckey_ = rkey[0], clo_ = rlo[0], chi_ = rhi[0];
+#pragma unroll
+                for (int k = 0; k < PREF; ++k) {
+                    rkey[k] = rkey[k + 1];
+                    rlo[k] = rlo[k + 1];
+                    rhi[k] = rhi[k + 1];
                 }
-            } else {
-                const SpEntry* ent_f = reinterpret_cast<const SpEntry*>(entries_v);
-                const SpEntry* centry = reinterpret_cast<const SpEntry*>(st);
-                constexpr int64_t STEP = IS_CWARPS * SLOTS;
-                SpEntry re, re2;
-                if (x < r_hi) re = ent_f[x];
-                if (x + STEP < r_hi) re2 = ent_f[x + STEP];
-                while (x < r_hi) {
-                    const SpEntry cur = re;
-                    const int64_t xn = x + STEP;
-                    re = re2;
-                    if (xn + STEP < r_hi) re2 = ent_f[xn + STEP];
-                    const uint32_t f = (cur.key >> 7) - (uint32_t)f0, r = cur.key & 127u;
+                load_block(xb + (PREF + 1) * STEP, rkey[PREF], rlo[PREF], rhi[PREF]);
+                const int nvalid = (int)(r_hi - xb < 32 ? r_hi - xb : 32);
+#pragma unroll 1
+                for (int rnd = 0; rnd * SLOTS < nvalid; ++rnd) {
+                    const int src = rnd * SLOTS + slot;
+                    const uint32_t key = __shfl_sync(0xffffffffu, ckey_, src);
+                    uint32_t vlo = 0u, vhi = 0u;
+                    if (MODE != IS_UNWEIGHTED) vlo = __shfl_sync(0xffffffffu, clo_, src);
+                    if (MODE == IS_WEIGHTED) vhi = __shfl_sync(0xffffffffu, chi_, src);
+                    if (src >= nvalid) continue;
+                    const uint32_t f = (key >> 7) - (uint32_t)f0, r = key & 127u;
                     const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
                     const uint32_t rbase = r * TILE, rx = r & 31u;
                     if (g == 0) nm += (unsigned)(e1 - e0);
-                    for (int e = e0 + g; e < e1; e += G) {
-                        const SpEntry ce = centry[e];
-                        const uint32_t add = MODE == IS_FEAT_COUNT ? 1u : (uint32_t)(cur.val < ce.val ? cur.val : ce.val);
-                        atomicAdd(&acc_lo[rbase + ((ce.key & 127u) ^ rx)], add);
+                    if (MODE == IS_WEIGHTED) {
+                        const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
+                        const unsigned long long rv = ((unsigned long long)vhi << 32) | vlo;
+#pragma unroll 2
+                        for (int e = e0 + g; e < e1; e += G) {
+                            const TipEntry ce = centry[e];
+                            const unsigned long long cv = (unsigned long long)ce.val;
+                            const unsigned long long add = rv < cv ? rv : cv;   // both non-negative, < 2^61
+                            const uint32_t cell = rbase + ((ce.key & 127u) ^ rx);
+                            const uint32_t alo = (uint32_t)add;
+                            const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                            atomicAdd(&acc_hi[cell], (uint32_t)(add >> 32) + (old + alo < old ? 1u : 0u));
+                        }
+                    } else if (MODE == IS_UNWEIGHTED) {
+                        const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
+                        const long long* lf = reinterpret_cast<const long long*>(st + ENT + Geo::run_bytes);
+                        const unsigned long long add = (unsigned long long)lf[f];
+                        const uint32_t alo = (uint32_t)add, ahi = (uint32_t)(add >> 32);
+#pragma unroll 2
+                        for (int e = e0 + g; e < e1; e += G) {
+                            const uint32_t cell = rbase + ((ckey[e] & 127u) ^ rx);
+                            const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                            atomicAdd(&acc_hi[cell], ahi + (old + alo < old ? 1u : 0u));
+                        }
+                    } else {
+                        const SpEntry* centry = reinterpret_cast<const SpEntry*>(st);
+                        const int rv = (int)vlo;
+                        for (int e = e0 + g; e < e1; e += G) {
+                            const SpEntry ce = centry[e];
+                            const uint32_t add = MODE == IS_FEAT_COUNT ? 1u : (uint32_t)(rv < ce.val ? rv : ce.val);
+                            atomicAdd(&acc_lo[rbase + ((ce.key & 127u) ^ rx)], add);
+                        }
                     }
-                    x = xn;
                 }
             }
             __syncwarp();

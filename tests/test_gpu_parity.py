@@ -979,7 +979,7 @@ def test_device_embedding_equals_vectorize_counts_and_tree(case):
         assert np.array_equal(prob.fetch_embedding(0, m), exp)
         assert np.array_equal(prob.fetch_embedding(1, m), exp)
         try:
-            _capi.set_option("emb_budget_bytes", 128 * 8 * 128)   # one 128-node stripe per pass
+            _capi.set_option("emb_budget_bytes", ((n + 127) // 128) * 128 * 8 * 128)   # one 128-node stripe per pass
             assert np.array_equal(prob.fetch_embedding(0, m), exp)
         finally:
             _capi.set_option("emb_budget_bytes", 0)
