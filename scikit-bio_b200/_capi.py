@@ -378,13 +378,18 @@ class PinnedBuffer:
     def __init__(self, n, dtype=np.float64):
         self._lib = load()
         self.n = int(n)
-        dt = np.dtype(dtype)
-        nbytes = max(self.n, 1) * dt.itemsize
-        self.ptr = self._lib.b2d_host_alloc(nbytes)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = max(self.n, 1) * self.dtype.itemsize
+        self.ptr = self._lib.b2d_host_alloc(self.nbytes)
         if not self.ptr:
             raise MemoryError("b2d_host_alloc failed")
-        buf = (ctypes.c_char * nbytes).from_address(self.ptr)
-        self.array = np.frombuffer(buf, dtype=dt, count=self.n)
+        self.array = self.new_array()
+
+    def new_array(self):
+        """A fresh ndarray over the buffer (the buffer itself keeps no reference to it when the
+        caller clears `.array`, so its lifetime can be tracked with a weakref)."""
+        buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
+        return np.frombuffer(buf, dtype=self.dtype, count=self.n)
 
     @classmethod
     def like(cls, a):
@@ -399,6 +404,7 @@ class PinnedBuffer:
             self.array = None
             self._lib.b2d_host_free(self.ptr)
             self.ptr = None
+            self.n = 0
 
     def __del__(self):  # pragma: no cover
         try:
