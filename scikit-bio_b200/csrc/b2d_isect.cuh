@@ -16,7 +16,8 @@
 //     next batch lands while the current one is consumed.
 //   * warps 0..30 are CONSUMERS.  Row entries come straight from global memory in warp-wide
 //     blocks of 32 (one coalesced load, several blocks in flight ahead: the loop is otherwise
-//     bound by the L2 round trip) and are handed out by shuffles; G = 4 lanes share one row
+//     bound by the L2 round trip), claimed dynamically through a counter in the stage header,
+//     and are handed out by shuffles; G = 4 lanes share one row
 //     entry and stride over the column run of its position, so a run of k column entries costs
 //     ceil(k / 4) steps instead of k (the one-thread-per-row-entry walk left 43 % of the lanes
 //     idle: run lengths differ from lane to lane).  Every match adds into a 128 x 128 tile of
@@ -48,7 +49,8 @@ struct IsHeader {
     int coff;               // column entry e (relative to its bucket) lives in slot e + coff
     int f0;                 // first position of the batch (multiple of 8)
     int done;               // 1: no more work for this tile
-    int pad[9];
+    int next;               // first row entry (relative to r_lo) not yet claimed by a consumer warp
+    int pad[8];
 };
 static_assert(sizeof(IsHeader) == 64, "header is 64 bytes");
 
@@ -146,11 +148,12 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                     re1 = (int)rrun[f1];
                 }
                 if (last || (ce1 > ce0 && re1 > re0)) {
-                    if (it >= IS_STAGES) mbar_wait(&empty[s], ph ^ 1u);
+                    if (it >= IS_STAGES) mbar_wait_sleepy(&empty[s], ph ^ 1u);
                     if (lane == 0) {
                         unsigned char* st = stage0 + (size_t)s * STAGE;
                         IsHeader* h = reinterpret_cast<IsHeader*>(st + HDR);
                         h->done = last ? 1 : 0;
+                        h->next = 0;
                         if (last) {
                             mbar_arrive(&full[s]);
                         } else {
@@ -192,27 +195,35 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
         int s = 0;
         uint32_t ph = 0;
         for (;;) {
-            mbar_wait(&full[s], ph);
+            mbar_wait_sleepy(&full[s], ph);
             const unsigned char* st = stage0 + (size_t)s * STAGE;
             const IsHeader* h = reinterpret_cast<const IsHeader*>(st + HDR);
             if (h->done) break;
             const unsigned short* fstart = reinterpret_cast<const unsigned short*>(st + ENT);
             const int coff = h->coff, f0 = h->f0;
             const int64_t r_lo = h->r_lo, r_hi = h->r_hi;
-            // Row entries: the warp takes them in blocks of 32, one coalesced load (lane l holds entry
-            // l of the block), PREF further blocks already in flight in registers - the walk of a
-            // block is far shorter than an L2 round trip, and a kernel that kept only a couple of
-            // entries per warp in flight was bound by exactly that latency (feature tables: one
-            // match per row entry).  The entries of a block are then handed to the SLOTS groups of
-            // G lanes by shuffles, SLOTS at a time.
-            constexpr int PREF = MODE == IS_WEIGHTED ? 2 : 4;
-            constexpr int64_t STEP = (int64_t)IS_CWARPS * 32;
+            // Row entries: a warp takes them in blocks of 32 - one coalesced load, lane l holds entry l
+            // of the block - handed out DYNAMICALLY through a counter in the stage header (a batch
+            // holds only a few blocks per warp: a static deal left warps idle at every stage
+            // boundary), with PREF further blocks already in flight in registers (the walk of a block
+            // is far shorter than an L2 round trip).  Every lane resolves the run of its own entry once
+            // (e0, length, row sample packed into one word); the entries of a block are then handed to
+            // the SLOTS groups of G lanes by shuffles, SLOTS at a time.
+            constexpr int PREF = MODE == IS_WEIGHTED ? 2 : 3;
+            int* next = const_cast<int*>(&h->next);
+            const int nrow = (int)(r_hi - r_lo);
+            auto grab = [&]() -> int {   // first entry of the next unclaimed block (>= nrow: none left)
+                int b = 0;
+                if (lane == 0) b = atomicAdd(next, 32);
+                return __shfl_sync(0xffffffffu, b, 0);
+            };
             uint32_t rkey[PREF + 1], rlo[PREF + 1], rhi[PREF + 1];
-            auto load_block = [&](int64_t xb, uint32_t& k, uint32_t& lo, uint32_t& hi) {
-                const int64_t idx = xb + lane;
+            int rb[PREF + 1];
+            auto load_block = [&](int b, uint32_t& k, uint32_t& lo, uint32_t& hi) {
+                const int64_t idx = r_lo + b + lane;
                 k = 0xffffffffu;
                 lo = hi = 0u;
-                if (idx < r_hi) {
+                if (b + lane < nrow) {
                     if (MODE == IS_WEIGHTED) {
                         const uint4 v = reinterpret_cast<const uint4*>(entries_v)[idx];   // {key, pad, val}
                         k = v.x;
@@ -227,31 +238,48 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                     }
                 }
             };
-            const int64_t xb0 = r_lo + (int64_t)warp * 32;
 #pragma unroll
-            for (int k = 0; k <= PREF; ++k) load_block(xb0 + k * STEP, rkey[k], rlo[k], rhi[k]);
-            for (int64_t xb = xb0; xb < r_hi; xb += STEP) {
-                const uint32_t ckey_ = rkey[0], clo_ = rlo[0], chi_ = rhi[0];
+            for (int k = 0; k <= PREF; ++k) {
+                rb[k] = grab();
+                load_block(rb[k], rkey[k], rlo[k], rhi[k]);
+            }
+            while (rb[0] < nrow) {
+                const uint32_t mykey = rkey[0];
+                uint32_t clo_ = rlo[0], chi_ = rhi[0];
+                const int nvalid = nrow - rb[0] < 32 ? nrow - rb[0] : 32;
 #pragma unroll
                 for (int k = 0; k < PREF; ++k) {
+                    rb[k] = rb[k + 1];
                     rkey[k] = rkey[k + 1];
                     rlo[k] = rlo[k + 1];
                     rhi[k] = rhi[k + 1];
                 }
-                load_block(xb + (PREF + 1) * STEP, rkey[PREF], rlo[PREF], rhi[PREF]);
-                const int nvalid = (int)(r_hi - xb < 32 ? r_hi - xb : 32);
+                rb[PREF] = grab();
+                load_block(rb[PREF], rkey[PREF], rlo[PREF], rhi[PREF]);
+                // this lane's own entry: run of its position in the staged column batch
+                uint32_t pe = 0u;   // e0 | length << 16 | row sample << 24
+                if (lane < nvalid) {
+                    const uint32_t f = (mykey >> 7) - (uint32_t)f0;
+                    const int e0 = (int)fstart[f] + coff, len = (int)fstart[f + 1] - (int)fstart[f];
+                    pe = (uint32_t)e0 | ((uint32_t)len << 16) | ((mykey & 127u) << 24);
+                    nm += (unsigned)len;
+                    if (MODE == IS_UNWEIGHTED) {   // what a match adds depends on the position only
+                        const unsigned long long add =
+                            (unsigned long long)reinterpret_cast<const long long*>(st + ENT + Geo::run_bytes)[f];
+                        clo_ = (uint32_t)add;
+                        chi_ = (uint32_t)(add >> 32);
+                    }
+                }
 #pragma unroll 1
                 for (int rnd = 0; rnd * SLOTS < nvalid; ++rnd) {
                     const int src = rnd * SLOTS + slot;
-                    const uint32_t key = __shfl_sync(0xffffffffu, ckey_, src);
-                    uint32_t vlo = 0u, vhi = 0u;
-                    if (MODE != IS_UNWEIGHTED) vlo = __shfl_sync(0xffffffffu, clo_, src);
-                    if (MODE == IS_WEIGHTED) vhi = __shfl_sync(0xffffffffu, chi_, src);
-                    if (src >= nvalid) continue;
-                    const uint32_t f = (key >> 7) - (uint32_t)f0, r = key & 127u;
-                    const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                    const uint32_t q = __shfl_sync(0xffffffffu, pe, src);
+                    const uint32_t vlo = __shfl_sync(0xffffffffu, clo_, src);
+                    uint32_t vhi = 0u;
+                    if (WIDE) vhi = __shfl_sync(0xffffffffu, chi_, src);
+                    const int e0 = (int)(q & 0xffffu), e1 = e0 + (int)((q >> 16) & 0xffu);
+                    const uint32_t r = q >> 24;
                     const uint32_t rbase = r * TILE, rx = r & 31u;
-                    if (g == 0) nm += (unsigned)(e1 - e0);
                     if (MODE == IS_WEIGHTED) {
                         const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
                         const unsigned long long rv = ((unsigned long long)vhi << 32) | vlo;
@@ -267,14 +295,11 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                         }
                     } else if (MODE == IS_UNWEIGHTED) {
                         const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
-                        const long long* lf = reinterpret_cast<const long long*>(st + ENT + Geo::run_bytes);
-                        const unsigned long long add = (unsigned long long)lf[f];
-                        const uint32_t alo = (uint32_t)add, ahi = (uint32_t)(add >> 32);
 #pragma unroll 2
                         for (int e = e0 + g; e < e1; e += G) {
                             const uint32_t cell = rbase + ((ckey[e] & 127u) ^ rx);
-                            const uint32_t old = atomicAdd(&acc_lo[cell], alo);
-                            atomicAdd(&acc_hi[cell], ahi + (old + alo < old ? 1u : 0u));
+                            const uint32_t old = atomicAdd(&acc_lo[cell], vlo);
+                            atomicAdd(&acc_hi[cell], vhi + (old + vlo < old ? 1u : 0u));
                         }
                     } else {
                         const SpEntry* centry = reinterpret_cast<const SpEntry*>(st);
