@@ -8,21 +8,22 @@
 //                                                                    Bray-Curtis / Jaccard, b2d_sparse.cuh)
 //
 // exact in 61-bit fixed point (32-bit integers for the feature tables).  One CTA per 128 x 128 tile of sample pairs:
-//   * warp 31 is the PRODUCER.  Per (tile, position chunk) it cuts the column bucket into
-//     batches at position boundaries (a whole bucket when it fits), and for every batch issues
-//     1-D bulk copies (cp.async.bulk, SASS UBLKCP) of the column entries, the slice of the
-//     column run table and - unweighted - the fixed-point lengths into one of two stages, with
-//     a small header (row-entry range, position range).  full / empty mbarriers per stage; the
-//     next batch lands while the current one is consumed.
-//   * warps 0..30 are CONSUMERS.  Row entries come straight from global memory in warp-wide
-//     blocks of 32 (one coalesced load, several blocks in flight ahead: the loop is otherwise
-//     bound by the L2 round trip), claimed dynamically through a counter in the stage header,
-//     and are handed out by shuffles; G = 4 lanes share one row
-//     entry and stride over the column run of its position, so a run of k column entries costs
-//     ceil(k / 4) steps instead of k (the one-thread-per-row-entry walk left 43 % of the lanes
-//     idle: run lengths differ from lane to lane).  Every match adds into a 128 x 128 tile of
-//     64-bit sums kept as two 32-bit halves (shared memory has native 32-bit atomic adds only;
-//     the add that wraps the low half carries into the high one), cells XOR-swizzled by the row.
+//   * warp 31 is the PRODUCER.  Per (tile, position chunk) it cuts the bucket pair into batches at
+//     position boundaries (both buckets whole when they fit; a two-step 32-lane search over the
+//     run tables otherwise), and for every batch issues 1-D bulk copies (cp.async.bulk, SASS
+//     UBLKCP) of the column entries, the ROW entries, the slice of the column run table and -
+//     unweighted - the fixed-point lengths into one of the stages, with a small header (counts,
+//     offsets, position range).  full / empty mbarriers per stage; the next batch lands while the
+//     current one is consumed.
+//   * warps 0..30 are CONSUMERS and touch shared memory only.  A warp claims eight row entries at
+//     a time through a counter in the stage header (dynamic: the cost of a row entry is the length
+//     of its column run, anything static leaves warps waiting at every stage boundary); G = 4
+//     lanes share one row entry and stride over the column run of its position, so a run of k
+//     column entries costs ceil(k / 4) steps instead of k (the one-thread-per-row-entry walk of
+//     the first generation left 43 % of the lanes idle: run lengths differ from lane to lane).
+//     Every match adds into a 128 x 128 tile of 64-bit sums kept as two 32-bit halves (shared
+//     memory has native 32-bit atomic adds only; the add that wraps the low half carries into the
+//     high one), cells XOR-swizzled by the row.
 //   * no __syncthreads between the prologue (zeroing the tile) and the epilogue (emit).
 #pragma once
 
@@ -43,14 +44,14 @@ enum IsMode : int {
 
 constexpr int IS_THREADS = 1024;
 constexpr int IS_CWARPS = 31;                       // consumer warps; warp 31 produces
-constexpr int IS_STAGES = 2;
 struct IsHeader {
-    long long r_lo, r_hi;   // global row-entry range of the batch
-    int coff;               // column entry e (relative to its bucket) lives in slot e + coff
+    int nrow;               // row entries of the batch
+    int roff;               // row entry k of the batch lives in row slot k + roff
+    int coff;               // column entry e (relative to its bucket) lives in column slot e + coff
     int f0;                 // first position of the batch (multiple of 8)
     int done;               // 1: no more work for this tile
-    int next;               // first row entry (relative to r_lo) not yet claimed by a consumer warp
-    int pad[8];
+    int next;               // first row entry of the batch not yet claimed by a consumer warp
+    int pad[10];
 };
 static_assert(sizeof(IsHeader) == 64, "header is 64 bytes");
 
@@ -58,14 +59,16 @@ template <int MODE, int CHUNK>
 struct IsGeom {
     static constexpr bool wide = MODE == IS_WEIGHTED || MODE == IS_UNWEIGHTED;        // 64-bit sums
     static constexpr int esize = MODE == IS_WEIGHTED ? 16 : MODE == IS_UNWEIGHTED ? 4 : 8;
-    static constexpr int ent_bytes = MODE == IS_UNWEIGHTED ? 24576 : 40960;           // column entries per stage
+    static constexpr int stages = wide ? 2 : 3;
+    // entries per stage and side (column block / row block)
+    static constexpr int ent_bytes = MODE == IS_WEIGHTED ? 20480 : MODE == IS_UNWEIGHTED ? 12288 : 16384;
     static constexpr int align_entries = 16 / esize;                                  // bulk copies: 16-byte units
-    static constexpr int cap = ent_bytes / esize - 2 * align_entries;                 // entries per batch
+    static constexpr int cap = ent_bytes / esize - 2 * align_entries;                 // entries per batch and side
     static constexpr int run_bytes = (CHUNK + 8) * 2 + 16;                            // run starts of a whole chunk
     static constexpr int lf_bytes = MODE == IS_UNWEIGHTED ? CHUNK * 8 : 0;            // fixed-point lengths
-    static constexpr int stage_bytes = ent_bytes + run_bytes + lf_bytes + 64;
+    static constexpr int stage_bytes = 2 * ent_bytes + run_bytes + lf_bytes + 64;
     static constexpr size_t acc_bytes = (size_t)TILE * TILE * (wide ? 8 : 4);
-    static constexpr size_t smem = acc_bytes + (size_t)IS_STAGES * stage_bytes + 4 * sizeof(uint64_t);
+    static constexpr size_t smem = acc_bytes + (size_t)stages * stage_bytes + 2 * stages * sizeof(uint64_t);
     static_assert(cap >= 8 * TILE, "eight positions of a block must fit one batch");
     static_assert(stage_bytes % 16 == 0 && smem <= 232448, "shared memory per CTA");
 };
@@ -80,20 +83,20 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
              unsigned long long* __restrict__ n_matches, PairArgs a) {
     using Geo = IsGeom<MODE, CHUNK>;
     constexpr bool WIDE = Geo::wide;
-    constexpr int ENT = Geo::ent_bytes, CAP = Geo::cap, STAGE = Geo::stage_bytes;
-    constexpr int HDR = ENT + Geo::run_bytes + Geo::lf_bytes;
+    constexpr int ENT = Geo::ent_bytes, CAP = Geo::cap, STAGE = Geo::stage_bytes, NST = Geo::stages;
+    constexpr int RUNS = 2 * ENT, LF = RUNS + Geo::run_bytes, HDR = LF + Geo::lf_bytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* acc_lo = reinterpret_cast<uint32_t*>(smem_raw);   // [128][128]
     uint32_t* acc_hi = acc_lo + TILE * TILE;                    // [128][128], 64-bit modes only
     unsigned char* stage0 = smem_raw + Geo::acc_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)IS_STAGES * STAGE);
-    uint64_t* empty = full + IS_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)NST * STAGE);
+    uint64_t* empty = full + NST;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bi = a.tiles[2 * blockIdx.x], bj = a.tiles[2 * blockIdx.x + 1];
     for (int x = tid; x < (WIDE ? 2 : 1) * TILE * TILE; x += IS_THREADS) acc_lo[x] = 0u;
     if (tid == 0) {
-        for (int s = 0; s < IS_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], IS_CWARPS);
         }
@@ -128,27 +131,29 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
             const int cn = (int)(c1 - c0), rn = (int)(r1 - r0);
             while (last || f0 < CHUNK) {
                 int f1 = CHUNK, ce1 = cn, re1 = rn;
-                if (!last && cn - ce0 > CAP) {
-                    // largest f1 in (f0, CHUNK], a multiple of 8, with crun[f1] - ce0 <= CAP: CHUNK / 32
-                    // position strides first, then 8-position strides (run starts are monotone)
+                if (!last && (cn - ce0 > CAP || rn - re0 > CAP)) {
+                    // largest f1 in (f0, CHUNK], a multiple of 8, with at most CAP column entries and at
+                    // most CAP row entries in [f0, f1): CHUNK / 32 position strides first, then 8-position
+                    // strides (run starts are monotone)
                     constexpr int S1 = CHUNK / 32;
                     int base = f0;
                     {
                         const int cand = base + S1 * (lane + 1);
-                        const bool ok = cand <= CHUNK && (int)crun[cand] - ce0 <= CAP;
+                        const bool ok = cand <= CHUNK && (int)crun[cand] - ce0 <= CAP && (int)rrun[cand] - re0 <= CAP;
                         base += S1 * __popc(__ballot_sync(0xffffffffu, ok));
                     }
                     {
                         const int cand = base + 8 * (lane + 1);
-                        const bool ok = lane < S1 / 8 - 1 && cand <= CHUNK && (int)crun[cand] - ce0 <= CAP;
+                        const bool ok = lane < S1 / 8 - 1 && cand <= CHUNK && (int)crun[cand] - ce0 <= CAP &&
+                                        (int)rrun[cand] - re0 <= CAP;
                         base += 8 * __popc(__ballot_sync(0xffffffffu, ok));
                     }
-                    f1 = base;   // > f0: eight positions hold at most 1024 entries <= CAP
+                    f1 = base;   // > f0: eight positions hold at most 1024 entries <= CAP on either side
                     ce1 = (int)crun[f1];
                     re1 = (int)rrun[f1];
                 }
                 if (last || (ce1 > ce0 && re1 > re0)) {
-                    if (it >= IS_STAGES) mbar_wait_sleepy(&empty[s], ph ^ 1u);
+                    if (it >= NST) mbar_wait_sleepy(&empty[s], ph ^ 1u);
                     if (lane == 0) {
                         unsigned char* st = stage0 + (size_t)s * STAGE;
                         IsHeader* h = reinterpret_cast<IsHeader*>(st + HDR);
@@ -157,27 +162,28 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                         if (last) {
                             mbar_arrive(&full[s]);
                         } else {
-                            // global index of smem slot 0, aligned down to a 16-byte unit
+                            // global index of slot 0 of either side, aligned down to a 16-byte unit
                             constexpr int64_t AL = Geo::align_entries;
-                            const int64_t g0 = (c0 + ce0) / AL * AL;
-                            const int64_t g1 = (c0 + ce1 + AL - 1) / AL * AL;
-                            const uint32_t ebytes = (uint32_t)(g1 - g0) * (uint32_t)Geo::esize;
+                            const int64_t gc0 = (c0 + ce0) / AL * AL, gc1 = (c0 + ce1 + AL - 1) / AL * AL;
+                            const int64_t gr0 = (r0 + re0) / AL * AL, gr1 = (r0 + re1 + AL - 1) / AL * AL;
+                            const uint32_t cbytes = (uint32_t)(gc1 - gc0) * (uint32_t)Geo::esize;
+                            const uint32_t wbytes = (uint32_t)(gr1 - gr0) * (uint32_t)Geo::esize;
                             const uint32_t rbytes = (uint32_t)(f1 - f0 + 8) * 2u;
                             const uint32_t lbytes = MODE == IS_UNWEIGHTED ? (uint32_t)(f1 - f0) * 8u : 0u;
-                            h->r_lo = r0 + re0;
-                            h->r_hi = r0 + re1;
-                            h->coff = (int)(c0 - g0);
+                            h->nrow = re1 - re0;
+                            h->roff = (int)(r0 + re0 - gr0);
+                            h->coff = (int)(c0 - gc0);
                             h->f0 = f0;
-                            mbar_arrive_expect_tx(&full[s], ebytes + rbytes + lbytes);
-                            bulk_g2s(st, ent_b + g0 * Geo::esize, ebytes, &full[s]);
-                            bulk_g2s(st + ENT, crun + f0, rbytes, &full[s]);
-                            if (MODE == IS_UNWEIGHTED)
-                                bulk_g2s(st + ENT + Geo::run_bytes, lenfx + ch * CHUNK + f0, lbytes, &full[s]);
+                            mbar_arrive_expect_tx(&full[s], cbytes + wbytes + rbytes + lbytes);
+                            bulk_g2s(st, ent_b + gc0 * Geo::esize, cbytes, &full[s]);
+                            bulk_g2s(st + ENT, ent_b + gr0 * Geo::esize, wbytes, &full[s]);
+                            bulk_g2s(st + RUNS, crun + f0, rbytes, &full[s]);
+                            if (MODE == IS_UNWEIGHTED) bulk_g2s(st + LF, lenfx + ch * CHUNK + f0, lbytes, &full[s]);
                         }
                     }
                     __syncwarp();
                     ++it;
-                    if (++s == IS_STAGES) {
+                    if (++s == NST) {
                         s = 0;
                         ph ^= 1u;
                     }
@@ -190,6 +196,10 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
         }
     } else {
         // ------------------------------- consumers -------------------------------
+        // Everything a batch needs is in the stage: column entries, ROW entries, the column run starts
+        // (and the lengths).  A warp claims SLOTS row entries at a time through the counter in the
+        // header (the next claim is already in flight while it works), each group of G lanes takes one
+        // of them and strides over the column run of its position.
         constexpr int SLOTS = 32 / G;
         const int slot = lane / G, g = lane % G;
         int s = 0;
@@ -199,90 +209,27 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
             const unsigned char* st = stage0 + (size_t)s * STAGE;
             const IsHeader* h = reinterpret_cast<const IsHeader*>(st + HDR);
             if (h->done) break;
-            const unsigned short* fstart = reinterpret_cast<const unsigned short*>(st + ENT);
-            const int coff = h->coff, f0 = h->f0;
-            const int64_t r_lo = h->r_lo, r_hi = h->r_hi;
-            // Row entries: a warp takes them in blocks of 32 - one coalesced load, lane l holds entry l
-            // of the block - handed out DYNAMICALLY through a counter in the stage header (a batch
-            // holds only a few blocks per warp: a static deal left warps idle at every stage
-            // boundary), with PREF further blocks already in flight in registers (the walk of a block
-            // is far shorter than an L2 round trip).  Every lane resolves the run of its own entry once
-            // (e0, length, row sample packed into one word); the entries of a block are then handed to
-            // the SLOTS groups of G lanes by shuffles, SLOTS at a time.
-            constexpr int PREF = MODE == IS_WEIGHTED ? 2 : 3;
+            const unsigned short* fstart = reinterpret_cast<const unsigned short*>(st + RUNS);
+            const int coff = h->coff, f0 = h->f0, nrow = h->nrow, roff = h->roff;
             int* next = const_cast<int*>(&h->next);
-            const int nrow = (int)(r_hi - r_lo);
-            auto grab = [&]() -> int {   // first entry of the next unclaimed block (>= nrow: none left)
+            auto grab = [&]() -> int {
                 int b = 0;
-                if (lane == 0) b = atomicAdd(next, 32);
+                if (lane == 0) b = atomicAdd(next, SLOTS);
                 return __shfl_sync(0xffffffffu, b, 0);
             };
-            uint32_t rkey[PREF + 1], rlo[PREF + 1], rhi[PREF + 1];
-            int rb[PREF + 1];
-            auto load_block = [&](int b, uint32_t& k, uint32_t& lo, uint32_t& hi) {
-                const int64_t idx = r_lo + b + lane;
-                k = 0xffffffffu;
-                lo = hi = 0u;
-                if (b + lane < nrow) {
-                    if (MODE == IS_WEIGHTED) {
-                        const uint4 v = reinterpret_cast<const uint4*>(entries_v)[idx];   // {key, pad, val}
-                        k = v.x;
-                        lo = v.z;
-                        hi = v.w;
-                    } else if (MODE == IS_UNWEIGHTED) {
-                        k = reinterpret_cast<const uint32_t*>(entries_v)[idx];
-                    } else {
-                        const uint2 v = reinterpret_cast<const uint2*>(entries_v)[idx];   // {key, count}
-                        k = v.x;
-                        lo = v.y;
-                    }
-                }
-            };
-#pragma unroll
-            for (int k = 0; k <= PREF; ++k) {
-                rb[k] = grab();
-                load_block(rb[k], rkey[k], rlo[k], rhi[k]);
-            }
-            while (rb[0] < nrow) {
-                const uint32_t mykey = rkey[0];
-                uint32_t clo_ = rlo[0], chi_ = rhi[0];
-                const int nvalid = nrow - rb[0] < 32 ? nrow - rb[0] : 32;
-#pragma unroll
-                for (int k = 0; k < PREF; ++k) {
-                    rb[k] = rb[k + 1];
-                    rkey[k] = rkey[k + 1];
-                    rlo[k] = rlo[k + 1];
-                    rhi[k] = rhi[k + 1];
-                }
-                rb[PREF] = grab();
-                load_block(rb[PREF], rkey[PREF], rlo[PREF], rhi[PREF]);
-                // this lane's own entry: run of its position in the staged column batch
-                uint32_t pe = 0u;   // e0 | length << 16 | row sample << 24
-                if (lane < nvalid) {
-                    const uint32_t f = (mykey >> 7) - (uint32_t)f0;
-                    const int e0 = (int)fstart[f] + coff, len = (int)fstart[f + 1] - (int)fstart[f];
-                    pe = (uint32_t)e0 | ((uint32_t)len << 16) | ((mykey & 127u) << 24);
-                    nm += (unsigned)len;
-                    if (MODE == IS_UNWEIGHTED) {   // what a match adds depends on the position only
-                        const unsigned long long add =
-                            (unsigned long long)reinterpret_cast<const long long*>(st + ENT + Geo::run_bytes)[f];
-                        clo_ = (uint32_t)add;
-                        chi_ = (uint32_t)(add >> 32);
-                    }
-                }
-#pragma unroll 1
-                for (int rnd = 0; rnd * SLOTS < nvalid; ++rnd) {
-                    const int src = rnd * SLOTS + slot;
-                    const uint32_t q = __shfl_sync(0xffffffffu, pe, src);
-                    const uint32_t vlo = __shfl_sync(0xffffffffu, clo_, src);
-                    uint32_t vhi = 0u;
-                    if (WIDE) vhi = __shfl_sync(0xffffffffu, chi_, src);
-                    const int e0 = (int)(q & 0xffffu), e1 = e0 + (int)((q >> 16) & 0xffu);
-                    const uint32_t r = q >> 24;
-                    const uint32_t rbase = r * TILE, rx = r & 31u;
+            int b = grab();
+            while (b < nrow) {
+                const int bn = grab();   // the next claim travels while this one is worked on
+                const int k = b + slot;
+                if (k < nrow) {
                     if (MODE == IS_WEIGHTED) {
                         const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
-                        const unsigned long long rv = ((unsigned long long)vhi << 32) | vlo;
+                        const TipEntry re = reinterpret_cast<const TipEntry*>(st + ENT)[k + roff];
+                        const uint32_t f = (re.key >> 7) - (uint32_t)f0, r = re.key & 127u;
+                        const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                        const uint32_t rbase = r * TILE, rx = r & 31u;
+                        const unsigned long long rv = (unsigned long long)re.val;
+                        if (g == 0) nm += (unsigned)(e1 - e0);
 #pragma unroll 2
                         for (int e = e0 + g; e < e1; e += G) {
                             const TipEntry ce = centry[e];
@@ -295,26 +242,38 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
                         }
                     } else if (MODE == IS_UNWEIGHTED) {
                         const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
+                        const uint32_t rk = reinterpret_cast<const uint32_t*>(st + ENT)[k + roff];
+                        const uint32_t f = (rk >> 7) - (uint32_t)f0, r = rk & 127u;
+                        const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                        const unsigned long long add = (unsigned long long)reinterpret_cast<const long long*>(st + LF)[f];
+                        const uint32_t alo = (uint32_t)add, ahi = (uint32_t)(add >> 32);
+                        const uint32_t rbase = r * TILE, rx = r & 31u;
+                        if (g == 0) nm += (unsigned)(e1 - e0);
 #pragma unroll 2
                         for (int e = e0 + g; e < e1; e += G) {
                             const uint32_t cell = rbase + ((ckey[e] & 127u) ^ rx);
-                            const uint32_t old = atomicAdd(&acc_lo[cell], vlo);
-                            atomicAdd(&acc_hi[cell], vhi + (old + vlo < old ? 1u : 0u));
+                            const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                            atomicAdd(&acc_hi[cell], ahi + (old + alo < old ? 1u : 0u));
                         }
                     } else {
                         const SpEntry* centry = reinterpret_cast<const SpEntry*>(st);
-                        const int rv = (int)vlo;
+                        const SpEntry re = reinterpret_cast<const SpEntry*>(st + ENT)[k + roff];
+                        const uint32_t f = (re.key >> 7) - (uint32_t)f0, r = re.key & 127u;
+                        const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                        const uint32_t rbase = r * TILE, rx = r & 31u;
+                        if (g == 0) nm += (unsigned)(e1 - e0);
                         for (int e = e0 + g; e < e1; e += G) {
                             const SpEntry ce = centry[e];
-                            const uint32_t add = MODE == IS_FEAT_COUNT ? 1u : (uint32_t)(rv < ce.val ? rv : ce.val);
+                            const uint32_t add = MODE == IS_FEAT_COUNT ? 1u : (uint32_t)(re.val < ce.val ? re.val : ce.val);
                             atomicAdd(&acc_lo[rbase + ((ce.key & 127u) ^ rx)], add);
                         }
                     }
                 }
+                b = bn;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
-            if (++s == IS_STAGES) {
+            if (++s == NST) {
                 s = 0;
                 ph ^= 1u;
             }
