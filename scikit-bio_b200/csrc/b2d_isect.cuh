@@ -197,9 +197,9 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
     } else {
         // ------------------------------- consumers -------------------------------
         // Everything a batch needs is in the stage: column entries, ROW entries, the column run starts
-        // (and the lengths).  A warp claims 2 * SLOTS row entries at a time through the counter in the
-        // header (the next claim is already in flight while it works), each group of G lanes takes two
-        // of them and strides over the column run of their position.
+        // (and the lengths).  A warp claims SLOTS row entries at a time through the counter in the
+        // header (the next claim is already in flight while it works), each group of G lanes takes one
+        // of them and strides over the column run of its position.
         constexpr int SLOTS = 32 / G;
         const int slot = lane / G, g = lane % G;
         int s = 0;
@@ -214,111 +214,58 @@ k_pair_isect(const void* __restrict__ entries_v, const int64_t* __restrict__ buc
             int* next = const_cast<int*>(&h->next);
             auto grab = [&]() -> int {
                 int b = 0;
-                if (lane == 0) b = atomicAdd(next, 2 * SLOTS);
+                if (lane == 0) b = atomicAdd(next, SLOTS);
                 return __shfl_sync(0xffffffffu, b, 0);
-            };
-            // one 64-bit add as two 32-bit atomics (the add that wraps the low half carries)
-            auto add64 = [&](uint32_t cell, unsigned long long v) {
-                const uint32_t alo = (uint32_t)v;
-                const uint32_t old = atomicAdd(&acc_lo[cell], alo);
-                atomicAdd(&acc_hi[cell], (uint32_t)(v >> 32) + (old + alo < old ? 1u : 0u));
             };
             int b = grab();
             while (b < nrow) {
                 const int bn = grab();   // the next claim travels while this one is worked on
-                // a group takes TWO consecutive row entries: at a position with many samples they share
-                // the position, and one read of a column entry then serves two matches
-                const int k0 = b + 2 * slot;
-                if (k0 < nrow) {
-                    const bool two = k0 + 1 < nrow;
+                const int k = b + slot;
+                if (k < nrow) {
                     if (MODE == IS_WEIGHTED) {
                         const TipEntry* centry = reinterpret_cast<const TipEntry*>(st);
-                        const TipEntry* rows = reinterpret_cast<const TipEntry*>(st + ENT) + roff;
-                        const TipEntry ra = rows[k0];
-                        TipEntry rb = ra;
-                        if (two) rb = rows[k0 + 1];
-                        const uint32_t fa = (ra.key >> 7) - (uint32_t)f0, fb = (rb.key >> 7) - (uint32_t)f0;
-                        const uint32_t rA = ra.key & 127u, rB = rb.key & 127u;
-                        const int e0 = (int)fstart[fa] + coff, e1 = (int)fstart[fa + 1] + coff;
-                        const unsigned long long va = (unsigned long long)ra.val, vb = (unsigned long long)rb.val;
-                        if (two && fa == fb) {
-                            if (g == 0) nm += 2u * (unsigned)(e1 - e0);
+                        const TipEntry re = reinterpret_cast<const TipEntry*>(st + ENT)[k + roff];
+                        const uint32_t f = (re.key >> 7) - (uint32_t)f0, r = re.key & 127u;
+                        const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                        const uint32_t rbase = r * TILE, rx = r & 31u;
+                        const unsigned long long rv = (unsigned long long)re.val;
+                        if (g == 0) nm += (unsigned)(e1 - e0);
 #pragma unroll 2
-                            for (int e = e0 + g; e < e1; e += G) {
-                                const TipEntry ce = centry[e];
-                                const unsigned long long cv = (unsigned long long)ce.val;
-                                const uint32_t cc = ce.key & 127u;
-                                add64(rA * TILE + (cc ^ (rA & 31u)), va < cv ? va : cv);   // both < 2^61
-                                add64(rB * TILE + (cc ^ (rB & 31u)), vb < cv ? vb : cv);
-                            }
-                        } else {
-                            if (g == 0) nm += (unsigned)(e1 - e0);
-#pragma unroll 2
-                            for (int e = e0 + g; e < e1; e += G) {
-                                const TipEntry ce = centry[e];
-                                const unsigned long long cv = (unsigned long long)ce.val;
-                                add64(rA * TILE + ((ce.key & 127u) ^ (rA & 31u)), va < cv ? va : cv);
-                            }
-                            if (two) {
-                                const int d0 = (int)fstart[fb] + coff, d1 = (int)fstart[fb + 1] + coff;
-                                if (g == 0) nm += (unsigned)(d1 - d0);
-#pragma unroll 2
-                                for (int e = d0 + g; e < d1; e += G) {
-                                    const TipEntry ce = centry[e];
-                                    const unsigned long long cv = (unsigned long long)ce.val;
-                                    add64(rB * TILE + ((ce.key & 127u) ^ (rB & 31u)), vb < cv ? vb : cv);
-                                }
-                            }
+                        for (int e = e0 + g; e < e1; e += G) {
+                            const TipEntry ce = centry[e];
+                            const unsigned long long cv = (unsigned long long)ce.val;
+                            const unsigned long long add = rv < cv ? rv : cv;   // both non-negative, < 2^61
+                            const uint32_t cell = rbase + ((ce.key & 127u) ^ rx);
+                            const uint32_t alo = (uint32_t)add;
+                            const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                            atomicAdd(&acc_hi[cell], (uint32_t)(add >> 32) + (old + alo < old ? 1u : 0u));
                         }
                     } else if (MODE == IS_UNWEIGHTED) {
                         const uint32_t* ckey = reinterpret_cast<const uint32_t*>(st);
-                        const uint32_t* rows = reinterpret_cast<const uint32_t*>(st + ENT) + roff;
-                        const long long* lf = reinterpret_cast<const long long*>(st + LF);
-                        const uint32_t ka = rows[k0];
-                        const uint32_t kb = two ? rows[k0 + 1] : ka;
-                        const uint32_t fa = (ka >> 7) - (uint32_t)f0, fb = (kb >> 7) - (uint32_t)f0;
-                        const uint32_t rA = ka & 127u, rB = kb & 127u;
-                        const int e0 = (int)fstart[fa] + coff, e1 = (int)fstart[fa + 1] + coff;
-                        const unsigned long long adda = (unsigned long long)lf[fa];
-                        if (two && fa == fb) {
-                            if (g == 0) nm += 2u * (unsigned)(e1 - e0);
+                        const uint32_t rk = reinterpret_cast<const uint32_t*>(st + ENT)[k + roff];
+                        const uint32_t f = (rk >> 7) - (uint32_t)f0, r = rk & 127u;
+                        const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                        const unsigned long long add = (unsigned long long)reinterpret_cast<const long long*>(st + LF)[f];
+                        const uint32_t alo = (uint32_t)add, ahi = (uint32_t)(add >> 32);
+                        const uint32_t rbase = r * TILE, rx = r & 31u;
+                        if (g == 0) nm += (unsigned)(e1 - e0);
 #pragma unroll 2
-                            for (int e = e0 + g; e < e1; e += G) {
-                                const uint32_t cc = ckey[e] & 127u;
-                                add64(rA * TILE + (cc ^ (rA & 31u)), adda);
-                                add64(rB * TILE + (cc ^ (rB & 31u)), adda);
-                            }
-                        } else {
-                            if (g == 0) nm += (unsigned)(e1 - e0);
-#pragma unroll 2
-                            for (int e = e0 + g; e < e1; e += G) add64(rA * TILE + ((ckey[e] & 127u) ^ (rA & 31u)), adda);
-                            if (two) {
-                                const int d0 = (int)fstart[fb] + coff, d1 = (int)fstart[fb + 1] + coff;
-                                const unsigned long long addb = (unsigned long long)lf[fb];
-                                if (g == 0) nm += (unsigned)(d1 - d0);
-#pragma unroll 2
-                                for (int e = d0 + g; e < d1; e += G)
-                                    add64(rB * TILE + ((ckey[e] & 127u) ^ (rB & 31u)), addb);
-                            }
+                        for (int e = e0 + g; e < e1; e += G) {
+                            const uint32_t cell = rbase + ((ckey[e] & 127u) ^ rx);
+                            const uint32_t old = atomicAdd(&acc_lo[cell], alo);
+                            atomicAdd(&acc_hi[cell], ahi + (old + alo < old ? 1u : 0u));
                         }
                     } else {
-                        // feature tables: a feature is held by ~1 % of the samples, runs of one or two
-                        // entries - one row entry after the other
                         const SpEntry* centry = reinterpret_cast<const SpEntry*>(st);
-                        const SpEntry* rows = reinterpret_cast<const SpEntry*>(st + ENT) + roff;
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            if (t == 1 && !two) break;
-                            const SpEntry re = rows[k0 + t];
-                            const uint32_t f = (re.key >> 7) - (uint32_t)f0, r = re.key & 127u;
-                            const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
-                            const uint32_t rbase = r * TILE, rx = r & 31u;
-                            if (g == 0) nm += (unsigned)(e1 - e0);
-                            for (int e = e0 + g; e < e1; e += G) {
-                                const SpEntry ce = centry[e];
-                                const uint32_t add = MODE == IS_FEAT_COUNT ? 1u : (uint32_t)(re.val < ce.val ? re.val : ce.val);
-                                atomicAdd(&acc_lo[rbase + ((ce.key & 127u) ^ rx)], add);
-                            }
+                        const SpEntry re = reinterpret_cast<const SpEntry*>(st + ENT)[k + roff];
+                        const uint32_t f = (re.key >> 7) - (uint32_t)f0, r = re.key & 127u;
+                        const int e0 = (int)fstart[f] + coff, e1 = (int)fstart[f + 1] + coff;
+                        const uint32_t rbase = r * TILE, rx = r & 31u;
+                        if (g == 0) nm += (unsigned)(e1 - e0);
+                        for (int e = e0 + g; e < e1; e += G) {
+                            const SpEntry ce = centry[e];
+                            const uint32_t add = MODE == IS_FEAT_COUNT ? 1u : (uint32_t)(re.val < ce.val ? re.val : ce.val);
+                            atomicAdd(&acc_lo[rbase + ((ce.key & 127u) ^ rx)], add);
                         }
                     }
                 }
