@@ -220,9 +220,11 @@ int b2d_beta_diversity_features(int metric, int device,
  *                       feature tables (Bray-Curtis / Jaccard)
  *   "walk_decomposed"   0: always the sequential tree walk;  "plain_kernels" 1: cross-check
  *                       kernels without bulk copies.
- *   "isect_kernel"      1 (default): pipelined intersection kernel for the sparse rows
- *                       (b2d_isect.cuh); 0: the first-generation kernels (cross-check)
- *   "isect_group"       lanes sharing one row entry in that kernel: 1, 2, 4 (default) or 8 */
+ *   "isect_kernel"      -1 (default): pipelined intersection kernel for the sparse rows (b2d_isect.cuh),
+ *                       except unweighted UniFrac with more than 6 000 keys per (block, chunk) bucket;
+ *                       1: always; 0: the first-generation kernels
+ *   "isect_group"       lanes sharing one row entry in that kernel: 1, 2, 4 or 8; 0 (default): 4 for
+ *                       weighted UniFrac, 2 for unweighted, 1 for feature tables */
 int b2d_set_option(const char* name, int64_t value);
 
 /* On-device micro-benchmarks used by bench.py for the roofline denominators:

@@ -46,8 +46,9 @@ static int g_cache_embedding = 1;              // park freed device buffers for 
 static int64_t g_cache_limit_bytes = (int64_t)4 << 30;  // ... but at most this much per device
 static int g_weighted_skip = 1;                // zero-block skipping in the weighted pair kernel
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
-static int g_isect_kernel = 1;                 // 1: pipelined intersection kernel (b2d_isect.cuh); 0: first generation
-static int g_isect_group = 4;                  // lanes sharing one row entry in that kernel (1, 2, 4 or 8)
+static int g_isect_kernel = -1;                // 1: pipelined intersection kernel (b2d_isect.cuh); 0: first generation;
+                                               // -1: pipelined, except unweighted UniFrac with large buckets (see use_isect)
+static int g_isect_group = 0;                  // lanes sharing one row entry in that kernel (1, 2, 4, 8; 0: per mode)
 
 static bool plain_kernels() {
     if (g_plain_kernels < 0) {
@@ -650,10 +651,13 @@ static int check_common(b2d_problem** out, int device, int64_t n, int64_t m,
 template <int MODE, int CHUNK>
 static int launch_isect(b2d_problem* p, cudaStream_t st, const void* entries, const int64_t* bucket_ptr,
                         const unsigned short* runs, const long long* lenfx, int64_t nch, const PairArgs& a) {
+    // lanes per row entry: long column runs (weighted: rows up to ~0.3 / density tips) take 4, the
+    // shorter runs of the unweighted threshold 2, feature tables (runs of one or two entries) 1
+    const int grp = g_isect_group ? g_isect_group : (MODE == IS_WEIGHTED ? 4 : MODE == IS_UNWEIGHTED ? 2 : 1);
     void (*kern)(const void*, const int64_t*, const unsigned short*, const long long*, int64_t, const long long*,
                  const double*, unsigned long long*, PairArgs) =
-        g_isect_group == 1 ? k_pair_isect<MODE, 1, CHUNK> : g_isect_group == 2 ? k_pair_isect<MODE, 2, CHUNK>
-        : g_isect_group == 8 ? k_pair_isect<MODE, 8, CHUNK> : k_pair_isect<MODE, 4, CHUNK>;
+        grp == 1 ? k_pair_isect<MODE, 1, CHUNK> : grp == 2 ? k_pair_isect<MODE, 2, CHUNK>
+        : grp == 8 ? k_pair_isect<MODE, 8, CHUNK> : k_pair_isect<MODE, 4, CHUNK>;
     constexpr size_t smem = IsGeom<MODE, CHUNK>::smem;
     B2D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)p->ntiles, IS_THREADS, smem, st>>>(entries, bucket_ptr, runs, lenfx, nch, p->d_tip_ufx,
@@ -719,9 +723,9 @@ int b2d_set_option(const char* name, int64_t value) {
     } else if (s == "weighted_skip") {
         g_weighted_skip = value ? 1 : 0;
     } else if (s == "isect_kernel") {
-        g_isect_kernel = value ? 1 : 0;
+        g_isect_kernel = value < 0 ? -1 : (value ? 1 : 0);
     } else if (s == "isect_group") {
-        g_isect_group = (value == 1 || value == 2 || value == 8) ? (int)value : 4;
+        g_isect_group = (value == 1 || value == 2 || value == 4 || value == 8) ? (int)value : 0;
     } else {
         return fail(B2D_ERR_INVALID_ARGUMENT, "unknown option " + s);
     }
@@ -1271,6 +1275,18 @@ static int skip_prepare_pass(b2d_problem* p, int64_t q0, int64_t rows, int64_t Q
     return B2D_OK;
 }
 
+// Which intersection kernel: the pipelined one, except (automatic mode) unweighted UniFrac with large
+// buckets - measured: 9 200 keys per bucket (10 000 x 100 000 tips) 38.7 ms first generation vs 43.2 ms,
+// 3 400 keys per bucket (one shard of 100 000 x 500 000 tips) 935 ms vs 868 ms: with few keys per
+// (block, chunk) the first generation's barriers and 1 024-entry rounds dominate, with many its
+// one-thread-per-entry walk over a whole staged bucket wins.
+static bool use_isect(const b2d_problem* p, bool unweighted) {
+    if (g_isect_kernel >= 0) return g_isect_kernel == 1;
+    if (!unweighted) return true;
+    const double per_bucket = p->rows_entries / std::max(1.0, (double)p->nb * (double)p->tip_nch);
+    return per_bucket < 6000.0;
+}
+
 static int launch_pairs_dense(b2d_problem* p, const double* emb, const double* len_rel,
                               int64_t q0, int64_t q1, int64_t QR, int epilogue, bool skip) {
     // node chunks [qa, qb) relative to the resident range; two-level fp64 summation:
@@ -1536,7 +1552,7 @@ static int compute_dense(b2d_problem* p, int metric) {
                 cudaStream_t st;
                 if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
                 B2D_CUDA(cudaEventRecord(p->ev[7], st));
-                if (g_isect_kernel) {
+                if (use_isect(p, false)) {
                     if ((rc = launch_isect<IS_WEIGHTED, TP_CHUNK>(p, st, p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, nullptr,
                                                                   p->tip_nch, a)))
                         return rc;
@@ -1681,7 +1697,7 @@ static int compute_bits(b2d_problem* p, int metric) {
             cudaStream_t st;
             if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
             B2D_CUDA(cudaEventRecord(p->ev[7], st));
-            if (g_isect_kernel) {
+            if (use_isect(p, true)) {
                 if ((rc = launch_isect<IS_UNWEIGHTED, TP_CHUNK>(p, st, p->d_ukeys, p->d_tip_ptr, p->d_tip_runs, p->d_lenfx,
                                                                 p->tip_nch, a)))
                     return rc;
@@ -1870,7 +1886,7 @@ static int compute_sparse(b2d_problem* p, int metric) {
         cudaStream_t st;
         int rc = chunk_target(p, &st, &a.out, &a.first);
         if (rc) return rc;
-        if (g_isect_kernel) {
+        if (g_isect_kernel != 0) {
             if (metric == B2D_JACCARD)
                 rc = launch_isect<IS_FEAT_COUNT, SP_CHUNK>(p, st, p->d_sp_entries, p->d_sp_ptr, p->d_sp_runs, nullptr,
                                                            p->sp_nch, a);

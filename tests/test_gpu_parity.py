@@ -910,8 +910,8 @@ def test_pipelined_intersection_kernel_matches_the_first_generation_bit_for_bit(
                             prob.fetch(out)
                     res[(kern, grp, shards)] = out
         finally:
-            _capi.set_option("isect_kernel", 1)
-            _capi.set_option("isect_group", 4)
+            _capi.set_option("isect_kernel", -1)
+            _capi.set_option("isect_group", 0)
         base = res[(0, 4, 1)]
         assert_close_rel(base, exp[key], UNIFRAC_RTOL, key + " first-generation kernel vs oracle")
         for k, v in res.items():
@@ -1142,5 +1142,5 @@ def test_pipelined_intersection_kernel_on_feature_tables():
                         assert np.array_equal(out, exp[key], equal_nan=True), (n, key, kern, grp, shards)
         finally:
             _capi.set_option("sparse_features", -1)
-            _capi.set_option("isect_kernel", 1)
-            _capi.set_option("isect_group", 4)
+            _capi.set_option("isect_kernel", -1)
+            _capi.set_option("isect_group", 0)
