@@ -520,7 +520,8 @@ def roofline_block(ctx, inp, t, pair_ms, prep_ms, P_shard, P_total, default_shap
         # accumulator update per (sample pair, shared feature) = sum_f C(n_f, 2).
         nf = np.bincount(inp["cols"], minlength=m).astype(np.float64)
         matches = float((nf * (nf - 1.0) / 2.0).sum()) * (P_shard / max(P_total, 1))
-        kernel, bound, unit = "k_pair_isect", "smem-atomic", "Tatom/s (shared-memory int32 atomic adds)"
+        kernel = "k_pair_isect" if t.get("isect_generation", 2) == 2 else "k_pair_sparse"
+        bound, unit = "smem-atomic", "Tatom/s (shared-memory int32 atomic adds)"
         peak, peak_source = atom_peak, atom_src
         alg_units = matches
         units_per_term = matches / max(P_shard * nodes_per_launch, 1)
@@ -556,7 +557,9 @@ def roofline_block(ctx, inp, t, pair_ms, prep_ms, P_shard, P_total, default_shap
     # dense kernel's numbers kept beside it.  Unit of work: one (sample pair, row) match = two
     # 32-bit shared-memory atomic adds (a 64-bit sum kept as two halves).
     if t["tips_ms"] > 0 and t["sparse_row_matches"] > 0:
-        kname = "k_pair_isect"   # b2d_isect.cuh, IS_UNWEIGHTED / IS_WEIGHTED instantiation
+        # which kernel the library chose: the pipelined one (b2d_isect.cuh) or the first generation
+        kname = "k_pair_isect" if t.get("isect_generation", 2) == 2 else (
+            "k_pair_utips" if key == "unweighted_unifrac" else "k_pair_tips")
         entry_bytes = 4.0 if key == "unweighted_unifrac" else 16.0
         atoms = 2.0 * t["sparse_row_matches"]
         a_rate = atoms / (t["tips_ms"] * 1e-3) / 1e12

@@ -177,7 +177,8 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * recomputed in floating point from the resident embedding,
  * [14] largest number of tips below a node whose row went through the sparse intersection
  * kernel (0: none, 1: tip rows only), [15] entries of those rows, [16] (sample pair, row) matches
- * that kernel accumulated.  n: slots to fill (<= 17). */
+ * that kernel accumulated, [17] which intersection kernel ran (2: pipelined, b2d_isect.cuh; 1: first
+ * generation; 0: none).  n: slots to fill (<= 18). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);

@@ -451,6 +451,7 @@ struct b2d_problem {
     double* d_rows_upart = nullptr;         // [nch * 4][npad]
     int64_t tip_nch = 0;
     double tips_flagged = 0, t_tips = 0, tip_matches = 0;
+    double isect_generation = 0;            // intersection kernel of the last compute: 2 pipelined, 1 first generation, 0 none
     unsigned* d_tip_cnt = nullptr;          // [npad] sparse-row entries per sample (guard: quantisation term)
     FlaggedPair* d_flag_list = nullptr;     // [FLAG_CAP] pairs the guard flagged (recomputed in floating point)
     // sparse feature-table path
@@ -1552,6 +1553,7 @@ static int compute_dense(b2d_problem* p, int metric) {
                 cudaStream_t st;
                 if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
                 B2D_CUDA(cudaEventRecord(p->ev[7], st));
+                p->isect_generation = use_isect(p, false) ? 2 : 1;
                 if (use_isect(p, false)) {
                     if ((rc = launch_isect<IS_WEIGHTED, TP_CHUNK>(p, st, p->d_tip_entries, p->d_tip_ptr, p->d_tip_runs, nullptr,
                                                                   p->tip_nch, a)))
@@ -1697,6 +1699,7 @@ static int compute_bits(b2d_problem* p, int metric) {
             cudaStream_t st;
             if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
             B2D_CUDA(cudaEventRecord(p->ev[7], st));
+            p->isect_generation = use_isect(p, true) ? 2 : 1;
             if (use_isect(p, true)) {
                 if ((rc = launch_isect<IS_UNWEIGHTED, TP_CHUNK>(p, st, p->d_ukeys, p->d_tip_ptr, p->d_tip_runs, p->d_lenfx,
                                                                 p->tip_nch, a)))
@@ -1886,6 +1889,7 @@ static int compute_sparse(b2d_problem* p, int metric) {
         cudaStream_t st;
         int rc = chunk_target(p, &st, &a.out, &a.first);
         if (rc) return rc;
+        p->isect_generation = g_isect_kernel != 0 ? 2 : 1;
         if (g_isect_kernel != 0) {
             if (metric == B2D_JACCARD)
                 rc = launch_isect<IS_FEAT_COUNT, SP_CHUNK>(p, st, p->d_sp_entries, p->d_sp_ptr, p->d_sp_runs, nullptr,
@@ -1928,6 +1932,7 @@ static int b2d_problem_compute_impl(b2d_problem* p, int metric) {
         B2D_CUDA(cudaMemsetAsync(p->d_out, 0, p->out_len * sizeof(double), p->stream));
     p->n_kernels = 0;
     p->tips_flagged = 0;
+    p->isect_generation = 0;
     int rc;
     switch (metric) {
         case B2D_UNWEIGHTED_UNIFRAC:
@@ -2235,14 +2240,15 @@ static int b2d_problem_sample_vector_impl(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[17] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+    double v[18] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
                     p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged,
                     p->urows_active ? (double)p->rows_S0
                                     : (p->tips_active ? (p->rows_general ? (double)p->rows_S0 : 1.0) : 0.0),
                     p->urows_active || (p->tips_active && p->rows_general) ? p->rows_entries : 0.0,
-                    p->urows_active || p->tips_active ? p->tip_matches : 0.0};
-    for (int i = 0; i < n && i < 17; ++i) ms[i] = v[i];
+                    p->urows_active || p->tips_active ? p->tip_matches : 0.0,
+                    p->isect_generation};
+    for (int i = 0; i < n && i < 18; ++i) ms[i] = v[i];
     return B2D_OK;
 }
 

@@ -78,7 +78,7 @@ class _FakeProblem:
                 "pair_launches": 1, "nodes_resident": 0 if self.kind == "features" else self.m, "passes": 1,
                 "visits_executed": 10.0, "visits_dense": 40.0, "skip_prep_ms": 0.5, "kernels": 12,
                 "tips_ms": 1.5, "tips_flagged": 0, "sparse_rows_max_tips": 4, "sparse_row_entries": 1000,
-                "sparse_row_matches": 5000.0}
+                "sparse_row_matches": 5000.0, "isect_generation": 2}
 
     def destroy(self):
         pass
