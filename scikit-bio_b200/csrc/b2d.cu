@@ -26,6 +26,7 @@
 #include "b2d_skip.cuh"
 #include "b2d_tips.cuh"
 #include "b2d_isect.cuh"
+#include "b2d_tc.cuh"
 #include "b2d_sparse.cuh"
 #include "b2d_permanova.cuh"
 #include "b2d_post.cuh"
@@ -48,6 +49,7 @@ static int g_weighted_skip = 1;                // zero-block skipping in the wei
 static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 never, 1 always if legal
 static int g_isect_kernel = -1;                // 1: pipelined intersection kernel (b2d_isect.cuh); 0: first generation;
                                                // -1: pipelined, except unweighted UniFrac with large buckets (see use_isect)
+static int g_udense_tc = 0;                    // unweighted UniFrac: dense rows on the tensor cores (b2d_tc.cuh) instead of the LUT kernel
 static int g_isect_group = 0;                  // lanes sharing one row entry in that kernel (1, 2, 4, 8; 0: per mode)
 
 static bool plain_kernels() {
@@ -453,6 +455,14 @@ struct b2d_problem {
     double tips_flagged = 0, t_tips = 0, tip_matches = 0;
     double isect_generation = 0;            // intersection kernel of the last compute: 2 pipelined, 1 first generation, 0 none
     unsigned* d_tip_cnt = nullptr;          // [npad] sparse-row entries per sample (guard: quantisation term)
+    // unweighted dense rows on the tensor cores: fixed-point lengths and per-sample sums of the dense part
+    double* d_ud_scale = nullptr;
+    long long* d_ud_lenfx = nullptr;
+    int64_t ud_lenfx_cap = 0;
+    long long* d_ud_Lfx = nullptr;
+    double* d_ud_Ld = nullptr;
+    unsigned* d_ud_Kd = nullptr;
+    bool ud_tc_active = false;
     FlaggedPair* d_flag_list = nullptr;     // [FLAG_CAP] pairs the guard flagged (recomputed in floating point)
     // sparse feature-table path
     SpEntry* d_sp_entries = nullptr;
@@ -497,6 +507,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend); b2d_free(p->d_hc_pos);
     b2d_free(p->d_ukeys); b2d_free(p->d_lenfx); b2d_free(p->d_bitsd); b2d_free(p->d_ulend);
     b2d_free(p->d_tip_cnt); b2d_free(p->d_flag_list);
+    b2d_free(p->d_ud_scale); b2d_free(p->d_ud_lenfx); b2d_free(p->d_ud_Lfx); b2d_free(p->d_ud_Ld); b2d_free(p->d_ud_Kd);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -725,6 +736,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_weighted_skip = value ? 1 : 0;
     } else if (s == "isect_kernel") {
         g_isect_kernel = value < 0 ? -1 : (value ? 1 : 0);
+    } else if (s == "udense_tc") {
+        g_udense_tc = value ? 1 : 0;
     } else if (s == "isect_group") {
         g_isect_group = (value == 1 || value == 2 || value == 4 || value == 8) ? (int)value : 0;
     } else {
@@ -1714,9 +1727,53 @@ static int compute_bits(b2d_problem* p, int metric) {
             utips_timed = true;
             p->n_kernels += 1;
         }
+        p->ud_tc_active = p->urows_active && g_udense_tc && metric == B2D_UNWEIGHTED_UNIFRAC;
+        if (p->ud_tc_active) {
+            // the packed dense rows as an exact int8 contraction on the tensor cores (b2d_tc.cuh)
+            const int64_t NSd = p->n_dense_pad / 128;
+            if (!p->d_ud_scale) {
+                B2D_CUDA(b2d_malloc(&p->d_ud_scale, 2 * sizeof(double)));
+                B2D_CUDA(b2d_malloc(&p->d_ud_Lfx, p->npad * sizeof(long long)));
+                B2D_CUDA(b2d_malloc(&p->d_ud_Ld, p->npad * sizeof(double)));
+                B2D_CUDA(b2d_malloc(&p->d_ud_Kd, p->npad * sizeof(unsigned)));
+            }
+            if (p->ud_lenfx_cap < p->n_dense_pad) {
+                b2d_free(p->d_ud_lenfx);
+                p->d_ud_lenfx = nullptr;
+                B2D_CUDA(b2d_malloc(&p->d_ud_lenfx, p->n_dense_pad * sizeof(long long)));
+                p->ud_lenfx_cap = p->n_dense_pad;
+            }
+            p->n_kernels += 3;
+            k_udense_scale<<<1, 256, 0, p->stream>>>(p->d_ulend, p->n_dense_pad, p->d_ud_scale);
+            k_udense_lenfx<<<(unsigned)((p->n_dense_pad + 255) / 256), 256, 0, p->stream>>>(p->d_ulend, p->d_ud_scale,
+                                                                                         p->n_dense_pad, p->d_ud_lenfx);
+            k_udense_sums<<<(unsigned)p->nb, TILE, 0, p->stream>>>(p->d_bitsd, p->d_ud_lenfx, NSd, p->d_ud_Lfx,
+                                                                  p->d_ud_Ld, p->d_ud_Kd);
+            if ((rc = fork_streams(p))) return rc;   // stream2 may need the sums too
+            PairArgs a;
+            a.tiles = p->d_tiles;
+            a.row_base = p->d_row_base;
+            a.out = p->d_out;
+            a.svec = p->d_svec;
+            a.total = p->d_total;
+            a.n = p->n;
+            a.qa = 0;
+            a.qb = p->n_dense_pad;
+            a.QR = 0;
+            a.NS = NSd;
+            a.last = 0;
+            a.epilogue = EPI_UNWEIGHTED;
+            cudaStream_t st;
+            if ((rc = chunk_target(p, &st, &a.out, &a.first))) return rc;
+            B2D_CUDA(cudaFuncSetAttribute(k_pair_udense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+            k_pair_udense_tc<<<(unsigned)(2 * p->ntiles), TC_THREADS, TC_SMEM, st>>>(p->d_bitsd, p->d_ud_lenfx, NSd,
+                                                                                    p->d_ud_Lfx, p->d_ud_scale, a);
+            B2D_CUDA(cudaGetLastError());
+            p->n_launch += 1;
+        }
         // bits kernels touch 8..32 nodes per instruction: use 4x longer node chunks per launch
         const int64_t chunk = 4 * g_chunk_nodes;
-        const int64_t rows_total = p->urows_active ? p->n_dense_pad : p->mpad;
+        const int64_t rows_total = p->ud_tc_active ? 0 : (p->urows_active ? p->n_dense_pad : p->mpad);
         const int64_t NSx = p->urows_active ? p->n_dense_pad / 128 : p->NS;
         const uint4* bits_x = p->urows_active ? (const uint4*)p->d_bitsd : (const uint4*)p->d_emb;
         const double* len_x = p->urows_active ? p->d_ulend : p->d_len;
@@ -1751,7 +1808,9 @@ static int compute_bits(b2d_problem* p, int metric) {
             p->n_kernels += 1;
             k_tip_guard<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                 p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, p->d_owned, p->d_row_base, p->n,
-                p->d_tip_u, p->d_tip_cnt, p->d_tip_scale, p->d_tip_word + 1, p->d_flag_list);
+                p->d_tip_u, p->d_tip_cnt, p->d_tip_scale, p->d_tip_word + 1, p->d_flag_list,
+                p->ud_tc_active ? p->d_ud_Ld : nullptr, p->ud_tc_active ? p->d_ud_Kd : nullptr,
+                p->ud_tc_active ? p->d_ud_scale : nullptr);
             p->n_kernels += 1;
             k_fix_pairs_unweighted<<<296, 256, 0, p->stream>>>(
                 (const uint4*)p->d_emb, p->d_len, p->NS, p->d_flag_list, p->d_tip_word + 1, p->d_out,

@@ -346,18 +346,27 @@ __global__ void __launch_bounds__(256)
 k_tip_guard(const double* __restrict__ out, const double* __restrict__ out2,
             const int64_t* __restrict__ owned, const int64_t* __restrict__ row_base, int64_t n,
             const double* __restrict__ U, const unsigned* __restrict__ nent, const double* __restrict__ scale,
-            unsigned long long* __restrict__ flagged, FlaggedPair* __restrict__ list) {
+            unsigned long long* __restrict__ flagged, FlaggedPair* __restrict__ list,
+            const double* __restrict__ Ld = nullptr, const unsigned* __restrict__ Kd = nullptr,
+            const double* __restrict__ scale_d = nullptr) {
+    // Ld / Kd / scale_d: a second fixed-point part of the same form (the dense rows of unweighted
+    // UniFrac on the tensor cores, b2d_tc.cuh): its per-sample sums (in units of its own quantum),
+    // entry counts and quantum join the two conditions
     const int64_t b = owned[blockIdx.x / TILE];
     const int64_t i0 = b * TILE, i = i0 + (blockIdx.x % TILE);
     if (i >= n - 1) return;
     const int64_t off = row_base[b] + (cond_row_start(i, n) - cond_row_start(i0, n));
     const int64_t cnt = n - 1 - i;
-    const double ui = U[i], q = scale[1], ki = (double)nent[i];
+    const double q = scale[1], qd = Ld ? scale_d[1] : 0.0;
+    const double ui = U[i] + (Ld ? Ld[i] * qd : 0.0);
+    const double ki = (double)nent[i] * q + (Ld ? (double)Kd[i] * qd : 0.0);
     for (int64_t t = threadIdx.x; t < cnt; t += blockDim.x) {
         double x = out[off + t];
         if (out2) x += out2[off + t];
         const int64_t j = i + 1 + t;
-        if (x != 0.0 && (x < 2.5e-4 * (ui + U[j]) || (ki + (double)nent[j]) * q > 1e-12 * x)) {
+        const double uj = U[j] + (Ld ? Ld[j] * qd : 0.0);
+        const double kj = (double)nent[j] * q + (Ld ? (double)Kd[j] * qd : 0.0);
+        if (x != 0.0 && (x < 2.5e-4 * (ui + uj) || ki + kj > 1e-12 * x)) {
             const unsigned long long slot = atomicAdd(flagged, 1ull);
             if (list && slot < (unsigned long long)FLAG_CAP) {
                 FlaggedPair fp;

@@ -1144,3 +1144,48 @@ def test_pipelined_intersection_kernel_on_feature_tables():
             _capi.set_option("sparse_features", -1)
             _capi.set_option("isect_kernel", -1)
             _capi.set_option("isect_group", 0)
+
+
+@pytest.mark.parametrize("cat", [False, True])
+def test_unweighted_dense_rows_on_the_tensor_cores(cat):
+    """Option udense_tc: the packed dense rows of unweighted UniFrac as an exact int8 contraction on
+    tcgen05 (b2d_tc.cuh) instead of the look-up-table kernel - same distances (1e-13 vs the LUT path,
+    1e-12 vs the oracle), for several sparse-row thresholds (few / many dense rows), shards, an exact
+    copy (distance exactly 0) and a near-duplicate (flagged and recomputed)."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 333, 4000
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.015, 171, caterpillar=cat)
+    rows = [cols[indptr[s]:indptr[s + 1]] for s in range(n)]
+    rows[1] = rows[0].copy()
+    cols2 = np.concatenate(rows)
+    indptr2 = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    dense = np.zeros((n, tips), dtype=np.int64)
+    for s in range(n):
+        dense[s, rows[s]] = 1
+    exp = oracle_fast.unifrac_all(dense, tip_node, parent, length)["unweighted_unifrac"]
+    total = n * (n - 1) // 2
+    res = {}
+    try:
+        for tc in (0, 1):
+            _capi.set_option("udense_tc", tc)
+            for k in (0, 1, 6, 200):
+                _capi.set_option("sparse_rows_max_tips", k)
+                for shards in (1, 2):
+                    out = np.full(total, -1.0)
+                    for sh in range(shards):
+                        with _capi.Problem.tree(parent, length, indptr2, tip_node[cols2], None, n, shard=sh,
+                                                n_shards=shards) as prob:
+                            prob.compute("unweighted_unifrac")
+                            assert prob.timings()["tips_ms"] > 0
+                            prob.fetch(out)
+                    res[(tc, k, shards)] = out
+    finally:
+        _capi.set_option("udense_tc", 0)
+        _capi.set_option("sparse_rows_max_tips", 0)
+    for key, v in res.items():
+        assert v[0] == 0.0, key                                   # samples 0 and 1 are identical
+        assert_close_rel(v, exp, UNIFRAC_RTOL, f"tensor-core dense rows {key} vs oracle")
+        assert_close_rel(v, res[(0, key[1], 1)], 1e-13, f"tensor-core dense rows {key} vs LUT")
