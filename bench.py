@@ -447,6 +447,11 @@ class Ctx:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             self.dist = dist
         self.device = self.local_rank
+        self.coll = None
+        if self.dist is not None and self.emulate == 1 and not getattr(args, "no_exchange", False):
+            from skbio_b200.distributed import TorchCollectives
+
+            self.coll = TorchCollectives(self.local_rank)
         if self.emulate > 1:
             self.shard, self.n_shards = 0, self.emulate
         else:
@@ -615,9 +620,12 @@ def bench_problem(ctx, inp, steps, warmup, e2e_reps, parity_rows, default_shape=
 
     def make_problem(src):
         if src["kind"] == "tree":
-            return _capi.Problem.tree(src["parent"], src["length"], src["indptr"], src["ids"],
+            prob = _capi.Problem.tree(src["parent"], src["length"], src["indptr"], src["ids"],
                                       src["vals"], n, device=device, shard=ctx.shard,
                                       n_shards=ctx.n_shards)
+            if ctx.coll is not None:   # distributed build: the ranks exchange the per-block products (NCCL)
+                ctx.coll.install(prob)
+            return prob
         return _capi.Problem.features(src["indptr"], src["ids"], src["vals"], n, m, device=device,
                                       shard=ctx.shard, n_shards=ctx.n_shards)
 
@@ -632,9 +640,12 @@ def bench_problem(ctx, inp, steps, warmup, e2e_reps, parity_rows, default_shape=
         sampler.start()
     t0 = time.perf_counter()
     dev_ms, pair_ms, embed_ms, prep_ms, tips_ms, launches = [], [], [], [], [], 0
+    xchg_ms, xchg_bytes = [], []
     for _ in range(steps):
         prob.compute(key)  # blocks until the shard's distances are complete in HBM
         t = prob.timings()
+        xchg_ms.append(t["exchange_ms"])
+        xchg_bytes.append(t["exchange_bytes"])
         dev_ms.append(t["compute_ms"])
         pair_ms.append(t["pair_ms"])
         embed_ms.append(t["embed_ms"])
@@ -645,8 +656,9 @@ def bench_problem(ctx, inp, steps, warmup, e2e_reps, parity_rows, default_shape=
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if sampler else None
     step_ms = float(np.mean(dev_ms))
-    step_ms_max, wall_step_ms_max, embed_max, prep_max = ctx.max_over_ranks(
-        [step_ms, wall_ms / steps, float(np.mean(embed_ms)), float(np.mean(prep_ms))])
+    step_ms_max, wall_step_ms_max, embed_max, prep_max, xchg_max, xchg_bytes_max = ctx.max_over_ranks(
+        [step_ms, wall_ms / steps, float(np.mean(embed_ms)), float(np.mean(prep_ms)), float(np.mean(xchg_ms)),
+         float(np.mean(xchg_bytes))])
     P_done = P_total if ctx.emulate == 1 else P_shard   # pairs actually computed by this job
     value = P_done / (step_ms_max * 1e-3)
 
@@ -711,7 +723,11 @@ def bench_problem(ctx, inp, steps, warmup, e2e_reps, parity_rows, default_shape=
                          f"shard 0 of {ctx.emulate} emulated on one GPU"),
             "embed_ms": float(np.mean(embed_ms)), "pair_ms": float(np.mean(pair_ms)),
             "prologue_ms": {"embed": embed_max, "sparse_rows_and_skip_prep": prep_max,
-                            "note": "replicated on every rank (all samples); max over ranks"},
+                            "exchange": xchg_max, "exchange_bytes_received_per_rank": xchg_bytes_max,
+                            "note": ("distributed build: every rank builds the per-block products of its own "
+                                     "block range, the ranks all-gather them over NCCL (exchange is part of "
+                                     "sparse_rows_and_skip_prep); max over ranks") if xchg_bytes_max > 0 else
+                                    "replicated on every rank (all samples); max over ranks"},
             "passes": int(t["passes"]),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "parity": {"checker": "oracle/oracle_c.c (C restatement of the reference, pinned to the "
@@ -904,6 +920,8 @@ def main():
     ap.add_argument("--tree", default="", choices=["", "random", "caterpillar"])
     ap.add_argument("--configs", default="auto",
                     help="auto: cfg3 at every N, cfg4 and cfg5 at N = 8; none; or a comma list")
+    ap.add_argument("--no-exchange", action="store_true",
+                    help="N > 1: every rank builds the per-block products of all samples itself (no collective)")
     ap.add_argument("--emulate-shards", type=int, default=1,
                     help="compute only shard 0 of N on this GPU (sizing runs for multi-GPU configs)")
     args = ap.parse_args()

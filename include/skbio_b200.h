@@ -141,6 +141,47 @@ int b2d_problem_select_tiles(b2d_problem* p, const int32_t* tiles, int64_t n_til
  * problem's device.  Blocks until the shard's distances are complete in device memory. */
 int b2d_problem_compute(b2d_problem* p, int metric);
 
+/* Distributed build of the per-block products (one process - or host thread - per GPU).
+ *
+ * Without this every shard builds the embedding, the sparse-row entries, the packed dense rows
+ * and the group bitmaps of ALL samples, because its tiles need every column block: replicated
+ * work that grows with the number of samples while the pair work per GPU stays fixed.  With
+ * collectives installed, rank r of `world` builds those products only for its contiguous range
+ * of 128-sample blocks and the ranks exchange them (everything is laid out block-major, so the
+ * exchange is an in-place all-gather of slices of the same buffers); the pair kernels then run
+ * exactly as before.  The library does not link a communication library: the host supplies two
+ * callbacks (torch.distributed / NCCL over NVLink under torchrun - skbio_b200.distributed; peer
+ * copies between host threads for beta_diversity(..., devices=[...])):
+ *
+ *   allgather_host(user, mine, all, bytes)   all[r * bytes .. ] = rank r's `mine` (host memory,
+ *                                            a few dozen bytes: votes, entry counts, max U)
+ *   allgatherv_device(user, n_buffers, bases, offsets, counts, world)
+ *                                            device memory, in place, for each buffer k < n_buffers:
+ *                                            on return every rank holds bytes [offsets[k*world + r],
+ *                                            + counts[k*world + r]) of bases[k] as rank r wrote them
+ *                                            (rank r's own slice is already there).  The library
+ *                                            has drained its streams before the call; the callback
+ *                                            returns when the data is usable by any stream of the
+ *                                            device.
+ * Both return 0 on success; every rank calls them in the same order.  Requires shard == rank and
+ * n_shards == world at creation (otherwise B2D_ERR_INVALID_ARGUMENT).  Used by weighted and
+ * unweighted UniFrac when the whole embedding is resident; a compute that cannot use it (several
+ * node passes, custom tiles, a rank that voted no) is replicated as before.  Pairs flagged by the
+ * fixed-point guard need the embedding of both samples: the rank that sees one redoes its own
+ * compute replicated and votes no from then on.  world <= 1 or NULL callbacks remove them. */
+typedef int (*b2d_allgather_host_fn)(void* user, const void* mine, void* all, int64_t bytes);
+typedef int (*b2d_allgatherv_device_fn)(void* user, int n_buffers, void* const* bases, const int64_t* offsets,
+                                        const int64_t* counts, int world);
+int b2d_problem_set_collectives(b2d_problem* p, int rank, int world, b2d_allgather_host_fn allgather_host,
+                                b2d_allgatherv_device_fn allgatherv_device, void* user);
+
+/* Block range [first, last) of 128-sample blocks rank `rank` of `world` builds (host arithmetic only). */
+int b2d_build_range(int64_t n_samples, int rank, int world, int64_t* first_block, int64_t* last_block);
+
+/* Device-to-device copy (same or peer device, unified addressing), blocking: what an in-process
+ * allgatherv_device callback is made of. */
+int b2d_device_copy(void* dst, const void* src, int64_t bytes);
+
 /* Number of condensed elements this shard owns. */
 int64_t b2d_problem_result_len(const b2d_problem* p);
 
@@ -178,7 +219,8 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * [14] largest number of tips below a node whose row went through the sparse intersection
  * kernel (0: none, 1: tip rows only), [15] entries of those rows, [16] (sample pair, row) matches
  * that kernel accumulated, [17] which intersection kernel ran (2: pipelined, b2d_isect.cuh; 1: first
- * generation; 0: none).  n: slots to fill (<= 18). */
+ * generation; 0: none), [18] host time of the exchanges of a distributed build (ms, 0 when the
+ * build was replicated) and [19] the bytes this rank received in them.  n: slots to fill (<= 20). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);

@@ -32,6 +32,12 @@ _i32p = ctypes.POINTER(ctypes.c_int32)
 _f64p = ctypes.POINTER(ctypes.c_double)
 
 
+# callbacks of b2d_problem_set_collectives (include/skbio_b200.h)
+ALLGATHER_HOST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+ALLGATHERV_DEVICE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                        _i64p, _i64p, ctypes.c_int)
+
+
 class EngineError(RuntimeError):
     """Raised when the native engine reports a failure (status code != 0)."""
 
@@ -124,6 +130,13 @@ def _declare(lib):
     lib.b2d_center_condensed.argtypes = [ctypes.c_int, ctypes.c_int64, _f64p, _f64p, _f64p, _f64p]
     lib.b2d_debug_fetch_embedding.restype = ctypes.c_int
     lib.b2d_debug_fetch_embedding.argtypes = [ctypes.c_void_p, ctypes.c_int, _i64p]
+    lib.b2d_problem_set_collectives.restype = ctypes.c_int
+    lib.b2d_problem_set_collectives.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ALLGATHER_HOST_FN,
+                                                ALLGATHERV_DEVICE_FN, ctypes.c_void_p]
+    lib.b2d_build_range.restype = ctypes.c_int
+    lib.b2d_build_range.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _i64p, _i64p]
+    lib.b2d_device_copy.restype = ctypes.c_int
+    lib.b2d_device_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     lib.b2d_debug_tree_order.restype = ctypes.c_int
     lib.b2d_debug_tree_order.argtypes = [
         ctypes.c_int64, _i32p, _f64p, _i32p, ctypes.POINTER(ctypes.c_uint8), _f64p, _f64p,
@@ -141,6 +154,7 @@ EXPORTED_SYMBOLS = [
     "b2d_flat_tree_free", "b2d_permanova_sw", "b2d_problem_phydiv", "b2d_debug_fetch_embedding",
     "b2d_problem_fetch_square_rows", "b2d_problem_center", "b2d_center_condensed",
     "b2d_problem_create_tree_columns", "b2d_names_lookup", "b2d_names_validate",
+    "b2d_problem_set_collectives", "b2d_build_range", "b2d_device_copy",
 ]
 
 
@@ -319,6 +333,18 @@ def newick_to_flat(text):
     return parent, length, NameBlob(buf.raw[:nb], off, has)
 
 
+def build_range(n_samples, rank, world):
+    """Blocks [first, last) of 128 samples whose per-block products rank `rank` builds - host only."""
+    a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+    _check(load().b2d_build_range(int(n_samples), int(rank), int(world), ctypes.byref(a), ctypes.byref(b)))
+    return int(a.value), int(b.value)
+
+
+def device_copy(dst, src, nbytes):
+    """Blocking device-to-device copy between raw pointers (same or peer device)."""
+    _check(load().b2d_device_copy(ctypes.c_void_p(int(dst)), ctypes.c_void_p(int(src)), int(nbytes)))
+
+
 def shard_layout(n_samples, shard, n_shards):
     """(offsets[k, 2] = {first condensed index, count} per owned row stripe, total) - host only."""
     lib = load()
@@ -468,8 +494,51 @@ class Problem:
         tiles = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 2)
         _check(load().b2d_problem_select_tiles(self._h, _ptr(tiles, _i32p), len(tiles)))
 
+    def set_collectives(self, rank, world, coll):
+        """Distributed build of the per-block products (b2d_problem_set_collectives).  `coll` offers
+        ``allgather_host(mine: bytes) -> bytes`` (the ranks' blobs back to back) and
+        ``allgatherv_device(bases, offsets, counts)`` (lists: one device pointer per buffer, byte
+        offsets / counts per buffer and rank; in place).  See skbio_b200.distributed."""
+        if coll is None or world <= 1:
+            _check(load().b2d_problem_set_collectives(self._h, 0, 1, ALLGATHER_HOST_FN(0), ALLGATHERV_DEVICE_FN(0), None))
+            self._coll = None
+            return
+        errors = []
+
+        def host_cb(user, mine, out, nbytes):
+            try:
+                blob = coll.allgather_host(ctypes.string_at(mine, nbytes))
+                if len(blob) != nbytes * world:
+                    raise ValueError("allgather_host returned %d bytes, expected %d" % (len(blob), nbytes * world))
+                ctypes.memmove(out, blob, len(blob))
+                return 0
+            except BaseException as e:   # must not propagate through the C frames
+                errors.append(e)
+                return 1
+
+        def dev_cb(user, nbuf, bases, offsets, counts, w):
+            try:
+                coll.allgatherv_device([int(bases[k] or 0) for k in range(nbuf)],
+                                       [[int(offsets[k * w + r]) for r in range(w)] for k in range(nbuf)],
+                                       [[int(counts[k * w + r]) for r in range(w)] for k in range(nbuf)])
+                return 0
+            except BaseException as e:
+                errors.append(e)
+                return 1
+
+        self._coll = (ALLGATHER_HOST_FN(host_cb), ALLGATHERV_DEVICE_FN(dev_cb), coll, errors)
+        _check(load().b2d_problem_set_collectives(self._h, int(rank), int(world), self._coll[0], self._coll[1], None))
+
     def compute(self, metric):
         mid = METRIC_IDS[metric] if isinstance(metric, str) else int(metric)
+        coll = getattr(self, "_coll", None)
+        if coll is not None:
+            del coll[3][:]
+            rc = load().b2d_problem_compute(self._h, mid)
+            if rc != 0 and coll[3]:
+                raise EngineError("collective callback failed: %r" % (coll[3][0],)) from coll[3][0]
+            _check(rc)
+            return
         _check(load().b2d_problem_compute(self._h, mid))
 
     def result_len(self):
@@ -531,15 +600,15 @@ class Problem:
         return out
 
     def timings(self):
-        t = np.zeros(18, dtype=np.float64)
-        _check(load().b2d_problem_timings(self._h, _ptr(t, _f64p), 18))
+        t = np.zeros(20, dtype=np.float64)
+        _check(load().b2d_problem_timings(self._h, _ptr(t, _f64p), 20))
         return {"embed_ms": t[0], "pair_ms": t[1], "compute_ms": t[2], "fetch_ms": t[3],
                 "upload_ms": t[4], "pair_launches": int(t[5]), "nodes_resident": int(t[6]),
                 "passes": int(t[7]), "visits_executed": float(t[8]), "visits_dense": float(t[9]),
                 "skip_prep_ms": t[10], "kernels": int(t[11]), "tips_ms": t[12],
                 "tips_flagged": int(t[13]), "sparse_rows_max_tips": int(t[14]),
                 "sparse_row_entries": int(t[15]), "sparse_row_matches": float(t[16]),
-                "isect_generation": int(t[17])}
+                "isect_generation": int(t[17]), "exchange_ms": t[18], "exchange_bytes": float(t[19])}
 
     def destroy(self):
         if self._h is not None:

@@ -121,21 +121,31 @@ def _result_vector(total):
 
 def _run_sharded(make_problem, metric_key, n, devices):
     """One problem (shard) per device, each driven by its own host thread; every shard writes
-    its own disjoint slices of ONE condensed vector (no gather step, no extra copy)."""
+    its own disjoint slices of ONE condensed vector (no gather step, no extra copy).  With
+    several shards the per-block products are built once - each shard builds its own block range
+    and the shards exchange them by peer copies (distributed.ThreadCollectives)."""
     if _capi.load().b2d_device_count() <= 0:
         raise _capi.EngineError(
             "no CUDA device visible: the B200 engine has no CPU fallback for "
             f"'{metric_key}'.")
     out = _result_vector(n * (n - 1) // 2)
     errors = []
+    coll = None
+    if len(devices) > 1:
+        from .distributed import ThreadCollectives
+        coll = ThreadCollectives(len(devices))
 
     def work(shard, dev):
         try:
             with make_problem(dev, shard, len(devices)) as prob:
+                if coll is not None:
+                    prob.set_collectives(shard, len(devices), coll.for_rank(shard))
                 prob.compute(metric_key)
                 prob.fetch(out)
         except BaseException as e:  # propagate to the caller thread
             errors.append(e)
+            if coll is not None:
+                coll.abort()        # the other shards must not wait for this one
 
     if len(devices) == 1:
         work(0, devices[0])
@@ -146,7 +156,8 @@ def _run_sharded(make_problem, metric_key, n, devices):
         for t in threads:
             t.join()
     if errors:
-        raise errors[0]
+        first = [e for e in errors if "BrokenBarrier" not in repr(e)] or errors
+        raise first[0]
     return out
 
 

@@ -17,6 +17,8 @@
 #include <unordered_map>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <chrono>
 
 #include <nvtx3/nvToolsExt.h>
 
@@ -471,6 +473,19 @@ struct b2d_problem {
     int64_t sp_nch = 0;
     int sp_ready = 0;           // 0 not built, 1 built, -1 not eligible
     int used_sparse = 0;
+    // distributed build (b2d_problem_set_collectives): this rank builds the per-block products of its
+    // own block range only, the ranks exchange them before the pair kernels
+    int coll_rank = 0, coll_world = 1;
+    b2d_allgather_host_fn coll_host = nullptr;
+    b2d_allgatherv_device_fn coll_dev = nullptr;
+    void* coll_user = nullptr;
+    bool dist_off = false;            // the guard flagged a pair once: this rank votes for replicated builds
+    bool dist_rerun = false;          // a compute re-running itself: no vote (the other ranks are not in one)
+    bool dist_active = false;         // the last compute exchanged its products
+    uint32_t* d_nz_full = nullptr;    // [npad/32][QR/32] bitmaps of all node rows (the exchange needs them beside d_nz)
+    size_t nz_full_bytes = 0;
+    double t_exchange = 0, exchange_bytes = 0;
+    std::vector<int64_t> coll_totals; // sparse-row entries of every rank (last exchange)
     bool computed = false;
     bool custom_tiles = false;  // b2d_problem_select_tiles: untouched entries of owned stripes stay 0
     int last_metric = -1;
@@ -506,7 +521,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_rows_qcount); b2d_free(p->d_rows_upart);
     b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend); b2d_free(p->d_hc_pos);
     b2d_free(p->d_ukeys); b2d_free(p->d_lenfx); b2d_free(p->d_bitsd); b2d_free(p->d_ulend);
-    b2d_free(p->d_tip_cnt); b2d_free(p->d_flag_list);
+    b2d_free(p->d_tip_cnt); b2d_free(p->d_flag_list); b2d_free(p->d_nz_full);
     b2d_free(p->d_ud_scale); b2d_free(p->d_ud_lenfx); b2d_free(p->d_ud_Lfx); b2d_free(p->d_ud_Ld); b2d_free(p->d_ud_Kd);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
@@ -867,6 +882,140 @@ static int b2d_problem_create_features_impl(b2d_problem** out, int device, int64
     return B2D_OK;
 }
 
+
+// ---- distributed build -----------------------------------------------------------------
+// The build kernels index samples and blocks from 0: run on a rank's own block range they get
+// pointers shifted to its first block / sample (every per-block product is laid out block-major)
+// and the local counts.  Replicated build: the view is the whole problem.
+struct BuildView {
+    int64_t b0 = 0, b1 = 0;   // blocks [b0, b1)
+    int64_t s0 = 0;           // first sample
+    int64_t n = 0;            // real samples in the range
+    int64_t nb = 0, npad = 0; // blocks, samples including padding
+};
+static void build_range(int64_t nb, int rank, int world, int64_t* b0, int64_t* b1) {
+    const int64_t per = (nb + world - 1) / std::max(world, 1);
+    *b0 = std::min<int64_t>(nb, (int64_t)rank * per);
+    *b1 = std::min<int64_t>(nb, *b0 + per);
+}
+static BuildView build_view(const b2d_problem* p, bool dist, int rank = -1) {
+    BuildView v;
+    if (dist) build_range(p->nb, rank < 0 ? p->coll_rank : rank, p->coll_world, &v.b0, &v.b1);
+    else v.b1 = p->nb;
+    v.s0 = v.b0 * TILE;
+    v.nb = v.b1 - v.b0;
+    v.npad = v.nb * TILE;
+    v.n = std::max<int64_t>(0, std::min<int64_t>(p->n, v.b1 * TILE) - v.s0);
+    return v;
+}
+static bool have_collectives(const b2d_problem* p) {
+    return p->coll_world > 1 && p->coll_host && p->coll_dev;
+}
+// every rank's `mine` (a few host bytes)
+static int coll_gather_host(b2d_problem* p, const void* mine, void* all, int64_t bytes) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (p->coll_host(p->coll_user, mine, all, bytes)) return fail(B2D_ERR_CUDA, "allgather_host callback failed");
+    p->t_exchange += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return B2D_OK;
+}
+// in-place all-gathers of byte ranges of device buffers, queued and issued as ONE callback (one drain of
+// the stream, one synchronisation on the host's side for all of them)
+struct CollBatch {
+    std::vector<void*> bases;
+    std::vector<int64_t> off, cnt;   // [buffer][rank]
+};
+static void coll_add_ranges(b2d_problem* p, CollBatch& cb, void* base, const std::vector<int64_t>& off,
+                            const std::vector<int64_t>& cnt) {
+    cb.bases.push_back(base);
+    cb.off.insert(cb.off.end(), off.begin(), off.end());
+    cb.cnt.insert(cb.cnt.end(), cnt.begin(), cnt.end());
+    for (int r = 0; r < p->coll_world; ++r)
+        if (r != p->coll_rank) p->exchange_bytes += (double)cnt[r];
+}
+// ... of a block-major array with `per_block` bytes per 128-sample block
+static void coll_add_blocks(b2d_problem* p, CollBatch& cb, void* base, size_t per_block) {
+    std::vector<int64_t> off(p->coll_world), cnt(p->coll_world);
+    for (int r = 0; r < p->coll_world; ++r) {
+        const BuildView v = build_view(p, true, r);
+        off[r] = v.b0 * (int64_t)per_block;
+        cnt[r] = v.nb * (int64_t)per_block;
+    }
+    coll_add_ranges(p, cb, base, off, cnt);
+}
+// entries of all ranks: rank r's sit behind those of the lower ranks (coll_rows_facts), `esize` bytes each
+static void coll_add_entries(b2d_problem* p, CollBatch& cb, void* entries, size_t esize) {
+    std::vector<int64_t> off(p->coll_world), cnt(p->coll_world);
+    int64_t run = 0;
+    for (int r = 0; r < p->coll_world; ++r) {
+        off[r] = run * (int64_t)esize;
+        cnt[r] = p->coll_totals[r] * (int64_t)esize;
+        run += p->coll_totals[r];
+    }
+    coll_add_ranges(p, cb, entries, off, cnt);
+}
+static int coll_flush(b2d_problem* p, CollBatch& cb) {
+    if (cb.bases.empty()) return B2D_OK;
+    NvtxRange range("b2d:exchange (all-gather of the per-block products)");
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    const auto t0 = std::chrono::steady_clock::now();
+    if (p->coll_dev(p->coll_user, (int)cb.bases.size(), cb.bases.data(), cb.off.data(), cb.cnt.data(), p->coll_world))
+        return fail(B2D_ERR_CUDA, "allgatherv_device callback failed");
+    p->t_exchange += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    cb = CollBatch();
+    return B2D_OK;
+}
+// One vote per compute: the build is distributed only when every rank can (whole embedding resident, ...)
+static int coll_vote(b2d_problem* p, bool mine, bool* all_yes) {
+    std::vector<int32_t> votes(p->coll_world, 0);
+    const int32_t v = mine ? 1 : 0;
+    int rc = coll_gather_host(p, &v, votes.data(), sizeof(int32_t));
+    if (rc) return rc;
+    *all_yes = true;
+    for (int32_t x : votes) *all_yes = *all_yes && x == 1;
+    return B2D_OK;
+}
+// the three facts the sparse-row build needs from every rank before it can quantise and scatter
+struct RowsFacts {
+    unsigned long long maxbits;   // max U of the rank's samples (bit pattern of a non-negative double)
+    long long total;              // its entries
+    int status;                   // a bucket too large
+    int pad;
+};
+__global__ void k_add_offset(int64_t* __restrict__ v, int64_t count, int64_t add) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) v[t] += add;
+}
+// local facts -> global: scale from the maximum over ranks, bucket offsets of the own range moved behind
+// the entries of the lower ranks, ptr[nbuckets] = entries of all ranks.  Returns status OR-ed, *grand.
+static int coll_rows_facts(b2d_problem* p, const BuildView& v, int64_t nch, int* status, int64_t* grand) {
+    RowsFacts mine{};
+    B2D_CUDA(cudaMemcpyAsync(&mine.maxbits, p->d_tip_word, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));
+    mine.total = *grand;
+    mine.status = *status;
+    std::vector<RowsFacts> all(p->coll_world);
+    int rc = coll_gather_host(p, &mine, all.data(), sizeof(RowsFacts));
+    if (rc) return rc;
+    unsigned long long mx = 0;
+    int64_t base = 0, sum = 0;
+    int st = 0;
+    for (int r = 0; r < p->coll_world; ++r) {
+        mx = std::max(mx, all[r].maxbits);
+        st |= all[r].status;
+        if (r < p->coll_rank) base += all[r].total;
+        sum += all[r].total;
+    }
+    *status = st;
+    *grand = sum;
+    p->coll_totals.resize(p->coll_world);
+    for (int r = 0; r < p->coll_world; ++r) p->coll_totals[r] = all[r].total;
+    B2D_CUDA(cudaMemcpyAsync(p->d_tip_word, &mx, sizeof(mx), cudaMemcpyHostToDevice, p->stream));
+    const int64_t cnt = v.nb * nch;
+    if (cnt && base) k_add_offset<<<(unsigned)((cnt + 255) / 256), 256, 0, p->stream>>>(p->d_tip_ptr + v.b0 * nch, cnt, base);
+    B2D_CUDA(cudaMemcpyAsync(p->d_tip_ptr + p->nb * nch, &sum, sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+    B2D_CUDA(cudaStreamSynchronize(p->stream));   // mx / sum live on this stack frame
+    return B2D_OK;
+}
 static int ensure_emb(b2d_problem* p, size_t bytes) {
     if (p->emb_bytes >= bytes) return B2D_OK;
     if (p->d_emb) {
@@ -1107,29 +1256,38 @@ static int rows_masks(b2d_problem* p, int which) {
     return B2D_OK;
 }
 
-static int rows_build(b2d_problem* p, int64_t QR) {
+static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist) {
     int rc;
     if ((rc = tips_buffers(p))) return rc;
     const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
+    // the view's slices of the per-bucket / per-sample arrays (the embedding itself starts at the view's first block)
+    unsigned* qcount = p->d_rows_qcount;
     for (;;) {
         if ((rc = rows_masks(p, 0))) return rc;
+        qcount = p->d_rows_qcount + v.b0 * nch * 4;
         const int64_t rows = p->mpad;
         p->n_kernels += 5;
-        k_rows_count<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const double*)p->d_emb, p->d_len, p->d_rows_sparse, rows, QR, nch, p->npad, p->d_rows_qcount,
-            p->d_rows_upart);
-        k_rows_bucket_counts<<<(unsigned)((nbuckets + 255) / 256), 256, 0, p->stream>>>(p->d_rows_qcount, nbuckets,
-                                                                                      p->d_tip_counts);
+        if (v.nb) {
+            k_rows_count<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
+                (const double*)p->d_emb, p->d_len, p->d_rows_sparse, rows, QR, nch, p->npad, qcount,
+                p->d_rows_upart + v.s0);
+            k_rows_bucket_counts<<<(unsigned)((v.nb * nch + 255) / 256), 256, 0, p->stream>>>(qcount, v.nb * nch,
+                                                                                         p->d_tip_counts + v.b0 * nch);
+        }
         k_tip_scan<<<1, 1024, 0, p->stream>>>(p->d_tip_counts, nbuckets, p->d_tip_ptr, p->d_tip_status, 65535u);
-        k_rows_ureduce<<<(unsigned)((p->npad + 255) / 256), 256, 0, p->stream>>>(p->d_rows_upart, nch * 4, p->npad,
-                                                                               p->d_tip_u, p->d_tip_word);
-        k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
+        if (v.nb)
+            k_rows_ureduce<<<(unsigned)((v.npad + 255) / 256), 256, 0, p->stream>>>(
+                p->d_rows_upart + v.s0, nch * 4, p->npad, v.npad, p->d_tip_u + v.s0, p->d_tip_word);
         int status = 0;
         int64_t total = 0;
         B2D_CUDA(cudaMemcpyAsync(&status, p->d_tip_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaMemcpyAsync(&total, p->d_tip_ptr + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
         B2D_CUDA(cudaGetLastError());
+        // distributed: the scale comes from the maximum over all ranks, this rank's entries go behind those of
+        // the lower ranks, and a bucket too large anywhere lowers the threshold everywhere
+        if (dist && (rc = coll_rows_facts(p, v, nch, &status, &total))) return rc;
+        k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
         if (status) {  // a bucket holds more than 65535 entries: fewer rows
             if (p->rows_S0 == 1) {
                 p->tips_mode = -1;
@@ -1138,15 +1296,18 @@ static int rows_build(b2d_problem* p, int64_t QR) {
             p->rows_S0_pref[0] = p->rows_S0 / 2;
             B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 2 * sizeof(unsigned long long), p->stream));
             B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
+            B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
             continue;
         }
         if ((rc = tips_entries_reserve(p, total))) return rc;
         p->rows_entries = (double)total;
         p->n_kernels += 1;
-        k_rows_scatter<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const double*)p->d_emb, p->d_len, p->d_rows_sparse, p->d_tip_scale, rows, QR, nch,
-            p->d_rows_qcount, p->d_tip_ptr, p->d_tip_entries, p->d_tip_runs,
-            (unsigned long long*)p->d_tip_ufx, p->d_tip_cnt);
+        if (v.nb)
+            k_rows_scatter<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
+                (const double*)p->d_emb, p->d_len, p->d_rows_sparse, p->d_tip_scale, rows, QR, nch,
+                qcount, p->d_tip_ptr + v.b0 * nch, p->d_tip_entries,
+                p->d_tip_runs + (size_t)v.b0 * nch * (TP_CHUNK + 8),
+                (unsigned long long*)p->d_tip_ufx + v.s0, p->d_tip_cnt + v.s0);
         // the rows left to the dense pair kernel, packed
         const size_t need = (size_t)p->nb * p->n_dense_pad * TILE * sizeof(double);
         if (p->embd_bytes < need) {
@@ -1160,9 +1321,10 @@ static int rows_build(b2d_problem* p, int64_t QR) {
             p->embd_bytes = need;
         }
         p->n_kernels += 1;
-        k_compact_rows<<<dim3((unsigned)p->n_dense_pad, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, nullptr,
-            p->d_embd, p->d_lend);
+        if (v.nb)
+            k_compact_rows<<<dim3((unsigned)p->n_dense_pad, (unsigned)v.nb), 128, 0, p->stream>>>(
+                (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, nullptr,
+                p->d_embd + (size_t)v.b0 * p->n_dense_pad * TILE, p->d_lend);
         B2D_CUDA(cudaGetLastError());
         p->tips_mode = 1;
         return B2D_OK;
@@ -1171,29 +1333,34 @@ static int rows_build(b2d_problem* p, int64_t QR) {
 
 // Unweighted UniFrac: keys of the sparse rows from the presence bits, fixed-point lengths, packed
 // dense stripes.  Same threshold and fall-backs as rows_build.
-static int urows_build(b2d_problem* p) {
+static int urows_build(b2d_problem* p, const BuildView& v, bool dist) {
     int rc;
     if ((rc = tips_buffers(p))) return rc;
     const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
     if (!p->d_lenfx) B2D_CUDA(b2d_malloc(&p->d_lenfx, (size_t)nch * TP_CHUNK * sizeof(long long)));
     for (;;) {
         if ((rc = rows_masks(p, 1))) return rc;
+        unsigned* qcount = p->d_rows_qcount + v.b0 * nch * 4;
         p->n_kernels += 5;
-        k_ubits_count<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const uint32_t*)p->d_emb, p->d_len, p->d_rows_sparse, p->mpad, p->NS, nch, p->npad,
-            p->d_rows_qcount, p->d_rows_upart);
-        k_rows_bucket_counts<<<(unsigned)((nbuckets + 255) / 256), 256, 0, p->stream>>>(p->d_rows_qcount, nbuckets,
-                                                                                      p->d_tip_counts);
+        if (v.nb) {
+            k_ubits_count<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
+                (const uint32_t*)p->d_emb, p->d_len, p->d_rows_sparse, p->mpad, p->NS, nch, p->npad,
+                qcount, p->d_rows_upart + v.s0);
+            k_rows_bucket_counts<<<(unsigned)((v.nb * nch + 255) / 256), 256, 0, p->stream>>>(qcount, v.nb * nch,
+                                                                                         p->d_tip_counts + v.b0 * nch);
+        }
         k_tip_scan<<<1, 1024, 0, p->stream>>>(p->d_tip_counts, nbuckets, p->d_tip_ptr, p->d_tip_status, 65535u);
-        k_rows_ureduce<<<(unsigned)((p->npad + 255) / 256), 256, 0, p->stream>>>(p->d_rows_upart, nch * 4, p->npad,
-                                                                               p->d_tip_u, p->d_tip_word);
-        k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
+        if (v.nb)
+            k_rows_ureduce<<<(unsigned)((v.npad + 255) / 256), 256, 0, p->stream>>>(
+                p->d_rows_upart + v.s0, nch * 4, p->npad, v.npad, p->d_tip_u + v.s0, p->d_tip_word);
         int status = 0;
         int64_t total = 0;
         B2D_CUDA(cudaMemcpyAsync(&status, p->d_tip_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaMemcpyAsync(&total, p->d_tip_ptr + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, p->stream));
         B2D_CUDA(cudaStreamSynchronize(p->stream));
         B2D_CUDA(cudaGetLastError());
+        if (dist && (rc = coll_rows_facts(p, v, nch, &status, &total))) return rc;   // see rows_build
+        k_tip_scale<<<1, 1, 0, p->stream>>>(p->d_tip_word, p->d_tip_scale);
         if (status) {
             if (p->rows_S0 == 1) {
                 p->tips_mode = -1;
@@ -1202,6 +1369,7 @@ static int urows_build(b2d_problem* p) {
             p->rows_S0_pref[1] = p->rows_S0 / 2;
             B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 4 * sizeof(unsigned long long), p->stream));
             B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
+            B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
             continue;
         }
         if (p->ukeys_cap < total || !p->d_ukeys) {
@@ -1227,11 +1395,15 @@ static int urows_build(b2d_problem* p) {
         p->n_kernels += 3;
         k_make_lenfx<<<(unsigned)((nch * TP_CHUNK + 255) / 256), 256, 0, p->stream>>>(p->d_len, p->d_tip_scale,
                                                                                     p->mpad, p->d_lenfx);
-        k_ubits_scatter<<<dim3((unsigned)nch, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const uint32_t*)p->d_emb, p->d_lenfx, p->d_rows_sparse, p->mpad, p->NS, nch, p->d_rows_qcount,
-            p->d_tip_ptr, p->d_ukeys, p->d_tip_runs, (unsigned long long*)p->d_tip_ufx, p->d_tip_cnt);
-        k_pack_bits<<<dim3((unsigned)NSd, (unsigned)p->nb), 128, 0, p->stream>>>(
-            (const uint32_t*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->NS, NSd, p->d_bitsd, p->d_ulend);
+        if (v.nb) {
+            k_ubits_scatter<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
+                (const uint32_t*)p->d_emb, p->d_lenfx, p->d_rows_sparse, p->mpad, p->NS, nch, qcount,
+                p->d_tip_ptr + v.b0 * nch, p->d_ukeys, p->d_tip_runs + (size_t)v.b0 * nch * (TP_CHUNK + 8),
+                (unsigned long long*)p->d_tip_ufx + v.s0, p->d_tip_cnt + v.s0);
+            k_pack_bits<<<dim3((unsigned)NSd, (unsigned)v.nb), 128, 0, p->stream>>>(
+                (const uint32_t*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->NS, NSd,
+                p->d_bitsd + (size_t)v.b0 * NSd * TILE * 4, p->d_ulend);
+        }
         B2D_CUDA(cudaGetLastError());
         p->tips_mode = 1;
         return B2D_OK;
@@ -1274,19 +1446,28 @@ static int skip_closed_form(b2d_problem* p, cudaStream_t st) {
 
 // group x node bitmaps of the resident rows [q0, q0 + rows): row-major for the pair kernel
 // (this pass only), transposed for the closed-form sums (all passes)
-static int skip_prepare_pass(b2d_problem* p, int64_t q0, int64_t rows, int64_t QR) {
-    const int64_t ng = p->npad / 32, words = QR / 32, nwords = (rows + 31) / 32;
-    const int64_t warps = ng * words;
-    p->n_kernels += 1;
-    k_group_nonzero<<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
-        (const double*)p->d_emb, ng, rows, QR, p->d_nz);
+static int skip_transpose(b2d_problem* p, const uint32_t* nz, int64_t q0, int64_t rows, int64_t QR) {
+    const int64_t words = QR / 32, nwords = (rows + 31) / 32;
     const int64_t tw = p->ngw * nwords;
     p->n_kernels += tw ? 1 : 0;
     if (tw)
         k_transpose_bitmaps<<<(unsigned)((tw + 7) / 8), 256, 0, p->stream>>>(
-            p->d_nz, p->d_gperm, p->ngw, words, nwords, q0, p->d_zt);
+            nz, p->d_gperm, p->ngw, words, nwords, q0, p->d_zt);
     B2D_CUDA(cudaGetLastError());
     return B2D_OK;
+}
+// `nz`: where the row-major bitmaps go (d_nz; the distributed build keeps those of all node rows in
+// d_nz_full, exchanges them and transposes afterwards: transpose = false)
+static int skip_prepare_pass(b2d_problem* p, int64_t q0, int64_t rows, int64_t QR, const BuildView& v,
+                             uint32_t* nz, bool transpose) {
+    const int64_t ng = v.npad / 32, words = QR / 32;
+    const int64_t warps = ng * words;
+    p->n_kernels += 1;
+    if (warps)
+        k_group_nonzero<<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
+            (const double*)p->d_emb, ng, rows, QR, nz + (size_t)(v.s0 / 32) * words);
+    B2D_CUDA(cudaGetLastError());
+    return transpose ? skip_transpose(p, nz, q0, rows, QR) : B2D_OK;
 }
 
 // Which intersection kernel: the pipelined one, except (automatic mode) unweighted UniFrac with large
@@ -1348,18 +1529,8 @@ static int compute_dense(b2d_problem* p, int metric) {
     const unsigned wpb = 8;  // warps per block for the per-sample kernels
     const unsigned sblocks = (unsigned)((p->n + wpb - 1) / wpb);
     float ms;
+    int rc = B2D_OK;
     B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
-    if (tree) {
-        p->n_kernels += 1;
-        k_sample_totals_tree<<<sblocks, wpb * 32, 0, p->stream>>>(
-            p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->d_flags,
-            metric == B2D_WEIGHTED_UNIFRAC_NORMALIZED ? p->d_tipdist : nullptr, p->n, p->d_total,
-            p->d_svec);
-    } else {
-        p->n_kernels += 1;
-        k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(
-            p->d_indptr, (const double*)p->d_values, p->n, p->d_svec);
-    }
     // the second raw-sum buffer must exist before the embedding takes its share of memory
     if (p->ntiles && p->mpad > g_chunk_nodes && !p->d_out2)
         B2D_CUDA(b2d_malloc(&p->d_out2, std::max<int64_t>(p->out_len, 1) * sizeof(double)));
@@ -1384,9 +1555,40 @@ static int compute_dense(b2d_problem* p, int metric) {
     QR = QR / NODE_STRIPE * NODE_STRIPE;
     if (QR < NODE_STRIPE) return fail(B2D_ERR_OUT_OF_MEMORY, "not enough device memory for one node stripe");
     QR = std::min<int64_t>(QR, p->mpad);
-    int rc = B2D_OK;
     // whole tree resident: sparse rows from the embedding (inside the pass); else tips from the CSR
     p->rows_general = want_tips && QR == p->mpad;
+    // Distributed build (collectives installed): one vote per compute, every rank takes part whatever
+    // its own answer.  A rank that re-runs after a flagged pair skips it (the others are not voting).
+    bool dist = false;
+    if (tree && have_collectives(p) && !p->dist_rerun) {
+        const bool mine = p->rows_general && !p->dist_off && build_view(p, true).nb > 0;
+        if ((rc = coll_vote(p, mine, &dist))) return rc;
+    }
+    p->dist_active = dist;
+    const BuildView v = build_view(p, dist);
+    const unsigned vblocks = (unsigned)((v.n + wpb - 1) / wpb);
+    if (dist) {  // the embedding holds this rank's blocks only
+        row_bytes = (size_t)v.nb * TILE * sizeof(double);
+        if (p->nz_full_bytes < (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t)) {
+            b2d_free(p->d_nz_full);
+            p->d_nz_full = nullptr;
+            p->nz_full_bytes = 0;
+            B2D_CUDA(b2d_malloc(&p->d_nz_full, (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t)));
+            p->nz_full_bytes = (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t);
+        }
+    }
+    if (tree) {
+        p->n_kernels += 1;
+        if (vblocks)
+            k_sample_totals_tree<<<vblocks, wpb * 32, 0, p->stream>>>(
+                p->d_indptr + v.s0, p->d_qidx, (const int64_t*)p->d_values, p->d_flags,
+                metric == B2D_WEIGHTED_UNIFRAC_NORMALIZED ? p->d_tipdist : nullptr, v.n, p->d_total + v.s0,
+                p->d_svec + v.s0);
+    } else {
+        p->n_kernels += 1;
+        k_sample_sums_features<<<sblocks, wpb * 32, 0, p->stream>>>(
+            p->d_indptr, (const double*)p->d_values, p->n, p->d_svec);
+    }
     p->pack_pass = false;
     if (want_tips && !p->rows_general) {
         if ((rc = tips_build(p))) return rc;
@@ -1459,40 +1661,40 @@ static int compute_dense(b2d_problem* p, int metric) {
         B2D_CUDA(cudaEventRecord(ea, p->stream));
         nvtxRangePushA("b2d:embed (scatter + propagate)");
         B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, (size_t)QR * row_bytes, p->stream));
-        if (p->n) {
+        if (p->n && (!tree || v.n)) {
             if (tree) {
                 p->n_kernels += 1;
-                k_scatter_dense<int64_t><<<sblocks, wpb * 32, 0, p->stream>>>(
-                    p->d_indptr, p->d_qidx, (const int64_t*)p->d_values, p->n, q0, q1, QR,
+                k_scatter_dense<int64_t><<<vblocks, wpb * 32, 0, p->stream>>>(
+                    p->d_indptr + v.s0, p->d_qidx, (const int64_t*)p->d_values, v.n, q0, q1, QR,
                     (unsigned long long*)p->d_emb, 0);
                 if (p->order.decomposed && QR == p->mpad && g_walk_decomposed) {
                     // whole tree resident: independent small subtrees in parallel, then the top
                     const int64_t nspans = (int64_t)p->order.spans.size() / 2;
                     if (nspans) {
-                        dim3 grid((unsigned)(p->npad / 128), (unsigned)nspans);
+                        dim3 grid((unsigned)(v.npad / 128), (unsigned)nspans);
                         p->n_kernels += 1;
                         k_propagate_weighted_spans<<<grid, 128, 0, p->stream>>>(
-                            (unsigned long long*)p->d_emb, p->d_flags1, p->d_spans, p->npad, QR);
+                            (unsigned long long*)p->d_emb, p->d_flags1, p->d_spans, v.npad, QR);
                     }
                     p->n_kernels += 1;
-                    k_propagate_weighted_top<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
+                    k_propagate_weighted_top<<<(unsigned)(v.npad / 128), 128, 0, p->stream>>>(
                         (unsigned long long*)p->d_emb, p->d_top_pos, p->d_top_flags,
-                        (int64_t)p->order.top_pos.size(), p->npad, QR);
+                        (int64_t)p->order.top_pos.size(), v.npad, QR);
                 } else {
                     p->n_kernels += 1;
-                    k_propagate_weighted<<<(unsigned)(p->npad / 128), 128, 0, p->stream>>>(
-                        (unsigned long long*)p->d_emb, p->d_flags, p->npad, q0, q1, QR,
+                    k_propagate_weighted<<<(unsigned)(v.npad / 128), 128, 0, p->stream>>>(
+                        (unsigned long long*)p->d_emb, p->d_flags, v.npad, q0, q1, QR,
                         p->d_state, p->order.depth_at[q0 / NODE_STRIPE]);
                 }
                 // when the rows with children are packed per pass (and the tips come from the CSR)
                 // nothing reads the resident embedding as proportions: the packing divides
                 if (!p->pack_pass) {
-                    const int64_t threads = p->nb * (TILE / 2);
+                    const int64_t threads = v.nb * (TILE / 2);
                     dim3 grid((unsigned)((threads + 255) / 256),
                               (unsigned)std::min<int64_t>(q1 - q0, 2048));
                     p->n_kernels += 1;
                     k_counts_to_proportions<<<grid, 256, 0, p->stream>>>(
-                        (unsigned long long*)p->d_emb, p->d_total, p->nb, q1 - q0, QR);
+                        (unsigned long long*)p->d_emb, p->d_total + v.s0, v.nb, q1 - q0, QR);
                 }
             } else {
                 p->n_kernels += 1;
@@ -1507,16 +1709,51 @@ static int compute_dense(b2d_problem* p, int metric) {
             NvtxRange pair_range("b2d:pair (sparse rows + tile kernels + closed form)");
             if (skip) {
                 if (p->rows_general) {
-                    if ((rc = rows_build(p, QR))) return rc;
+                    if ((rc = rows_build(p, QR, v, dist))) return rc;
                     p->tips_active = p->tips_mode == 1;
                 }
-                if ((rc = skip_prepare_pass(p, q0, q1 - q0, QR))) return rc;
+                if (dist && !p->tips_active) {
+                    // no sparse rows after all (a bucket too large even for tip rows - on every rank, the
+                    // status was OR-ed): the pair kernel would need the whole embedding.  Replicated from now on.
+                    p->dist_off = true;
+                    p->dist_rerun = true;
+                    rc = compute_dense(p, metric);
+                    p->dist_rerun = false;
+                    return rc;
+                }
+                if ((rc = skip_prepare_pass(p, q0, q1 - q0, QR, v, dist ? p->d_nz_full : p->d_nz, !dist))) return rc;
                 if (p->tips_active && p->rows_general) {
                     // the pair kernel streams the packed dense rows only: their own bitmaps
-                    const int64_t ng = p->npad / 32, wd = p->n_dense_pad / 32;
+                    const int64_t ng = v.npad / 32, wd = p->n_dense_pad / 32;
                     p->n_kernels += 1;
-                    k_group_nonzero<<<(unsigned)((ng * wd + 7) / 8), 256, 0, p->stream>>>(
-                        p->d_embd, ng, p->n_dense_pad, p->n_dense_pad, p->d_nz);
+                    if (ng)
+                        k_group_nonzero<<<(unsigned)((ng * wd + 7) / 8), 256, 0, p->stream>>>(
+                            p->d_embd + (size_t)v.b0 * p->n_dense_pad * TILE, ng, p->n_dense_pad, p->n_dense_pad,
+                            p->d_nz + (size_t)(v.s0 / 32) * wd);
+                }
+                if (dist) {
+                    // every rank's slice of every per-block product, in place (NVLink under torchrun);
+                    // the transposed bitmaps of all groups follow from the gathered row-major ones.
+                    // tips_mode is the same on every rank here (the bucket-overflow status was OR-ed)
+                    CollBatch cb;
+                    const int64_t nch = p->tip_nch;
+                    coll_add_blocks(p, cb, p->d_nz_full, 4 * (size_t)(QR / 32) * sizeof(uint32_t));
+                    coll_add_blocks(p, cb, p->d_total, TILE * sizeof(long long));
+                    coll_add_blocks(p, cb, p->d_svec, TILE * sizeof(double));
+                    if (p->tips_active) {
+                        coll_add_blocks(p, cb, p->d_tip_ptr, (size_t)nch * sizeof(int64_t));
+                        coll_add_entries(p, cb, p->d_tip_entries, sizeof(TipEntry));
+                        coll_add_blocks(p, cb, p->d_tip_runs, (size_t)nch * (TP_CHUNK + 8) * sizeof(unsigned short));
+                        coll_add_blocks(p, cb, p->d_embd, (size_t)p->n_dense_pad * TILE * sizeof(double));
+                        coll_add_blocks(p, cb, p->d_nz, 4 * (size_t)(p->n_dense_pad / 32) * sizeof(uint32_t));
+                        coll_add_blocks(p, cb, p->d_tip_u, TILE * sizeof(double));
+                        coll_add_blocks(p, cb, p->d_tip_ufx, TILE * sizeof(long long));
+                        coll_add_blocks(p, cb, p->d_tip_cnt, TILE * sizeof(unsigned));
+                    }
+                    if ((rc = coll_flush(p, cb))) return rc;
+                    if ((rc = skip_transpose(p, p->d_nz_full, q0, q1 - q0, QR))) return rc;
+                }
+                if (p->tips_active && p->rows_general) {
                 } else if (p->tips_active && p->pack_pass) {
                     // rows with children of this pass, packed, and their bitmaps
                     const auto lo = std::lower_bound(p->hc_pos.begin(), p->hc_pos.end(), (int32_t)q0);
@@ -1600,8 +1837,8 @@ static int compute_dense(b2d_problem* p, int metric) {
                         k_tip_guard<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                             p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, p->d_owned,
                             p->d_row_base, p->n, p->d_tip_u, p->d_tip_cnt, p->d_tip_scale, p->d_tip_word + 1,
-                            p->rows_general ? p->d_flag_list : nullptr);
-                        if (p->rows_general) {
+                            p->rows_general && !dist ? p->d_flag_list : nullptr);
+                        if (p->rows_general && !dist) {
                             // whole embedding resident (proportions): the flagged pairs again in fp64
                             p->n_kernels += 1;
                             k_fix_pairs_weighted<<<296, 256, 0, p->stream>>>(
@@ -1638,9 +1875,21 @@ static int compute_dense(b2d_problem* p, int metric) {
         p->tips_flagged = (double)flagged;
         // several node passes (no resident embedding to recompute pairs from) or more flagged pairs
         // than the list holds: redo the whole compute with every row in the dense kernel
+        if (flagged && dist) {
+            // the recomputation needs the embedding of both samples of a pair: this rank redoes its own
+            // compute replicated (no collective involved) and votes for replicated builds from now on
+            p->dist_off = true;
+            p->dist_rerun = true;
+            rc = compute_dense(p, metric);
+            p->dist_rerun = false;
+            return rc;
+        }
         if (flagged && (!p->rows_general || flagged > (unsigned long long)FLAG_CAP)) {
             p->tips_mode = -1;
-            return compute_dense(p, metric);
+            p->dist_rerun = true;   // a re-run inside one compute: the other ranks are not voting
+            rc = compute_dense(p, metric);
+            p->dist_rerun = false;
+            return rc;
         }
     }
     if (skip) {
@@ -1657,22 +1906,33 @@ static int compute_dense(b2d_problem* p, int metric) {
 
 static int compute_bits(b2d_problem* p, int metric) {
     const unsigned wpb = 8;
-    const unsigned sblocks = (unsigned)((p->n + wpb - 1) / wpb);
     float ms;
-    size_t bytes = (size_t)p->nb * p->NS * TILE * sizeof(uint4);
-    int rc = ensure_emb(p, std::max<size_t>(bytes, 16));
+    int rc;
+    const bool want_urows = p->ntiles && metric == B2D_UNWEIGHTED_UNIFRAC && p->kind == 0 && g_tips_sparse &&
+                            g_weighted_skip && p->tips_mode >= 0 && !plain_kernels() && !p->custom_tiles && p->n > 0;
+    // distributed build: see compute_dense (the presence bits of all samples are always resident)
+    bool dist = false;
+    if (metric == B2D_UNWEIGHTED_UNIFRAC && p->kind == 0 && have_collectives(p) && !p->dist_rerun) {
+        const bool mine = want_urows && !p->dist_off && !g_udense_tc && build_view(p, true).nb > 0;
+        if ((rc = coll_vote(p, mine, &dist))) return rc;
+    }
+    p->dist_active = dist;
+    const BuildView v = build_view(p, dist);
+    const unsigned sblocks = (unsigned)((v.n + wpb - 1) / wpb);
+    size_t bytes = (size_t)v.nb * p->NS * TILE * sizeof(uint4);
+    rc = ensure_emb(p, std::max<size_t>(bytes, 16));
     if (rc) return rc;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     B2D_CUDA(cudaEventRecord(ea, p->stream));
     nvtxRangePushA("b2d:embed (scatter + propagate bits)");
     B2D_CUDA(cudaMemsetAsync(p->d_emb, 0, bytes, p->stream));
-    if (p->n) {
+    if (v.n) {
         p->n_kernels += 1;
-        k_scatter_bits<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, p->d_qidx, p->n, p->NS,
+        k_scatter_bits<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr + v.s0, p->d_qidx, v.n, p->NS,
                                                            (uint32_t*)p->d_emb);
         p->n_kernels += 1;
-        k_propagate_bits<<<(unsigned)p->nb, TILE, 0, p->stream>>>(
-            (uint4*)p->d_emb, p->d_hc, p->d_fold, p->d_len, p->NS, p->d_svec);
+        k_propagate_bits<<<(unsigned)v.nb, TILE, 0, p->stream>>>(
+            (uint4*)p->d_emb, p->d_hc, p->d_fold, p->d_len, p->NS, p->d_svec + v.s0);
     }
     nvtxRangePop();
     B2D_CUDA(cudaEventRecord(eb, p->stream));
@@ -1686,11 +1946,30 @@ static int compute_bits(b2d_problem* p, int metric) {
     p->tips_active = false;
     p->t_tips = 0;
     bool utips_timed = false;
-    if (p->ntiles && metric == B2D_UNWEIGHTED_UNIFRAC && p->kind == 0 && g_tips_sparse && g_weighted_skip &&
-        p->tips_mode >= 0 && !plain_kernels() && !p->custom_tiles && p->n > 0) {
+    if (want_urows) {
         // sparse rows through the intersection kernel, the others packed for the LUT kernel
-        if ((rc = urows_build(p))) return rc;
+        if ((rc = urows_build(p, v, dist))) return rc;
         p->urows_active = p->tips_mode == 1;
+        if (dist && !p->urows_active) {   // every rank (the status was OR-ed): all rows in the LUT kernel, replicated
+            p->dist_off = true;
+            p->dist_rerun = true;
+            rc = compute_bits(p, metric);
+            p->dist_rerun = false;
+            return rc;
+        }
+        if (dist) {
+            CollBatch cbat;
+            const int64_t nch = p->tip_nch, NSd = p->n_dense_pad / 128;
+            coll_add_blocks(p, cbat, p->d_svec, TILE * sizeof(double));
+            coll_add_blocks(p, cbat, p->d_tip_ptr, (size_t)nch * sizeof(int64_t));
+            coll_add_entries(p, cbat, p->d_ukeys, sizeof(uint32_t));
+            coll_add_blocks(p, cbat, p->d_tip_runs, (size_t)nch * (TP_CHUNK + 8) * sizeof(unsigned short));
+            coll_add_blocks(p, cbat, p->d_bitsd, (size_t)NSd * TILE * sizeof(uint4));
+            coll_add_blocks(p, cbat, p->d_tip_u, TILE * sizeof(double));
+            coll_add_blocks(p, cbat, p->d_tip_ufx, TILE * sizeof(long long));
+            coll_add_blocks(p, cbat, p->d_tip_cnt, TILE * sizeof(unsigned));
+            if ((rc = coll_flush(p, cbat))) return rc;
+        }
         B2D_CUDA(cudaEventRecord(p->ev[4], p->stream));
     }
     if (p->ntiles && metric != B2D_FAITH_PD) {
@@ -1808,13 +2087,15 @@ static int compute_bits(b2d_problem* p, int metric) {
             p->n_kernels += 1;
             k_tip_guard<<<(unsigned)(p->owned.size() * TILE), 256, 0, p->stream>>>(
                 p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, p->d_owned, p->d_row_base, p->n,
-                p->d_tip_u, p->d_tip_cnt, p->d_tip_scale, p->d_tip_word + 1, p->d_flag_list,
+                p->d_tip_u, p->d_tip_cnt, p->d_tip_scale, p->d_tip_word + 1, dist ? nullptr : p->d_flag_list,
                 p->ud_tc_active ? p->d_ud_Ld : nullptr, p->ud_tc_active ? p->d_ud_Kd : nullptr,
                 p->ud_tc_active ? p->d_ud_scale : nullptr);
-            p->n_kernels += 1;
-            k_fix_pairs_unweighted<<<296, 256, 0, p->stream>>>(
-                (const uint4*)p->d_emb, p->d_len, p->NS, p->d_flag_list, p->d_tip_word + 1, p->d_out,
-                p->chunk_counter >= 2 ? p->d_out2 : nullptr);
+            if (!dist) {
+                p->n_kernels += 1;
+                k_fix_pairs_unweighted<<<296, 256, 0, p->stream>>>(
+                    (const uint4*)p->d_emb, p->d_len, p->NS, p->d_flag_list, p->d_tip_word + 1, p->d_out,
+                    p->chunk_counter >= 2 ? p->d_out2 : nullptr);
+            }
         }
         if ((rc = finalize(p, metric == B2D_JACCARD ? EPI_JACCARD : EPI_UNWEIGHTED))) return rc;
     }
@@ -1826,9 +2107,19 @@ static int compute_bits(b2d_problem* p, int metric) {
         B2D_CUDA(cudaMemcpy(fm, p->d_tip_word + 1, sizeof(fm), cudaMemcpyDeviceToHost));
         p->tip_matches = (double)fm[1];
         p->tips_flagged = (double)fm[0];
+        if (fm[0] && dist) {   // see compute_dense: this rank alone, replicated, and it votes no from now on
+            p->dist_off = true;
+            p->dist_rerun = true;
+            rc = compute_bits(p, metric);
+            p->dist_rerun = false;
+            return rc;
+        }
         if (fm[0] > (unsigned long long)FLAG_CAP) {  // more than the list holds: every row in the LUT kernel
             p->tips_mode = -1;
-            return compute_bits(p, metric);
+            p->dist_rerun = true;
+            rc = compute_bits(p, metric);
+            p->dist_rerun = false;
+            return rc;
         }
         if (utips_timed) {
             cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]);
@@ -1992,6 +2283,9 @@ static int b2d_problem_compute_impl(b2d_problem* p, int metric) {
     p->n_kernels = 0;
     p->tips_flagged = 0;
     p->isect_generation = 0;
+    p->dist_active = false;
+    p->t_exchange = 0;
+    p->exchange_bytes = 0;
     int rc;
     switch (metric) {
         case B2D_UNWEIGHTED_UNIFRAC:
@@ -2299,15 +2593,49 @@ static int b2d_problem_sample_vector_impl(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[18] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+    double v[20] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
                     p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged,
                     p->urows_active ? (double)p->rows_S0
                                     : (p->tips_active ? (p->rows_general ? (double)p->rows_S0 : 1.0) : 0.0),
                     p->urows_active || (p->tips_active && p->rows_general) ? p->rows_entries : 0.0,
                     p->urows_active || p->tips_active ? p->tip_matches : 0.0,
-                    p->isect_generation};
-    for (int i = 0; i < n && i < 18; ++i) ms[i] = v[i];
+                    p->isect_generation, p->dist_active ? p->t_exchange : 0.0, p->dist_active ? p->exchange_bytes : 0.0};
+    for (int i = 0; i < n && i < 20; ++i) ms[i] = v[i];
+    return B2D_OK;
+}
+
+int b2d_problem_set_collectives(b2d_problem* p, int rank, int world, b2d_allgather_host_fn allgather_host,
+                                b2d_allgatherv_device_fn allgatherv_device, void* user) {
+    if (!p) return fail(B2D_ERR_INVALID_ARGUMENT, "problem is NULL");
+    if (world <= 1 || !allgather_host || !allgatherv_device) {
+        p->coll_rank = 0;
+        p->coll_world = 1;
+        p->coll_host = nullptr;
+        p->coll_dev = nullptr;
+        p->coll_user = nullptr;
+        return B2D_OK;
+    }
+    if (rank != p->shard || world != p->n_shards)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "collectives need rank == shard and world == n_shards of the problem");
+    p->coll_rank = rank;
+    p->coll_world = world;
+    p->coll_host = allgather_host;
+    p->coll_dev = allgatherv_device;
+    p->coll_user = user;
+    return B2D_OK;
+}
+
+int b2d_build_range(int64_t n_samples, int rank, int world, int64_t* first_block, int64_t* last_block) {
+    if (n_samples < 0 || world < 1 || rank < 0 || rank >= world || !first_block || !last_block)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "need n_samples >= 0 and 0 <= rank < world");
+    build_range((n_samples + TILE - 1) / TILE, rank, world, first_block, last_block);
+    return B2D_OK;
+}
+
+int b2d_device_copy(void* dst, const void* src, int64_t bytes) {
+    if (bytes < 0 || (bytes && (!dst || !src))) return fail(B2D_ERR_INVALID_ARGUMENT, "bad copy arguments");
+    if (bytes) B2D_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault));
     return B2D_OK;
 }
 

@@ -506,10 +506,11 @@ __global__ void k_rows_bucket_counts(const unsigned* __restrict__ qcount, int64_
 }
 
 // U_i = sum of the partials in a fixed order; maximum for the scale
-__global__ void k_rows_ureduce(const double* __restrict__ upart, int64_t nparts, int64_t npad,
+__global__ void k_rows_ureduce(const double* __restrict__ upart, int64_t nparts, int64_t npad, int64_t count,
                                double* __restrict__ U, unsigned long long* __restrict__ maxbits) {
+    // npad: stride between the partials of one sample; count: samples to reduce (from the pointers on)
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= npad) return;
+    if (s >= count) return;
     double u = 0.0;
     for (int64_t k = 0; k < nparts; ++k) u += upart[k * npad + s];
     U[s] = u;

@@ -83,3 +83,79 @@ def test_shard_layout_partitions_the_triangle(n, shards):
     assert (covered == 1).all()
     if n >= 5000 and shards > 1:  # snake dealing balances the work
         assert max(sizes) / (sum(sizes) / shards) < 1.08
+
+
+@pytest.mark.parametrize("n", [0, 1, 128, 129, 700, 10000, 28284])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_build_ranges_partition_the_sample_blocks(n, world):
+    """The block ranges of the distributed build (b2d_build_range) are contiguous, disjoint, in rank
+    order and cover every 128-sample block - what makes the exchange an in-place all-gather."""
+    from skbio_b200 import _capi
+
+    nb = (n + 127) // 128
+    edge = 0
+    for r in range(world):
+        a, b = _capi.build_range(n, r, world)
+        assert a == min(edge, nb) and a <= b <= nb
+        edge = b
+    assert edge == nb
+
+
+def _blob_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    from skbio_b200 import distributed
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        coll = distributed.TorchCollectives(None)
+        mine = bytes([rank + 1]) * 24
+        got = coll.allgather_host(mine)
+        q.put(("ok", got == b"".join(bytes([r + 1]) * 24 for r in range(world)), coll.rank))
+    except Exception as e:  # pragma: no cover
+        q.put(("err", repr(e), rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_host_blobs_of_the_exchange():
+    """The host half of the exchange (votes, entry counts, max U: TorchCollectives.allgather_host)
+    between two gloo ranks; the device half needs GPUs (tests/test_gpu_parity.py runs it between
+    host threads, bench.py under torchrun)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_blob_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[0] == "ok" and r[1] for r in res), res
+
+
+def test_thread_collectives_host_blobs():
+    import threading
+
+    from skbio_b200.distributed import ThreadCollectives
+
+    world = 3
+    coll = ThreadCollectives(world, timeout=30.0)
+    got = [None] * world
+
+    def work(r):
+        c = coll.for_rank(r)
+        for rep in range(3):
+            got[r] = c.allgather_host(bytes([10 * rep + r]) * 4)
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert all(g == b"".join(bytes([20 + r]) * 4 for r in range(world)) for g in got)

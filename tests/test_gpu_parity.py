@@ -1038,6 +1038,107 @@ def test_devices_argument_runs_one_shard_per_host_thread():
             assert np.array_equal(one, many, equal_nan=True), (metric, devs)
 
 
+def _run_shards_in_threads(world, make, key, computes=2, exchange=True):
+    """One problem per shard, one host thread per shard (all on device 0), the distributed build's
+    collectives between the threads: (full condensed vector, timings of every shard)."""
+    import threading
+
+    from skbio_b200.distributed import ThreadCollectives
+
+    coll = ThreadCollectives(world, timeout=120.0)
+    n = make(0, 1).n
+    out = np.full(n * (n - 1) // 2, -1.0)
+    tms, errors = [None] * world, []
+
+    def work(r):
+        try:
+            with make(r, world) as prob:
+                if exchange:
+                    prob.set_collectives(r, world, coll.for_rank(r))
+                for _ in range(computes):     # the second compute reuses every buffer of the first
+                    prob.compute(key)
+                tms[r] = prob.timings()
+                prob.fetch(out)
+        except BaseException as e:
+            errors.append(e)
+            coll.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    return out, tms
+
+
+@pytest.mark.parametrize("key", ["weighted_unifrac_normalized", "weighted_unifrac", "unweighted_unifrac"])
+def test_distributed_build_gives_the_same_bits_as_the_replicated_one(key):
+    """b2d_problem_set_collectives: every shard builds the embedding, sparse-row entries, packed
+    dense rows and bitmaps of its own block range only and the shards all-gather them; the pair
+    kernels then see exactly the arrays a replicated build produces, so the distances are
+    bit-identical - block counts that divide evenly, that do not, and more shards than blocks
+    (a shard with nothing to build votes no and everybody builds everything)."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    for n, tips, lam, seed in ((700, 1200, 0.04, 91), (530, 2600, 0.02, 92)):
+        parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, lam, seed)
+        exp = oracle_fast.unifrac_all(synthetic.csr_to_dense(indptr, cols, vals, tips), tip_node, parent, length)
+
+        def make(r, w):
+            return _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n, shard=r, n_shards=w)
+
+        base, tm = _run_shards_in_threads(1, make, key)
+        assert tm[0]["exchange_bytes"] == 0
+        assert_close_rel(base, exp[key], UNIFRAC_RTOL, key + " single shard vs oracle")
+        nb = (n + 127) // 128
+        for world in (2, 3, 4, 8):
+            got, tms = _run_shards_in_threads(world, make, key)
+            assert np.array_equal(got, base), (key, n, world)
+            per = (nb + world - 1) // world
+            everyone_builds = per * (world - 1) < nb
+            for t in tms:
+                assert (t["exchange_bytes"] > 0) == everyone_builds, (key, n, world, t)
+            rep, tms = _run_shards_in_threads(world, make, key, exchange=False)
+            assert np.array_equal(rep, base)
+            assert all(t["exchange_bytes"] == 0 for t in tms)
+
+
+def test_distributed_build_with_flagged_pairs_falls_back_per_rank():
+    """Near-duplicate samples: the fixed-point guard flags their pairs, and recomputing a flagged pair
+    needs the embedding of both samples, which a distributed build does not hold.  The shard that sees
+    one redoes its own compute replicated (the others are not involved) and the result still meets
+    the tolerance; the next compute votes for a replicated build everywhere."""
+    _skbio_b200()
+    from oracle import oracle_fast
+    from skbio_b200 import _capi, synthetic
+
+    n, tips = 600, 1500
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.05, 93)
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    big = 10 ** 7
+    for a, b in ((5, 400), (130, 131), (300, 590)):   # b = a scaled, one count off: distance ~1e-7 of U
+        dense[b] = dense[a] * big
+        dense[b, np.flatnonzero(dense[a])[0]] += 1
+    import scipy.sparse as sp
+
+    csr = sp.csr_matrix(dense)
+    indptr, cols, vals = csr.indptr.astype(np.int64), csr.indices.astype(np.int32), csr.data.astype(np.int64)
+    exp = oracle_fast.unifrac_all(dense, tip_node, parent, length)
+    for key in ("weighted_unifrac_normalized", "unweighted_unifrac"):
+        def make(r, w):
+            return _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n, shard=r, n_shards=w)
+
+        base, tm = _run_shards_in_threads(1, make, key, computes=1)
+        got, tms = _run_shards_in_threads(2, make, key, computes=3)
+        assert_close_rel(got, exp[key], UNIFRAC_RTOL, key + " distributed build with near-duplicates")
+        if tm[0]["tips_flagged"]:
+            assert sum(t["tips_flagged"] for t in tms) == tm[0]["tips_flagged"]
+            assert all(t["exchange_bytes"] == 0 for t in tms)   # third compute: everybody voted replicated
+
+
 def test_pcoa_centering_and_square_rows_on_the_resident_result():
     """Gower centering (pcoa's first step, /root/reference/skbio/stats/ordination/_cutils.pyx:19-123)
     and square-row gathering on the device-resident condensed result, against NumPy on the fetched
