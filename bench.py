@@ -644,8 +644,8 @@ def bench_problem(ctx, inp, steps, warmup, e2e_reps, parity_rows, default_shape=
     for _ in range(steps):
         prob.compute(key)  # blocks until the shard's distances are complete in HBM
         t = prob.timings()
-        xchg_ms.append(t["exchange_ms"])
-        xchg_bytes.append(t["exchange_bytes"])
+        xchg_ms.append(t.get("exchange_ms", 0.0))
+        xchg_bytes.append(t.get("exchange_bytes", 0.0))
         dev_ms.append(t["compute_ms"])
         pair_ms.append(t["pair_ms"])
         embed_ms.append(t["embed_ms"])
