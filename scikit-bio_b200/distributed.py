@@ -36,8 +36,8 @@ class TorchCollectives:
     """The two collectives of the distributed build on a `torch.distributed` process group.
 
     NCCL group: device buffers are all-gathered in place (`all_gather_into_tensor` when every rank
-    contributes the same number of bytes, one broadcast per rank otherwise); the small host blobs
-    ride through a device tensor.  A gloo group carries the host blobs only (CPU tests)."""
+    contributes the same number of bytes, grouped point-to-point transfers otherwise); the small
+    host blobs ride through a device tensor.  A gloo group carries the host blobs only (CPU tests)."""
 
     def __init__(self, device, group=None):
         import torch
@@ -64,7 +64,7 @@ class TorchCollectives:
     def allgatherv_device(self, bases, offsets, counts):
         torch, dist = self.torch, self.dist
         self.calls += 1
-        pending = []
+        pending, p2p = [], []
         with torch.cuda.device(self.device):
             for base, off, cnt in zip(bases, offsets, counts):
                 lo = min(o for o, c in zip(off, cnt) if c) if any(cnt) else 0
@@ -72,16 +72,24 @@ class TorchCollectives:
                 if hi == lo:
                     continue
                 whole = torch.as_tensor(_DeviceBytes(base + lo, hi - lo), device=self.device)
+                views = [whole[off[r] - lo: off[r] - lo + cnt[r]] for r in range(self.world)]
                 even = len(set(cnt)) == 1 and all(off[r] == lo + r * cnt[0] for r in range(self.world))
                 if even:
-                    mine = whole[off[self.rank] - lo: off[self.rank] - lo + cnt[self.rank]]
-                    pending.append(dist.all_gather_into_tensor(whole, mine, group=self.group, async_op=True))
-                else:
-                    for r in range(self.world):
-                        if cnt[r]:
-                            view = whole[off[r] - lo: off[r] - lo + cnt[r]]
-                            src = dist.get_global_rank(self.group, r) if self.group is not None else r
-                            pending.append(dist.broadcast(view, src=src, group=self.group, async_op=True))
+                    pending.append(dist.all_gather_into_tensor(whole, views[self.rank], group=self.group, async_op=True))
+                    continue
+                # ranks contribute different byte counts (the last block range is shorter, entry counts
+                # differ): every slice goes straight to its final place on every peer, all transfers of
+                # all buffers in ONE NCCL group (full-duplex over NVLink / NVSwitch, nothing staged)
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    peer = dist.get_global_rank(self.group, r) if self.group is not None else r
+                    if cnt[self.rank]:
+                        p2p.append(dist.P2POp(dist.isend, views[self.rank], peer, self.group))
+                    if cnt[r]:
+                        p2p.append(dist.P2POp(dist.irecv, views[r], peer, self.group))
+            if p2p:
+                pending.extend(dist.batch_isend_irecv(p2p))
             for w in pending:
                 w.wait()
             torch.cuda.current_stream(self.device).synchronize()
