@@ -220,7 +220,8 @@ int b2d_problem_phydiv(b2d_problem* p, int rooted, double weight, double* out_n)
  * kernel (0: none, 1: tip rows only), [15] entries of those rows, [16] (sample pair, row) matches
  * that kernel accumulated, [17] which intersection kernel ran (2: pipelined, b2d_isect.cuh; 1: first
  * generation; 0: none), [18] host time of the exchanges of a distributed build (ms, 0 when the
- * build was replicated) and [19] the bytes this rank received in them.  n: slots to fill (<= 20). */
+ * build was replicated) and [19] the bytes this rank received in them, [20] CSR bytes (indptr, indices,
+ * values) uploaded from the host when the problem was created.  n: slots to fill (<= 21). */
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n);
 
 int b2d_problem_destroy(b2d_problem* p);
@@ -263,6 +264,10 @@ int b2d_beta_diversity_features(int metric, int device,
  *                       feature tables (Bray-Curtis / Jaccard)
  *   "walk_decomposed"   0: always the sequential tree walk;  "plain_kernels" 1: cross-check
  *                       kernels without bulk copies.
+ *   "partial_upload"    1: tree problems created with n_shards > 1 upload only the CSR rows of the shard's own
+ *                       build range (b2d_build_range); the first compute (or phydiv) all-gathers the other
+ *                       shards' rows device to device, so collectives must be installed before it.  Set it
+ *                       on every rank before creating the problems.  Default 0: every shard uploads all rows
  *   "isect_kernel"      -1 (default): pipelined intersection kernel for the sparse rows (b2d_isect.cuh),
  *                       except unweighted UniFrac with more than 6 000 keys per (block, chunk) bucket;
  *                       1: always; 0: the first-generation kernels

@@ -600,15 +600,16 @@ class Problem:
         return out
 
     def timings(self):
-        t = np.zeros(20, dtype=np.float64)
-        _check(load().b2d_problem_timings(self._h, _ptr(t, _f64p), 20))
+        t = np.zeros(21, dtype=np.float64)
+        _check(load().b2d_problem_timings(self._h, _ptr(t, _f64p), 21))
         return {"embed_ms": t[0], "pair_ms": t[1], "compute_ms": t[2], "fetch_ms": t[3],
                 "upload_ms": t[4], "pair_launches": int(t[5]), "nodes_resident": int(t[6]),
                 "passes": int(t[7]), "visits_executed": float(t[8]), "visits_dense": float(t[9]),
                 "skip_prep_ms": t[10], "kernels": int(t[11]), "tips_ms": t[12],
                 "tips_flagged": int(t[13]), "sparse_rows_max_tips": int(t[14]),
                 "sparse_row_entries": int(t[15]), "sparse_row_matches": float(t[16]),
-                "isect_generation": int(t[17]), "exchange_ms": t[18], "exchange_bytes": float(t[19])}
+                "isect_generation": int(t[17]), "exchange_ms": t[18], "exchange_bytes": float(t[19]),
+                "csr_upload_bytes": float(t[20])}
 
     def destroy(self):
         if self._h is not None:

@@ -52,6 +52,8 @@ static int g_sparse_features = -1;             // -1 auto (density < 2.5 %), 0 n
 static int g_isect_kernel = -1;                // 1: pipelined intersection kernel (b2d_isect.cuh); 0: first generation;
                                                // -1: pipelined, except unweighted UniFrac with large buckets (see use_isect)
 static int g_udense_tc = 0;                    // unweighted UniFrac: dense rows on the tensor cores (b2d_tc.cuh) instead of the LUT kernel
+static int g_partial_upload = 0;               // tree problems with n_shards > 1: upload only the CSR rows of the shard's own
+                                               // build range; the first compute all-gathers the rest (collectives required)
 static int g_isect_group = 0;                  // lanes sharing one row entry in that kernel (1, 2, 4, 8; 0: per mode)
 
 static bool plain_kernels() {
@@ -484,8 +486,10 @@ struct b2d_problem {
     bool dist_active = false;         // the last compute exchanged its products
     uint32_t* d_nz_full = nullptr;    // [npad/32][QR/32] bitmaps of all node rows (the exchange needs them beside d_nz)
     size_t nz_full_bytes = 0;
-    double t_exchange = 0, exchange_bytes = 0;
+    double t_exchange = 0, exchange_bytes = 0, upload_bytes = 0;
     std::vector<int64_t> coll_totals; // sparse-row entries of every rank (last exchange)
+    bool csr_partial = false;         // only this shard's rows of the CSR are on the device yet (partial_upload)
+    std::vector<int64_t> csr_edges;   // [n_shards + 1] first CSR entry of every shard's build range
     bool computed = false;
     bool custom_tiles = false;  // b2d_problem_select_tiles: untouched entries of owned stripes stay 0
     int last_metric = -1;
@@ -532,6 +536,13 @@ static void free_problem(b2d_problem* p) {
     delete p;
 }
 
+// blocks [b0, b1) whose per-block products rank `rank` of `world` builds (distributed build)
+static void build_range_of(int64_t nb, int rank, int world, int64_t* b0, int64_t* b1) {
+    const int64_t per = (nb + world - 1) / std::max(world, 1);
+    *b0 = std::min<int64_t>(nb, (int64_t)rank * per);
+    *b1 = std::min<int64_t>(nb, *b0 + per);
+}
+
 template <typename T>
 static int upload(T** dst, const T* src, size_t count, cudaStream_t s) {
     B2D_CUDA(b2d_malloc(dst, std::max<size_t>(count, 1) * sizeof(T)));
@@ -556,13 +567,31 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     const TreeOrder& o = p->order;
     int rc;
     if ((rc = upload(&p->d_indptr, indptr, (size_t)p->n + 1, p->stream))) return rc;
-    if ((rc = upload(&p->d_qidx, ids, (size_t)p->nnz, p->stream))) return rc;
+    // CSR entries to upload now: all of them, or (partial_upload, several shards of a tree problem) only the
+    // rows of this shard's build range - the shards all-gather the rest device to device before the first compute
+    int64_t ea = 0, eb = p->nnz;
+    if (g_partial_upload && p->kind == 0 && p->n_shards > 1) {
+        p->csr_edges.assign(p->n_shards + 1, p->nnz);
+        for (int r = 0; r < p->n_shards; ++r) {
+            int64_t b0, b1;
+            build_range_of(p->nb, r, p->n_shards, &b0, &b1);
+            p->csr_edges[r] = indptr[std::min<int64_t>(p->n, b0 * TILE)];
+        }
+        ea = p->csr_edges[p->shard];
+        eb = p->csr_edges[p->shard + 1];
+        p->csr_partial = true;
+    }
+    B2D_CUDA(b2d_malloc(&p->d_qidx, std::max<size_t>(p->nnz, 1) * sizeof(int32_t)));
+    if (eb > ea)
+        B2D_CUDA(cudaMemcpyAsync(p->d_qidx + ea, ids + ea, (size_t)(eb - ea) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                 p->stream));
     if (values) {
         B2D_CUDA(b2d_malloc(&p->d_values, std::max<size_t>(p->nnz, 1) * value_size));
-        if (p->nnz)
-            B2D_CUDA(cudaMemcpyAsync(p->d_values, values, p->nnz * value_size,
-                                     cudaMemcpyHostToDevice, p->stream));
+        if (eb > ea)
+            B2D_CUDA(cudaMemcpyAsync((char*)p->d_values + ea * value_size, (const char*)values + ea * value_size,
+                                     (size_t)(eb - ea) * value_size, cudaMemcpyHostToDevice, p->stream));
     }
+    p->upload_bytes = (double)((p->n + 1) * sizeof(int64_t) + (eb - ea) * (sizeof(int32_t) + (values ? value_size : 0)));
     if ((rc = upload(&p->d_flags, o.flags.data(), o.flags.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_hc, o.hc_mask.data(), o.hc_mask.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_fold, o.fold_mask.data(), o.fold_mask.size(), p->stream))) return rc;
@@ -585,10 +614,10 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
         if (node_of_col && (rc = upload(&d_noc, node_of_col, (size_t)n_cols, p->stream))) return rc;
         B2D_CUDA(b2d_malloc(&d_err, sizeof(int)));
         B2D_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), p->stream));
-        if (p->nnz) {
-            int64_t blocks = (p->nnz + 255) / 256;
-            k_map_ids<<<(unsigned)blocks, 256, 0, p->stream>>>(p->d_qidx, d_noc, n_cols, d_qof, p->d_qidx,
-                                                               p->nnz, p->m, d_err);
+        if (eb > ea) {
+            int64_t blocks = (eb - ea + 255) / 256;
+            k_map_ids<<<(unsigned)blocks, 256, 0, p->stream>>>(p->d_qidx + ea, d_noc, n_cols, d_qof, p->d_qidx + ea,
+                                                               eb - ea, p->m, d_err);
         }
         int herr = 0;
         B2D_CUDA(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
@@ -751,6 +780,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_weighted_skip = value ? 1 : 0;
     } else if (s == "isect_kernel") {
         g_isect_kernel = value < 0 ? -1 : (value ? 1 : 0);
+    } else if (s == "partial_upload") {
+        g_partial_upload = value ? 1 : 0;
     } else if (s == "udense_tc") {
         g_udense_tc = value ? 1 : 0;
     } else if (s == "isect_group") {
@@ -894,9 +925,7 @@ struct BuildView {
     int64_t nb = 0, npad = 0; // blocks, samples including padding
 };
 static void build_range(int64_t nb, int rank, int world, int64_t* b0, int64_t* b1) {
-    const int64_t per = (nb + world - 1) / std::max(world, 1);
-    *b0 = std::min<int64_t>(nb, (int64_t)rank * per);
-    *b1 = std::min<int64_t>(nb, *b0 + per);
+    build_range_of(nb, rank, world, b0, b1);
 }
 static BuildView build_view(const b2d_problem* p, bool dist, int rank = -1) {
     BuildView v;
@@ -964,6 +993,30 @@ static int coll_flush(b2d_problem* p, CollBatch& cb) {
     cb = CollBatch();
     return B2D_OK;
 }
+// partial_upload: the other shards' rows of the CSR, device to device, once per problem
+static int ensure_csr(b2d_problem* p) {
+    if (!p->csr_partial) return B2D_OK;
+    if (!have_collectives(p))
+        return fail(B2D_ERR_STATE, "the problem was created with partial_upload: install collectives "
+                                   "(b2d_problem_set_collectives) before the first compute");
+    CollBatch cb;
+    std::vector<int64_t> off(p->coll_world), cnt(p->coll_world);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int64_t es = pass == 0 ? (int64_t)sizeof(int32_t) : (int64_t)sizeof(int64_t);
+        void* base = pass == 0 ? (void*)p->d_qidx : p->d_values;
+        if (!base) continue;
+        for (int r = 0; r < p->coll_world; ++r) {
+            off[r] = p->csr_edges[r] * es;
+            cnt[r] = (p->csr_edges[r + 1] - p->csr_edges[r]) * es;
+        }
+        coll_add_ranges(p, cb, base, off, cnt);
+    }
+    int rc = coll_flush(p, cb);
+    if (rc) return rc;
+    p->csr_partial = false;
+    return B2D_OK;
+}
+
 // One vote per compute: the build is distributed only when every rank can (whole embedding resident, ...)
 static int coll_vote(b2d_problem* p, bool mine, bool* all_yes) {
     std::vector<int32_t> votes(p->coll_world, 0);
@@ -2287,6 +2340,7 @@ static int b2d_problem_compute_impl(b2d_problem* p, int metric) {
     p->t_exchange = 0;
     p->exchange_bytes = 0;
     int rc;
+    if ((rc = ensure_csr(p))) return rc;
     switch (metric) {
         case B2D_UNWEIGHTED_UNIFRAC:
         case B2D_FAITH_PD:
@@ -2394,6 +2448,7 @@ static int b2d_problem_phydiv_impl(b2d_problem* p, int rooted, double weight, do
     if (!(weight >= 0.0 && weight <= 1.0)) return fail(B2D_ERR_INVALID_ARGUMENT, "weight must be in [0, 1]");
     B2D_CUDA(cudaSetDevice(p->device));
     if (p->n == 0) return B2D_OK;
+    if (int rc0 = ensure_csr(p)) return rc0;
     const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
     B2D_CUDA(cudaMemsetAsync(p->d_total, 0, p->npad * sizeof(long long), p->stream));
     k_sample_totals_all<<<sblocks, wpb * 32, 0, p->stream>>>(p->d_indptr, (const int64_t*)p->d_values, p->n,
@@ -2457,6 +2512,7 @@ static int b2d_debug_fetch_embedding_impl(b2d_problem* p, int variant, int64_t* 
     if (variant != 2 && !p->has_values) return fail(B2D_ERR_INVALID_ARGUMENT, "count variants need count values");
     B2D_CUDA(cudaSetDevice(p->device));
     if (p->n == 0) return B2D_OK;
+    if (int rc0 = ensure_csr(p)) return rc0;
     const unsigned wpb = 8, sblocks = (unsigned)((p->n + wpb - 1) / wpb);
     const std::vector<int32_t>& qof = p->order.q_of_id;
     p->computed = false;
@@ -2593,15 +2649,15 @@ static int b2d_problem_sample_vector_impl(b2d_problem* p, double* out_n) {
 
 int b2d_problem_timings(const b2d_problem* p, double* ms, int n) {
     if (!p || !ms) return fail(B2D_ERR_INVALID_ARGUMENT, "NULL argument");
-    double v[20] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
+    double v[21] = {p->t_embed, p->t_pair, p->t_total, p->t_fetch, p->t_upload,
                     p->n_launch, p->nodes_resident, p->n_pass, p->skip_executed, p->skip_dense,
                     p->t_skip_prep, p->n_kernels, p->t_tips, p->tips_flagged,
                     p->urows_active ? (double)p->rows_S0
                                     : (p->tips_active ? (p->rows_general ? (double)p->rows_S0 : 1.0) : 0.0),
                     p->urows_active || (p->tips_active && p->rows_general) ? p->rows_entries : 0.0,
                     p->urows_active || p->tips_active ? p->tip_matches : 0.0,
-                    p->isect_generation, p->dist_active ? p->t_exchange : 0.0, p->dist_active ? p->exchange_bytes : 0.0};
-    for (int i = 0; i < n && i < 20; ++i) ms[i] = v[i];
+                    p->isect_generation, p->t_exchange, p->exchange_bytes, p->upload_bytes};
+    for (int i = 0; i < n && i < 21; ++i) ms[i] = v[i];
     return B2D_OK;
 }
 

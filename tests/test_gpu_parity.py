@@ -1104,6 +1104,34 @@ def test_distributed_build_gives_the_same_bits_as_the_replicated_one(key):
             rep, tms = _run_shards_in_threads(world, make, key, exchange=False)
             assert np.array_equal(rep, base)
             assert all(t["exchange_bytes"] == 0 for t in tms)
+            # partial upload: every shard uploads the CSR rows of its own block range only, the first
+            # compute gathers the others' device to device (also when the build itself is replicated)
+            try:
+                _capi.set_option("partial_upload", 1)
+                got, tms2 = _run_shards_in_threads(world, make, key)
+            finally:
+                _capi.set_option("partial_upload", 0)
+            assert np.array_equal(got, base), (key, n, world, "partial upload")
+            full_bytes = (n + 1) * 8 + len(cols) * 12
+            assert sum(t["csr_upload_bytes"] for t in tms2) == full_bytes + (world - 1) * (n + 1) * 8
+
+
+def test_partial_upload_without_collectives_is_an_error():
+    _skbio_b200()
+    from skbio_b200 import _capi
+
+    n, tips = 300, 500
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.05, 94)
+    try:
+        _capi.set_option("partial_upload", 1)
+        with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n, shard=0, n_shards=2) as prob:
+            with pytest.raises(_capi.EngineError, match="partial_upload"):
+                prob.compute("weighted_unifrac")
+        # a single shard is never partial
+        with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+            prob.compute("weighted_unifrac")
+    finally:
+        _capi.set_option("partial_upload", 0)
 
 
 def test_distributed_build_with_flagged_pairs_falls_back_per_rank():
