@@ -178,6 +178,16 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def sm_clock_hz(device):
+    """Current SM clock (the pair kernels have just run: the boost clock under load)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=clocks.sm", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=10).stdout
+        return float(out.strip().splitlines()[0]) * 1e6
+    except Exception:
+        return 1.965e9
+
+
 def ncu_traffic():
     """Per-launch DRAM bytes of the pair kernels from the committed `ncu --set full` captures
     (profiles/ncu_traffic.json, regenerated by tools/ncu_summary.py), keyed by workload."""
@@ -591,6 +601,22 @@ def roofline_block(ctx, inp, t, pair_ms, prep_ms, P_shard, P_total, default_shap
                                "profiles/ncu_traffic.json") if traffic_tab.get(kname) else None,
             "avg_launch_ms": float(t["tips_ms"]), "launches_per_step": 1,
             "matches_per_launch": t["sparse_row_matches"], "units_per_match": 2.0,
+            # what ncu shows to be the binding resource: every shared-memory load and atomic is a
+            # wavefront of the SM's data pipe (one per clock).  Algorithmic wavefronts per match = the
+            # column entry read by a full warp (entry bytes / 128) + two atomic adds of a full warp
+            # without bank conflicts (2 / 32); the executed count is higher by the bank conflicts of the
+            # scattered atomics and partly filled warps (profiles/: measured pipe utilisation)
+            "shared_memory_pipe": (lambda wpm, pk: {
+                "algorithmic_wavefronts_per_match": wpm,
+                "achieved": wpm * t["sparse_row_matches"] / (t["tips_ms"] * 1e-3) / 1e9,
+                "peak": pk / 1e9, "unit": "Gwavefront/s (l1tex data pipe, 1 per clock per SM)",
+                "frac": wpm * t["sparse_row_matches"] / (t["tips_ms"] * 1e-3) / pk,
+                "peak_source": "148 SMs x SM clock sampled in this run (nvidia-smi)",
+                "measured_pipe_utilisation": traffic_tab.get(kname + ":lsu_pipe_pct"),
+                "measured_source": ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed of the "
+                                    "launch, ncu --set full, profiles/ncu_traffic.json")
+                if traffic_tab.get(kname + ":lsu_pipe_pct") else None,
+            })(entry_bytes / 128.0 + 2.0 / 32.0, 148 * sm_clock_hz(device)),
             "sparse_rows_max_tips": t["sparse_rows_max_tips"],
             "sparse_row_entries": t["sparse_row_entries"],
             # every bucket is read by about n/128 tiles (as row or as column block)

@@ -1425,6 +1425,24 @@ static int urows_build(b2d_problem* p, const BuildView& v, bool dist) {
             B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
             continue;
         }
+        // The pipelined kernel stages a bucket pair in one batch when both fit a stage (3 064 keys); buckets just
+        // above that are cut in two and every cut costs a producer search and a drain of the consumers
+        // (one shard of config 4: 516 ms at 2 890 keys per bucket, 660 ms at 3 040).  While the average bucket
+        // does not fit, lower the threshold (once per problem: the choice is remembered).
+        {
+            const double per_bucket = (double)total / std::max(1.0, (double)nbuckets);
+            constexpr double fit = 0.95 * IsGeom<IS_UNWEIGHTED, TP_CHUNK>::cap;
+            if (!g_sparse_rows_max_tips && per_bucket > fit && per_bucket < 1.6 * fit && p->rows_S0 > 8) {
+                p->rows_S0_pref[1] = std::max(8, (int)(p->rows_S0 * std::max(0.75, 0.97 * fit / per_bucket)));
+                if (p->rows_S0_pref[1] < p->rows_S0) {
+                    B2D_CUDA(cudaMemsetAsync(p->d_tip_word, 0, 4 * sizeof(unsigned long long), p->stream));
+                    B2D_CUDA(cudaMemsetAsync(p->d_tip_status, 0, sizeof(int), p->stream));
+                    B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
+                    B2D_CUDA(cudaMemsetAsync(p->d_tip_u, 0, p->npad * sizeof(double), p->stream));
+                    continue;
+                }
+            }
+        }
         if (p->ukeys_cap < total || !p->d_ukeys) {
             b2d_free(p->d_ukeys);
             p->d_ukeys = nullptr;

@@ -9,7 +9,11 @@ KEYS = [
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.per_cycle_active",
@@ -52,6 +56,9 @@ def main(path, traffic_json=None, workload=None, kernel_alias=None):
                 tot += float(r[i].replace(",", "")) * UNIT_BYTES[units[i]]
             tab = json.load(open(traffic_json)) if os.path.exists(traffic_json) else {}
             tab.setdefault(workload, {})[kernel_alias or name] = tot
+            k = "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"
+            if k in hdr:
+                tab[workload][(kernel_alias or name) + ":lsu_pipe_pct"] = float(r[hdr.index(k)].replace(",", ""))
             json.dump(tab, open(traffic_json, "w"), indent=1, sort_keys=True)
 
 

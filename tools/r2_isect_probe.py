@@ -83,5 +83,19 @@ if "u4" in which:   # one shard of eight of BASELINE config 4
                   f"entries={t['sparse_row_entries']:.3e}", flush=True)
     _capi.set_option("isect_kernel", -1)
     _capi.set_option("isect_group", 0)
+if "u4s" in which:   # sparse-row threshold sweep on one shard of eight of BASELINE config 4
+    parent, length, names, tip_node = synthetic.random_join_tree(500000, seed=1)
+    indptr, cols, vals = synthetic.poisson_csr(100000, 500000, 0.004, seed=0)
+    ids = tip_node[cols].astype(np.int32)
+    for s0 in (0,):   # the threshold is fixed when a problem first builds its sparse rows
+        _capi.set_option("sparse_rows_max_tips", s0)
+        with _capi.Problem.tree(parent, length, indptr, ids, None, 100000, shard=0, n_shards=8) as prob:
+            for rep in range(2):
+                prob.compute("unweighted_unifrac")
+                t = prob.timings()
+            print(f"cfg4 shard 0/8 S0={t['sparse_rows_max_tips']}: tips_ms={t['tips_ms']:.1f} pair_ms={t['pair_ms']:.1f} compute_ms={t['compute_ms']:.1f} "
+                  f"prep={t['skip_prep_ms']:.1f} embed={t['embed_ms']:.1f} matches={t['sparse_row_matches']:.3e} "
+                  f"entries={t['sparse_row_entries']:.3e}", flush=True)
+    _capi.set_option("sparse_rows_max_tips", 0)
 if "us" in which: tree_case("unweighted_unifrac", 10000, 100000, 0.02, [(1, 4)], s0s=(6, 8, 12, 16, 24, 32))
 json.dump(res, open("gpurun_out/r2_isect_probe.json", "w"), indent=1)
