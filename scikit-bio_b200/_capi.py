@@ -277,16 +277,21 @@ class NameBlob:
 
 def query_blob(names):
     """(bytes, offsets int64[k + 1]) of a list of strings."""
-    names = [x if isinstance(x, str) else str(x) for x in names]
-    joined = "\0".join(names)
-    buf = joined.encode("utf-8")
+    try:
+        joined = "\0".join(names)
+    except TypeError:                    # non-string taxa (numbers, ...): their str() as the reference does
+        names = [x if isinstance(x, str) else str(x) for x in names]
+        joined = "\0".join(names)
+    buf = joined.encode("utf-8") + b"\0"
     off = np.zeros(len(names) + 1, dtype=np.int64)
-    if len(buf) == len(joined):     # ASCII: byte lengths are the string lengths
-        np.cumsum(np.fromiter(map(len, names), dtype=np.int64, count=len(names)) + 1, out=off[1:])
-    else:
+    # entry k is buf[off[k] : off[k + 1] - 1]: the offsets are the positions after the separators
+    ends = np.flatnonzero(np.frombuffer(buf, dtype=np.uint8) == 0)
+    if len(ends) == len(names):
+        off[1:] = ends + 1
+    elif len(names):                     # a name contains a NUL byte itself: count bytes name by name
         np.cumsum([len(x.encode("utf-8")) + 1 for x in names], out=off[1:])
-    # the separators are part of the buffer but of no entry: entry k is buf[off[k] : off[k + 1] - 1]
-    return buf + b"\0", off
+    # the separators are part of the buffer but of no entry
+    return buf, off
 
 
 def names_lookup(blob, queries, qblob=None):

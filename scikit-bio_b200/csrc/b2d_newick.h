@@ -6,6 +6,7 @@
 // unquoted labels become spaces, whitespace outside quotes is ignored between tokens and
 // rejected inside an unquoted label, an empty label is "no name", ':' introduces a length.
 #pragma once
+#include <cstring>
 
 #include <stdint.h>
 #include <stdlib.h>
@@ -211,6 +212,55 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
     return "";
 }
 
+// Node names -> node id: open addressing over the name blob itself (no per-name allocation; a
+// std::unordered_map of 200 000 string_views costs three times the probe loop below).
+class NameIndex {
+ public:
+    NameIndex(const char* buf, const int64_t* off, size_t expected) : buf_(buf), off_(off) {
+        size_t cap = 16;
+        while (cap < expected * 2 + 2) cap <<= 1;
+        mask_ = cap - 1;
+        ids_.assign(cap, -1);
+    }
+    static uint64_t hash(const char* p, size_t n) {
+        uint64_t h = 0xcbf29ce484222325ull;   // FNV-1a, folded
+        for (size_t i = 0; i < n; ++i) {
+            h ^= (unsigned char)p[i];
+            h *= 0x100000001b3ull;
+        }
+        return h ^ (h >> 29);
+    }
+    // the node stored under v's name before the call (-1: none); v is stored when there was none or `overwrite`
+    int32_t put(int32_t v, bool overwrite) {
+        const char* p = buf_ + off_[v];
+        const size_t n = (size_t)(off_[v + 1] - off_[v]);
+        for (size_t s = hash(p, n) & mask_;; s = (s + 1) & mask_) {
+            const int32_t u = ids_[s];
+            if (u < 0) {
+                ids_[s] = v;
+                return -1;
+            }
+            if ((size_t)(off_[u + 1] - off_[u]) == n && memcmp(buf_ + off_[u], p, n) == 0) {
+                if (overwrite) ids_[s] = v;
+                return u;
+            }
+        }
+    }
+    int32_t find(const char* p, size_t n) const {
+        for (size_t s = hash(p, n) & mask_;; s = (s + 1) & mask_) {
+            const int32_t u = ids_[s];
+            if (u < 0) return -1;
+            if ((size_t)(off_[u + 1] - off_[u]) == n && memcmp(buf_ + off_[u], p, n) == 0) return u;
+        }
+    }
+
+ private:
+    const char* buf_;
+    const int64_t* off_;
+    size_t mask_;
+    std::vector<int32_t> ids_;
+};
+
 // Name -> node id for a list of query names, with the reference's lookup semantics
 // (/root/reference/skbio/diversity/_phylogenetic.pyx:195-199): every node name is scanned in id order,
 // tips and internal nodes alike, and a later node with the same name overwrites an earlier one.
@@ -218,15 +268,11 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
 // followed by `query_sep` separator bytes that are not part of the name.
 inline void lookup_names(const char* name_buf, const int64_t* name_off, const uint8_t* has_name, int64_t m,
                          const char* query_buf, const int64_t* query_off, int64_t k, int query_sep, int32_t* out) {
-    std::unordered_map<std::string_view, int32_t> map;
-    map.reserve((size_t)m * 2);
+    NameIndex map(name_buf, name_off, (size_t)m);
     for (int64_t v = 0; v < m; ++v)
-        if (has_name[v])
-            map[std::string_view(name_buf + name_off[v], (size_t)(name_off[v + 1] - name_off[v]))] = (int32_t)v;
-    for (int64_t q = 0; q < k; ++q) {
-        const auto it = map.find(std::string_view(query_buf + query_off[q], (size_t)(query_off[q + 1] - query_off[q] - query_sep)));
-        out[q] = it == map.end() ? -1 : it->second;
-    }
+        if (has_name[v]) map.put((int32_t)v, true);
+    for (int64_t q = 0; q < k; ++q)
+        out[q] = map.find(query_buf + query_off[q], (size_t)(query_off[q + 1] - query_off[q] - query_sep));
 }
 
 // The name checks of _validate_taxa_and_tree (/root/reference/skbio/tree/_utils.py:83-90) on flat
@@ -236,10 +282,13 @@ inline void validate_names(const char* name_buf, const int64_t* name_off, const 
                            const int32_t* parent, int64_t m, const char* query_buf, const int64_t* query_off,
                            int64_t k, int query_sep, int* dup_tips, int64_t* n_missing) {
     std::vector<uint8_t> has_child((size_t)m, 0);
+    int64_t ntips = m;
     for (int64_t v = 0; v < m; ++v)
-        if (parent[v] >= 0) has_child[parent[v]] = 1;
-    std::unordered_map<std::string_view, int32_t> tips;
-    tips.reserve((size_t)m);
+        if (parent[v] >= 0 && !has_child[parent[v]]) {
+            has_child[parent[v]] = 1;
+            --ntips;
+        }
+    NameIndex tips(name_buf, name_off, (size_t)std::max<int64_t>(ntips, 1));
     int dup = 0;
     int64_t unnamed = 0;
     for (int64_t v = 0; v < m; ++v) {
@@ -248,14 +297,14 @@ inline void validate_names(const char* name_buf, const int64_t* name_off, const 
             if (++unnamed > 1) dup = 1;
             continue;
         }
-        const auto r = tips.emplace(std::string_view(name_buf + name_off[v], (size_t)(name_off[v + 1] - name_off[v])), 0);
-        if (!r.second) dup = 1;
+        if (tips.put((int32_t)v, false) >= 0) dup = 1;
     }
     int64_t missing = 0;
-    std::unordered_map<std::string_view, int32_t> seen;
+    std::unordered_map<std::string_view, int32_t> seen;   // queries that are no tip name: normally none
     for (int64_t q = 0; q < k; ++q) {
-        const std::string_view sv(query_buf + query_off[q], (size_t)(query_off[q + 1] - query_off[q] - query_sep));
-        if (tips.find(sv) == tips.end() && seen.emplace(sv, 0).second) ++missing;
+        const char* p = query_buf + query_off[q];
+        const size_t n = (size_t)(query_off[q + 1] - query_off[q] - query_sep);
+        if (tips.find(p, n) < 0 && seen.emplace(std::string_view(p, n), 0).second) ++missing;
     }
     *dup_tips = dup;
     *n_missing = missing;
