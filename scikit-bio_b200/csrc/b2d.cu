@@ -365,6 +365,8 @@ struct b2d_problem {
     cudaEvent_t ev_cf[2] = {nullptr, nullptr};
     cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_sync[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};   // around the uploads of the creation
+    int64_t csr_ea = 0, csr_eb = 0;              // CSR entries uploaded at creation
     TreeOrder order;
     // device inputs
     int64_t* d_indptr = nullptr;
@@ -529,6 +531,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_ud_scale); b2d_free(p->d_ud_lenfx); b2d_free(p->d_ud_Lfx); b2d_free(p->d_ud_Ld); b2d_free(p->d_ud_Kd);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
+    for (auto& e : p->ev_up) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->stream2) cudaStreamDestroy(p->stream2);
     if (p->stream3) cudaStreamDestroy(p->stream3);
@@ -550,21 +553,20 @@ static int upload(T** dst, const T* src, size_t count, cudaStream_t s) {
     return B2D_OK;
 }
 
-static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* ids,
-                        const void* values, size_t value_size, const int32_t* node_of_col = nullptr,
-                        int64_t n_cols = 0) {
-    cudaEvent_t e0, e1;
-    NvtxRange range("b2d:create (H2D of tree + CSR)");
+// Streams, events and the CSR uploads.  The copies are asynchronous (page-locked inputs: plain DMA), so the
+// caller can build the tree order on the host while they run.
+static int setup_csr(b2d_problem* p, const int64_t* indptr, const int32_t* ids, const void* values,
+                     size_t value_size) {
+    NvtxRange range("b2d:create (H2D of the CSR)");
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
     B2D_CUDA(cudaStreamCreateWithFlags(&p->stream3, cudaStreamNonBlocking));
     for (auto& e : p->ev_cf) B2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : p->ev) B2D_CUDA(cudaEventCreate(&e));
     for (auto& e : p->ev_sync) B2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    B2D_CUDA(cudaEventCreate(&e0));
-    B2D_CUDA(cudaEventCreate(&e1));
-    B2D_CUDA(cudaEventRecord(e0, p->stream));
-    const TreeOrder& o = p->order;
+    B2D_CUDA(cudaEventCreate(&p->ev_up[0]));
+    B2D_CUDA(cudaEventCreate(&p->ev_up[1]));
+    B2D_CUDA(cudaEventRecord(p->ev_up[0], p->stream));
     int rc;
     if ((rc = upload(&p->d_indptr, indptr, (size_t)p->n + 1, p->stream))) return rc;
     // CSR entries to upload now: all of them, or (partial_upload, several shards of a tree problem) only the
@@ -592,6 +594,17 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
                                      (size_t)(eb - ea) * value_size, cudaMemcpyHostToDevice, p->stream));
     }
     p->upload_bytes = (double)((p->n + 1) * sizeof(int64_t) + (eb - ea) * (sizeof(int32_t) + (values ? value_size : 0)));
+    p->csr_ea = ea;
+    p->csr_eb = eb;
+    return B2D_OK;
+}
+
+// The rest of the creation: tree arrays, node id -> engine position on the device, shard geometry.
+static int setup_common(b2d_problem* p, const int32_t* node_of_col = nullptr, int64_t n_cols = 0) {
+    NvtxRange range("b2d:create (H2D of the tree, id mapping, tiles)");
+    const TreeOrder& o = p->order;
+    const int64_t ea = p->csr_ea, eb = p->csr_eb;
+    int rc;
     if ((rc = upload(&p->d_flags, o.flags.data(), o.flags.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_hc, o.hc_mask.data(), o.hc_mask.size(), p->stream))) return rc;
     if ((rc = upload(&p->d_fold, o.fold_mask.data(), o.fold_mask.size(), p->stream))) return rc;
@@ -669,13 +682,11 @@ static int setup_common(b2d_problem* p, const int64_t* indptr, const int32_t* id
     B2D_CUDA(b2d_malloc(&p->d_svec, p->npad * sizeof(double)));
     B2D_CUDA(cudaMemsetAsync(p->d_total, 0, p->npad * sizeof(long long), p->stream));
     B2D_CUDA(cudaMemsetAsync(p->d_svec, 0, p->npad * sizeof(double), p->stream));
-    B2D_CUDA(cudaEventRecord(e1, p->stream));
+    B2D_CUDA(cudaEventRecord(p->ev_up[1], p->stream));
     B2D_CUDA(cudaStreamSynchronize(p->stream));
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventElapsedTime(&ms, p->ev_up[0], p->ev_up[1]);
     p->t_upload = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return B2D_OK;
 }
 
@@ -810,6 +821,12 @@ static int create_tree_common(b2d_problem** out, int device, int64_t n_samples, 
     p->n_shards = n_shards;
     p->nnz = indptr[n_samples];
     p->has_values = values != nullptr;
+    // the CSR copies run while the host builds the engine's node order
+    rc = setup_csr(p, indptr, node_ids, values, sizeof(int64_t));
+    if (rc) {
+        free_problem(p);
+        return rc;
+    }
     std::string err = build_tree_order(n_nodes, parent, length, p->order);
     if (!err.empty()) {
         free_problem(p);
@@ -824,7 +841,7 @@ static int create_tree_common(b2d_problem** out, int device, int64_t n_samples, 
             p->tips_mode = -1;
             break;
         }
-    rc = setup_common(p, indptr, node_ids, values, sizeof(int64_t), node_of_col, n_cols);
+    rc = setup_common(p, node_of_col, n_cols);
     if (rc) {
         free_problem(p);
         return rc;
@@ -904,7 +921,8 @@ static int b2d_problem_create_features_impl(b2d_problem** out, int device, int64
     o.rd_lo.assign(o.mpad, 0.0);
     p->mpad = o.mpad;
     p->NS = p->mpad / NODE_STRIPE;
-    rc = setup_common(p, indptr, feature_ids, values, sizeof(double));
+    rc = setup_csr(p, indptr, feature_ids, values, sizeof(double));
+    if (!rc) rc = setup_common(p);
     if (rc) {
         free_problem(p);
         return rc;
@@ -1309,7 +1327,10 @@ static int rows_masks(b2d_problem* p, int which) {
     return B2D_OK;
 }
 
-static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist) {
+static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist, bool counts) {
+    // counts: the embedding still holds the int64 subtree counts; the kernels here divide by the totals
+    // themselves (non-zero elements only), no pass over the whole embedding
+    const long long* tot = counts ? p->d_total + v.s0 : nullptr;
     int rc;
     if ((rc = tips_buffers(p))) return rc;
     const int64_t nch = p->tip_nch, nbuckets = p->nb * nch;
@@ -1323,7 +1344,7 @@ static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist)
         if (v.nb) {
             k_rows_count<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
                 (const double*)p->d_emb, p->d_len, p->d_rows_sparse, rows, QR, nch, p->npad, qcount,
-                p->d_rows_upart + v.s0);
+                p->d_rows_upart + v.s0, tot);
             k_rows_bucket_counts<<<(unsigned)((v.nb * nch + 255) / 256), 256, 0, p->stream>>>(qcount, v.nb * nch,
                                                                                          p->d_tip_counts + v.b0 * nch);
         }
@@ -1360,7 +1381,7 @@ static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist)
                 (const double*)p->d_emb, p->d_len, p->d_rows_sparse, p->d_tip_scale, rows, QR, nch,
                 qcount, p->d_tip_ptr + v.b0 * nch, p->d_tip_entries,
                 p->d_tip_runs + (size_t)v.b0 * nch * (TP_CHUNK + 8),
-                (unsigned long long*)p->d_tip_ufx + v.s0, p->d_tip_cnt + v.s0);
+                (unsigned long long*)p->d_tip_ufx + v.s0, p->d_tip_cnt + v.s0, tot);
         // the rows left to the dense pair kernel, packed
         const size_t need = (size_t)p->nb * p->n_dense_pad * TILE * sizeof(double);
         if (p->embd_bytes < need) {
@@ -1376,7 +1397,7 @@ static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist)
         p->n_kernels += 1;
         if (v.nb)
             k_compact_rows<<<dim3((unsigned)p->n_dense_pad, (unsigned)v.nb), 128, 0, p->stream>>>(
-                (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, nullptr,
+                (const double*)p->d_emb, p->d_len, p->d_dense_pos, p->n_dense, p->n_dense_pad, QR, 0, tot,
                 p->d_embd + (size_t)v.b0 * p->n_dense_pad * TILE, p->d_lend);
         B2D_CUDA(cudaGetLastError());
         p->tips_mode = 1;
@@ -1724,7 +1745,7 @@ static int compute_dense(b2d_problem* p, int metric) {
     p->chunk_counter = 0;
     p->nodes_resident = (double)QR;
     double t_embed = 0, t_pair = 0, t_prep = 0;
-    bool closed_form_queued = false, tips_timed = false;
+    bool closed_form_queued = false, tips_timed = false, lazy_prop = false;
     int64_t pass_nd = 0, pass_nd_pad = 128;
     cudaEvent_t ea = p->ev[1], eb = p->ev[2], ec = p->ev[3];
     for (int64_t q0 = 0; q0 < p->mpad; q0 += QR) {
@@ -1759,7 +1780,10 @@ static int compute_dense(b2d_problem* p, int metric) {
                 }
                 // when the rows with children are packed per pass (and the tips come from the CSR)
                 // nothing reads the resident embedding as proportions: the packing divides
-                if (!p->pack_pass) {
+                // ... and with the whole tree resident and sparse rows the consumers of the embedding (entry
+                // extraction, row packing, the flagged-pair recomputation) divide the elements they use
+                lazy_prop = p->rows_general;
+                if (!p->pack_pass && !lazy_prop) {
                     const int64_t threads = v.nb * (TILE / 2);
                     dim3 grid((unsigned)((threads + 255) / 256),
                               (unsigned)std::min<int64_t>(q1 - q0, 2048));
@@ -1780,8 +1804,17 @@ static int compute_dense(b2d_problem* p, int metric) {
             NvtxRange pair_range("b2d:pair (sparse rows + tile kernels + closed form)");
             if (skip) {
                 if (p->rows_general) {
-                    if ((rc = rows_build(p, QR, v, dist))) return rc;
+                    if ((rc = rows_build(p, QR, v, dist, lazy_prop))) return rc;
                     p->tips_active = p->tips_mode == 1;
+                    if (!p->tips_active && lazy_prop && !dist) {
+                        // no sparse rows after all: the dense kernel reads the embedding as proportions
+                        const int64_t threads = v.nb * (TILE / 2);
+                        dim3 grid((unsigned)((threads + 255) / 256), (unsigned)std::min<int64_t>(q1 - q0, 2048));
+                        p->n_kernels += 1;
+                        k_counts_to_proportions<<<grid, 256, 0, p->stream>>>(
+                            (unsigned long long*)p->d_emb, p->d_total + v.s0, v.nb, q1 - q0, QR);
+                        lazy_prop = false;
+                    }
                 }
                 if (dist && !p->tips_active) {
                     // no sparse rows after all (a bucket too large even for tip rows - on every rank, the
@@ -1914,7 +1947,7 @@ static int compute_dense(b2d_problem* p, int metric) {
                             p->n_kernels += 1;
                             k_fix_pairs_weighted<<<296, 256, 0, p->stream>>>(
                                 (const double*)p->d_emb, p->d_len, QR, p->mpad, p->d_flag_list, p->d_tip_word + 1,
-                                p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr);
+                                p->d_out, p->chunk_counter >= 2 ? p->d_out2 : nullptr, lazy_prop ? p->d_total : nullptr);
                         }
                     }
                 }

@@ -379,6 +379,17 @@ k_tip_guard(const double* __restrict__ out, const double* __restrict__ out2,
     }
 }
 
+// An embedding element as a proportion.  With `tot` < 0 the element already is one; otherwise it still holds
+// the int64 subtree count of the propagation and the division k_counts_to_proportions would do (one correctly
+// rounded count / total, the count itself when the total is 0: beta/_unifrac.py:399-410) is taken here, for
+// the non-zero elements only - the separate pass over the whole embedding is then not needed.
+__device__ __forceinline__ double emb_proportion(double raw, long long tot) {
+    if (tot < 0 || raw == 0.0) return raw;
+    double v = (double)__double_as_longlong(raw);
+    if (tot > 0) v = v / (double)tot;
+    return v;
+}
+
 // deterministic block sum (fixed tree), result valid in thread 0
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
     const int tid = threadIdx.x;
@@ -397,7 +408,8 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
 __global__ void __launch_bounds__(256)
 k_fix_pairs_weighted(const double* __restrict__ emb, const double* __restrict__ len, int64_t QR, int64_t rows,
                      const FlaggedPair* __restrict__ list, const unsigned long long* __restrict__ flagged,
-                     double* __restrict__ out, double* __restrict__ out2) {
+                     double* __restrict__ out, double* __restrict__ out2,
+                     const long long* __restrict__ totals = nullptr) {
     __shared__ double sh[256];
     const unsigned long long total = *flagged;
     const int64_t cnt = total < (unsigned long long)FLAG_CAP ? (int64_t)total : FLAG_CAP;
@@ -405,15 +417,20 @@ k_fix_pairs_weighted(const double* __restrict__ emb, const double* __restrict__ 
         const FlaggedPair fp = list[k];
         const double* pa = emb + ((int64_t)(fp.i / TILE) * QR) * TILE + fp.i % TILE;
         const double* pb = emb + ((int64_t)(fp.j / TILE) * QR) * TILE + fp.j % TILE;
+        // the embedding holds proportions, or (totals given) still the int64 subtree counts
+        const long long ta = totals ? totals[fp.i] : -1, tb = totals ? totals[fp.j] : -1;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int64_t q = threadIdx.x;
+        auto term = [&](int64_t r) {
+            return fabs(emb_proportion(pa[r * TILE], ta) - emb_proportion(pb[r * TILE], tb));
+        };
         for (; q + 768 < rows; q += 1024) {
-            s0 = fma(fabs(pa[q * TILE] - pb[q * TILE]), len[q], s0);
-            s1 = fma(fabs(pa[(q + 256) * TILE] - pb[(q + 256) * TILE]), len[q + 256], s1);
-            s2 = fma(fabs(pa[(q + 512) * TILE] - pb[(q + 512) * TILE]), len[q + 512], s2);
-            s3 = fma(fabs(pa[(q + 768) * TILE] - pb[(q + 768) * TILE]), len[q + 768], s3);
+            s0 = fma(term(q), len[q], s0);
+            s1 = fma(term(q + 256), len[q + 256], s1);
+            s2 = fma(term(q + 512), len[q + 512], s2);
+            s3 = fma(term(q + 768), len[q + 768], s3);
         }
-        for (; q < rows; q += 256) s0 = fma(fabs(pa[q * TILE] - pb[q * TILE]), len[q], s0);
+        for (; q < rows; q += 256) s0 = fma(term(q), len[q], s0);
         const double s = block_sum_256((s0 + s1) + (s2 + s3), sh);
         if (threadIdx.x == 0) {
             out[fp.off] = s;
@@ -472,23 +489,27 @@ k_fix_pairs_unweighted(const uint4* __restrict__ bits, const double* __restrict_
 // ---------------------------------------------------------------------------------------
 constexpr int TP_QROWS = TP_CHUNK / 4;
 
+
 // pass 1: entries per (bucket, quarter) and per-sample partial sums of len * p (double)
 __global__ void __launch_bounds__(128)
 k_rows_count(const double* __restrict__ emb, const double* __restrict__ len, const uint32_t* __restrict__ sparse,
              int64_t rows, int64_t QR, int64_t nch, int64_t npad, unsigned* __restrict__ qcount /*[nb*nch][4]*/,
-             double* __restrict__ upart /*[nch*4][npad]*/) {
+             double* __restrict__ upart /*[nch*4][npad]*/, const long long* __restrict__ total = nullptr) {
     const int64_t b = blockIdx.y, ch = blockIdx.x;  // chunks (up to 2^19) in x, sample blocks in y
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t qa = ch * TP_CHUNK + (int64_t)warp * TP_QROWS, qb = min(rows, qa + TP_QROWS);
     const double* p = emb + (b * QR) * TILE + lane;
     double u[4] = {0.0, 0.0, 0.0, 0.0};
+    long long tot[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tot[k] = total ? total[b * TILE + 32 * k + lane] : -1;
     unsigned cnt = 0;
     for (int64_t q = qa; q < qb; ++q) {
         if (!((sparse[q >> 5] >> (q & 31)) & 1u)) continue;  // warp-uniform
         const double l = len[q];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double v = p[q * TILE + 32 * k];
+            const double v = emb_proportion(p[q * TILE + 32 * k], tot[k]);
             cnt += __popc(__ballot_sync(0xffffffffu, v != 0.0));
             u[k] += l * v;
         }
@@ -523,7 +544,8 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
                const double* __restrict__ scale, int64_t rows, int64_t QR, int64_t nch,
                const unsigned* __restrict__ qcount, const int64_t* __restrict__ bucket_ptr,
                TipEntry* __restrict__ entries, unsigned short* __restrict__ runs,
-               unsigned long long* __restrict__ Ufx, unsigned* __restrict__ nent) {
+               unsigned long long* __restrict__ Ufx, unsigned* __restrict__ nent,
+               const long long* __restrict__ total = nullptr) {
     const int64_t b = blockIdx.y, ch = blockIdx.x;  // chunks (up to 2^19) in x, sample blocks in y
     const int64_t bucket = b * nch + ch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -537,13 +559,16 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
     const double sc = scale[0];
     long long ufx[4] = {0, 0, 0, 0};
     unsigned kcnt[4] = {0u, 0u, 0u, 0u};
+    long long tot[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tot[k] = total ? total[b * TILE + 32 * k + lane] : -1;
     for (int64_t q = qa; q < qa + TP_QROWS; ++q) {
         if (lane == 0) rs[q - ch * TP_CHUNK] = (unsigned short)run;
         if (q >= qb || !((sparse[q >> 5] >> (q & 31)) & 1u)) continue;  // warp-uniform
         const double l = len[q];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double v = p[q * TILE + 32 * k];
+            const double v = emb_proportion(p[q * TILE + 32 * k], tot[k]);
             const uint32_t m = __ballot_sync(0xffffffffu, v != 0.0);
             if (v != 0.0) {
                 const long long wv = __double2ll_rn(l * v * sc);
