@@ -54,6 +54,7 @@ static int g_isect_kernel = -1;                // 1: pipelined intersection kern
 static int g_udense_tc = 0;                    // unweighted UniFrac: dense rows on the tensor cores (b2d_tc.cuh) instead of the LUT kernel
 static int g_partial_upload = 0;               // tree problems with n_shards > 1: upload only the CSR rows of the shard's own
                                                // build range; the first compute all-gathers the rest (collectives required)
+static int g_lazy_proportions = 0;             // see compute_dense: count -> proportion division inside the consumers of the embedding
 static int g_isect_group = 0;                  // lanes sharing one row entry in that kernel (1, 2, 4, 8; 0: per mode)
 
 static bool plain_kernels() {
@@ -791,6 +792,8 @@ int b2d_set_option(const char* name, int64_t value) {
         g_weighted_skip = value ? 1 : 0;
     } else if (s == "isect_kernel") {
         g_isect_kernel = value < 0 ? -1 : (value ? 1 : 0);
+    } else if (s == "lazy_proportions") {
+        g_lazy_proportions = value ? 1 : 0;
     } else if (s == "partial_upload") {
         g_partial_upload = value ? 1 : 0;
     } else if (s == "udense_tc") {
@@ -1780,9 +1783,12 @@ static int compute_dense(b2d_problem* p, int metric) {
                 }
                 // when the rows with children are packed per pass (and the tips come from the CSR)
                 // nothing reads the resident embedding as proportions: the packing divides
-                // ... and with the whole tree resident and sparse rows the consumers of the embedding (entry
-                // extraction, row packing, the flagged-pair recomputation) divide the elements they use
-                lazy_prop = p->rows_general;
+                // The consumers of the embedding (entry extraction, row packing, the flagged-pair recomputation)
+                // can divide the elements they use themselves (`lazy_prop`, option "lazy_proportions"), which
+                // drops this pass - measured at config 2: embedding 14.7 -> 7.8 ms but entry extraction 10.2 ->
+                // 17.9 ms, because a warp pays a whole fp64 division sequence whenever ONE of its 32 elements is
+                // non-zero, in both extraction passes.  Off by default.
+                lazy_prop = p->rows_general && g_lazy_proportions;
                 if (!p->pack_pass && !lazy_prop) {
                     const int64_t threads = v.nb * (TILE / 2);
                     dim3 grid((unsigned)((threads + 255) / 256),

@@ -1116,6 +1116,30 @@ def test_distributed_build_gives_the_same_bits_as_the_replicated_one(key):
             assert sum(t["csr_upload_bytes"] for t in tms2) == full_bytes + (world - 1) * (n + 1) * 8
 
 
+def test_lazy_proportions_option_gives_identical_bits():
+    """Option lazy_proportions: the consumers of the embedding divide count / total themselves instead of a
+    separate pass over the whole embedding - the same correctly rounded division, so identical bits
+    (near-duplicate pairs included: their recomputation reads the counts too)."""
+    _skbio_b200()
+    from skbio_b200 import _capi
+
+    n, tips = 520, 2600
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.05, 95)
+    res = {}
+    try:
+        for lazy in (0, 1):
+            _capi.set_option("lazy_proportions", lazy)
+            for key in ("weighted_unifrac_normalized", "weighted_unifrac"):
+                with _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n) as prob:
+                    prob.compute(key)
+                    assert prob.timings()["tips_ms"] > 0
+                    res[(lazy, key)] = prob.fetch(np.empty(n * (n - 1) // 2))
+    finally:
+        _capi.set_option("lazy_proportions", 0)
+    for key in ("weighted_unifrac_normalized", "weighted_unifrac"):
+        assert np.array_equal(res[(0, key)], res[(1, key)]), key
+
+
 def test_partial_upload_without_collectives_is_an_error():
     _skbio_b200()
     from skbio_b200 import _capi
