@@ -1140,6 +1140,68 @@ def test_lazy_proportions_option_gives_identical_bits():
         assert np.array_equal(res[(0, key)], res[(1, key)]), key
 
 
+def test_distributed_build_votes_no_when_a_compute_cannot_use_it():
+    """Collectives installed, but the compute cannot be distributed: several node passes (the embedding
+    does not fit the budget), Faith's PD (no pair work), a problem smaller than the number of shards.
+    Every rank still takes part in the vote, the build is replicated, the bits are the same."""
+    _skbio_b200()
+    from skbio_b200 import _capi
+
+    n, tips = 420, 1800
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.03, 96)
+
+    def make(r, w):
+        return _capi.Problem.tree(parent, length, indptr, tip_node[cols], vals, n, shard=r, n_shards=w)
+
+    base, _ = _run_shards_in_threads(1, make, "weighted_unifrac_normalized", computes=1)
+    try:
+        _capi.set_option("emb_budget_bytes", 512 * 8 * 512)   # a few hundred node rows per pass
+        multi, _ = _run_shards_in_threads(1, make, "weighted_unifrac_normalized", computes=1)
+        got, tms = _run_shards_in_threads(2, make, "weighted_unifrac_normalized")
+    finally:
+        _capi.set_option("emb_budget_bytes", 0)
+    assert np.array_equal(got, multi)
+    assert_close_rel(got, base, 1e-13, "several passes vs one")
+    assert all(t["exchange_bytes"] == 0 and t["passes"] > 1 for t in tms)
+    # 130 samples = 2 blocks, 4 shards: shards 2 and 3 have nothing to build
+    n2 = 130
+    ip2, c2, v2 = indptr[: n2 + 1], cols[: indptr[n2]], vals[: indptr[n2]]
+
+    def make2(r, w):
+        return _capi.Problem.tree(parent, length, ip2, tip_node[c2], v2, n2, shard=r, n_shards=w)
+
+    for key in ("weighted_unifrac", "unweighted_unifrac"):
+        one, _ = _run_shards_in_threads(1, make2, key, computes=1)
+        four, tms = _run_shards_in_threads(4, make2, key)
+        assert np.array_equal(one, four), key
+        assert all(t["exchange_bytes"] == 0 for t in tms)
+    # Faith's PD with collectives installed: no vote, no exchange
+    import threading
+
+    from skbio_b200.distributed import ThreadCollectives
+
+    coll = ThreadCollectives(2, timeout=60.0)
+    pds, errs = [None, None], []
+
+    def work(r):
+        try:
+            with make(r, 2) as prob:
+                prob.set_collectives(r, 2, coll.for_rank(r))
+                prob.compute("faith_pd")
+                pds[r] = prob.sample_vector()
+        except BaseException as e:
+            errs.append(e)
+            coll.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    assert np.array_equal(pds[0], pds[1])
+
+
 def test_partial_upload_without_collectives_is_an_error():
     _skbio_b200()
     from skbio_b200 import _capi
