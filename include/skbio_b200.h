@@ -264,6 +264,9 @@ int b2d_beta_diversity_features(int metric, int device,
  *                       feature tables (Bray-Curtis / Jaccard)
  *   "walk_decomposed"   0: always the sequential tree walk;  "plain_kernels" 1: cross-check
  *                       kernels without bulk copies.
+ *   "lazy_proportions"  1 (default): with the whole embedding resident and sparse rows in use, the kernels that read
+ *                       the embedding divide count / total themselves (same correctly rounded division, identical
+ *                       bits) instead of a separate pass over the whole embedding; 0: the separate pass
  *   "partial_upload"    1: tree problems created with n_shards > 1 upload only the CSR rows of the shard's own
  *                       build range (b2d_build_range); the first compute (or phydiv) all-gathers the other
  *                       shards' rows device to device, so collectives must be installed before it.  Set it

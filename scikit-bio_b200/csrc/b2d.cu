@@ -54,7 +54,7 @@ static int g_isect_kernel = -1;                // 1: pipelined intersection kern
 static int g_udense_tc = 0;                    // unweighted UniFrac: dense rows on the tensor cores (b2d_tc.cuh) instead of the LUT kernel
 static int g_partial_upload = 0;               // tree problems with n_shards > 1: upload only the CSR rows of the shard's own
                                                // build range; the first compute all-gathers the rest (collectives required)
-static int g_lazy_proportions = 0;             // see compute_dense: count -> proportion division inside the consumers of the embedding
+static int g_lazy_proportions = 1;             // see compute_dense: count -> proportion division inside the consumers of the embedding
 static int g_isect_group = 0;                  // lanes sharing one row entry in that kernel (1, 2, 4, 8; 0: per mode)
 
 static bool plain_kernels() {
@@ -1345,7 +1345,7 @@ static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist,
         const int64_t rows = p->mpad;
         p->n_kernels += 5;
         if (v.nb) {
-            k_rows_count<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
+            (counts ? k_rows_count<true> : k_rows_count<false>)<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
                 (const double*)p->d_emb, p->d_len, p->d_rows_sparse, rows, QR, nch, p->npad, qcount,
                 p->d_rows_upart + v.s0, tot);
             k_rows_bucket_counts<<<(unsigned)((v.nb * nch + 255) / 256), 256, 0, p->stream>>>(qcount, v.nb * nch,
@@ -1380,7 +1380,7 @@ static int rows_build(b2d_problem* p, int64_t QR, const BuildView& v, bool dist,
         p->rows_entries = (double)total;
         p->n_kernels += 1;
         if (v.nb)
-            k_rows_scatter<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
+            (counts ? k_rows_scatter<true> : k_rows_scatter<false>)<<<dim3((unsigned)nch, (unsigned)v.nb), 128, 0, p->stream>>>(
                 (const double*)p->d_emb, p->d_len, p->d_rows_sparse, p->d_tip_scale, rows, QR, nch,
                 qcount, p->d_tip_ptr + v.b0 * nch, p->d_tip_entries,
                 p->d_tip_runs + (size_t)v.b0 * nch * (TP_CHUNK + 8),
@@ -1783,11 +1783,12 @@ static int compute_dense(b2d_problem* p, int metric) {
                 }
                 // when the rows with children are packed per pass (and the tips come from the CSR)
                 // nothing reads the resident embedding as proportions: the packing divides
-                // The consumers of the embedding (entry extraction, row packing, the flagged-pair recomputation)
-                // can divide the elements they use themselves (`lazy_prop`, option "lazy_proportions"), which
-                // drops this pass - measured at config 2: embedding 14.7 -> 7.8 ms but entry extraction 10.2 ->
-                // 17.9 ms, because a warp pays a whole fp64 division sequence whenever ONE of its 32 elements is
-                // non-zero, in both extraction passes.  Off by default.
+                // With the whole tree resident and sparse rows, the consumers of the embedding (entry extraction,
+                // row packing, the flagged-pair recomputation) divide the elements they use themselves
+                // (`lazy_prop`, option "lazy_proportions", default on) and this pass over the whole embedding is
+                // dropped: config 2 embedding 14.7 -> 7.8 ms, entry extraction 8.1 -> 11.5 ms (a warp pays an fp64
+                // division sequence whenever one of its 32 elements is non-zero, in both extraction passes; the
+                // four loads of a row are issued before any of it), identical bits.
                 lazy_prop = p->rows_general && g_lazy_proportions;
                 if (!p->pack_pass && !lazy_prop) {
                     const int64_t threads = v.nb * (TILE / 2);

@@ -491,6 +491,7 @@ constexpr int TP_QROWS = TP_CHUNK / 4;
 
 
 // pass 1: entries per (bucket, quarter) and per-sample partial sums of len * p (double)
+template <bool LAZY>   // LAZY: the embedding holds counts, `total` given (see emb_proportion)
 __global__ void __launch_bounds__(128)
 k_rows_count(const double* __restrict__ emb, const double* __restrict__ len, const uint32_t* __restrict__ sparse,
              int64_t rows, int64_t QR, int64_t nch, int64_t npad, unsigned* __restrict__ qcount /*[nb*nch][4]*/,
@@ -502,14 +503,17 @@ k_rows_count(const double* __restrict__ emb, const double* __restrict__ len, con
     double u[4] = {0.0, 0.0, 0.0, 0.0};
     long long tot[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tot[k] = total ? total[b * TILE + 32 * k + lane] : -1;
+    for (int k = 0; k < 4; ++k) tot[k] = LAZY ? total[b * TILE + 32 * k + lane] : -1;
     unsigned cnt = 0;
     for (int64_t q = qa; q < qb; ++q) {
         if (!((sparse[q >> 5] >> (q & 31)) & 1u)) continue;  // warp-uniform
         const double l = len[q];
+        double raw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) raw[k] = p[q * TILE + 32 * k];   // four loads in flight, whatever follows
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double v = emb_proportion(p[q * TILE + 32 * k], tot[k]);
+            const double v = LAZY ? emb_proportion(raw[k], tot[k]) : raw[k];
             cnt += __popc(__ballot_sync(0xffffffffu, v != 0.0));
             u[k] += l * v;
         }
@@ -539,6 +543,7 @@ __global__ void k_rows_ureduce(const double* __restrict__ upart, int64_t nparts,
 }
 
 // pass 2: the entries (sorted by position by construction), run starts, U_i in fixed point
+template <bool LAZY>
 __global__ void __launch_bounds__(128)
 k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, const uint32_t* __restrict__ sparse,
                const double* __restrict__ scale, int64_t rows, int64_t QR, int64_t nch,
@@ -561,14 +566,17 @@ k_rows_scatter(const double* __restrict__ emb, const double* __restrict__ len, c
     unsigned kcnt[4] = {0u, 0u, 0u, 0u};
     long long tot[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tot[k] = total ? total[b * TILE + 32 * k + lane] : -1;
+    for (int k = 0; k < 4; ++k) tot[k] = LAZY ? total[b * TILE + 32 * k + lane] : -1;
     for (int64_t q = qa; q < qa + TP_QROWS; ++q) {
         if (lane == 0) rs[q - ch * TP_CHUNK] = (unsigned short)run;
         if (q >= qb || !((sparse[q >> 5] >> (q & 31)) & 1u)) continue;  // warp-uniform
         const double l = len[q];
+        double raw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) raw[k] = p[q * TILE + 32 * k];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double v = emb_proportion(p[q * TILE + 32 * k], tot[k]);
+            const double v = LAZY ? emb_proportion(raw[k], tot[k]) : raw[k];
             const uint32_t m = __ballot_sync(0xffffffffu, v != 0.0);
             if (v != 0.0) {
                 const long long wv = __double2ll_rn(l * v * sc);
