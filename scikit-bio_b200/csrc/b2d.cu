@@ -487,8 +487,6 @@ struct b2d_problem {
     bool dist_off = false;            // the guard flagged a pair once: this rank votes for replicated builds
     bool dist_rerun = false;          // a compute re-running itself: no vote (the other ranks are not in one)
     bool dist_active = false;         // the last compute exchanged its products
-    uint32_t* d_nz_full = nullptr;    // [npad/32][QR/32] bitmaps of all node rows (the exchange needs them beside d_nz)
-    size_t nz_full_bytes = 0;
     double t_exchange = 0, exchange_bytes = 0, upload_bytes = 0;
     std::vector<int64_t> coll_totals; // sparse-row entries of every rank (last exchange)
     bool csr_partial = false;         // only this shard's rows of the CSR are on the device yet (partial_upload)
@@ -528,7 +526,7 @@ static void free_problem(b2d_problem* p) {
     b2d_free(p->d_rows_qcount); b2d_free(p->d_rows_upart);
     b2d_free(p->d_dense_pos); b2d_free(p->d_embd); b2d_free(p->d_lend); b2d_free(p->d_hc_pos);
     b2d_free(p->d_ukeys); b2d_free(p->d_lenfx); b2d_free(p->d_bitsd); b2d_free(p->d_ulend);
-    b2d_free(p->d_tip_cnt); b2d_free(p->d_flag_list); b2d_free(p->d_nz_full);
+    b2d_free(p->d_tip_cnt); b2d_free(p->d_flag_list);
     b2d_free(p->d_ud_scale); b2d_free(p->d_ud_lenfx); b2d_free(p->d_ud_Lfx); b2d_free(p->d_ud_Ld); b2d_free(p->d_ud_Kd);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_sync) if (e) cudaEventDestroy(e);
@@ -1551,8 +1549,7 @@ static int skip_transpose(b2d_problem* p, const uint32_t* nz, int64_t q0, int64_
     B2D_CUDA(cudaGetLastError());
     return B2D_OK;
 }
-// `nz`: where the row-major bitmaps go (d_nz; the distributed build keeps those of all node rows in
-// d_nz_full, exchanges them and transposes afterwards: transpose = false)
+// `nz`: where the row-major bitmaps go (d_nz)
 static int skip_prepare_pass(b2d_problem* p, int64_t q0, int64_t rows, int64_t QR, const BuildView& v,
                              uint32_t* nz, bool transpose) {
     const int64_t ng = v.npad / 32, words = QR / 32;
@@ -1664,13 +1661,6 @@ static int compute_dense(b2d_problem* p, int metric) {
     const unsigned vblocks = (unsigned)((v.n + wpb - 1) / wpb);
     if (dist) {  // the embedding holds this rank's blocks only
         row_bytes = (size_t)v.nb * TILE * sizeof(double);
-        if (p->nz_full_bytes < (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t)) {
-            b2d_free(p->d_nz_full);
-            p->d_nz_full = nullptr;
-            p->nz_full_bytes = 0;
-            B2D_CUDA(b2d_malloc(&p->d_nz_full, (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t)));
-            p->nz_full_bytes = (size_t)(p->npad / 32) * (QR / 32) * sizeof(uint32_t);
-        }
     }
     if (tree) {
         p->n_kernels += 1;
@@ -1832,7 +1822,9 @@ static int compute_dense(b2d_problem* p, int metric) {
                     p->dist_rerun = false;
                     return rc;
                 }
-                if ((rc = skip_prepare_pass(p, q0, q1 - q0, QR, v, dist ? p->d_nz_full : p->d_nz, !dist))) return rc;
+                // sparse rows in use: the closed form needs the bitmaps of the packed dense rows only (below)
+                const bool packed_bits = p->tips_active && p->rows_general;
+                if (!packed_bits && (rc = skip_prepare_pass(p, q0, q1 - q0, QR, v, p->d_nz, true))) return rc;
                 if (p->tips_active && p->rows_general) {
                     // the pair kernel streams the packed dense rows only: their own bitmaps
                     const int64_t ng = v.npad / 32, wd = p->n_dense_pad / 32;
@@ -1848,7 +1840,6 @@ static int compute_dense(b2d_problem* p, int metric) {
                     // tips_mode is the same on every rank here (the bucket-overflow status was OR-ed)
                     CollBatch cb;
                     const int64_t nch = p->tip_nch;
-                    coll_add_blocks(p, cb, p->d_nz_full, 4 * (size_t)(QR / 32) * sizeof(uint32_t));
                     coll_add_blocks(p, cb, p->d_total, TILE * sizeof(long long));
                     coll_add_blocks(p, cb, p->d_svec, TILE * sizeof(double));
                     if (p->tips_active) {
@@ -1862,7 +1853,16 @@ static int compute_dense(b2d_problem* p, int metric) {
                         coll_add_blocks(p, cb, p->d_tip_cnt, TILE * sizeof(unsigned));
                     }
                     if ((rc = coll_flush(p, cb))) return rc;
-                    if ((rc = skip_transpose(p, p->d_nz_full, q0, q1 - q0, QR))) return rc;
+                }
+                if (packed_bits) {
+                    // transposed zero bitmaps of all groups from the packed rows' bitmaps (every other row: 0)
+                    B2D_CUDA(cudaMemsetAsync(p->d_zt, 0, (size_t)p->mpad * p->ngw * sizeof(uint32_t), p->stream));
+                    const int64_t warps = p->n_dense * p->ngw;
+                    p->n_kernels += 1;
+                    if (warps)
+                        k_scatter_zero_bits<<<(unsigned)((warps + 7) / 8), 256, 0, p->stream>>>(
+                            p->d_nz, p->n_dense_pad / 32, p->d_dense_pos, p->n_dense, p->d_gperm, p->ngw, p->d_zt);
+                    B2D_CUDA(cudaGetLastError());
                 }
                 if (p->tips_active && p->rows_general) {
                 } else if (p->tips_active && p->pack_pass) {

@@ -67,6 +67,26 @@ k_transpose_bitmaps(const uint32_t* __restrict__ nz, const int32_t* __restrict__
     zt[(q0 + w * 32 + lane) * ngw + gw] = mine;
 }
 
+// The same transposed bitmaps from the bitmaps of the PACKED dense rows (sparse rows handled by the
+// intersection kernel, b2d_tips.cuh): zt[pos[r]][w] for the packed rows r, every other row of zt left 0
+// ("present").  The rows not packed are whole small subtrees whose branches are left out of the root
+// distances the closed form uses (d_rdR: they inherit their parent's value), so a zero subtree rooted
+// inside one contributes exactly 0 and its bits are not needed; a zero subtree rooted at a packed row
+// covers its position range whatever the bits below say.  One warp per (packed row, 32 groups).
+__global__ void __launch_bounds__(256)
+k_scatter_zero_bits(const uint32_t* __restrict__ nzd /*[groups][words_d]*/, int64_t words_d,
+                    const int32_t* __restrict__ pos, int64_t nd, const int32_t* __restrict__ gperm, int64_t ngw,
+                    uint32_t* __restrict__ zt /*[mpad][ngw]*/) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nd * ngw) return;
+    const int64_t r = warp / ngw, gw = warp % ngw;
+    const int g = gperm[32 * gw + lane];
+    const bool zero = g >= 0 && !((nzd[(int64_t)g * words_d + (r >> 5)] >> (r & 31)) & 1u);
+    const uint32_t m = __ballot_sync(0xffffffffu, zero);
+    if (lane == 0) zt[(int64_t)pos[r] * ngw + gw] = m;
+}
+
 // E[x][gl] for the GW words [kbeg, kbeg + GW) of the permuted group list (gl = 32 * word + lane);
 // E is zero-initialised.  One warp per (node q, word): lanes whose group has a maximal zero
 // subtree rooted at q fill the subtree's position range [q - size + 1, q].
