@@ -1271,7 +1271,7 @@ static int tips_build(b2d_problem* p) {
 // table's density (a node with s tips below is non-zero for about s * nnz / (n * tips) of the
 // samples; measured optimum: up to ~30 % of the samples) and is halved while a bucket overflows.
 // sparse-row threshold, masks, root distances and the list of dense positions for the current S0
-// which: 0 weighted (rows up to ~0.32 / density tips: the dense alternative is the FP64 kernel),
+// which: 0 weighted (rows up to ~0.40 / density tips: the dense alternative is the FP64 kernel),
 // 1 unweighted (~0.16 / density: the look-up-table kernel is four times cheaper per row)
 static int rows_masks(b2d_problem* p, int which) {
     const TreeOrder& o = p->order;
@@ -1281,7 +1281,7 @@ static int rows_masks(b2d_problem* p, int which) {
         int64_t ntips = 0;
         for (int64_t q = 0; q < p->mpad; ++q) ntips = std::max<int64_t>(ntips, o.tips_q[q]);
         const double dens = (double)p->nnz / std::max(1.0, (double)p->n * (double)std::max<int64_t>(ntips, 1));
-        const double factor = which == 0 ? 0.32 : 0.16;
+        const double factor = which == 0 ? 0.40 : 0.16;
         int s0 = g_sparse_rows_max_tips ? g_sparse_rows_max_tips : (int)std::min(256.0, std::max(1.0, factor / std::max(dens, 1e-9)));
         p->rows_S0_pref[which] = std::max(1, s0);
     }
