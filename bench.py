@@ -806,7 +806,7 @@ def cpu_baseline_block(inp, n_sub, gpu_vec_fn):
     return out
 
 
-def api_e2e_block(ctx, inp, reps=3):
+def api_e2e_block(ctx, inp, reps=5):
     """The public call a user makes: beta_diversity(metric, sparse table, ids, tree=<Newick text
     read into flat arrays>, taxa=<names>) -> DistanceMatrix, host objects in, host object out."""
     import scipy.sparse as sp
