@@ -368,6 +368,7 @@ struct PageableUpload {
     std::atomic<size_t> next{0};
     std::atomic<int> error{0};
     std::unique_lock<std::mutex> pool_lock;
+    bool download = false;   // jobs copy device -> pageable host (fetch) instead of host -> device
     static constexpr size_t PIECE = (size_t)4 << 20;
     static constexpr int MAX_THREADS = 4;
 
@@ -402,7 +403,7 @@ struct PageableUpload {
         char* stage = staging();
         if (!stage) {   // no page-locked memory to be had: the plain way
             for (const Job& j : jobs)
-                if (cudaMemcpy(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice) != cudaSuccess) error = 1;
+                if (cudaMemcpy(j.dst, j.src, j.bytes, download ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice) != cudaSuccess) error = 1;
             jobs.clear();
             pool_lock.unlock();
             return;
@@ -421,6 +422,26 @@ struct PageableUpload {
                 cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
                 char* mine[2] = {stage + (size_t)(2 * t) * PIECE, stage + (size_t)(2 * t + 1) * PIECE};
                 int used[2] = {0, 0}, k = 0;
+                if (download) {
+                    // piece i + 1 is on its way from the device while piece i is copied out of its chunk
+                    size_t pending[2] = {0, 0};
+                    auto drain = [&](int c) {
+                        if (!used[c]) return;
+                        if (cudaEventSynchronize(ev[c]) != cudaSuccess) error = 1;
+                        memcpy(jobs[pending[c]].dst, mine[c], jobs[pending[c]].bytes);
+                        used[c] = 0;
+                    };
+                    for (size_t i = next.fetch_add(1); i < jobs.size() && !error; i = next.fetch_add(1), k ^= 1) {
+                        drain(k);
+                        if (cudaMemcpyAsync(mine[k], jobs[i].src, jobs[i].bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) error = 1;
+                        cudaEventRecord(ev[k], st);
+                        used[k] = 1;
+                        pending[k] = i;
+                        drain(k ^ 1);
+                    }
+                    drain(0);
+                    drain(1);
+                } else
                 for (size_t i = next.fetch_add(1); i < jobs.size() && !error; i = next.fetch_add(1), k ^= 1) {
                     if (used[k] && cudaEventSynchronize(ev[k]) != cudaSuccess) error = 1;
                     memcpy(mine[k], jobs[i].src, jobs[i].bytes);
@@ -442,7 +463,7 @@ struct PageableUpload {
         if (pool_lock.owns_lock()) pool_lock.unlock();
         if (error) {
             cudaGetLastError();
-            return fail(B2D_ERR_CUDA, "host -> device copy of the CSR failed");
+            return fail(B2D_ERR_CUDA, download ? "device -> host copy of the result failed" : "host -> device copy of the CSR failed");
         }
         return B2D_OK;
     }
@@ -2769,6 +2790,22 @@ static int b2d_problem_fetch_impl(b2d_problem* p, double* out) {
     if (!p->computed) return fail(B2D_ERR_STATE, "fetch before compute");
     B2D_CUDA(cudaSetDevice(p->device));
     NvtxRange range("b2d:fetch (D2H)");
+    if ((size_t)p->out_len * sizeof(double) >= ((size_t)32 << 20) && PageableUpload::pageable(out)) {
+        // an ordinary (pageable) result vector: staged through page-locked chunks by a few host threads
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        const auto t0 = std::chrono::steady_clock::now();
+        PageableUpload dl;
+        dl.download = true;
+        for (int64_t b : p->owned) {
+            int64_t first, cnt;
+            stripe_range(p, b, &first, &cnt);
+            dl.add(out + first, p->d_out + p->row_base[b], (size_t)cnt * sizeof(double));
+        }
+        dl.start(p->device);
+        int rc = dl.wait();
+        p->t_fetch = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
+    }
     B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
     for (int64_t b : p->owned) {
         int64_t first, cnt;
@@ -2790,15 +2827,27 @@ static int b2d_problem_fetch_compact_impl(b2d_problem* p, double* out, int64_t* 
     if (!p->computed) return fail(B2D_ERR_STATE, "fetch before compute");
     B2D_CUDA(cudaSetDevice(p->device));
     NvtxRange range("b2d:fetch_compact (D2H)");
-    B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
-    if (p->out_len)
-        B2D_CUDA(cudaMemcpyAsync(out, p->d_out, p->out_len * sizeof(double), cudaMemcpyDeviceToHost,
-                                 p->stream));
-    B2D_CUDA(cudaEventRecord(p->ev[1], p->stream));
-    B2D_CUDA(cudaStreamSynchronize(p->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
-    p->t_fetch = ms;
+    if ((size_t)p->out_len * sizeof(double) >= ((size_t)32 << 20) && PageableUpload::pageable(out)) {
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        const auto t0 = std::chrono::steady_clock::now();
+        PageableUpload dl;
+        dl.download = true;
+        dl.add(out, p->d_out, (size_t)p->out_len * sizeof(double));
+        dl.start(p->device);
+        int rc = dl.wait();
+        p->t_fetch = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (rc) return rc;
+    } else {
+        B2D_CUDA(cudaEventRecord(p->ev[0], p->stream));
+        if (p->out_len)
+            B2D_CUDA(cudaMemcpyAsync(out, p->d_out, p->out_len * sizeof(double), cudaMemcpyDeviceToHost,
+                                     p->stream));
+        B2D_CUDA(cudaEventRecord(p->ev[1], p->stream));
+        B2D_CUDA(cudaStreamSynchronize(p->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+        p->t_fetch = ms;
+    }
     if (stripe_offsets) {
         int64_t k = 0;
         for (int64_t b : p->owned) {
