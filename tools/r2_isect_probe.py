@@ -58,11 +58,6 @@ def feature_case(n, f, lam, variants):
 
 which = sys.argv[1:] or ["w", "u", "f", "ws", "us"]
 V = [(0, 4), (1, 2), (1, 4), (1, 8)]
-if "flat" in which:
-    which = [w for w in which if w != "flat"]
-    tree_case("weighted_unifrac_normalized", 10000, 100000, 0.02, [(1, 4), (1, -2), (1, -4), (1, -8)])
-    tree_case("unweighted_unifrac", 10000, 100000, 0.02, [(0, 4), (1, 2), (1, -1), (1, -2), (1, -4)])
-    feature_case(50000, 50000, 0.01, [(1, 1), (1, -1), (1, -2)])
 if "w" in which: tree_case("weighted_unifrac_normalized", 10000, 100000, 0.02, V)
 if "u" in which: tree_case("unweighted_unifrac", 10000, 100000, 0.02, [(0, 4), (1, 1), (1, 2), (1, 4)])
 if "f" in which: feature_case(50000, 50000, 0.01, [(0, 4), (1, 1), (1, 2), (1, 4)])
