@@ -94,4 +94,5 @@ if "u4s" in which:   # sparse-row threshold sweep on one shard of eight of BASEL
                   f"entries={t['sparse_row_entries']:.3e}", flush=True)
     _capi.set_option("sparse_rows_max_tips", 0)
 if "us" in which: tree_case("unweighted_unifrac", 10000, 100000, 0.02, [(1, 4)], s0s=(6, 8, 12, 16, 24, 32))
+if "us2" in which: tree_case("unweighted_unifrac", 10000, 100000, 0.02, [(-1, 0)], s0s=(6, 7, 8, 9, 10, 12))
 json.dump(res, open("gpurun_out/r2_isect_probe.json", "w"), indent=1)
