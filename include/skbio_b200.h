@@ -178,6 +178,12 @@ int b2d_problem_set_collectives(b2d_problem* p, int rank, int world, b2d_allgath
 /* Block range [first, last) of 128-sample blocks rank `rank` of `world` builds (host arithmetic only). */
 int b2d_build_range(int64_t n_samples, int rank, int world, int64_t* first_block, int64_t* last_block);
 
+/* Host only: minimum, number of non-zero and number of positive elements of a value array in one
+ * multi-threaded pass (dtype: 0 int64, 1 float64, 2 int32, 3 float32; NaN never becomes the minimum).
+ * What the host needs of the table's stored values for `_validate_counts_matrix`'s negativity check
+ * (/root/reference/skbio/diversity/_util.py:51-54) and for the CSR conversion. */
+int b2d_host_scan(const void* data, int64_t n, int dtype, double* min_out, int64_t* nonzero_out, int64_t* positive_out);
+
 /* Device-to-device copy (same or peer device, unified addressing), blocking: what an in-process
  * allgatherv_device callback is made of. */
 int b2d_device_copy(void* dst, const void* src, int64_t bytes);

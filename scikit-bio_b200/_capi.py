@@ -135,6 +135,8 @@ def _declare(lib):
                                                 ALLGATHERV_DEVICE_FN, ctypes.c_void_p]
     lib.b2d_build_range.restype = ctypes.c_int
     lib.b2d_build_range.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _i64p, _i64p]
+    lib.b2d_host_scan.restype = ctypes.c_int
+    lib.b2d_host_scan.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, _f64p, _i64p, _i64p]
     lib.b2d_device_copy.restype = ctypes.c_int
     lib.b2d_device_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     lib.b2d_debug_tree_order.restype = ctypes.c_int
@@ -154,7 +156,7 @@ EXPORTED_SYMBOLS = [
     "b2d_flat_tree_free", "b2d_permanova_sw", "b2d_problem_phydiv", "b2d_debug_fetch_embedding",
     "b2d_problem_fetch_square_rows", "b2d_problem_center", "b2d_center_condensed",
     "b2d_problem_create_tree_columns", "b2d_names_lookup", "b2d_names_validate",
-    "b2d_problem_set_collectives", "b2d_build_range", "b2d_device_copy",
+    "b2d_problem_set_collectives", "b2d_build_range", "b2d_device_copy", "b2d_host_scan",
 ]
 
 
@@ -343,6 +345,25 @@ def build_range(n_samples, rank, world):
     a, b = ctypes.c_int64(0), ctypes.c_int64(0)
     _check(load().b2d_build_range(int(n_samples), int(rank), int(world), ctypes.byref(a), ctypes.byref(b)))
     return int(a.value), int(b.value)
+
+
+_SCAN_DTYPES = {np.dtype(np.int64): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2, np.dtype(np.float32): 3}
+
+
+def host_scan(values):
+    """(minimum, number of non-zero, number of positive) elements of a 1-D array - one multi-threaded
+    native pass for large contiguous int64 / float64 / int32 / float32 arrays, NumPy otherwise.  Host only."""
+    values = np.asarray(values)
+    code = _SCAN_DTYPES.get(values.dtype)
+    if code is None or values.ndim != 1 or not values.flags.c_contiguous or values.size < (1 << 16):
+        if values.size == 0:
+            return 0.0, 0, 0
+        return float(values.min()), int(np.count_nonzero(values)), int(np.count_nonzero(values > 0))
+    mn = ctypes.c_double(0.0)
+    nz, pos = ctypes.c_int64(0), ctypes.c_int64(0)
+    _check(load().b2d_host_scan(values.ctypes.data, values.size, code, ctypes.byref(mn), ctypes.byref(nz),
+                                ctypes.byref(pos)))
+    return mn.value, int(nz.value), int(pos.value)
 
 
 def device_copy(dst, src, nbytes):

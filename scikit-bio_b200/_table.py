@@ -74,6 +74,19 @@ def ingest_table(table, sample_ids=None, feature_ids=None, expand=True):
     return data, sample_ids, feature_ids
 
 
+def _stored_values_scan(data):
+    """(min, non-zero, positive) of a sparse table's stored values: one native multi-threaded pass when the
+    library is there (host code only, no GPU needed), NumPy otherwise."""
+    try:
+        from . import _capi
+        return _capi.host_scan(data)
+    except Exception:
+        data = np.asarray(data)
+        if data.size == 0:
+            return 0.0, 0, 0
+        return float(data.min()), int(np.count_nonzero(data)), int(np.count_nonzero(data > 0))
+
+
 def validate_counts_matrix(counts):
     """dtype / negativity / dimensionality checks with the reference's messages."""
     if _is_sparse(counts):
@@ -81,7 +94,7 @@ def validate_counts_matrix(counts):
         if not (np.issubdtype(dtype, np.floating) or np.issubdtype(dtype, np.integer)
                 or dtype == np.dtype("bool")):
             raise ValueError("Counts must be integers or floating-point numbers.")
-        if counts.nnz and counts.data.min() < 0:
+        if counts.nnz and _stored_values_scan(counts.data)[0] < 0:
             raise ValueError("Counts cannot contain negative values.")
         return counts
     counts = np.asarray(counts)
@@ -112,13 +125,13 @@ def to_csr(counts, mode):
         data = csr.data
         # the common case - every stored entry counts - passes the caller's arrays on untouched
         if mode == "presence":
-            nkeep = int(np.count_nonzero(data > 0.0))
+            nkeep = _stored_values_scan(data)[2]
         elif mode == "int64":
             data = data.astype(np.int64, copy=False)
-            nkeep = int(np.count_nonzero(data))
+            nkeep = _stored_values_scan(data)[1]
         else:
             data = data.astype(np.float64, copy=False)
-            nkeep = int(np.count_nonzero(data))
+            nkeep = _stored_values_scan(data)[1]
         indptr = csr.indptr.astype(np.int64)
         cols = csr.indices
         if nkeep != len(data):

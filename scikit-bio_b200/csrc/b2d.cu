@@ -867,6 +867,24 @@ static int launch_isect(b2d_problem* p, cudaStream_t st, const void* entries, co
     return B2D_OK;
 }
 
+// Host only: minimum, number of non-zero and number of positive elements of a large value array in one
+// multi-threaded pass (the negativity check of _validate_counts_matrix and the "does every stored entry
+// count" test of the CSR conversion are memory-bound scans of the same 160 MB at config 2).
+template <typename T>
+static void scan_slice(const T* x, int64_t a, int64_t b, double* mn, int64_t* nz, int64_t* pos) {
+    T m = a < b ? x[a] : T(0);
+    int64_t z = 0, p = 0;
+    for (int64_t i = a; i < b; ++i) {
+        const T v = x[i];
+        if (v < m) m = v;       // false for NaN: a NaN never becomes the minimum, like `x.min() < 0` never fires on it
+        z += v != T(0);
+        p += v > T(0);
+    }
+    *mn = (double)m;
+    *nz = z;
+    *pos = p;
+}
+
 extern "C" {
 
 int b2d_api_version(void) { return B2D_API_VERSION; }
@@ -2907,6 +2925,44 @@ int b2d_build_range(int64_t n_samples, int rank, int world, int64_t* first_block
     if (n_samples < 0 || world < 1 || rank < 0 || rank >= world || !first_block || !last_block)
         return fail(B2D_ERR_INVALID_ARGUMENT, "need n_samples >= 0 and 0 <= rank < world");
     build_range((n_samples + TILE - 1) / TILE, rank, world, first_block, last_block);
+    return B2D_OK;
+}
+
+int b2d_host_scan(const void* data, int64_t n, int dtype, double* min_out, int64_t* nonzero_out, int64_t* positive_out) {
+    if (n < 0 || (n && !data) || !min_out || !nonzero_out || !positive_out || dtype < 0 || dtype > 3)
+        return fail(B2D_ERR_INVALID_ARGUMENT, "bad arguments (dtype: 0 int64, 1 float64, 2 int32, 3 float32)");
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), n / (1 << 18) + 1}));
+    std::vector<double> mn(nt, 0.0);
+    std::vector<int64_t> nz(nt, 0), pos(nt, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        auto work = [=, &mn, &nz, &pos]() {
+            switch (dtype) {
+                case 0: scan_slice((const int64_t*)data, a, b, &mn[t], &nz[t], &pos[t]); break;
+                case 1: scan_slice((const double*)data, a, b, &mn[t], &nz[t], &pos[t]); break;
+                case 2: scan_slice((const int32_t*)data, a, b, &mn[t], &nz[t], &pos[t]); break;
+                default: scan_slice((const float*)data, a, b, &mn[t], &nz[t], &pos[t]); break;
+            }
+        };
+        if (t + 1 < nt) th.emplace_back(work);
+        else work();
+    }
+    for (auto& x : th) x.join();
+    double m = 0.0;
+    int64_t z = 0, p = 0;
+    bool first = true;
+    for (int t = 0; t < nt; ++t) {
+        if (n * t / nt < n * (t + 1) / nt) {
+            if (first || mn[t] < m) m = mn[t];
+            first = false;
+        }
+        z += nz[t];
+        p += pos[t];
+    }
+    *min_out = m;
+    *nonzero_out = z;
+    *positive_out = p;
     return B2D_OK;
 }
 

@@ -368,3 +368,34 @@ def test_flat_tree_validation_messages():
     with pytest.raises(skbio_b200.DuplicateNodeError):
         skbio_b200.validate_taxa_and_tree(OIDS, skbio_b200.read_newick_flat(
             "((OTU1:0.1,OTU2:0.2):0.3,((OTU3:0.5,OTU4:0.7):1,(OTU5:1.1,OTU2:1):1):1)root;"))
+
+
+def test_native_scan_of_stored_values_matches_numpy():
+    """b2d_host_scan (the negativity check of _validate_counts_matrix and the 'every stored entry counts'
+    test of the CSR conversion in one multi-threaded pass): minimum, non-zero and positive counts for the
+    four dtypes, NaN included, small arrays through the NumPy branch."""
+    from skbio_b200 import _capi, _table
+
+    rng = np.random.default_rng(5)
+    for dt in (np.int64, np.float64, np.int32, np.float32):
+        for n in (0, 3, 70001, 1_200_003):
+            if np.issubdtype(dt, np.integer):
+                x = rng.integers(-2, 7, n).astype(dt)
+            else:
+                x = (rng.normal(size=n) * (rng.random(n) < 0.6)).astype(dt)
+                if n > 10:
+                    x[5] = np.nan
+            mn, nz, pos = _capi.host_scan(x)
+            assert nz == int(np.count_nonzero(x)) and pos == int(np.count_nonzero(x > 0))
+            if n:
+                with np.errstate(all="ignore"):
+                    assert mn == float(np.nanmin(x))
+    import scipy.sparse as sp
+
+    bad = sp.csr_matrix(np.array([[0, 2, -1], [3, 0, 0]]))
+    with pytest.raises(ValueError, match="negative"):
+        _table.validate_counts_matrix(bad)
+    big = sp.random(300, 2000, density=0.2, random_state=3, format="csr", dtype=np.float64)
+    big.data[17] = 0.0      # an explicit zero must not become an entry
+    indptr, cols, vals = _table.to_csr(big, "float64")
+    assert len(vals) == big.nnz - 1 and indptr[-1] == len(vals) and np.all(vals != 0)
