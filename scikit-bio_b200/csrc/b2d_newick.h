@@ -110,8 +110,23 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
         }
         return true;
     };
+    // Fast path for the overwhelmingly common token: unquoted, no whitespace, no comment.  kind[c]: 1 = a
+    // structural character ends the token, 2 = whitespace / '[' / quote: the general reader takes over.
+    static const struct Kinds {
+        unsigned char k[256];
+        Kinds() {
+            memset(k, 0, sizeof(k));
+            for (const char* d = "(),:;"; *d; ++d) k[(unsigned char)*d] = 1;
+            for (const char* d = " \t\n\r\f\v['"; *d; ++d) k[(unsigned char)*d] = 2;
+        }
+    } kinds;
+    auto plain_token_end = [&](int64_t from) -> int64_t {   // end of a plain token starting at `from`, or -1
+        int64_t j = from;
+        while (j < n && kinds.k[(unsigned char)s[j]] == 0) ++j;
+        return (j >= n || kinds.k[(unsigned char)s[j]] == 1) ? j : -1;
+    };
     while (!done) {
-        if (!skip_ws_comments()) return "unbalanced [comment] in Newick text";
+        if (i < n && kinds.k[(unsigned char)s[i]] == 2 && !skip_ws_comments()) return "unbalanced [comment] in Newick text";
         if (i >= n) break;
         char c = s[i];
         if (c == '(') {
@@ -136,6 +151,18 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
             ++i;
         } else if (c == ':') {
             ++i;
+            {
+                const int64_t j = plain_token_end(i);
+                double fv = 0.0;
+                if (j > i) {
+                    const auto ff = std::from_chars(s + i, s + j, fv);
+                    if (ff.ec == std::errc() && ff.ptr == s + j) {
+                        nodes[cur].length = fv;
+                        i = j;
+                        continue;
+                    }
+                }
+            }
             if (!skip_ws_comments()) return "unbalanced [comment] in Newick text";
             std::string tok;
             bool quoted;
@@ -155,6 +182,19 @@ inline std::string parse_newick(const char* s, int64_t n, FlatTree& out) {
             }
             nodes[cur].length = v;
         } else {
+            {
+                const int64_t j = plain_token_end(i);
+                if (j > i) {   // a plain label: straight into the name blob, '_' -> ' '
+                    nodes[cur].has_name = true;
+                    nodes[cur].name_b = (int64_t)names.size();
+                    names.append(s + i, (size_t)(j - i));
+                    for (int64_t x = nodes[cur].name_b; x < (int64_t)names.size(); ++x)
+                        if (names[x] == '_') names[x] = ' ';
+                    nodes[cur].name_e = (int64_t)names.size();
+                    i = j;
+                    continue;
+                }
+            }
             std::string tok;
             bool quoted;
             if (!read_token(tok, quoted)) return "could not parse Newick: unbalanced quotes or whitespace in a label";
