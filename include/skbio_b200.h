@@ -184,7 +184,8 @@ int b2d_build_range(int64_t n_samples, int rank, int world, int64_t* first_block
  * (/root/reference/skbio/diversity/_util.py:51-54) and for the CSR conversion. */
 int b2d_host_scan(const void* data, int64_t n, int dtype, double* min_out, int64_t* nonzero_out, int64_t* positive_out);
 
-/* Device-to-device copy (same or peer device, unified addressing), blocking: what an in-process
+/* Device-to-device copy (same or peer device, unified addressing) that returns when the data is in place
+ * (a plain device-to-device cudaMemcpy does not wait on the host's side): what an in-process
  * allgatherv_device callback is made of. */
 int b2d_device_copy(void* dst, const void* src, int64_t bytes);
 

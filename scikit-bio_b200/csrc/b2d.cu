@@ -2968,7 +2968,12 @@ int b2d_host_scan(const void* data, int64_t n, int dtype, double* min_out, int64
 
 int b2d_device_copy(void* dst, const void* src, int64_t bytes) {
     if (bytes < 0 || (bytes && (!dst || !src))) return fail(B2D_ERR_INVALID_ARGUMENT, "bad copy arguments");
-    if (bytes) B2D_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault));
+    // a device-to-device cudaMemcpy does NOT wait on the host's side (same device or peer): the copy goes to
+    // the calling thread's own stream and the call returns when it has completed there
+    if (bytes) {
+        B2D_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, cudaStreamPerThread));
+        B2D_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    }
     return B2D_OK;
 }
 

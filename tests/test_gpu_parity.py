@@ -1253,6 +1253,28 @@ def test_distributed_build_with_flagged_pairs_falls_back_per_rank():
             assert all(t["exchange_bytes"] == 0 for t in tms)   # third compute: everybody voted replicated
 
 
+def test_devices_argument_on_two_real_gpus():
+    """beta_diversity(..., devices=[0, 1]) on a box with two GPUs: one shard and one host thread per
+    device, the per-block products exchanged by peer copies between the two devices, identical to the
+    single-device result.  Skipped on a single-GPU box (devices=[0, 0] covers the logic there)."""
+    sb = _skbio_b200()
+    from skbio_b200 import _capi, synthetic
+
+    if _capi.load().b2d_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    n, tips = 900, 2400
+    parent, length, names, tip_node, indptr, cols, vals = _random_problem(n, tips, 0.03, 97)
+    dense = synthetic.csr_to_dense(indptr, cols, vals, tips)
+    tree = sb.FlatTree(parent, length, names)
+    taxa = [f"T{i}" for i in range(tips)]
+    for metric, kw in (("weighted_unifrac", {"normalized": True}), ("unweighted_unifrac", {}), ("braycurtis", {})):
+        if "unifrac" in metric:
+            kw = dict(kw, tree=tree, taxa=taxa)
+        one = sb.beta_diversity(metric, dense, **kw).condensed_form()
+        two = sb.beta_diversity(metric, dense, devices=[0, 1], **kw).condensed_form()
+        assert np.array_equal(one, two, equal_nan=True), metric
+
+
 def test_pcoa_centering_and_square_rows_on_the_resident_result():
     """Gower centering (pcoa's first step, /root/reference/skbio/stats/ordination/_cutils.pyx:19-123)
     and square-row gathering on the device-resident condensed result, against NumPy on the fetched
