@@ -61,6 +61,7 @@ V = [(0, 4), (1, 2), (1, 4), (1, 8)]
 if "w" in which: tree_case("weighted_unifrac_normalized", 10000, 100000, 0.02, V)
 if "u" in which: tree_case("unweighted_unifrac", 10000, 100000, 0.02, [(0, 4), (1, 1), (1, 2), (1, 4)])
 if "f" in which: feature_case(50000, 50000, 0.01, [(0, 4), (1, 1), (1, 2), (1, 4)])
+if "f1" in which: feature_case(50000, 50000, 0.01, [(1, 1)])
 if "ws" in which: tree_case("weighted_unifrac_normalized", 10000, 100000, 0.02, [(1, 4)], s0s=(12, 16, 24, 32, 48))
 if "ws2" in which: tree_case("weighted_unifrac_normalized", 10000, 100000, 0.02, [(-1, 0)], s0s=(14, 16, 18, 20, 22))
 if "u4" in which:   # one shard of eight of BASELINE config 4
