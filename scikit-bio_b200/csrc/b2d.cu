@@ -1600,10 +1600,11 @@ static int urows_build(b2d_problem* p, const BuildView& v, bool dist) {
             B2D_CUDA(cudaMemsetAsync(p->d_tip_counts, 0, (nbuckets + 1) * sizeof(unsigned), p->stream));
             continue;
         }
-        // The pipelined kernel stages a bucket pair in one batch when both fit a stage (3 064 keys); buckets just
-        // above that are cut in two and every cut costs a producer search and a drain of the consumers
-        // (one shard of config 4: 516 ms at 2 890 keys per bucket, 660 ms at 3 040).  While the average bucket
-        // does not fit, lower the threshold (once per problem: the choice is remembered).
+        // The pipelined kernel stages a bucket pair in one batch when both fit a stage (3 576 keys; 3 064 before the
+        // stage grew to what shared memory allows); buckets just above that are cut in two and every cut costs a
+        // producer search and a drain of the consumers (one shard of config 4 with 3 064-key stages: 516 ms at
+        // 2 890 keys per bucket, 660 ms at 3 040; with 3 576-key stages the default threshold of 40 tips fits: step
+        // 1 516 -> 1 403 ms).  While the average bucket does not fit, lower the threshold (once per problem).
         {
             const double per_bucket = (double)total / std::max(1.0, (double)nbuckets);
             constexpr double fit = 0.95 * IsGeom<IS_UNWEIGHTED, TP_CHUNK>::cap;

@@ -63,7 +63,7 @@ struct IsGeom {
     // 1 532 (41 ms): a (tile, chunk) holds few matches, so the fixed cost of a batch is what counts
     static constexpr int stages = 2;
     // entries per stage and side (column block / row block)
-    static constexpr int ent_bytes = MODE == IS_WEIGHTED ? 20480 : MODE == IS_UNWEIGHTED ? 12288 : 32768;
+    static constexpr int ent_bytes = MODE == IS_WEIGHTED ? 20480 : MODE == IS_UNWEIGHTED ? 14336 : 32768;
     static constexpr int align_entries = 16 / esize;                                  // bulk copies: 16-byte units
     static constexpr int cap = ent_bytes / esize - 2 * align_entries;                 // entries per batch and side
     static constexpr int run_bytes = (CHUNK + 8) * 2 + 16;                            // run starts of a whole chunk
